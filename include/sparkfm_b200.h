@@ -1,0 +1,242 @@
+/*
+ * sparkfm_b200.h -- C ABI of libsparkfm_b200.so: the B200-native (sm_100a) replacement for
+ * SparkFM's data-parallel hot path (FM predict + mini-batch SGD training).
+ *
+ * This is the drop-in boundary: what a JVM host (Scala `SGD extends FMLearn`, `FMWithSGD.train`,
+ * `FMModel.predict`) binds through Panama / JNI.  Plain pointers and sizes only.  The reference
+ * (edmundhung/SparkFM) has no native interface of its own, so every entry point cites the Scala
+ * member it stands in for; paths are relative to src/main/scala/io/edstud/spark/ in the
+ * reference tree.  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - every function returns SFM_OK (0) or a negative sfm_status; sfm_last_error(h) gives the
+ *     message of the last failure on that handle (library-owned, valid until the next call).
+ *   - one handle drives ONE GPU (one process per GPU under multi-GPU; ranks are joined with
+ *     sfm_comm_init).  Calls on a handle must be serialised by the caller.
+ *   - all host buffers are caller-owned and borrowed for the duration of the call only.
+ *   - the model is fp32 on the device: w0, w[n_slots], V[n_slots][k] feature-major -- the memory
+ *     order of the reference's column-major DenseMatrix(k, n+1) (fm/FMModel.scala:19).
+ *     n_slots = num_attribute + 1 = max feature index + 1 (fm/FMModel.scala:18, DataSet.scala:27-29).
+ *   - CSR: row_ptr int64[n_rows+1], idx int32[nnz], val float[nnz] (NULL = every value is 1.0f),
+ *     label float[n_rows].  Entries keep their stored order; duplicate indices and explicit
+ *     zeros are legal (Breeze activeIterator semantics, fm/FMModel.scala:45,58).  An index
+ *     outside [0, n_slots) is a reported error (SFM_ERR_INDEX), never undefined behaviour.
+ *   - there is NO CPU fallback: without a CUDA device sfm_create fails with SFM_ERR_CUDA.
+ */
+#ifndef SPARKFM_B200_H
+#define SPARKFM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFM_ABI_VERSION 1
+
+typedef enum {
+    SFM_OK = 0,
+    SFM_ERR_ARG = -1,    /* bad argument / bad state                                   */
+    SFM_ERR_CUDA = -2,   /* CUDA runtime failure (incl. no device)                     */
+    SFM_ERR_NCCL = -3,   /* NCCL failure                                               */
+    SFM_ERR_OOM = -4,    /* host or device allocation failed                           */
+    SFM_ERR_INDEX = -5,  /* feature index outside [0, n_slots) or malformed CSR        */
+    SFM_ERR_IO = -6,     /* file / text parse error                                    */
+    SFM_ERR_STATE = -7   /* call not valid now (no dataset loaded, comm not initialised) */
+} sfm_status;
+
+#define SFM_TASK_REGRESSION 0     /* Task.Regression      (Task.scala:5) */
+#define SFM_TASK_CLASSIFICATION 1 /* Task.Classification  (Task.scala:5) */
+
+/* Model + learner configuration.  Replaces the constructor arguments and vars of
+ * fm/FMModel.scala:9-31 (num_attribute, num_factor, k0, k1, reg0/regw/regv) and the `task`
+ * of fm/FM.scala:25-30 (ignored by the reference, fm/impl/FactorizationMachines.scala:12;
+ * here it selects the loss). */
+typedef struct sfm_config {
+    int32_t abi_version;       /* must be SFM_ABI_VERSION                                   */
+    int32_t task;              /* SFM_TASK_*                                                */
+    int32_t k;                 /* num_factor, 0..128                    FMModel.scala:11    */
+    int32_t k0;                /* use global bias                       FMModel.scala:25    */
+    int32_t k1;                /* use linear term                       FMModel.scala:26    */
+    int32_t device;            /* CUDA device ordinal                                       */
+    int64_t n_slots;           /* num_attribute + 1                     FMModel.scala:18    */
+    float reg0;                /* L2 on w0                              FMModel.scala:29    */
+    float regw;                /* L2 on w                               FMModel.scala:30    */
+    float regv;                /* L2 on V                               FMModel.scala:31    */
+    float step_size;           /* SGD step; eta_t = step_size / sqrt(t)                     */
+    float mini_batch_fraction; /* Bernoulli row-sampling rate per iteration, (0, 1]         */
+    int32_t reserved0;
+    uint64_t sampler_seed;     /* iteration t samples with seed sampler_seed + t (MLlib: 42) */
+} sfm_config;
+
+typedef struct sfm_handle sfm_handle;
+
+/* Counters and phase timers accumulated since sfm_create / sfm_stats_reset. */
+typedef struct sfm_stats {
+    int64_t train_steps;
+    int64_t train_rows;       /* samples that went through the gradient                     */
+    int64_t train_nnz;
+    int64_t predict_rows;
+    int64_t predict_nnz;
+    int64_t kernel_launches;  /* launches of THIS library's kernels (incl. its sort passes)  */
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+    double ms_forward;        /* CUDA-event time per phase, only while timing is enabled     */
+    double ms_sort;
+    double ms_reduce;         /* reduce-by-feature (+ fused update on one GPU)               */
+    double ms_allreduce;
+    double ms_update;
+    double ms_predict;
+    double ms_total_train;
+} sfm_stats;
+
+/* ---------------------------------------------------------------- library ------------- */
+int32_t sfm_abi_version(void);
+const char* sfm_status_string(int32_t status);
+/* Number of visible CUDA devices (0 when there is none or no driver). */
+int32_t sfm_device_count(void);
+
+/* Pinned host memory for batch buffers (a JVM wraps it as a direct ByteBuffer / MemorySegment). */
+int32_t sfm_host_alloc(void** ptr, uint64_t bytes);
+int32_t sfm_host_free(void* ptr);
+
+/* ---------------------------------------------------------------- handle -------------- */
+/* new FMModel(num_attribute, num_factor)  (fm/FMModel.scala:9-31): allocates w0 = 0, w = 0,
+ * V = 0 on cfg->device.  Call sfm_init_model or sfm_set_model next. */
+int32_t sfm_create(const sfm_config* cfg, sfm_handle** out);
+int32_t sfm_destroy(sfm_handle* h);
+const char* sfm_last_error(const sfm_handle* h);
+int32_t sfm_get_config(const sfm_handle* h, sfm_config* out);
+/* Mutable learner hyper-parameters (reg0/regw/regv are `var`s at fm/FMModel.scala:29-31). */
+int32_t sfm_set_hyper(sfm_handle* h, float reg0, float regw, float regv, float step_size,
+                      float mini_batch_fraction);
+
+/* ---------------------------------------------------------------- model --------------- */
+/* V ~ N(mean, stdev^2) i.i.d., w = 0, w0 = 0 -- the initial state of fm/FMModel.scala:17-22
+ * (defaults mean 0, stdev 0.01 at :12-13).  The reference ignores its `seed` (:14); here the
+ * draw is a documented counter-based Box-Muller, reproducible. */
+int32_t sfm_init_model(sfm_handle* h, double mean, double stdev, uint64_t seed);
+/* Import / export the parameters (w may be NULL when k1 == 0, v when k == 0). */
+int32_t sfm_set_model(sfm_handle* h, float w0, const float* w, const float* v);
+int32_t sfm_get_model(sfm_handle* h, float* w0, float* w, float* v);
+/* Same with the reference's element type (Double, fm/FMModel.scala:17-19). */
+int32_t sfm_set_model_f64(sfm_handle* h, double w0, const double* w, const double* v);
+int32_t sfm_get_model_f64(sfm_handle* h, double* w0, double* w, double* v);
+/* Model persistence (absent from the reference; format in DESIGN.md section 6). */
+int32_t sfm_save(sfm_handle* h, const char* path);
+int32_t sfm_load(const char* path, int32_t device, sfm_handle** out);
+
+/* ---------------------------------------------------------------- scorer -------------- */
+/* Batched FMModel.predict (fm/FMModel.scala:34-63) over host CSR rows -> out[n_rows].
+ * Replaces `dataset.rdd.mapValues(predict)` (Model.scala:14,22,29; fm/lib/ALS.scala:143). */
+int32_t sfm_predict(sfm_handle* h, const int64_t* row_ptr, const int32_t* idx, const float* val,
+                    int64_t n_rows, float* out);
+
+/* ---------------------------------------------------------------- resident data set ---- */
+/* DataSet.cache() (DataSet.scala:50-54, called at fm/impl/FactorizationMachines.scala:36):
+ * copies this rank's rows to the device once.  global_row_offset is the index of row 0 of this
+ * shard in the whole data set (0 on one GPU); the sampler hashes GLOBAL row numbers so that the
+ * union of all ranks' batches equals the single-GPU batch. */
+int32_t sfm_load_dataset(sfm_handle* h, const int64_t* row_ptr, const int32_t* idx,
+                         const float* val, const float* label, int64_t n_rows,
+                         int64_t global_row_offset);
+int32_t sfm_unload_dataset(sfm_handle* h); /* DataSet.unpersist, DataSet.scala:56-60 */
+/* Fills the resident data set ON THE DEVICE with the Criteo/Avazu-shaped synthetic CTR rows of
+ * DESIGN.md section 5 (n_fields one-hot ids per row, Zipf within field, hashed into n_slots;
+ * rows [global_row_offset, +n_rows)).  Bit-identical to sparkfm_b200.synth.ctr_rows. */
+int32_t sfm_synth_ctr_dataset(sfm_handle* h, int64_t n_rows, int64_t global_row_offset,
+                              int32_t n_fields, const int32_t* field_log2_card,
+                              const uint32_t* zipf_cdf, const int64_t* zipf_cdf_off,
+                              uint64_t seed);
+/* Copies resident rows [row_lo, row_hi) back as CSR (val may be NULL). */
+int32_t sfm_get_dataset_rows(sfm_handle* h, int64_t row_lo, int64_t row_hi, int64_t* row_ptr,
+                             int32_t* idx, float* val, float* label);
+int32_t sfm_dataset_info(sfm_handle* h, int64_t* n_rows, int64_t* nnz, int32_t* max_index);
+/* Scores resident rows [row_lo, row_hi) -> out (host). */
+int32_t sfm_predict_resident(sfm_handle* h, int64_t row_lo, int64_t row_hi, float* out);
+/* Model.computeRMSE / computeMAE / computeAccuracy (Model.scala:13-30) over the resident rows of
+ * ALL ranks, fused into one scoring pass: metrics[0] = sqrt(sum (y-yhat)^2 / N) (:14-15),
+ * [1] = sum (y-yhat) / N (the reference's "MAE" has no abs, :22), [2] = fraction with
+ * sign(y) == sign(yhat), >= 0 counted positive (:29, without its integer division),
+ * [3] = mean logistic loss, [4] = N. */
+int32_t sfm_evaluate(sfm_handle* h, double metrics[5]);
+
+/* ---------------------------------------------------------------- learner -------------- */
+/* One call of the learner plugin, `FMLearn.learn(fm, dataset)` (fm/FMLearn.scala:12), for an
+ * SGD learner (FMGradient + FMUpdater + gradient sum of BASELINE.json north_star; none of them
+ * exists in the reference -- semantics in DESIGN.md section 2): iteration `iter` (1-based) on
+ * the given rows of the RESIDENT data set.  row_ids are shard-local, int64, any order (the
+ * order fixes the summation order); NULL + n_ids < 0 means "sample with the built-in sampler
+ * at mini_batch_fraction".  mean_loss_out receives the mean per-sample loss over the GLOBAL
+ * batch before the update (the analogue of the per-iteration RMSE log,
+ * fm/impl/FactorizationMachines.scala:43); batch_out (may be NULL) the global batch size. */
+int32_t sfm_train_step(sfm_handle* h, const int64_t* row_ids, int64_t n_ids, int64_t iter,
+                       double* mean_loss_out, int64_t* batch_out);
+/* Same, on a mini-batch the host packed into CSR buffers (the north_star boundary: "the Scala
+ * host packs each mini-batch into CSR buffers (indices, values, labels)").  Copies host->device
+ * inside the call. */
+int32_t sfm_train_step_csr(sfm_handle* h, const int64_t* row_ptr, const int32_t* idx,
+                           const float* val, const float* label, int64_t n_rows, int64_t iter,
+                           double* mean_loss_out, int64_t* batch_out);
+/* The loop of FM.learnWith (fm/impl/FactorizationMachines.scala:42-46) with the built-in
+ * sampler: iterations first_iter .. first_iter + n_iters - 1 on the resident data set, no host
+ * round trip in between.  loss_history[n_iters] (may be NULL) gets each iteration's mean loss. */
+int32_t sfm_train(sfm_handle* h, int64_t first_iter, int64_t n_iters, double* loss_history);
+/* The built-in sampler, host side: global row ids of
+ * [row_lo, row_hi) selected in iteration iter.  out has capacity row_hi - row_lo. */
+int32_t sfm_sample_rows(uint64_t seed, int64_t iter, double fraction, int64_t row_lo,
+                        int64_t row_hi, int64_t* out, int64_t* n_out);
+/* Gradient of the current model on resident rows, no update: grad_v[n_slots][k], grad_w[n_slots],
+ * grad_w0 (any may be NULL), loss_sum.  After sfm_comm_init the result is the sum over ranks.
+ * For tests and for hosts that run their own updater. */
+int32_t sfm_gradient(sfm_handle* h, const int64_t* row_ids, int64_t n_ids, float* grad_v,
+                     float* grad_w, float* grad_w0, double* loss_sum, int64_t* batch_out);
+
+/* ---------------------------------------------------------------- multi-GPU ------------ */
+/* Replaces Spark's driver-side combination of partition results (`.sum()` Model.scala:14,
+ * `.reduce(_+_)` fm/lib/ALS.scala:153; MLlib treeAggregate in north_star) by an NCCL all-reduce
+ * of the (V, w, w0) gradient over NVLink.  Rank 0 makes the id, every rank (one process per
+ * GPU) passes the same 128 bytes. */
+#define SFM_UNIQUE_ID_BYTES 128
+int32_t sfm_comm_unique_id(uint8_t id[SFM_UNIQUE_ID_BYTES]);
+int32_t sfm_comm_init(sfm_handle* h, const uint8_t id[SFM_UNIQUE_ID_BYTES], int32_t rank,
+                      int32_t world_size);
+int32_t sfm_comm_info(const sfm_handle* h, int32_t* rank, int32_t* world_size);
+/* Copies rank 0's model to every rank. */
+int32_t sfm_comm_broadcast_model(sfm_handle* h);
+
+/* ---------------------------------------------------------------- text ingest ---------- */
+/* FMUtils.loadLibFMFile (fm/FMUtils.scala:23-53) on an in-memory buffer: trims each line,
+ * skips empty and '#' lines, splits on ' ', label = first token, `index:value` tokens with NO
+ * index shift (:32), stored order and duplicates preserved.  Two-call protocol: call with
+ * idx == NULL to get n_rows / nnz / max_index, allocate, call again.  num_features <= 0 means
+ * "infer": then a row without features is an error like the Scala's `indices.max` (:45).
+ * dimension_out = num_features > 0 ? num_features : max index  (vector length is +1, :50).
+ * err_line (may be NULL) receives the 1-based line of a parse error. */
+int32_t sfm_parse_libfm(const char* text, uint64_t len, int32_t num_features, int64_t* n_rows,
+                        int64_t* nnz, int32_t* dimension_out, double* label, int64_t* row_ptr,
+                        int32_t* idx, double* val, int64_t* err_line);
+/* FMUtils.saveAsLibFMFile row formatter (fm/FMUtils.scala:58-74): label and `i+1:value` tokens
+ * (the +1 asymmetry with the loader is the reference's, :63), numbers through
+ * DecimalFormat("#.###") / "#" (HALF_EVEN).  Returns the needed size in *needed; writes when
+ * cap is large enough. */
+int32_t sfm_format_libfm(const double* label, const int64_t* row_ptr, const int32_t* idx,
+                         const double* val, int64_t n_rows, char* out, uint64_t cap,
+                         uint64_t* needed);
+
+/* ---------------------------------------------------------------- stats ---------------- */
+int32_t sfm_stats_get(sfm_handle* h, sfm_stats* out);
+int32_t sfm_stats_reset(sfm_handle* h);
+/* Per-phase CUDA-event timing costs a synchronisation per phase: off by default. */
+int32_t sfm_set_phase_timing(sfm_handle* h, int32_t enabled);
+/* Blocks until all work queued on the handle has finished. */
+int32_t sfm_synchronize(sfm_handle* h);
+/* Device time of kernels on the handle's compute stream between the two marks, in ms
+ * (CUDA events on the launching stream; torch.cuda.Event cannot see this stream). */
+int32_t sfm_timer_start(sfm_handle* h);
+int32_t sfm_timer_stop(sfm_handle* h, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPARKFM_B200_H */

@@ -1,0 +1,275 @@
+/*
+ * fm_oracle.c -- CPU oracle (fp64) for the SparkFM hot path.  See fm_oracle.h: TEST
+ * INFRASTRUCTURE ONLY, PARITY UNPINNED (no runnable reference, no reference golden vectors).
+ *
+ * Reference citations are relative to /root/reference/src/main/scala/io/edstud/spark/.
+ */
+#include "fm_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+uint64_t fmo_mix64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+int fmo_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* fm/FMModel.scala:57-63 computeFactorComponents: materialise f_j = v(i, idx_j) * x_j over the
+ * stored entries, then sum_f = f.reduce(_+_), sum_sqr_f = f.map(x*x).reduce(_+_) -- two left
+ * folds in stored order. */
+static void factor_components(const double* v, int32_t k, int32_t f, const int32_t* idx,
+                              const double* val, int64_t nnz, double* sum_f, double* sum_sqr_f) {
+    double s = 0.0, q = 0.0;
+    for (int64_t j = 0; j < nnz; ++j) {
+        double t = v[(int64_t)idx[j] * k + f] * val[j];
+        if (j == 0) { s = t; q = t * t; }      /* reduce starts from the first element */
+        else        { s = s + t; q = q + t * t; }
+    }
+    *sum_f = s;
+    *sum_sqr_f = q;
+}
+
+/* fm/FMModel.scala:34-55 */
+double fmo_predict_row(const fmo_params* p, double w0, const double* w, const double* v,
+                       const int32_t* idx, const double* val, int64_t nnz) {
+    double result = 0.0;                       /* :36 */
+    if (p->k0) result += w0;                   /* :38-40 */
+    if (nnz > 0) {                             /* :42 features.used > 0 */
+        if (p->k1) {                           /* :44-46 map(w(i)*x).reduce(_+_) */
+            double lin = w[idx[0]] * val[0];
+            for (int64_t j = 1; j < nnz; ++j) lin = lin + w[idx[j]] * val[j];
+            result += lin;
+        }
+        for (int32_t f = 0; f < p->k; ++f) {   /* :48-51 */
+            double s, q;
+            factor_components(v, p->k, f, idx, val, nnz, &s, &q);
+            result += 0.5 * (s * s - q);
+        }
+    }
+    return result;                             /* :54 */
+}
+
+void fmo_predict(const fmo_params* p, double w0, const double* w, const double* v,
+                 const int64_t* row_ptr, const int32_t* idx, const double* val,
+                 int64_t n_rows, double* out) {
+    for (int64_t r = 0; r < n_rows; ++r) {
+        int64_t b = row_ptr[r];
+        out[r] = fmo_predict_row(p, w0, w, v, idx + b, val + b, row_ptr[r + 1] - b);
+    }
+}
+
+/* One pass over the row: s_f and q_f for all factors at once.  Returns yhat and leaves the
+ * per-factor sums in s[0..k) (needed by the gradient). */
+static double forward_row(const fmo_params* p, double w0, const double* w, const double* v,
+                          const int32_t* idx, const double* val, int64_t nnz, double* s,
+                          double* q) {
+    const int32_t k = p->k;
+    double result = p->k0 ? w0 : 0.0;
+    for (int32_t f = 0; f < k; ++f) { s[f] = 0.0; q[f] = 0.0; }
+    if (nnz <= 0) return result;
+    double lin = 0.0;
+    for (int64_t j = 0; j < nnz; ++j) {
+        const double x = val[j];
+        const double* vi = v + (int64_t)idx[j] * k;
+        lin += w[idx[j]] * x;
+        for (int32_t f = 0; f < k; ++f) {
+            double t = vi[f] * x;
+            s[f] += t;
+            q[f] += t * t;
+        }
+    }
+    if (p->k1) result += lin;
+    for (int32_t f = 0; f < k; ++f) result += 0.5 * (s[f] * s[f] - q[f]);
+    return result;
+}
+
+void fmo_predict_fast(const fmo_params* p, double w0, const double* w, const double* v,
+                      const int64_t* row_ptr, const int32_t* idx, const double* val,
+                      int64_t n_rows, double* out, int n_threads) {
+    if (n_threads < 1) n_threads = 1;
+#pragma omp parallel num_threads(n_threads)
+    {
+        double* s = (double*)malloc(sizeof(double) * 2 * (size_t)(p->k > 0 ? p->k : 1));
+        double* q = s + (p->k > 0 ? p->k : 1);
+#pragma omp for schedule(static)
+        for (int64_t r = 0; r < n_rows; ++r) {
+            int64_t b = row_ptr[r];
+            out[r] = forward_row(p, w0, w, v, idx + b, val + b, row_ptr[r + 1] - b, s, q);
+        }
+        free(s);
+    }
+}
+
+void fmo_loss_mult(int32_t task, double yhat, double label, double* loss, double* mult) {
+    if (task == FMO_TASK_CLASSIFICATION) {
+        const double y = label > 0.0 ? 1.0 : -1.0;
+        const double m = y * yhat;
+        /* log(1+exp(-m)) and sigmoid(-m) without overflow */
+        const double e = exp(-fabs(m));
+        *loss = (m > 0.0 ? 0.0 : -m) + log1p(e);
+        const double sig_neg_m = m > 0.0 ? e / (1.0 + e) : 1.0 / (1.0 + e); /* 1 - 1/(1+exp(-m)) */
+        *mult = -y * sig_neg_m;
+    } else {
+        const double d = yhat - label;
+        *loss = d * d;
+        *mult = d;
+    }
+}
+
+/* Adds one sample's gradient into grad = [V (n_slots*k) | w (n_slots) | w0] and returns its
+ * loss.  dV_if = (x_i*s_f - v_if*x_i^2)*mult, dw_i = x_i*mult, dw0 = mult. */
+static double accumulate_row(const fmo_params* p, double w0, const double* w, const double* v,
+                             const int32_t* idx, const double* val, int64_t nnz, double label,
+                             double* grad, double* s, double* q) {
+    const int32_t k = p->k;
+    const int64_t n = p->n_slots;
+    double loss, mult;
+    const double yhat = forward_row(p, w0, w, v, idx, val, nnz, s, q);
+    fmo_loss_mult(p->task, yhat, label, &loss, &mult);
+    if (p->k0) grad[n * k + n] += mult;
+    for (int64_t j = 0; j < nnz; ++j) {
+        const int64_t i = idx[j];
+        const double x = val[j];
+        if (p->k1) grad[n * k + i] += x * mult;
+        const double* vi = v + i * k;
+        double* gi = grad + i * k;
+        for (int32_t f = 0; f < k; ++f) gi[f] += (x * s[f] - vi[f] * x * x) * mult;
+    }
+    return loss;
+}
+
+double fmo_gradient(const fmo_params* p, double w0, const double* w, const double* v,
+                    const int64_t* row_ptr, const int32_t* idx, const double* val,
+                    const double* label, const int64_t* row_ids, int64_t n_ids, double* grad) {
+    const int64_t len = p->n_slots * (p->k + 1) + 1;
+    memset(grad, 0, sizeof(double) * (size_t)len);
+    double* s = (double*)malloc(sizeof(double) * 2 * (size_t)(p->k > 0 ? p->k : 1));
+    double* q = s + (p->k > 0 ? p->k : 1);
+    double loss_sum = 0.0;
+    for (int64_t t = 0; t < n_ids; ++t) {
+        const int64_t r = row_ids ? row_ids[t] : t;
+        const int64_t b = row_ptr[r];
+        loss_sum += accumulate_row(p, w0, w, v, idx + b, val + b, row_ptr[r + 1] - b, label[r],
+                                   grad, s, q);
+    }
+    free(s);
+    return loss_sum;
+}
+
+void fmo_update(const fmo_params* p, double* w0, double* w, double* v, const double* grad,
+                int64_t iter, double step_size, int64_t batch_count) {
+    if (batch_count <= 0) return;
+    const int32_t k = p->k;
+    const int64_t n = p->n_slots;
+    const double eta = step_size / sqrt((double)iter);
+    const double inv = 1.0 / (double)batch_count;
+    for (int64_t e = 0; e < n * k; ++e) v[e] -= eta * (grad[e] * inv + p->regv * v[e]);
+    if (p->k1)
+        for (int64_t i = 0; i < n; ++i) w[i] -= eta * (grad[n * k + i] * inv + p->regw * w[i]);
+    if (p->k0) *w0 -= eta * (grad[n * k + n] * inv + p->reg0 * *w0);
+}
+
+double fmo_train_step(const fmo_params* p, double* w0, double* w, double* v,
+                      const int64_t* row_ptr, const int32_t* idx, const double* val,
+                      const double* label, const int64_t* row_ids, int64_t n_ids,
+                      int64_t iter, double step_size, int64_t batch_count, double* grad) {
+    const double loss_sum =
+        fmo_gradient(p, *w0, w, v, row_ptr, idx, val, label, row_ids, n_ids, grad);
+    fmo_update(p, w0, w, v, grad, iter, step_size, batch_count);
+    return loss_sum;
+}
+
+double fmo_train_step_mt(const fmo_params* p, double* w0, double* w, double* v,
+                         const int64_t* row_ptr, const int32_t* idx, const double* val,
+                         const double* label, const int64_t* row_ids, int64_t n_ids,
+                         int64_t iter, double step_size, int64_t batch_count,
+                         double* scratch, int n_threads) {
+    if (n_threads < 1) n_threads = 1;
+    const int32_t k = p->k;
+    const int64_t n = p->n_slots;
+    const int64_t len = n * (k + 1) + 1;
+    double* losses = (double*)calloc((size_t)n_threads, sizeof(double));
+    const double w0v = *w0;
+#pragma omp parallel num_threads(n_threads)
+    {
+#ifdef _OPENMP
+        const int t = omp_get_thread_num();
+#else
+        const int t = 0;
+#endif
+        double* g = scratch + (int64_t)t * len;
+        memset(g, 0, sizeof(double) * (size_t)len);
+        double* s = (double*)malloc(sizeof(double) * 2 * (size_t)(k > 0 ? k : 1));
+        double* q = s + (k > 0 ? k : 1);
+        const int64_t lo = n_ids * t / n_threads, hi = n_ids * (t + 1) / n_threads;
+        double ls = 0.0;
+        for (int64_t u = lo; u < hi; ++u) {
+            const int64_t r = row_ids ? row_ids[u] : u;
+            const int64_t b = row_ptr[r];
+            ls += accumulate_row(p, w0v, w, v, idx + b, val + b, row_ptr[r + 1] - b, label[r], g,
+                                 s, q);
+        }
+        losses[t] = ls;
+        free(s);
+#pragma omp barrier
+        /* partial sums added in thread order, then the update, both split by slot */
+        if (batch_count > 0) {
+            const double eta = step_size / sqrt((double)iter);
+            const double inv = 1.0 / (double)batch_count;
+#pragma omp for schedule(static)
+            for (int64_t e = 0; e < len; ++e) {
+                double acc = scratch[e];
+                for (int u = 1; u < n_threads; ++u) acc += scratch[(int64_t)u * len + e];
+                if (e < n * k) v[e] -= eta * (acc * inv + p->regv * v[e]);
+                else if (e < n * k + n) {
+                    if (p->k1) w[e - n * k] -= eta * (acc * inv + p->regw * w[e - n * k]);
+                } else if (p->k0) *w0 -= eta * (acc * inv + p->reg0 * *w0);
+            }
+        }
+    }
+    double loss_sum = 0.0;
+    for (int t = 0; t < n_threads; ++t) loss_sum += losses[t];
+    free(losses);
+    return loss_sum;
+}
+
+int64_t fmo_sample_rows(uint64_t seed, int64_t iter, double fraction, int64_t row_lo,
+                        int64_t row_hi, int64_t* out) {
+    int64_t n = 0;
+    if (fraction >= 1.0) {
+        for (int64_t r = row_lo; r < row_hi; ++r) out[n++] = r;
+        return n;
+    }
+    if (!(fraction > 0.0)) return 0;
+    const uint64_t thr = (uint64_t)floor(fraction * 9007199254740992.0); /* 2^53 */
+    const uint64_t key = fmo_mix64(seed + (uint64_t)iter);
+    for (int64_t r = row_lo; r < row_hi; ++r)
+        if ((fmo_mix64(key ^ fmo_mix64((uint64_t)r)) >> 11) < thr) out[n++] = r;
+    return n;
+}
+
+void fmo_init_v(double* v, int64_t count, double mean, double stdev, uint64_t seed) {
+    const uint64_t s = fmo_mix64(seed);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int64_t e = 0; e < count; ++e) {
+        const double u1 =
+            (double)((fmo_mix64(s + 2ULL * (uint64_t)e) >> 11) + 1ULL) * 0x1.0p-53;
+        const double u2 = (double)(fmo_mix64(s + 2ULL * (uint64_t)e + 1ULL) >> 11) * 0x1.0p-53;
+        const double z = sqrt(-2.0 * log(u1)) * cos(two_pi * u2);
+        v[e] = (double)(float)(mean + stdev * z);
+    }
+}

@@ -1,0 +1,1179 @@
+// sfm_api.cu -- the C ABI of include/sparkfm_b200.h: handle management, host<->device plumbing
+// and the per-iteration launch sequence.  No arithmetic of the hot path happens on the host.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "sfm_common.h"
+
+using namespace sfm;
+
+namespace sfm {
+
+int set_err(sfm_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+static int cuda_fail(sfm_handle* h, cudaError_t e, const char* what) {
+    std::string m = what;
+    m += ": ";
+    m += cudaGetErrorString(e);
+    return set_err(h, e == cudaErrorMemoryAllocation ? SFM_ERR_OOM : SFM_ERR_CUDA, m);
+}
+
+#define CU(call)                                                       \
+    do {                                                               \
+        cudaError_t e_ = (call);                                       \
+        if (e_ != cudaSuccess) return cuda_fail(h, e_, #call);         \
+    } while (0)
+
+#define RC(call)                     \
+    do {                             \
+        int rc_ = (call);            \
+        if (rc_ != SFM_OK) return rc_; \
+    } while (0)
+
+int ensure(sfm_handle* h, Buf& b, size_t bytes) {
+    if (bytes <= b.cap) return SFM_OK;
+    if (b.p) {
+        cudaStreamSynchronize(h->stream);
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;  // a little slack so slowly growing batches settle
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        want = bytes;
+        e = cudaMalloc(&b.p, want);
+    }
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return cuda_fail(h, e, "cudaMalloc(scratch)");
+    }
+    b.cap = want;
+    return SFM_OK;
+}
+
+static void free_buf(Buf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+static int ensure_pinned(sfm_handle* h, size_t bytes) {
+    if (bytes <= h->h_pinned_cap) return SFM_OK;
+    if (h->h_pinned) {
+        cudaStreamSynchronize(h->stream);
+        cudaFreeHost(h->h_pinned);
+        h->h_pinned = nullptr;
+        h->h_pinned_cap = 0;
+    }
+    const size_t want = bytes + bytes / 4 + 4096;
+    CU(cudaMallocHost(&h->h_pinned, want));
+    h->h_pinned_cap = want;
+    return SFM_OK;
+}
+
+static int kp_for(int k) {  // pad k to 4 * 2^j so a V row is a power-of-two number of float4
+    int q = (k + 3) / 4;
+    if (q < 1) q = 1;
+    int p = 1;
+    while (p < q) p <<= 1;
+    return 4 * p;
+}
+
+static int bits_for(int64_t n_slots) {
+    int b = 1;
+    while (b < 32 && ((int64_t)1 << b) < n_slots) ++b;
+    return b;
+}
+
+struct PhaseTimer {
+    sfm_handle* h;
+    explicit PhaseTimer(sfm_handle* hh) : h(hh) {
+        if (h->phase_timing) cudaEventRecord(h->ev_a, h->stream);
+    }
+    void lap(double* acc) {
+        if (!h->phase_timing) return;
+        cudaEventRecord(h->ev_b, h->stream);
+        cudaEventSynchronize(h->ev_b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
+        *acc += ms;
+        cudaEventRecord(h->ev_a, h->stream);
+    }
+};
+
+static UpdateParams update_params(const sfm_handle* h, int64_t iter) {
+    UpdateParams up;
+    up.eta = (float)((double)h->cfg.step_size / sqrt((double)(iter < 1 ? 1 : iter)));
+    up.reg0 = h->cfg.reg0;
+    up.regw = h->cfg.regw;
+    up.regv = h->cfg.regv;
+    return up;
+}
+
+static size_t grad_len(const sfm_handle* h) {
+    return (size_t)h->m.n_slots * (size_t)(h->m.kp + 1) + 1;
+}
+
+// Upload an unpadded [n_slots][k] fp32 host matrix into the padded device V.
+static int upload_v(sfm_handle* h, const float* v) {
+    const ModelView& m = h->m;
+    if (m.k == 0 || !v) {
+        CU(cudaMemsetAsync(m.v, 0, sizeof(float) * (size_t)m.n_slots * m.kp, h->stream));
+        return SFM_OK;
+    }
+    const size_t bytes = sizeof(float) * (size_t)m.n_slots * m.k;
+    if (m.k == m.kp) {
+        CU(cudaMemcpyAsync(m.v, v, bytes, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        RC(ensure(h, h->b_grad, bytes));
+        CU(cudaMemcpyAsync(h->b_grad.p, v, bytes, cudaMemcpyHostToDevice, h->stream));
+        CU(launch_pad_v((const float*)h->b_grad.p, m.v, m.n_slots, m.k, m.kp, false, h->stream,
+                        &h->stats.kernel_launches));
+    }
+    h->stats.h2d_bytes += (int64_t)bytes;
+    return SFM_OK;
+}
+
+static int download_v(sfm_handle* h, const float* dev_padded, float* v) {
+    const ModelView& m = h->m;
+    if (m.k == 0 || !v) return SFM_OK;
+    const size_t bytes = sizeof(float) * (size_t)m.n_slots * m.k;
+    if (m.k == m.kp) {
+        CU(cudaMemcpyAsync(v, dev_padded, bytes, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        RC(ensure(h, h->b_yhat, bytes));
+        CU(launch_pad_v(dev_padded, (float*)h->b_yhat.p, m.n_slots, m.k, m.kp, true, h->stream,
+                        &h->stats.kernel_launches));
+        CU(cudaMemcpyAsync(v, h->b_yhat.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
+    h->stats.d2h_bytes += (int64_t)bytes;
+    return SFM_OK;
+}
+
+// Copies a host CSR batch into the staging buffers and returns a view of it.
+static int stage_csr(sfm_handle* h, const int64_t* row_ptr, const int32_t* idx, const float* val,
+                     const float* label, int64_t n_rows, BatchView* out) {
+    if (n_rows < 0 || (n_rows > 0 && !row_ptr)) return set_err(h, SFM_ERR_ARG, "bad CSR arguments");
+    const int64_t nnz = n_rows > 0 ? row_ptr[n_rows] - row_ptr[0] : 0;
+    if (nnz < 0 || nnz >= 2147483647LL) return set_err(h, SFM_ERR_ARG, "batch nnz out of range [0, 2^31-1)");
+    if (nnz > 0 && !idx) return set_err(h, SFM_ERR_ARG, "idx is NULL");
+    if (n_rows > 0 && row_ptr[0] != 0) return set_err(h, SFM_ERR_INDEX, "row_ptr[0] must be 0");
+    RC(ensure(h, h->b_stage_rowptr, sizeof(int64_t) * (size_t)(n_rows + 1)));
+    RC(ensure(h, h->b_stage_idx, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1)));
+    if (val) RC(ensure(h, h->b_stage_val, sizeof(float) * (size_t)(nnz > 0 ? nnz : 1)));
+    if (label) RC(ensure(h, h->b_stage_label, sizeof(float) * (size_t)(n_rows > 0 ? n_rows : 1)));
+    if (n_rows > 0) {
+        CU(cudaMemcpyAsync(h->b_stage_rowptr.p, row_ptr, sizeof(int64_t) * (size_t)(n_rows + 1),
+                           cudaMemcpyHostToDevice, h->stream));
+        h->stats.h2d_bytes += (int64_t)sizeof(int64_t) * (n_rows + 1);
+        if (label) {
+            CU(cudaMemcpyAsync(h->b_stage_label.p, label, sizeof(float) * (size_t)n_rows,
+                               cudaMemcpyHostToDevice, h->stream));
+            h->stats.h2d_bytes += (int64_t)sizeof(float) * n_rows;
+        }
+    } else {
+        CU(cudaMemsetAsync(h->b_stage_rowptr.p, 0, sizeof(int64_t), h->stream));
+    }
+    if (nnz > 0) {
+        CU(cudaMemcpyAsync(h->b_stage_idx.p, idx, sizeof(int32_t) * (size_t)nnz,
+                           cudaMemcpyHostToDevice, h->stream));
+        h->stats.h2d_bytes += (int64_t)sizeof(int32_t) * nnz;
+        if (val) {
+            CU(cudaMemcpyAsync(h->b_stage_val.p, val, sizeof(float) * (size_t)nnz,
+                               cudaMemcpyHostToDevice, h->stream));
+            h->stats.h2d_bytes += (int64_t)sizeof(float) * nnz;
+        }
+    }
+    // row_ptr monotonicity is checked on the host (cheap, sequential): malformed CSR is an error
+    for (int64_t r = 0; r < n_rows; ++r)
+        if (row_ptr[r + 1] < row_ptr[r]) return set_err(h, SFM_ERR_INDEX, "row_ptr is not non-decreasing");
+    out->row_ptr = (const int64_t*)h->b_stage_rowptr.p;
+    out->idx = (const int32_t*)h->b_stage_idx.p;
+    out->val = val ? (const float*)h->b_stage_val.p : nullptr;
+    out->label = label ? (const float*)h->b_stage_label.p : nullptr;
+    out->row_ids = nullptr;
+    out->row_lo = 0;
+    out->n_rows = n_rows;
+    out->nnz = nnz;
+    out->out_ptr = (const int64_t*)h->b_stage_rowptr.p;
+    out->out_base = 0;
+    out->uniform_m = -1;
+    return SFM_OK;
+}
+
+static int read_err_flag(sfm_handle* h) {
+    CU(cudaMemcpyAsync(h->h_flags, h->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->h_flags[0])
+        return set_err(h, SFM_ERR_INDEX, "feature index outside [0, n_slots) in the batch");
+    return SFM_OK;
+}
+
+// The launch sequence of one SGD iteration on one rank.  Asynchronous: the caller
+// synchronises.  If grad_keep, the (all-reduced) dense gradient stays in h->b_grad and no update
+// is applied.
+static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad_keep) {
+    ModelView& m = h->m;
+    const int64_t n = b.n_rows, nnz = b.nnz;
+    int64_t* L = &h->stats.kernel_launches;
+    RC(ensure(h, h->b_S, sizeof(float) * (size_t)(n > 0 ? n : 1) * m.kp));
+    RC(ensure(h, h->b_mult, sizeof(float) * (size_t)(n > 0 ? n : 1)));
+    RC(ensure(h, h->b_loss, sizeof(float) * (size_t)(n > 0 ? n : 1)));
+    for (int i = 0; i < 2; ++i) {
+        RC(ensure(h, h->b_keys[i], sizeof(uint32_t) * (size_t)(nnz > 0 ? nnz : 1)));
+        RC(ensure(h, h->b_pay[i], sizeof(uint2) * (size_t)(nnz > 0 ? nnz : 1)));
+    }
+    RC(ensure(h, h->b_seg, sizeof(int32_t) * (size_t)(m.n_slots + 1)));
+    RC(ensure(h, h->b_partials, sizeof(double) * 4 * 512));
+    const int end_bit = bits_for(m.n_slots);
+    size_t sort_bytes = 0;
+    if (nnz > 0) {
+        sort_bytes = sort_pairs_temp_bytes(nnz, end_bit);
+        RC(ensure(h, h->b_sort_tmp, sort_bytes));
+    }
+    const bool multi = h->world > 1;
+    const bool fused = !multi && !grad_keep;
+    if (!fused) RC(ensure(h, h->b_grad, sizeof(float) * grad_len(h)));
+
+    PhaseTimer pt(h);
+    CU(cudaMemsetAsync(h->d_err, 0, sizeof(int32_t), h->stream));
+    FwdOut o;
+    o.S = (float*)h->b_S.p;
+    o.mult = (float*)h->b_mult.p;
+    o.loss = (float*)h->b_loss.p;
+    o.yhat = nullptr;
+    o.keys = (uint32_t*)h->b_keys[0].p;
+    o.pay = (uint2*)h->b_pay[0].p;
+    CU(launch_forward(m, b, o, true, h->d_err, h->sm_count, h->stream, L));
+    CU(launch_scalar_reduce(o.loss, o.mult, n, (double*)h->b_partials.p, h->d_scal, h->stream, L));
+    pt.lap(&h->stats.ms_forward);
+    if (multi) {
+        RC(nccl_allreduce_f64(h->nccl, h->comm, h->d_scal, SC_N, h->stream, &h->err));
+        pt.lap(&h->stats.ms_allreduce);
+    }
+    const uint32_t* keys_sorted = (const uint32_t*)h->b_keys[1].p;
+    const uint2* pay_sorted = (const uint2*)h->b_pay[1].p;
+    if (nnz > 0)
+        CU(sort_pairs(h->b_sort_tmp.p, sort_bytes, o.keys, (uint32_t*)h->b_keys[1].p, o.pay,
+                      (uint2*)h->b_pay[1].p, nnz, end_bit, h->stream, L));
+    CU(launch_segments(keys_sorted, nnz, m.n_slots, (int32_t*)h->b_seg.p, h->stream, L));
+    pt.lap(&h->stats.ms_sort);
+    const UpdateParams up = update_params(h, iter);
+    CU(launch_pull(m, (const int32_t*)h->b_seg.p, pay_sorted, o.S, o.mult, h->d_scal, h->d_err, up,
+                   fused, fused ? nullptr : (float*)h->b_grad.p, h->sm_count, h->stream, L));
+    pt.lap(&h->stats.ms_reduce);
+    if (multi) {
+        RC(nccl_allreduce_f32(h->nccl, h->comm, (float*)h->b_grad.p, grad_len(h), h->stream,
+                              &h->err));
+        pt.lap(&h->stats.ms_allreduce);
+    }
+    if (!fused && !grad_keep) {
+        CU(launch_update(m, (const float*)h->b_grad.p, h->d_scal, h->d_err, up, h->stream, L));
+        pt.lap(&h->stats.ms_update);
+    }
+    h->stats.train_steps += grad_keep ? 0 : 1;
+    h->stats.train_rows += n;
+    h->stats.train_nnz += nnz;
+    return SFM_OK;
+}
+
+// Builds the view of a batch of resident rows.  ids_dev: device int32 row ids or nullptr (all).
+static int resident_batch(sfm_handle* h, const int32_t* ids_dev, int64_t n_ids, BatchView* b) {
+    const Dataset& ds = h->ds;
+    b->row_ptr = ds.row_ptr;
+    b->idx = ds.idx;
+    b->val = ds.val;
+    b->label = ds.label;
+    b->row_ids = ids_dev;
+    b->row_lo = 0;
+    b->uniform_m = ds.uniform_m;
+    b->out_base = 0;
+    if (!ids_dev) {
+        b->n_rows = ds.n_rows;
+        b->nnz = ds.nnz;
+        b->out_ptr = ds.row_ptr;  // identity batch: output slot = CSR position
+        b->uniform_m = -1;
+        return SFM_OK;
+    }
+    b->n_rows = n_ids;
+    if (ds.uniform_m >= 0) {
+        b->nnz = n_ids * ds.uniform_m;
+        b->out_ptr = nullptr;
+        return SFM_OK;
+    }
+    // ragged rows: lengths -> exclusive scan -> output offsets; total read back
+    RC(ensure(h, h->b_lens, sizeof(int64_t) * (size_t)(n_ids + 1)));
+    RC(ensure(h, h->b_out_ptr, sizeof(int64_t) * (size_t)(n_ids + 1)));
+    CU(cudaMemsetAsync((int64_t*)h->b_lens.p + n_ids, 0, sizeof(int64_t), h->stream));
+    CU(launch_row_lens(ds.row_ptr, ids_dev, n_ids, (int64_t*)h->b_lens.p, h->stream,
+                       &h->stats.kernel_launches));
+    const size_t sb = scan_temp_bytes(n_ids + 1);
+    RC(ensure(h, h->b_sel_tmp, sb));
+    CU(exclusive_scan_i64(h->b_sel_tmp.p, sb, (const int64_t*)h->b_lens.p,
+                          (int64_t*)h->b_out_ptr.p, n_ids + 1, h->stream,
+                          &h->stats.kernel_launches));
+    int64_t* total = (int64_t*)(h->h_flags + 2);
+    CU(cudaMemcpyAsync(total, (int64_t*)h->b_out_ptr.p + n_ids, sizeof(int64_t),
+                       cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    b->nnz = *total;
+    b->out_ptr = (const int64_t*)h->b_out_ptr.p;
+    b->uniform_m = -1;
+    return SFM_OK;
+}
+
+// Built-in sampler on the device; returns the local batch size.
+static int sample_device(sfm_handle* h, int64_t iter, const int32_t** ids_dev, int64_t* n_ids) {
+    const Dataset& ds = h->ds;
+    const double frac = (double)h->cfg.mini_batch_fraction;
+    if (frac >= 1.0) {
+        *ids_dev = nullptr;
+        *n_ids = ds.n_rows;
+        return SFM_OK;
+    }
+    RC(ensure(h, h->b_row_ids, sizeof(int32_t) * (size_t)(ds.n_rows > 0 ? ds.n_rows : 1)));
+    if (ds.n_rows == 0 || !(frac > 0.0)) {
+        *ids_dev = (const int32_t*)h->b_row_ids.p;
+        *n_ids = 0;
+        return SFM_OK;
+    }
+    const uint64_t thr = (uint64_t)floor(frac * 9007199254740992.0);
+    const uint64_t key = mix64(h->cfg.sampler_seed + (uint64_t)iter);
+    const size_t sb = select_temp_bytes(ds.n_rows);
+    RC(ensure(h, h->b_sel_tmp, sb));
+    CU(sample_rows_device(h->b_sel_tmp.p, sb, ds.n_rows, ds.global_offset, key, thr,
+                          (int32_t*)h->b_row_ids.p, h->d_count, h->stream,
+                          &h->stats.kernel_launches));
+    CU(cudaMemcpyAsync(h->h_flags + 1, h->d_count, sizeof(int32_t), cudaMemcpyDeviceToHost,
+                       h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->stats.d2h_bytes += 4;
+    *ids_dev = (const int32_t*)h->b_row_ids.p;
+    *n_ids = h->h_flags[1];
+    return SFM_OK;
+}
+
+static int finish_step(sfm_handle* h, double* mean_loss_out, int64_t* batch_out) {
+    CU(cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(double) * SC_N, cudaMemcpyDeviceToHost,
+                       h->stream));
+    h->stats.d2h_bytes += (int64_t)sizeof(double) * SC_N + 4;
+    RC(read_err_flag(h));
+    const double cnt = h->h_scal[SC_COUNT];
+    if (mean_loss_out) *mean_loss_out = cnt > 0.0 ? h->h_scal[SC_LOSS] / cnt : 0.0;
+    if (batch_out) *batch_out = (int64_t)cnt;
+    return SFM_OK;
+}
+
+static int upload_row_ids(sfm_handle* h, const int64_t* row_ids, int64_t n_ids,
+                          const int32_t** ids_dev) {
+    RC(ensure_pinned(h, sizeof(int32_t) * (size_t)(n_ids > 0 ? n_ids : 1)));
+    int32_t* st = (int32_t*)h->h_pinned;
+    for (int64_t i = 0; i < n_ids; ++i) {
+        if (row_ids[i] < 0 || row_ids[i] >= h->ds.n_rows)
+            return set_err(h, SFM_ERR_ARG, "row id outside the resident data set");
+        st[i] = (int32_t)row_ids[i];
+    }
+    RC(ensure(h, h->b_row_ids, sizeof(int32_t) * (size_t)(n_ids > 0 ? n_ids : 1)));
+    if (n_ids > 0) {
+        CU(cudaMemcpyAsync(h->b_row_ids.p, st, sizeof(int32_t) * (size_t)n_ids,
+                           cudaMemcpyHostToDevice, h->stream));
+        h->stats.h2d_bytes += (int64_t)sizeof(int32_t) * n_ids;
+    }
+    *ids_dev = (const int32_t*)h->b_row_ids.p;
+    return SFM_OK;
+}
+
+}  // namespace sfm
+
+// =============================================================================== exports ===
+extern "C" {
+
+int32_t sfm_abi_version(void) { return SFM_ABI_VERSION; }
+
+const char* sfm_status_string(int32_t s) {
+    switch (s) {
+        case SFM_OK: return "ok";
+        case SFM_ERR_ARG: return "bad argument";
+        case SFM_ERR_CUDA: return "CUDA error";
+        case SFM_ERR_NCCL: return "NCCL error";
+        case SFM_ERR_OOM: return "out of memory";
+        case SFM_ERR_INDEX: return "feature index out of range or malformed CSR";
+        case SFM_ERR_IO: return "I/O or parse error";
+        case SFM_ERR_STATE: return "invalid state for this call";
+    }
+    return "unknown status";
+}
+
+int32_t sfm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int32_t sfm_host_alloc(void** ptr, uint64_t bytes) {
+    if (!ptr) return SFM_ERR_ARG;
+    *ptr = nullptr;
+    if (bytes == 0) return SFM_OK;
+    return cudaMallocHost(ptr, bytes) == cudaSuccess ? SFM_OK : SFM_ERR_OOM;
+}
+
+int32_t sfm_host_free(void* ptr) {
+    if (!ptr) return SFM_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? SFM_OK : SFM_ERR_CUDA;
+}
+
+int32_t sfm_create(const sfm_config* cfg, sfm_handle** out) {
+    if (!cfg || !out) return SFM_ERR_ARG;
+    *out = nullptr;
+    if (cfg->abi_version != SFM_ABI_VERSION) return SFM_ERR_ARG;
+    if (cfg->k < 0 || cfg->k > 128 || cfg->n_slots < 1 || cfg->n_slots > 2147483647LL)
+        return SFM_ERR_ARG;
+    if (cfg->task != SFM_TASK_REGRESSION && cfg->task != SFM_TASK_CLASSIFICATION) return SFM_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return SFM_ERR_CUDA;  // no CPU fallback, by design
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return SFM_ERR_ARG;
+    sfm_handle* h = new (std::nothrow) sfm_handle;
+    if (!h) return SFM_ERR_OOM;
+    h->cfg = *cfg;
+    h->device = cfg->device;
+    ModelView& m = h->m;
+    m.n_slots = cfg->n_slots;
+    m.k = cfg->k;
+    m.kp = kp_for(cfg->k);
+    m.lpr = m.kp / 4;
+    m.k0 = cfg->k0 ? 1 : 0;
+    m.k1 = cfg->k1 ? 1 : 0;
+    m.task = cfg->task;
+    m.v = m.w = m.w0 = nullptr;
+#define CK(call)                      \
+    if ((call) != cudaSuccess) {      \
+        cudaGetLastError();           \
+        sfm_destroy(h);               \
+        return SFM_ERR_CUDA;          \
+    }
+    CK(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    h->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->ev_a));
+    CK(cudaEventCreate(&h->ev_b));
+    CK(cudaEventCreate(&h->ev_t0));
+    CK(cudaEventCreate(&h->ev_t1));
+    CK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+    CK(cudaMalloc(&m.v, sizeof(float) * (size_t)m.n_slots * m.kp));
+    CK(cudaMalloc(&m.w, sizeof(float) * (size_t)m.n_slots));
+    CK(cudaMalloc(&m.w0, sizeof(float) * 4));
+    CK(cudaMalloc(&h->d_scal, sizeof(double) * 8));
+    CK(cudaMalloc(&h->d_err, sizeof(int32_t) * 4));
+    CK(cudaMalloc(&h->d_count, sizeof(int32_t) * 4));
+    CK(cudaMallocHost(&h->h_scal, sizeof(double) * 8));
+    CK(cudaMallocHost(&h->h_flags, sizeof(int32_t) * 8));
+    CK(cudaMemsetAsync(m.v, 0, sizeof(float) * (size_t)m.n_slots * m.kp, h->stream));
+    CK(cudaMemsetAsync(m.w, 0, sizeof(float) * (size_t)m.n_slots, h->stream));
+    CK(cudaMemsetAsync(m.w0, 0, sizeof(float) * 4, h->stream));
+    CK(cudaMemsetAsync(h->d_scal, 0, sizeof(double) * 8, h->stream));
+    CK(cudaMemsetAsync(h->d_err, 0, sizeof(int32_t) * 4, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+#undef CK
+    *out = h;
+    return SFM_OK;
+}
+
+int32_t sfm_destroy(sfm_handle* h) {
+    if (!h) return SFM_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm) nccl_destroy(h->nccl, h->comm);
+    sfm_unload_dataset(h);
+    Buf* bufs[] = {&h->b_row_ids, &h->b_out_ptr, &h->b_S, &h->b_mult, &h->b_loss, &h->b_yhat,
+                   &h->b_keys[0], &h->b_keys[1], &h->b_pay[0], &h->b_pay[1], &h->b_seg,
+                   &h->b_sort_tmp, &h->b_grad, &h->b_partials, &h->b_stage_rowptr,
+                   &h->b_stage_idx, &h->b_stage_val, &h->b_stage_label, &h->b_sel_tmp, &h->b_lens};
+    for (Buf* b : bufs) free_buf(*b);
+    if (h->m.v) cudaFree(h->m.v);
+    if (h->m.w) cudaFree(h->m.w);
+    if (h->m.w0) cudaFree(h->m.w0);
+    if (h->d_scal) cudaFree(h->d_scal);
+    if (h->d_err) cudaFree(h->d_err);
+    if (h->d_count) cudaFree(h->d_count);
+    if (h->h_scal) cudaFreeHost(h->h_scal);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    cudaEvent_t evs[] = {h->ev_a, h->ev_b, h->ev_t0, h->ev_t1, h->ev_copy};
+    for (cudaEvent_t e : evs)
+        if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    delete h;
+    return SFM_OK;
+}
+
+const char* sfm_last_error(const sfm_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int32_t sfm_get_config(const sfm_handle* h, sfm_config* out) {
+    if (!h || !out) return SFM_ERR_ARG;
+    *out = h->cfg;
+    return SFM_OK;
+}
+
+int32_t sfm_set_hyper(sfm_handle* h, float reg0, float regw, float regv, float step_size,
+                      float mini_batch_fraction) {
+    if (!h) return SFM_ERR_ARG;
+    h->cfg.reg0 = reg0;
+    h->cfg.regw = regw;
+    h->cfg.regv = regv;
+    h->cfg.step_size = step_size;
+    h->cfg.mini_batch_fraction = mini_batch_fraction;
+    return SFM_OK;
+}
+
+// ------------------------------------------------------------------------------ model ----
+int32_t sfm_set_model(sfm_handle* h, float w0, const float* w, const float* v) {
+    if (!h) return SFM_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    ModelView& m = h->m;
+    if (m.k > 0 && !v) return set_err(h, SFM_ERR_ARG, "v is NULL");
+    RC(ensure_pinned(h, 64));
+    float* st = (float*)h->h_pinned;
+    st[0] = w0;
+    CU(cudaMemcpyAsync(m.w0, st, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    if (w) {
+        CU(cudaMemcpyAsync(m.w, w, sizeof(float) * (size_t)m.n_slots, cudaMemcpyHostToDevice,
+                           h->stream));
+        h->stats.h2d_bytes += (int64_t)sizeof(float) * m.n_slots;
+    } else {
+        CU(cudaMemsetAsync(m.w, 0, sizeof(float) * (size_t)m.n_slots, h->stream));
+    }
+    RC(upload_v(h, v));
+    CU(cudaStreamSynchronize(h->stream));
+    return SFM_OK;
+}
+
+int32_t sfm_get_model(sfm_handle* h, float* w0, float* w, float* v) {
+    if (!h) return SFM_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    ModelView& m = h->m;
+    RC(ensure_pinned(h, 64));
+    float* st = (float*)h->h_pinned;
+    CU(cudaMemcpyAsync(st, m.w0, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (w) {
+        CU(cudaMemcpyAsync(w, m.w, sizeof(float) * (size_t)m.n_slots, cudaMemcpyDeviceToHost,
+                           h->stream));
+        h->stats.d2h_bytes += (int64_t)sizeof(float) * m.n_slots;
+    }
+    RC(download_v(h, m.v, v));
+    CU(cudaStreamSynchronize(h->stream));
+    if (w0) *w0 = st[0];
+    return SFM_OK;
+}
+
+int32_t sfm_set_model_f64(sfm_handle* h, double w0, const double* w, const double* v) {
+    if (!h) return SFM_ERR_ARG;
+    const ModelView& m = h->m;
+    std::vector<float> wf, vf;
+    try {
+        if (w) {
+            wf.resize((size_t)m.n_slots);
+            for (int64_t i = 0; i < m.n_slots; ++i) wf[(size_t)i] = (float)w[i];
+        }
+        if (v && m.k > 0) {
+            vf.resize((size_t)m.n_slots * m.k);
+            for (size_t i = 0; i < vf.size(); ++i) vf[i] = (float)v[i];
+        }
+    } catch (const std::bad_alloc&) {
+        return set_err(h, SFM_ERR_OOM, "host allocation failed");
+    }
+    return sfm_set_model(h, (float)w0, w ? wf.data() : nullptr, vf.empty() ? nullptr : vf.data());
+}
+
+int32_t sfm_get_model_f64(sfm_handle* h, double* w0, double* w, double* v) {
+    if (!h) return SFM_ERR_ARG;
+    const ModelView& m = h->m;
+    std::vector<float> wf, vf;
+    try {
+        if (w) wf.resize((size_t)m.n_slots);
+        if (v && m.k > 0) vf.resize((size_t)m.n_slots * m.k);
+    } catch (const std::bad_alloc&) {
+        return set_err(h, SFM_ERR_OOM, "host allocation failed");
+    }
+    float w0f = 0.f;
+    RC(sfm_get_model(h, &w0f, w ? wf.data() : nullptr, vf.empty() ? nullptr : vf.data()));
+    if (w0) *w0 = w0f;
+    for (size_t i = 0; i < wf.size(); ++i) w[i] = wf[i];
+    for (size_t i = 0; i < vf.size(); ++i) v[i] = vf[i];
+    return SFM_OK;
+}
+
+int32_t sfm_init_model(sfm_handle* h, double mean, double stdev, uint64_t seed) {
+    if (!h) return SFM_ERR_ARG;
+    const ModelView& m = h->m;
+    std::vector<float> vf;
+    try {
+        vf.resize((size_t)m.n_slots * (size_t)m.k);
+    } catch (const std::bad_alloc&) {
+        return set_err(h, SFM_ERR_OOM, "host allocation failed");
+    }
+    if (!vf.empty()) init_gaussian_f32(vf.data(), (int64_t)vf.size(), mean, stdev, seed);
+    return sfm_set_model(h, 0.f, nullptr, vf.empty() ? nullptr : vf.data());
+}
+
+struct SfmFileHeader {
+    char magic[8];
+    uint32_t version;
+    int32_t task, k, k0, k1;
+    int64_t n_slots;
+    float reg0, regw, regv, step_size, mini_batch_fraction;
+    uint32_t pad;
+    uint64_t sampler_seed;
+};
+
+int32_t sfm_save(sfm_handle* h, const char* path) {
+    if (!h || !path) return SFM_ERR_ARG;
+    const ModelView& m = h->m;
+    std::vector<float> wf((size_t)m.n_slots), vf((size_t)m.n_slots * m.k);
+    float w0 = 0.f;
+    RC(sfm_get_model(h, &w0, wf.data(), vf.empty() ? nullptr : vf.data()));
+    SfmFileHeader hd;
+    memset(&hd, 0, sizeof hd);
+    memcpy(hd.magic, "SFMB200", 8);
+    hd.version = 1;
+    hd.task = h->cfg.task; hd.k = m.k; hd.k0 = m.k0; hd.k1 = m.k1; hd.n_slots = m.n_slots;
+    hd.reg0 = h->cfg.reg0; hd.regw = h->cfg.regw; hd.regv = h->cfg.regv;
+    hd.step_size = h->cfg.step_size; hd.mini_batch_fraction = h->cfg.mini_batch_fraction;
+    hd.sampler_seed = h->cfg.sampler_seed;
+    FILE* f = fopen(path, "wb");
+    if (!f) return set_err(h, SFM_ERR_IO, std::string("cannot open for writing: ") + path);
+    bool ok = fwrite(&hd, sizeof hd, 1, f) == 1 && fwrite(&w0, sizeof w0, 1, f) == 1 &&
+              fwrite(wf.data(), sizeof(float), wf.size(), f) == wf.size() &&
+              fwrite(vf.data(), sizeof(float), vf.size(), f) == vf.size();
+    ok = (fclose(f) == 0) && ok;
+    return ok ? SFM_OK : set_err(h, SFM_ERR_IO, std::string("short write: ") + path);
+}
+
+int32_t sfm_load(const char* path, int32_t device, sfm_handle** out) {
+    if (!path || !out) return SFM_ERR_ARG;
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) return SFM_ERR_IO;
+    SfmFileHeader hd;
+    if (fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, "SFMB200", 8) != 0 || hd.version != 1 ||
+        hd.n_slots < 1 || hd.k < 0 || hd.k > 128) {
+        fclose(f);
+        return SFM_ERR_IO;
+    }
+    std::vector<float> wf((size_t)hd.n_slots), vf((size_t)hd.n_slots * hd.k);
+    float w0 = 0.f;
+    const bool ok = fread(&w0, sizeof w0, 1, f) == 1 &&
+                    fread(wf.data(), sizeof(float), wf.size(), f) == wf.size() &&
+                    fread(vf.data(), sizeof(float), vf.size(), f) == vf.size();
+    fclose(f);
+    if (!ok) return SFM_ERR_IO;
+    sfm_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.abi_version = SFM_ABI_VERSION;
+    cfg.task = hd.task; cfg.k = hd.k; cfg.k0 = hd.k0; cfg.k1 = hd.k1; cfg.device = device;
+    cfg.n_slots = hd.n_slots; cfg.reg0 = hd.reg0; cfg.regw = hd.regw; cfg.regv = hd.regv;
+    cfg.step_size = hd.step_size; cfg.mini_batch_fraction = hd.mini_batch_fraction;
+    cfg.sampler_seed = hd.sampler_seed;
+    sfm_handle* h = nullptr;
+    RC(sfm_create(&cfg, &h));
+    const int rc = sfm_set_model(h, w0, wf.data(), vf.empty() ? nullptr : vf.data());
+    if (rc != SFM_OK) {
+        sfm_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return SFM_OK;
+}
+
+// ------------------------------------------------------------------------------ scorer ---
+static int predict_view(sfm_handle* h, const BatchView& b, float* out_host) {
+    RC(ensure(h, h->b_yhat, sizeof(float) * (size_t)(b.n_rows > 0 ? b.n_rows : 1)));
+    PhaseTimer pt(h);
+    CU(cudaMemsetAsync(h->d_err, 0, sizeof(int32_t), h->stream));
+    FwdOut o;
+    memset(&o, 0, sizeof o);
+    o.yhat = (float*)h->b_yhat.p;
+    CU(launch_forward(h->m, b, o, false, h->d_err, h->sm_count, h->stream,
+                      &h->stats.kernel_launches));
+    pt.lap(&h->stats.ms_predict);
+    if (b.n_rows > 0 && out_host) {
+        CU(cudaMemcpyAsync(out_host, o.yhat, sizeof(float) * (size_t)b.n_rows,
+                           cudaMemcpyDeviceToHost, h->stream));
+        h->stats.d2h_bytes += (int64_t)sizeof(float) * b.n_rows;
+    }
+    h->stats.predict_rows += b.n_rows;
+    h->stats.predict_nnz += b.nnz;
+    return read_err_flag(h);
+}
+
+int32_t sfm_predict(sfm_handle* h, const int64_t* row_ptr, const int32_t* idx, const float* val,
+                    int64_t n_rows, float* out) {
+    if (!h) return SFM_ERR_ARG;
+    if (n_rows > 0 && !out) return set_err(h, SFM_ERR_ARG, "out is NULL");
+    CU(cudaSetDevice(h->device));
+    BatchView b;
+    RC(stage_csr(h, row_ptr, idx, val, nullptr, n_rows, &b));
+    return predict_view(h, b, out);
+}
+
+// ------------------------------------------------------------------------------ data set --
+int32_t sfm_unload_dataset(sfm_handle* h) {
+    if (!h) return SFM_ERR_ARG;
+    Dataset& ds = h->ds;
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (ds.row_ptr) cudaFree(ds.row_ptr);
+    if (ds.idx) cudaFree(ds.idx);
+    if (ds.val) cudaFree(ds.val);
+    if (ds.label) cudaFree(ds.label);
+    ds = Dataset();
+    return SFM_OK;
+}
+
+static int alloc_dataset(sfm_handle* h, int64_t n_rows, int64_t nnz, bool with_val) {
+    Dataset& ds = h->ds;
+    sfm_unload_dataset(h);
+    CU(cudaMalloc(&ds.row_ptr, sizeof(int64_t) * (size_t)(n_rows + 1)));
+    CU(cudaMalloc(&ds.idx, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1)));
+    if (with_val) CU(cudaMalloc(&ds.val, sizeof(float) * (size_t)(nnz > 0 ? nnz : 1)));
+    CU(cudaMalloc(&ds.label, sizeof(float) * (size_t)(n_rows > 0 ? n_rows : 1)));
+    ds.n_rows = n_rows;
+    ds.nnz = nnz;
+    return SFM_OK;
+}
+
+static int check_dataset_indices(sfm_handle* h) {
+    Dataset& ds = h->ds;
+    ds.max_index = -1;
+    if (ds.nnz == 0) return SFM_OK;
+    int32_t* mm = h->d_count + 1;  // 2 ints
+    const int32_t init[2] = {INT32_MAX, INT32_MIN};
+    RC(ensure_pinned(h, 64));
+    memcpy(h->h_pinned, init, sizeof init);
+    CU(cudaMemcpyAsync(mm, h->h_pinned, sizeof init, cudaMemcpyHostToDevice, h->stream));
+    CU(launch_idx_range(ds.idx, ds.nnz, mm, h->stream, &h->stats.kernel_launches));
+    CU(cudaMemcpyAsync(h->h_flags + 4, mm, sizeof init, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    const int32_t lo = h->h_flags[4], hi = h->h_flags[5];
+    ds.max_index = hi;
+    if (lo < 0 || (int64_t)hi >= h->m.n_slots) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "data set feature indices span [%d, %d], model has n_slots = %lld",
+                 lo, hi, (long long)h->m.n_slots);
+        sfm_unload_dataset(h);
+        return set_err(h, SFM_ERR_INDEX, msg);
+    }
+    return SFM_OK;
+}
+
+int32_t sfm_load_dataset(sfm_handle* h, const int64_t* row_ptr, const int32_t* idx,
+                         const float* val, const float* label, int64_t n_rows,
+                         int64_t global_row_offset) {
+    if (!h) return SFM_ERR_ARG;
+    if (n_rows < 0 || n_rows >= 2147483647LL || (n_rows > 0 && (!row_ptr || !label)))
+        return set_err(h, SFM_ERR_ARG, "bad data set arguments");
+    CU(cudaSetDevice(h->device));
+    const int64_t nnz = n_rows > 0 ? row_ptr[n_rows] : 0;
+    if (n_rows > 0 && row_ptr[0] != 0) return set_err(h, SFM_ERR_INDEX, "row_ptr[0] must be 0");
+    if (nnz > 0 && !idx) return set_err(h, SFM_ERR_ARG, "idx is NULL");
+    int32_t um = n_rows > 0 ? (int32_t)(row_ptr[1] - row_ptr[0]) : -1;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int64_t len = row_ptr[r + 1] - row_ptr[r];
+        if (len < 0) return set_err(h, SFM_ERR_INDEX, "row_ptr is not non-decreasing");
+        if (len != um) um = -1;
+    }
+    RC(alloc_dataset(h, n_rows, nnz, val != nullptr));
+    Dataset& ds = h->ds;
+    if (n_rows > 0) {
+        CU(cudaMemcpyAsync(ds.row_ptr, row_ptr, sizeof(int64_t) * (size_t)(n_rows + 1),
+                           cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(ds.label, label, sizeof(float) * (size_t)n_rows, cudaMemcpyHostToDevice,
+                           h->stream));
+    } else {
+        CU(cudaMemsetAsync(ds.row_ptr, 0, sizeof(int64_t), h->stream));
+    }
+    if (nnz > 0) {
+        CU(cudaMemcpyAsync(ds.idx, idx, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice,
+                           h->stream));
+        if (val)
+            CU(cudaMemcpyAsync(ds.val, val, sizeof(float) * (size_t)nnz, cudaMemcpyHostToDevice,
+                               h->stream));
+    }
+    h->stats.h2d_bytes += (int64_t)(sizeof(int64_t) * (n_rows + 1) + sizeof(float) * n_rows +
+                                    (sizeof(int32_t) + (val ? sizeof(float) : 0)) * nnz);
+    ds.global_offset = global_row_offset;
+    ds.uniform_m = um;
+    RC(check_dataset_indices(h));
+    ds.loaded = true;
+    return SFM_OK;
+}
+
+int32_t sfm_synth_ctr_dataset(sfm_handle* h, int64_t n_rows, int64_t global_row_offset,
+                              int32_t n_fields, const int32_t* field_log2_card,
+                              const uint32_t* zipf_cdf, const int64_t* zipf_cdf_off,
+                              uint64_t seed) {
+    if (!h) return SFM_ERR_ARG;
+    if (n_rows < 0 || n_fields < 1 || n_fields > 1024 || !field_log2_card || !zipf_cdf ||
+        !zipf_cdf_off)
+        return set_err(h, SFM_ERR_ARG, "bad synthetic data set arguments");
+    const int64_t nnz = n_rows * n_fields;
+    if (n_rows >= 2147483647LL / n_fields) return set_err(h, SFM_ERR_ARG, "synthetic shard too large");
+    CU(cudaSetDevice(h->device));
+    int64_t cdf_len = 0;
+    for (int f = 0; f < n_fields; ++f) {
+        if (field_log2_card[f] < 0 || field_log2_card[f] > 24 || zipf_cdf_off[f] < 0)
+            return set_err(h, SFM_ERR_ARG, "bad field cardinality");
+        const int64_t e = zipf_cdf_off[f] + ((int64_t)1 << field_log2_card[f]);
+        if (e > cdf_len) cdf_len = e;
+    }
+    RC(alloc_dataset(h, n_rows, nnz, false));
+    Dataset& ds = h->ds;
+    Buf tab_card, tab_cdf, tab_off;
+    int rc = ensure(h, tab_card, sizeof(int32_t) * n_fields);
+    if (rc == SFM_OK) rc = ensure(h, tab_cdf, sizeof(uint32_t) * (size_t)cdf_len);
+    if (rc == SFM_OK) rc = ensure(h, tab_off, sizeof(int64_t) * n_fields);
+    cudaError_t e = cudaSuccess;
+    if (rc == SFM_OK) {
+        e = cudaMemcpyAsync(tab_card.p, field_log2_card, sizeof(int32_t) * n_fields,
+                            cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(tab_cdf.p, zipf_cdf, sizeof(uint32_t) * (size_t)cdf_len,
+                                cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(tab_off.p, zipf_cdf_off, sizeof(int64_t) * n_fields,
+                                cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess && n_rows == 0) e = cudaMemsetAsync(ds.row_ptr, 0, sizeof(int64_t), h->stream);
+        if (e == cudaSuccess)
+            e = launch_synth_ctr(n_rows, global_row_offset, n_fields, (const int32_t*)tab_card.p,
+                                 (const uint32_t*)tab_cdf.p, (const int64_t*)tab_off.p, seed,
+                                 h->m.n_slots, ds.idx, ds.label, ds.row_ptr, h->stream,
+                                 &h->stats.kernel_launches);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    }
+    free_buf(tab_card);
+    free_buf(tab_cdf);
+    free_buf(tab_off);
+    if (rc != SFM_OK) return rc;
+    if (e != cudaSuccess) return cuda_fail(h, e, "synthetic data set generation");
+    ds.global_offset = global_row_offset;
+    ds.uniform_m = n_fields;
+    RC(check_dataset_indices(h));
+    ds.loaded = true;
+    return SFM_OK;
+}
+
+int32_t sfm_get_dataset_rows(sfm_handle* h, int64_t row_lo, int64_t row_hi, int64_t* row_ptr,
+                             int32_t* idx, float* val, float* label) {
+    if (!h) return SFM_ERR_ARG;
+    const Dataset& ds = h->ds;
+    if (!ds.loaded) return set_err(h, SFM_ERR_STATE, "no resident data set");
+    if (row_lo < 0 || row_hi < row_lo || row_hi > ds.n_rows || !row_ptr)
+        return set_err(h, SFM_ERR_ARG, "bad row range");
+    CU(cudaSetDevice(h->device));
+    const int64_t n = row_hi - row_lo;
+    CU(cudaMemcpyAsync(row_ptr, ds.row_ptr + row_lo, sizeof(int64_t) * (size_t)(n + 1),
+                       cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    const int64_t base = row_ptr[0], cnt = row_ptr[n] - base;
+    for (int64_t r = 0; r <= n; ++r) row_ptr[r] -= base;
+    if (idx && cnt > 0)
+        CU(cudaMemcpyAsync(idx, ds.idx + base, sizeof(int32_t) * (size_t)cnt,
+                           cudaMemcpyDeviceToHost, h->stream));
+    if (val && cnt > 0) {
+        if (ds.val)
+            CU(cudaMemcpyAsync(val, ds.val + base, sizeof(float) * (size_t)cnt,
+                               cudaMemcpyDeviceToHost, h->stream));
+        else
+            for (int64_t j = 0; j < cnt; ++j) val[j] = 1.f;
+    }
+    if (label && n > 0)
+        CU(cudaMemcpyAsync(label, ds.label + row_lo, sizeof(float) * (size_t)n,
+                           cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return SFM_OK;
+}
+
+int32_t sfm_dataset_info(sfm_handle* h, int64_t* n_rows, int64_t* nnz, int32_t* max_index) {
+    if (!h) return SFM_ERR_ARG;
+    if (!h->ds.loaded) return set_err(h, SFM_ERR_STATE, "no resident data set");
+    if (n_rows) *n_rows = h->ds.n_rows;
+    if (nnz) *nnz = h->ds.nnz;
+    if (max_index) *max_index = h->ds.max_index;
+    return SFM_OK;
+}
+
+int32_t sfm_predict_resident(sfm_handle* h, int64_t row_lo, int64_t row_hi, float* out) {
+    if (!h) return SFM_ERR_ARG;
+    const Dataset& ds = h->ds;
+    if (!ds.loaded) return set_err(h, SFM_ERR_STATE, "no resident data set");
+    if (row_lo < 0 || row_hi < row_lo || row_hi > ds.n_rows) return set_err(h, SFM_ERR_ARG, "bad row range");
+    CU(cudaSetDevice(h->device));
+    BatchView b;
+    RC(resident_batch(h, nullptr, 0, &b));
+    b.row_lo = row_lo;
+    b.n_rows = row_hi - row_lo;
+    b.nnz = 0;  // statistics only; not read back for a sub-range
+    return predict_view(h, b, out);
+}
+
+int32_t sfm_evaluate(sfm_handle* h, double metrics[5]) {
+    if (!h || !metrics) return SFM_ERR_ARG;
+    const Dataset& ds = h->ds;
+    if (!ds.loaded) return set_err(h, SFM_ERR_STATE, "no resident data set");
+    CU(cudaSetDevice(h->device));
+    const int64_t tile = 1 << 22;
+    RC(ensure(h, h->b_yhat, sizeof(float) * (size_t)(ds.n_rows < tile ? (ds.n_rows > 0 ? ds.n_rows : 1) : tile)));
+    RC(ensure(h, h->b_partials, sizeof(double) * 4 * 512));
+    double* acc = h->d_scal + 4;  // 4 doubles
+    CU(cudaMemsetAsync(acc, 0, sizeof(double) * 4, h->stream));
+    CU(cudaMemsetAsync(h->d_err, 0, sizeof(int32_t), h->stream));
+    for (int64_t lo = 0; lo < ds.n_rows; lo += tile) {
+        BatchView b;
+        RC(resident_batch(h, nullptr, 0, &b));
+        b.row_lo = lo;
+        b.n_rows = (ds.n_rows - lo) < tile ? (ds.n_rows - lo) : tile;
+        FwdOut o;
+        memset(&o, 0, sizeof o);
+        o.yhat = (float*)h->b_yhat.p;
+        CU(launch_forward(h->m, b, o, false, h->d_err, h->sm_count, h->stream,
+                          &h->stats.kernel_launches));
+        CU(launch_metrics(o.yhat, ds.label + lo, b.n_rows, (double*)h->b_partials.p, acc,
+                          h->stream, &h->stats.kernel_launches));
+        h->stats.predict_rows += b.n_rows;
+    }
+    // [4..7] = sums, reuse slot layout: sums[0..3], then N
+    double* h5 = h->h_scal;
+    if (h->world > 1) {
+        // fold N into the all-reduce: stash it in d_scal[3]... keep simple: reduce 4 sums, N apart
+        RC(nccl_allreduce_f64(h->nccl, h->comm, acc, 4, h->stream, &h->err));
+    }
+    CU(cudaMemcpyAsync(h5, acc, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->stream));
+    RC(read_err_flag(h));
+    double n_total = (double)ds.n_rows;
+    if (h->world > 1) {
+        double* dn = h->d_scal + 3;
+        h->h_scal[4] = n_total;
+        CU(cudaMemcpyAsync(dn, h->h_scal + 4, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        RC(nccl_allreduce_f64(h->nccl, h->comm, dn, 1, h->stream, &h->err));
+        CU(cudaMemcpyAsync(h->h_scal + 4, dn, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        n_total = h->h_scal[4];
+    }
+    if (n_total > 0) {
+        metrics[0] = sqrt(h5[0] / n_total);
+        metrics[1] = h5[1] / n_total;
+        metrics[2] = h5[2] / n_total;
+        metrics[3] = h5[3] / n_total;
+    } else {
+        metrics[0] = metrics[1] = metrics[2] = metrics[3] = 0.0;
+    }
+    metrics[4] = n_total;
+    return SFM_OK;
+}
+
+// ------------------------------------------------------------------------------ learner ---
+int32_t sfm_train_step(sfm_handle* h, const int64_t* row_ids, int64_t n_ids, int64_t iter,
+                       double* mean_loss_out, int64_t* batch_out) {
+    if (!h) return SFM_ERR_ARG;
+    if (!h->ds.loaded) return set_err(h, SFM_ERR_STATE, "no resident data set");
+    if (iter < 1) return set_err(h, SFM_ERR_ARG, "iter is 1-based");
+    CU(cudaSetDevice(h->device));
+    const int32_t* ids_dev = nullptr;
+    int64_t n = 0;
+    if (row_ids || n_ids >= 0) {
+        if (n_ids < 0 || (n_ids > 0 && !row_ids)) return set_err(h, SFM_ERR_ARG, "bad row id list");
+        RC(upload_row_ids(h, row_ids, n_ids, &ids_dev));
+        n = n_ids;
+    } else {
+        RC(sample_device(h, iter, &ids_dev, &n));
+    }
+    BatchView b;
+    RC(resident_batch(h, ids_dev, n, &b));
+    if (b.nnz >= 2147483647LL) return set_err(h, SFM_ERR_ARG, "batch nnz must be < 2^31-1");
+    RC(train_core(h, b, iter, false));
+    return finish_step(h, mean_loss_out, batch_out);
+}
+
+int32_t sfm_train_step_csr(sfm_handle* h, const int64_t* row_ptr, const int32_t* idx,
+                           const float* val, const float* label, int64_t n_rows, int64_t iter,
+                           double* mean_loss_out, int64_t* batch_out) {
+    if (!h) return SFM_ERR_ARG;
+    if (iter < 1) return set_err(h, SFM_ERR_ARG, "iter is 1-based");
+    if (n_rows > 0 && !label) return set_err(h, SFM_ERR_ARG, "label is NULL");
+    CU(cudaSetDevice(h->device));
+    BatchView b;
+    RC(stage_csr(h, row_ptr, idx, val, label, n_rows, &b));
+    RC(train_core(h, b, iter, false));
+    return finish_step(h, mean_loss_out, batch_out);
+}
+
+int32_t sfm_train(sfm_handle* h, int64_t first_iter, int64_t n_iters, double* loss_history) {
+    if (!h) return SFM_ERR_ARG;
+    if (!h->ds.loaded) return set_err(h, SFM_ERR_STATE, "no resident data set");
+    if (first_iter < 1 || n_iters < 0) return set_err(h, SFM_ERR_ARG, "bad iteration range");
+    CU(cudaSetDevice(h->device));
+    double* hist = nullptr;
+    if (n_iters > 0) CU(cudaMallocHost(&hist, sizeof(double) * SC_N * (size_t)n_iters));
+    int rc = SFM_OK;
+    for (int64_t t = 0; t < n_iters && rc == SFM_OK; ++t) {
+        const int32_t* ids_dev = nullptr;
+        int64_t n = 0;
+        rc = sample_device(h, first_iter + t, &ids_dev, &n);
+        BatchView b;
+        if (rc == SFM_OK) rc = resident_batch(h, ids_dev, n, &b);
+        if (rc == SFM_OK && b.nnz >= 2147483647LL) rc = set_err(h, SFM_ERR_ARG, "batch nnz must be < 2^31-1");
+        if (rc == SFM_OK) rc = train_core(h, b, first_iter + t, false);
+        if (rc == SFM_OK &&
+            cudaMemcpyAsync(hist + SC_N * t, h->d_scal, sizeof(double) * SC_N,
+                            cudaMemcpyDeviceToHost, h->stream) != cudaSuccess)
+            rc = set_err(h, SFM_ERR_CUDA, "loss history copy failed");
+    }
+    if (rc == SFM_OK) rc = read_err_flag(h);
+    else cudaStreamSynchronize(h->stream);
+    if (rc == SFM_OK && loss_history)
+        for (int64_t t = 0; t < n_iters; ++t) {
+            const double c = hist[SC_N * t + SC_COUNT];
+            loss_history[t] = c > 0.0 ? hist[SC_N * t + SC_LOSS] / c : 0.0;
+        }
+    h->stats.d2h_bytes += (int64_t)sizeof(double) * SC_N * n_iters;
+    if (hist) cudaFreeHost(hist);
+    return rc;
+}
+
+int32_t sfm_gradient(sfm_handle* h, const int64_t* row_ids, int64_t n_ids, float* grad_v,
+                     float* grad_w, float* grad_w0, double* loss_sum, int64_t* batch_out) {
+    if (!h) return SFM_ERR_ARG;
+    if (!h->ds.loaded) return set_err(h, SFM_ERR_STATE, "no resident data set");
+    CU(cudaSetDevice(h->device));
+    const int32_t* ids_dev = nullptr;
+    int64_t n = h->ds.n_rows;
+    if (row_ids || n_ids >= 0) {
+        if (n_ids < 0 || (n_ids > 0 && !row_ids)) return set_err(h, SFM_ERR_ARG, "bad row id list");
+        RC(upload_row_ids(h, row_ids, n_ids, &ids_dev));
+        n = n_ids;
+    }
+    BatchView b;
+    RC(resident_batch(h, ids_dev, n, &b));
+    RC(train_core(h, b, 1, true));
+    const ModelView& m = h->m;
+    const float* g = (const float*)h->b_grad.p;
+    RC(download_v(h, g, grad_v));
+    if (grad_w)
+        CU(cudaMemcpyAsync(grad_w, g + m.n_slots * m.kp, sizeof(float) * (size_t)m.n_slots,
+                           cudaMemcpyDeviceToHost, h->stream));
+    RC(ensure_pinned(h, 64));
+    CU(cudaMemcpyAsync(h->h_pinned, g + m.n_slots * m.kp + m.n_slots, sizeof(float),
+                       cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(double) * SC_N, cudaMemcpyDeviceToHost,
+                       h->stream));
+    RC(read_err_flag(h));
+    if (grad_w0) *grad_w0 = *(float*)h->h_pinned;
+    if (loss_sum) *loss_sum = h->h_scal[SC_LOSS];
+    if (batch_out) *batch_out = (int64_t)h->h_scal[SC_COUNT];
+    return SFM_OK;
+}
+
+// ------------------------------------------------------------------------------ multi-GPU -
+int32_t sfm_comm_unique_id(uint8_t id[SFM_UNIQUE_ID_BYTES]) {
+    if (!id) return SFM_ERR_ARG;
+    std::string err;
+    Nccl* n = nccl_load(&err);
+    if (!n) return SFM_ERR_NCCL;
+    return nccl_unique_id(n, id, &err);
+}
+
+int32_t sfm_comm_init(sfm_handle* h, const uint8_t id[SFM_UNIQUE_ID_BYTES], int32_t rank,
+                      int32_t world_size) {
+    if (!h || !id) return SFM_ERR_ARG;
+    if (world_size < 1 || rank < 0 || rank >= world_size) return set_err(h, SFM_ERR_ARG, "bad rank / world size");
+    if (h->comm) return set_err(h, SFM_ERR_STATE, "communicator already initialised");
+    CU(cudaSetDevice(h->device));
+    h->nccl = nccl_load(&h->err);
+    if (!h->nccl) return SFM_ERR_NCCL;
+    RC(nccl_init(h->nccl, &h->comm, id, rank, world_size, &h->err));
+    h->rank = rank;
+    h->world = world_size;
+    return SFM_OK;
+}
+
+int32_t sfm_comm_info(const sfm_handle* h, int32_t* rank, int32_t* world_size) {
+    if (!h) return SFM_ERR_ARG;
+    if (rank) *rank = h->rank;
+    if (world_size) *world_size = h->world;
+    return SFM_OK;
+}
+
+int32_t sfm_comm_broadcast_model(sfm_handle* h) {
+    if (!h) return SFM_ERR_ARG;
+    if (h->world <= 1) return SFM_OK;
+    CU(cudaSetDevice(h->device));
+    const ModelView& m = h->m;
+    RC(nccl_bcast_f32(h->nccl, h->comm, m.v, (size_t)m.n_slots * m.kp, 0, h->stream, &h->err));
+    RC(nccl_bcast_f32(h->nccl, h->comm, m.w, (size_t)m.n_slots, 0, h->stream, &h->err));
+    RC(nccl_bcast_f32(h->nccl, h->comm, m.w0, 1, 0, h->stream, &h->err));
+    CU(cudaStreamSynchronize(h->stream));
+    return SFM_OK;
+}
+
+// ------------------------------------------------------------------------------ stats -----
+int32_t sfm_stats_get(sfm_handle* h, sfm_stats* out) {
+    if (!h || !out) return SFM_ERR_ARG;
+    *out = h->stats;
+    return SFM_OK;
+}
+
+int32_t sfm_stats_reset(sfm_handle* h) {
+    if (!h) return SFM_ERR_ARG;
+    memset(&h->stats, 0, sizeof h->stats);
+    return SFM_OK;
+}
+
+int32_t sfm_set_phase_timing(sfm_handle* h, int32_t enabled) {
+    if (!h) return SFM_ERR_ARG;
+    h->phase_timing = enabled != 0;
+    return SFM_OK;
+}
+
+int32_t sfm_synchronize(sfm_handle* h) {
+    if (!h) return SFM_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return SFM_OK;
+}
+
+int32_t sfm_timer_start(sfm_handle* h) {
+    if (!h) return SFM_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->ev_t0, h->stream));
+    return SFM_OK;
+}
+
+int32_t sfm_timer_stop(sfm_handle* h, float* ms) {
+    if (!h || !ms) return SFM_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->ev_t1, h->stream));
+    CU(cudaEventSynchronize(h->ev_t1));
+    CU(cudaEventElapsedTime(ms, h->ev_t0, h->ev_t1));
+    return SFM_OK;
+}
+
+}  // extern "C"

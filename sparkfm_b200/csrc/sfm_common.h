@@ -1,0 +1,174 @@
+// sfm_common.h -- internal declarations shared by the translation units of libsparkfm_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/sparkfm_b200.h"
+
+namespace sfm {
+
+// ---- device scalar block (doubles): written by the forward reduction, all-reduced across
+// ranks, read by the update kernels.
+enum { SC_LOSS = 0, SC_COUNT = 1, SC_GW0 = 2, SC_N = 4 };
+
+struct Buf {  // growable device allocation
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct Dataset {
+    int64_t n_rows = 0, nnz = 0, global_offset = 0;
+    int64_t* row_ptr = nullptr;  // [n_rows+1]
+    int32_t* idx = nullptr;      // [nnz]
+    float* val = nullptr;        // [nnz] or nullptr (all ones)
+    float* label = nullptr;      // [n_rows]
+    int32_t uniform_m = -1;      // every row has exactly this many entries, or -1
+    int32_t max_index = -1;
+    bool loaded = false;
+};
+
+// One mini-batch as the kernels see it.
+struct BatchView {
+    const int64_t* row_ptr;  // CSR row pointers of the array the rows live in
+    const int32_t* idx;
+    const float* val;        // may be nullptr
+    const float* label;
+    const int32_t* row_ids;  // batch position -> row of that CSR, or nullptr = row_lo + pos
+    int64_t row_lo;
+    int64_t n_rows;          // batch rows on this rank
+    int64_t nnz;             // batch entries on this rank
+    const int64_t* out_ptr;  // batch position -> first output slot (+out_base), nullptr = pos*m
+    int64_t out_base;
+    int32_t uniform_m;
+};
+
+struct ModelView {
+    float* v;   // [n_slots][kp]
+    float* w;   // [n_slots]
+    float* w0;  // [1]
+    int64_t n_slots;
+    int32_t k, kp, lpr;
+    int32_t k0, k1, task;
+};
+
+struct Nccl;  // sfm_nccl.cpp
+
+}  // namespace sfm
+
+struct sfm_handle {
+    sfm_config cfg;
+    sfm::ModelView m;
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_copy = nullptr;
+    sfm::Dataset ds;
+    // batch scratch (all growable)
+    sfm::Buf b_row_ids, b_out_ptr, b_S, b_mult, b_loss, b_yhat, b_keys[2], b_pay[2], b_seg,
+        b_sort_tmp, b_grad, b_partials, b_stage_rowptr, b_stage_idx, b_stage_val, b_stage_label,
+        b_sel_tmp, b_lens;
+    double* d_scal = nullptr;  // [SC_N] device
+    int32_t* d_err = nullptr;  // device error flag
+    int32_t* d_count = nullptr;  // device int (sampler count)
+    double* h_scal = nullptr;  // pinned [SC_N]
+    int32_t* h_flags = nullptr;  // pinned [4]: err, count
+    void* h_pinned = nullptr;  // pinned staging for small host copies
+    size_t h_pinned_cap = 0;
+    // comm
+    sfm::Nccl* nccl = nullptr;
+    void* comm = nullptr;
+    int rank = 0, world = 1;
+    bool phase_timing = false;
+    sfm_stats stats{};
+    std::string err;
+};
+
+namespace sfm {
+
+// ---- helpers (sfm_api.cu)
+int set_err(sfm_handle* h, int code, const std::string& msg);
+int ensure(sfm_handle* h, Buf& b, size_t bytes);
+
+// ---- kernel launchers (sfm_kernels.cu); all asynchronous on `st`, return cudaError_t
+struct FwdOut {
+    float* S;        // [n_rows][kp]   per-row factor sums (train)
+    float* mult;     // [n_rows]       dLoss/dyhat (train)
+    float* loss;     // [n_rows]       per-row loss (train)
+    float* yhat;     // [n_rows]       predictions (predict) or nullptr
+    uint32_t* keys;  // [nnz]          feature id of every batch entry (train)
+    uint2* pay;      // [nnz]          {batch row, x bits} (train)
+};
+cudaError_t launch_forward(const ModelView& m, const BatchView& b, const FwdOut& o, bool train,
+                           int32_t* d_err, int sm_count, cudaStream_t st, int64_t* launches);
+// loss / mult -> d_scal[SC_LOSS], [SC_GW0], [SC_COUNT] (fixed-shape fp64 tree, deterministic)
+cudaError_t launch_scalar_reduce(const float* loss, const float* mult, int64_t n, double* partials,
+                                 double* d_scal, cudaStream_t st, int64_t* launches);
+// sorted keys -> seg[f] = first position with key >= f, f in [0, n_slots]
+cudaError_t launch_segments(const uint32_t* keys, int64_t nnz, int64_t n_slots, int32_t* seg,
+                            cudaStream_t st, int64_t* launches);
+struct UpdateParams {
+    float eta, reg0, regw, regv;
+};
+// reduce-by-feature over the sorted entries.  fused: apply the SGD update in place (one GPU);
+// else write the dense gradient grad = [gV n_slots*kp | gw n_slots | gw0].
+cudaError_t launch_pull(const ModelView& m, const int32_t* seg, const uint2* pay, const float* S,
+                        const float* mult, const double* d_scal, const int32_t* d_err,
+                        UpdateParams up, bool fused, float* grad, int sm_count, cudaStream_t st,
+                        int64_t* launches);
+// dense update from an (all-reduced) gradient buffer
+cudaError_t launch_update(const ModelView& m, const float* grad, const double* d_scal,
+                          const int32_t* d_err, UpdateParams up, cudaStream_t st,
+                          int64_t* launches);
+// per-row evaluation sums {sum (y-yhat)^2, sum (y-yhat), #sign agree, sum logloss} -> out[4]
+cudaError_t launch_metrics(const float* yhat, const float* label, int64_t n, double* partials,
+                           double* out4, cudaStream_t st, int64_t* launches);
+cudaError_t launch_row_lens(const int64_t* row_ptr, const int32_t* row_ids, int64_t n,
+                            int64_t* lens, cudaStream_t st, int64_t* launches);
+cudaError_t launch_idx_range(const int32_t* idx, int64_t nnz, int32_t* d_minmax, cudaStream_t st,
+                             int64_t* launches);
+cudaError_t launch_pad_v(const float* src, float* dst, int64_t n_slots, int k, int kp, bool unpad,
+                         cudaStream_t st, int64_t* launches);
+cudaError_t launch_synth_ctr(int64_t n_rows, int64_t row_off, int n_fields,
+                             const int32_t* d_log2card, const uint32_t* d_cdf,
+                             const int64_t* d_cdf_off, uint64_t seed, int64_t n_slots,
+                             int32_t* idx, float* label, int64_t* row_ptr, cudaStream_t st,
+                             int64_t* launches);
+
+// ---- CUB wrappers (sfm_sort.cu)
+size_t sort_pairs_temp_bytes(int64_t n, int end_bit);
+// sorts (keys_in, pay_in) -> (keys_out, pay_out) by bits [0, end_bit), stable
+cudaError_t sort_pairs(void* tmp, size_t tmp_bytes, const uint32_t* keys_in, uint32_t* keys_out,
+                       const uint2* pay_in, uint2* pay_out, int64_t n, int end_bit,
+                       cudaStream_t st, int64_t* launches);
+size_t scan_temp_bytes(int64_t n);
+cudaError_t exclusive_scan_i64(void* tmp, size_t tmp_bytes, const int64_t* in, int64_t* out,
+                               int64_t n, cudaStream_t st, int64_t* launches);
+size_t select_temp_bytes(int64_t n);
+// Bernoulli row sampler of DESIGN.md section 2.5 over local rows [0, n): global id = off + r
+cudaError_t sample_rows_device(void* tmp, size_t tmp_bytes, int64_t n, int64_t global_off,
+                               uint64_t key, uint64_t thr, int32_t* out_rows, int32_t* d_count,
+                               cudaStream_t st, int64_t* launches);
+
+// ---- host side (sfm_host.cpp)
+uint64_t mix64(uint64_t x);
+void init_gaussian_f32(float* v, int64_t count, double mean, double stdev, uint64_t seed);
+
+// ---- NCCL via dlopen (sfm_nccl.cpp)
+Nccl* nccl_load(std::string* err);
+int nccl_unique_id(Nccl* n, uint8_t* id128, std::string* err);
+int nccl_init(Nccl* n, void** comm, const uint8_t* id128, int rank, int world, std::string* err);
+int nccl_destroy(Nccl* n, void* comm);
+int nccl_allreduce_f32(Nccl* n, void* comm, float* buf, size_t count, cudaStream_t st,
+                       std::string* err);
+int nccl_allreduce_f64(Nccl* n, void* comm, double* buf, size_t count, cudaStream_t st,
+                       std::string* err);
+int nccl_bcast_f32(Nccl* n, void* comm, float* buf, size_t count, int root, cudaStream_t st,
+                   std::string* err);
+int nccl_group_start(Nccl* n);
+int nccl_group_end(Nccl* n);
+
+}  // namespace sfm

@@ -1,0 +1,264 @@
+// sfm_host.cpp -- host-side pieces of the hot path's boundary: LibFM text ingest / export
+// (fm/FMUtils.scala:23-74 of the reference), the mini-batch sampler and the seeded model
+// initialiser.  No CUDA here.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "sfm_common.h"
+
+namespace sfm {
+
+uint64_t mix64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+// DESIGN.md 2.1.  Box-Muller in fp64 with glibc's log/cos, rounded once to fp32.
+void init_gaussian_f32(float* v, int64_t count, double mean, double stdev, uint64_t seed) {
+    const uint64_t s = mix64(seed);
+    const double two_pi = 6.283185307179586476925286766559;
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > 32) nt = 32;
+    if (count < (1 << 16)) nt = 1;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) {
+        const int64_t lo = count * t / nt, hi = count * (t + 1) / nt;
+        th.emplace_back([=] {
+            for (int64_t e = lo; e < hi; ++e) {
+                const double u1 =
+                    (double)((mix64(s + 2ULL * (uint64_t)e) >> 11) + 1ULL) * 0x1.0p-53;
+                const double u2 = (double)(mix64(s + 2ULL * (uint64_t)e + 1ULL) >> 11) * 0x1.0p-53;
+                const double z = sqrt(-2.0 * log(u1)) * cos(two_pi * u2);
+                v[e] = (float)(mean + stdev * z);
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+}
+
+// ---- java.lang number grammar ------------------------------------------------------------
+// Double.parseDouble: chars <= ' ' trimmed at both ends, [sign] (NaN | Infinity | decimal
+// [fFdD]).  Hex float literals are not supported (documented deviation).
+static bool java_double(const char* b, const char* e, double* out) {
+    while (b < e && (unsigned char)*b <= ' ') ++b;
+    while (e > b && (unsigned char)e[-1] <= ' ') --e;
+    if (b >= e) return false;
+    const char* p = b;
+    bool neg = false;
+    if (*p == '+' || *p == '-') { neg = *p == '-'; ++p; }
+    const size_t rest = (size_t)(e - p);
+    if (rest == 3 && memcmp(p, "NaN", 3) == 0) { *out = NAN; return true; }
+    if (rest == 8 && memcmp(p, "Infinity", 8) == 0) { *out = neg ? -INFINITY : INFINITY; return true; }
+    const char* q = p;
+    int digits = 0;
+    while (q < e && *q >= '0' && *q <= '9') { ++q; ++digits; }
+    if (q < e && *q == '.') {
+        ++q;
+        while (q < e && *q >= '0' && *q <= '9') { ++q; ++digits; }
+    }
+    if (digits == 0) return false;
+    if (q < e && (*q == 'e' || *q == 'E')) {
+        ++q;
+        if (q < e && (*q == '+' || *q == '-')) ++q;
+        int ed = 0;
+        while (q < e && *q >= '0' && *q <= '9') { ++q; ++ed; }
+        if (ed == 0) return false;
+    }
+    const char* num_end = q;
+    if (q < e && (*q == 'f' || *q == 'F' || *q == 'd' || *q == 'D')) ++q;
+    if (q != e) return false;
+    char buf[64];
+    std::string big;
+    const size_t n = (size_t)(num_end - b);
+    const char* src;
+    if (n < sizeof(buf)) { memcpy(buf, b, n); buf[n] = 0; src = buf; }
+    else { big.assign(b, n); src = big.c_str(); }
+    *out = strtod(src, nullptr);
+    return true;
+}
+
+// Integer.parseInt: [sign] digits, no whitespace, 32-bit range.
+static bool java_int(const char* b, const char* e, int32_t* out) {
+    if (b >= e) return false;
+    bool neg = false;
+    if (*b == '+' || *b == '-') { neg = *b == '-'; ++b; }
+    if (b >= e) return false;
+    int64_t v = 0;
+    for (; b < e; ++b) {
+        if (*b < '0' || *b > '9') return false;
+        v = v * 10 + (*b - '0');
+        if (v > 2147483648LL) return false;
+    }
+    if (neg) v = -v;
+    if (v > 2147483647LL || v < -2147483648LL) return false;
+    *out = (int32_t)v;
+    return true;
+}
+
+}  // namespace sfm
+
+using namespace sfm;
+
+extern "C" int32_t sfm_parse_libfm(const char* text, uint64_t len, int32_t num_features,
+                                   int64_t* n_rows, int64_t* nnz, int32_t* dimension_out,
+                                   double* label, int64_t* row_ptr, int32_t* idx, double* val,
+                                   int64_t* err_line) {
+    if (!text && len) return SFM_ERR_ARG;
+    if (!n_rows || !nnz) return SFM_ERR_ARG;
+    const bool fill = idx != nullptr || label != nullptr || row_ptr != nullptr || val != nullptr;
+    int64_t rows = 0, ents = 0, line_no = 0;
+    int32_t max_index = INT32_MIN;
+    bool empty_row = false;
+    const char* p = text;
+    const char* end = text + len;
+    if (fill && row_ptr) row_ptr[0] = 0;
+    while (p < end) {
+        // one physical line: terminated by \n, \r\n or \r (Hadoop LineReader, used by sc.textFile)
+        const char* le = p;
+        while (le < end && *le != '\n' && *le != '\r') ++le;
+        const char* next = le;
+        if (next < end) next += (*next == '\r' && next + 1 < end && next[1] == '\n') ? 2 : 1;
+        ++line_no;
+        const char* b = p;
+        const char* e = le;
+        p = next;
+        while (b < e && (unsigned char)*b <= ' ') ++b;        // .map(_.trim)          FMUtils:25
+        while (e > b && (unsigned char)e[-1] <= ' ') --e;
+        if (b == e || *b == '#') continue;                    // isEmpty || startsWith("#") :26
+        // items = line.split(' ')                                                     :28
+        const char* t = b;
+        const char* te = t;
+        while (te < e && *te != ' ') ++te;
+        double lab;
+        if (!java_double(t, te, &lab)) {                      // items.head.toDouble         :29
+            if (err_line) *err_line = line_no;
+            return SFM_ERR_IO;
+        }
+        if (fill && label) label[rows] = lab;
+        int64_t row_ents = 0;
+        t = te;
+        while (t < e) {
+            ++t;  // skip the separating space
+            te = t;
+            while (te < e && *te != ' ') ++te;
+            if (te == t) continue;                            // .filter(_.nonEmpty)         :30
+            // item.split(':') -> indexAndValue(0).toInt, indexAndValue(1).toDouble  :31-34
+            const char* c0 = t;
+            while (c0 < te && *c0 != ':') ++c0;
+            if (c0 == te) {                                   // no ':' -> indexAndValue(1) throws
+                if (err_line) *err_line = line_no;
+                return SFM_ERR_IO;
+            }
+            const char* v0 = c0 + 1;
+            const char* v1 = v0;
+            while (v1 < te && *v1 != ':') ++v1;               // extra ":..." parts are ignored
+            int32_t id;
+            double x;
+            // "3:" -> split drops the trailing empty string -> only one part -> throws
+            bool rest_empty = true;
+            for (const char* z = v0; z < te; ++z) if (*z != ':') { rest_empty = false; break; }
+            if (rest_empty || !java_int(t, c0, &id) || !java_double(v0, v1, &x)) {
+                if (err_line) *err_line = line_no;
+                return SFM_ERR_IO;
+            }
+            if (fill) {
+                if (idx) idx[ents] = id;
+                if (val) val[ents] = x;
+            }
+            if (id > max_index) max_index = id;
+            ++ents;
+            ++row_ents;
+            t = te;
+        }
+        if (row_ents == 0) empty_row = true;
+        ++rows;
+        if (fill && row_ptr) row_ptr[rows] = ents;
+    }
+    *n_rows = rows;
+    *nnz = ents;
+    int32_t d;
+    if (num_features > 0) {
+        d = num_features;                                     // :40-41
+    } else {
+        // parsed.map(indices.max).reduce(math.max): throws on an empty RDD and on a row
+        // without features                                                         :43-46
+        if (rows == 0 || empty_row) {
+            if (err_line) *err_line = 0;
+            return SFM_ERR_IO;
+        }
+        d = max_index;
+    }
+    if (dimension_out) *dimension_out = d;
+    return SFM_OK;
+}
+
+// DecimalFormat("#") / DecimalFormat("#.###"), RoundingMode.HALF_EVEN  (FMUtils.scala:71-74)
+static void minimize_string(double v, std::string& out) {
+    char buf[400];
+    if (v != v) { out += "NaN"; return; }
+    if (isinf(v)) { out += v < 0 ? "-Infinity" : "Infinity"; return; }
+    if (v == floor(v)) {
+        snprintf(buf, sizeof buf, "%.0f", v);
+        if (strcmp(buf, "-0") == 0 || strcmp(buf, "0") == 0) { out += (signbit(v) ? "-0" : "0"); return; }
+        out += buf;
+        return;
+    }
+    snprintf(buf, sizeof buf, "%.3f", v);  // glibc rounds the exact binary value half-to-even
+    std::string s(buf);
+    while (!s.empty() && s.back() == '0') s.pop_back();
+    if (!s.empty() && s.back() == '.') s.pop_back();
+    // "#.###" has no mandatory integer digit: 0.5 -> ".5", -0.25 -> "-.25", 0.0004 -> "0"
+    bool neg = !s.empty() && s[0] == '-';
+    std::string body = neg ? s.substr(1) : s;
+    if (body == "0" || body.empty()) { out += neg ? "-0" : "0"; return; }
+    if (body.size() > 1 && body[0] == '0' && body[1] == '.') body.erase(0, 1);
+    if (neg) out += '-';
+    out += body;
+}
+
+extern "C" int32_t sfm_format_libfm(const double* label, const int64_t* row_ptr,
+                                    const int32_t* idx, const double* val, int64_t n_rows,
+                                    char* out, uint64_t cap, uint64_t* needed) {
+    if (n_rows < 0 || (n_rows > 0 && (!label || !row_ptr))) return SFM_ERR_ARG;
+    std::string s;
+    char buf[32];
+    for (int64_t r = 0; r < n_rows; ++r) {
+        minimize_string(label[r], s);                          // :60
+        for (int64_t j = row_ptr[r]; j < row_ptr[r + 1]; ++j) {
+            s += ' ';
+            snprintf(buf, sizeof buf, "%lld:", (long long)idx[j] + 1);  // i + 1   :63
+            s += buf;
+            minimize_string(val[j], s);
+        }
+        s += '\n';
+    }
+    if (needed) *needed = s.size();
+    if (out && cap >= s.size()) memcpy(out, s.data(), s.size());
+    else if (out) return SFM_ERR_ARG;
+    return SFM_OK;
+}
+
+extern "C" int32_t sfm_sample_rows(uint64_t seed, int64_t iter, double fraction, int64_t row_lo,
+                                   int64_t row_hi, int64_t* out, int64_t* n_out) {
+    if (!n_out || (row_hi > row_lo && !out)) return SFM_ERR_ARG;
+    int64_t n = 0;
+    if (fraction >= 1.0) {
+        for (int64_t r = row_lo; r < row_hi; ++r) out[n++] = r;
+    } else if (fraction > 0.0) {
+        const uint64_t thr = (uint64_t)floor(fraction * 9007199254740992.0);
+        const uint64_t key = mix64(seed + (uint64_t)iter);
+        for (int64_t r = row_lo; r < row_hi; ++r)
+            if ((mix64(key ^ mix64((uint64_t)r)) >> 11) < thr) out[n++] = r;
+    }
+    *n_out = n;
+    return SFM_OK;
+}

@@ -1,0 +1,683 @@
+// sfm_kernels.cu -- hand-written sm_100a kernels of the SparkFM hot path.
+//
+// Reference citations: /root/reference/src/main/scala/io/edstud/spark/ (the reference has no
+// native code; each kernel names the Scala it replaces).  Spec sections: DESIGN.md.
+//
+//   fm_forward_kernel   FMModel.predict (fm/FMModel.scala:34-63) for a batch of CSR rows, one
+//                       warp per row; in TRAIN mode also the per-sample loss / multiplier of the
+//                       SGD gradient and the (feature, row) entry list that the
+//                       reduce-by-feature consumes.
+//   fm_pull_kernel      deterministic reduce-by-feature: for every feature the
+//                       gradient is PULLED from the rows that contain it, in sorted (fixed)
+//                       order -- no float atomics, no per-entry gradient is ever materialised.
+//                       Fused with the SGD update on one GPU.
+//   fm_update_kernel    dense regularised update from the all-reduced gradient (multi-GPU).
+//
+// All of it is HBM / L2 bound gather + reduction work: tensor cores do not apply.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sfm_common.h"
+
+namespace sfm {
+
+#define FULL 0xffffffffu
+
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+__device__ __forceinline__ float4 shfl_xor4(float4 a, int off) {
+    float4 r;
+    r.x = __shfl_xor_sync(FULL, a.x, off);
+    r.y = __shfl_xor_sync(FULL, a.y, off);
+    r.z = __shfl_xor_sync(FULL, a.z, off);
+    r.w = __shfl_xor_sync(FULL, a.w, off);
+    return r;
+}
+
+// Per-sample loss and dLoss/dyhat, DESIGN.md 2.2 (oracle: fmo_loss_mult).
+__device__ __forceinline__ void loss_mult(int task, float yhat, float label, float& loss,
+                                          float& mult) {
+    if (task == SFM_TASK_CLASSIFICATION) {
+        const float y = label > 0.f ? 1.f : -1.f;
+        const float m = y * yhat;
+        const float e = expf(-fabsf(m));
+        loss = fmaxf(-m, 0.f) + log1pf(e);
+        const float sig = m > 0.f ? e / (1.f + e) : 1.f / (1.f + e);
+        mult = -y * sig;
+    } else {
+        const float d = yhat - label;
+        loss = d * d;
+        mult = d;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Forward.  One warp per row.  A V row is kp floats = LPR float4; the warp's 32 lanes are
+// NPP = 32/LPR "entry slots" x LPR "factor quads": lane = slot*LPR + fq.  A tile of 32 CSR
+// entries is read coalesced (one idx + one val per lane) and kept in registers; each pass
+// broadcasts NPP of them with shuffles and every lane gathers ONE float4 of the entry's V row,
+// so a pass issues NPP fully-used 16*LPR-byte row reads per warp.
+//
+// The pairwise term is accumulated as  P <- P + a*S; S <- S + a  (a = v_if * x_i), i.e.
+// sum_{i<j} a_i a_j, which equals the reference's 0.5*(S^2 - sum a^2) (FMModel.scala:50) exactly
+// in real arithmetic but has no cancellation in fp32; partial (S, P) pairs of different lanes
+// merge with P = P1 + P2 + S1*S2.
+// ------------------------------------------------------------------------------------------
+template <int LPR, bool TRAIN, bool HAS_VAL>
+__global__ void __launch_bounds__(256)
+fm_forward_kernel(const float4* __restrict__ V4, const float* __restrict__ W,
+                  const float* __restrict__ W0, int64_t n_slots, int k0, int k1, int task,
+                  const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ idx,
+                  const float* __restrict__ val, const float* __restrict__ label,
+                  const int32_t* __restrict__ row_ids, int64_t row_lo, int64_t n_rows,
+                  const int64_t* __restrict__ out_ptr, int64_t out_base, int uniform_m,
+                  float4* __restrict__ S4, float* __restrict__ mult_out,
+                  float* __restrict__ loss_out, float* __restrict__ yhat_out,
+                  uint32_t* __restrict__ keys, uint2* __restrict__ pay, int32_t* __restrict__ err) {
+    constexpr int NPP = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int slot = lane / LPR;
+    const int fq = lane % LPR;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const float w0 = k0 ? __ldg(W0) : 0.f;
+
+    for (int64_t pos = warp0; pos < n_rows; pos += nwarps) {
+        const int64_t r = row_ids ? (int64_t)__ldg(row_ids + pos) : row_lo + pos;
+        const int64_t beg = __ldg(row_ptr + r);
+        const int64_t end = __ldg(row_ptr + r + 1);
+        int64_t obase = 0;
+        if (TRAIN) obase = out_ptr ? __ldg(out_ptr + pos) - out_base : pos * (int64_t)uniform_m;
+
+        float4 s = f4_zero(), p = f4_zero();
+        float lin = 0.f;
+        for (int64_t tile = beg; tile < end; tile += 32) {
+            const int64_t j = tile + lane;
+            int id = -1;
+            float x = 0.f;
+            if (j < end) {
+                id = __ldg(idx + j);
+                x = HAS_VAL ? __ldg(val + j) : 1.f;
+                if ((uint32_t)id >= (uint64_t)n_slots) {  // reported, never dereferenced
+                    atomicExch(err, 1);
+                    id = -1;
+                }
+                if (TRAIN) {
+                    keys[obase + (j - beg)] = id < 0 ? 0u : (uint32_t)id;
+                    pay[obase + (j - beg)] =
+                        make_uint2((uint32_t)pos, id < 0 ? 0u : __float_as_uint(x));
+                }
+            }
+            const int cnt = (int)min((int64_t)32, end - tile);
+            if (cnt == 32) {
+                // full tile: LPR passes, all gathers independent -> issued back to back
+                constexpr int PCH = LPR < 8 ? LPR : 8;  // passes in flight (bounds registers)
+#pragma unroll
+                for (int t0 = 0; t0 < LPR; t0 += PCH) {
+                float4 vv[PCH];
+                float xx[PCH], ww[PCH];
+#pragma unroll
+                for (int t = 0; t < PCH; ++t) {
+                    const int pid = __shfl_sync(FULL, id, (t0 + t) * NPP + slot);
+                    xx[t] = __shfl_sync(FULL, x, (t0 + t) * NPP + slot);
+                    const int64_t row = pid < 0 ? 0 : pid;
+                    if (pid < 0) xx[t] = 0.f;
+                    vv[t] = __ldg(V4 + row * LPR + fq);
+                    ww[t] = (fq == 0) ? __ldg(W + row) : 0.f;
+                }
+#pragma unroll
+                for (int t = 0; t < PCH; ++t) {
+                    const float px = xx[t];
+                    const float ax = px != 0.f ? vv[t].x * px : 0.f;
+                    const float ay = px != 0.f ? vv[t].y * px : 0.f;
+                    const float az = px != 0.f ? vv[t].z * px : 0.f;
+                    const float aw = px != 0.f ? vv[t].w * px : 0.f;
+                    p.x = fmaf(ax, s.x, p.x); s.x += ax;
+                    p.y = fmaf(ay, s.y, p.y); s.y += ay;
+                    p.z = fmaf(az, s.z, p.z); s.z += az;
+                    p.w = fmaf(aw, s.w, p.w); s.w += aw;
+                    lin = px != 0.f ? fmaf(ww[t], px, lin) : lin;
+                }
+                }
+            } else {
+                for (int t = 0; t * NPP < cnt; ++t) {
+                    const int pid = __shfl_sync(FULL, id, t * NPP + slot);
+                    float px = __shfl_sync(FULL, x, t * NPP + slot);
+                    const int64_t row = pid < 0 ? 0 : pid;
+                    if (pid < 0) px = 0.f;
+                    const float4 v = __ldg(V4 + row * LPR + fq);
+                    const float wv = (fq == 0) ? __ldg(W + row) : 0.f;
+                    const float ax = px != 0.f ? v.x * px : 0.f;
+                    const float ay = px != 0.f ? v.y * px : 0.f;
+                    const float az = px != 0.f ? v.z * px : 0.f;
+                    const float aw = px != 0.f ? v.w * px : 0.f;
+                    p.x = fmaf(ax, s.x, p.x); s.x += ax;
+                    p.y = fmaf(ay, s.y, p.y); s.y += ay;
+                    p.z = fmaf(az, s.z, p.z); s.z += az;
+                    p.w = fmaf(aw, s.w, p.w); s.w += aw;
+                    lin = px != 0.f ? fmaf(wv, px, lin) : lin;
+                }
+            }
+        }
+        // merge the NPP entry slots (lanes that differ in `slot`, same fq)
+#pragma unroll
+        for (int off = LPR; off < 32; off <<= 1) {
+            const float4 so = shfl_xor4(s, off);
+            const float4 po = shfl_xor4(p, off);
+            p.x = (p.x + po.x) + s.x * so.x; s.x += so.x;
+            p.y = (p.y + po.y) + s.y * so.y; s.y += so.y;
+            p.z = (p.z + po.z) + s.z * so.z; s.z += so.z;
+            p.w = (p.w + po.w) + s.w * so.w; s.w += so.w;
+            lin += __shfl_xor_sync(FULL, lin, off);
+        }
+        float pair = (p.x + p.y) + (p.z + p.w);
+#pragma unroll
+        for (int off = 1; off < LPR; off <<= 1) pair += __shfl_xor_sync(FULL, pair, off);
+        // lin lives in fq == 0 lanes only (already merged over slots)
+        const float lin0 = __shfl_sync(FULL, lin, 0);
+        float yhat = w0;
+        if (k1) yhat += lin0;
+        yhat += pair;
+        if (TRAIN) {
+            if (lane < LPR) S4[pos * LPR + fq] = s;
+            if (lane == 0) {
+                float ls, mu;
+                loss_mult(task, yhat, __ldg(label + r), ls, mu);
+                loss_out[pos] = ls;
+                mult_out[pos] = mu;
+            }
+        } else {
+            if (lane == 0) yhat_out[pos] = yhat;
+        }
+    }
+}
+
+template <int LPR>
+static cudaError_t forward_dispatch(const ModelView& m, const BatchView& b, const FwdOut& o,
+                                    bool train, int32_t* d_err, int sm_count, cudaStream_t st) {
+    if (b.n_rows <= 0) return cudaSuccess;
+    const int wpb = 8;
+    int64_t blocks = (b.n_rows + wpb - 1) / wpb;
+    const int64_t cap = (int64_t)sm_count * 16;  // persistent: <= 16 CTAs of 8 warps per SM queued
+    if (blocks > cap) blocks = cap;
+#define FWD_ARGS                                                                              \
+    (const float4*)m.v, m.w, m.w0, m.n_slots, m.k0, m.k1, m.task, b.row_ptr, b.idx, b.val,    \
+        b.label, b.row_ids, b.row_lo, b.n_rows, b.out_ptr, b.out_base, b.uniform_m,           \
+        (float4*)o.S, o.mult, o.loss, o.yhat, o.keys, o.pay, d_err
+    const dim3 g((unsigned)blocks), t(256);
+    if (train) {
+        if (b.val) fm_forward_kernel<LPR, true, true><<<g, t, 0, st>>>(FWD_ARGS);
+        else       fm_forward_kernel<LPR, true, false><<<g, t, 0, st>>>(FWD_ARGS);
+    } else {
+        if (b.val) fm_forward_kernel<LPR, false, true><<<g, t, 0, st>>>(FWD_ARGS);
+        else       fm_forward_kernel<LPR, false, false><<<g, t, 0, st>>>(FWD_ARGS);
+    }
+#undef FWD_ARGS
+    return cudaGetLastError();
+}
+
+cudaError_t launch_forward(const ModelView& m, const BatchView& b, const FwdOut& o, bool train,
+                           int32_t* d_err, int sm_count, cudaStream_t st, int64_t* launches) {
+    if (b.n_rows > 0) ++*launches;
+    switch (m.lpr) {
+        case 1: return forward_dispatch<1>(m, b, o, train, d_err, sm_count, st);
+        case 2: return forward_dispatch<2>(m, b, o, train, d_err, sm_count, st);
+        case 4: return forward_dispatch<4>(m, b, o, train, d_err, sm_count, st);
+        case 8: return forward_dispatch<8>(m, b, o, train, d_err, sm_count, st);
+        case 16: return forward_dispatch<16>(m, b, o, train, d_err, sm_count, st);
+        case 32: return forward_dispatch<32>(m, b, o, train, d_err, sm_count, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fixed-shape fp64 reductions (deterministic: the mapping element -> thread -> tree slot depends
+// on n only).  Stage 1: RED_BLOCKS blocks, each a contiguous span; stage 2: one block.
+// ------------------------------------------------------------------------------------------
+constexpr int RED_BLOCKS = 296;
+constexpr int RED_THREADS = 256;
+
+template <int NV>
+__device__ __forceinline__ void block_tree(double (&acc)[NV], double* sm /* [NV][RED_THREADS] */) {
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) sm[v * RED_THREADS + t] = acc[v];
+    __syncthreads();
+    for (int off = RED_THREADS / 2; off > 0; off >>= 1) {
+        if (t < off) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) sm[v * RED_THREADS + t] += sm[v * RED_THREADS + t + off];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = sm[v * RED_THREADS];
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+scalar_reduce1_kernel(const float* __restrict__ loss, const float* __restrict__ mult, int64_t n,
+                      double* __restrict__ partials) {
+    __shared__ double sm[2 * RED_THREADS];
+    const int64_t span = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * span;
+    const int64_t hi = min(n, lo + span);
+    double acc[2] = {0.0, 0.0};
+    for (int64_t i = lo + threadIdx.x; i < hi; i += RED_THREADS) {
+        acc[0] += (double)loss[i];
+        acc[1] += (double)mult[i];
+    }
+    block_tree<2>(acc, sm);
+    if (threadIdx.x == 0) {
+        partials[2 * blockIdx.x] = acc[0];
+        partials[2 * blockIdx.x + 1] = acc[1];
+    }
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+scalar_reduce2_kernel(const double* __restrict__ partials, int nblocks, int64_t n,
+                      double* __restrict__ d_scal) {
+    __shared__ double sm[2 * RED_THREADS];
+    double acc[2] = {0.0, 0.0};
+    for (int i = threadIdx.x; i < nblocks; i += RED_THREADS) {
+        acc[0] += partials[2 * i];
+        acc[1] += partials[2 * i + 1];
+    }
+    block_tree<2>(acc, sm);
+    if (threadIdx.x == 0) {
+        d_scal[SC_LOSS] = acc[0];
+        d_scal[SC_GW0] = acc[1];
+        d_scal[SC_COUNT] = (double)n;
+        d_scal[3] = 0.0;
+    }
+}
+
+cudaError_t launch_scalar_reduce(const float* loss, const float* mult, int64_t n, double* partials,
+                                 double* d_scal, cudaStream_t st, int64_t* launches) {
+    *launches += 2;
+    scalar_reduce1_kernel<<<RED_BLOCKS, RED_THREADS, 0, st>>>(loss, mult, n, partials);
+    scalar_reduce2_kernel<<<1, RED_THREADS, 0, st>>>(partials, RED_BLOCKS, n, d_scal);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+metrics1_kernel(const float* __restrict__ yhat, const float* __restrict__ label, int64_t n,
+                double* __restrict__ partials) {
+    __shared__ double sm[4 * RED_THREADS];
+    const int64_t span = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * span;
+    const int64_t hi = min(n, lo + span);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int64_t i = lo + threadIdx.x; i < hi; i += RED_THREADS) {
+        const float y = label[i], p = yhat[i];
+        const double e = (double)y - (double)p;  // Model.scala:14 (y - yhat)
+        acc[0] += e * e;
+        acc[1] += e;
+        acc[2] += ((y >= 0.f && p >= 0.f) || (y < 0.f && p < 0.f)) ? 1.0 : 0.0;  // Model.scala:29
+        float ls, mu;
+        loss_mult(SFM_TASK_CLASSIFICATION, p, y, ls, mu);
+        acc[3] += (double)ls;
+    }
+    block_tree<4>(acc, sm);
+    if (threadIdx.x == 0)
+        for (int v = 0; v < 4; ++v) partials[4 * blockIdx.x + v] = acc[v];
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+metrics2_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ out4) {
+    __shared__ double sm[4 * RED_THREADS];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < nblocks; i += RED_THREADS)
+        for (int v = 0; v < 4; ++v) acc[v] += partials[4 * i + v];
+    block_tree<4>(acc, sm);
+    if (threadIdx.x == 0)
+        for (int v = 0; v < 4; ++v) out4[v] += acc[v];  // accumulates over tiles of rows
+}
+
+cudaError_t launch_metrics(const float* yhat, const float* label, int64_t n, double* partials,
+                           double* out4, cudaStream_t st, int64_t* launches) {
+    *launches += 2;
+    metrics1_kernel<<<RED_BLOCKS, RED_THREADS, 0, st>>>(yhat, label, n, partials);
+    metrics2_kernel<<<1, RED_THREADS, 0, st>>>(partials, RED_BLOCKS, out4);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// seg[f] = first sorted position whose key >= f  (f in [0, n_slots]).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+segments_kernel(const uint32_t* __restrict__ keys, int64_t nnz, int64_t n_slots,
+                int32_t* __restrict__ seg) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p <= nnz; p += stride) {
+        const int64_t prev = p == 0 ? -1 : (int64_t)keys[p - 1];
+        const int64_t cur = p == nnz ? n_slots : (int64_t)keys[p];
+        for (int64_t f = prev + 1; f <= cur; ++f) seg[f] = (int32_t)p;
+    }
+}
+
+cudaError_t launch_segments(const uint32_t* keys, int64_t nnz, int64_t n_slots, int32_t* seg,
+                            cudaStream_t st, int64_t* launches) {
+    ++*launches;
+    int64_t blocks = (nnz + 1 + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    segments_kernel<<<(unsigned)blocks, 256, 0, st>>>(keys, nnz, n_slots, seg);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Reduce-by-feature, pull form.  With c = mult_r * x_ri:
+//     gV_if = sum_r c * S_rf  -  v_if * sum_r c * x_ri        gw_i = sum_r c
+// so a feature needs only the rows' factor sums S_r (kp floats) and multipliers, gathered in
+// the sorted (feature, batch position) order.  A group of LPR lanes owns one feature and walks
+// its segment; the running sums are in registers, the order is fixed -> bitwise reproducible.
+// FUSED: theta <- theta - eta*(g/B + lambda*theta) applied on the spot (every feature is
+// visited, so untouched slots get their L2 decay too).
+// ------------------------------------------------------------------------------------------
+template <int LPR, bool FUSED>
+__global__ void __launch_bounds__(256)
+fm_pull_kernel(float4* __restrict__ V4, float* __restrict__ W, float* __restrict__ W0,
+               int64_t n_slots, int k0, int k1, const int32_t* __restrict__ seg,
+               const uint2* __restrict__ pay, const float4* __restrict__ S4,
+               const float* __restrict__ mult, const double* __restrict__ d_scal,
+               const int32_t* __restrict__ err, UpdateParams up, float4* __restrict__ G4,
+               float* __restrict__ Gw, float* __restrict__ Gw0) {
+    if (FUSED && *err) return;  // a bad index was seen: leave the model untouched
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / LPR;
+    const int fq = threadIdx.x % LPR;
+    const double count = d_scal[SC_COUNT];
+    const float inv = count > 0.0 ? (float)(1.0 / count) : 0.f;
+    const bool active = count > 0.0;
+
+    if (tid == 0) {
+        const float g0 = (float)d_scal[SC_GW0];
+        if (FUSED) {
+            if (k0 && active) {
+                const float w0 = *W0;
+                *W0 = w0 - up.eta * (g0 * inv + up.reg0 * w0);
+            }
+        } else {
+            *Gw0 = k0 ? g0 : 0.f;
+        }
+    }
+    for (int64_t i = tid / LPR; i < n_slots; i += ngroups) {
+        const int b = seg[i], e = seg[i + 1];
+        float4 A = f4_zero();
+        float D = 0.f, C = 0.f;
+        for (int p = b; p < e; ++p) {
+            const uint2 pl = __ldg(pay + p);
+            const float x = __uint_as_float(pl.y);
+            const float c = __ldg(mult + pl.x) * x;
+            const float4 sv = __ldg(S4 + (int64_t)pl.x * LPR + fq);
+            A.x = fmaf(c, sv.x, A.x);
+            A.y = fmaf(c, sv.y, A.y);
+            A.z = fmaf(c, sv.z, A.z);
+            A.w = fmaf(c, sv.w, A.w);
+            D = fmaf(c, x, D);
+            C += c;
+        }
+        float4 v = V4[i * LPR + fq];
+        float4 g;
+        g.x = A.x - v.x * D;
+        g.y = A.y - v.y * D;
+        g.z = A.z - v.z * D;
+        g.w = A.w - v.w * D;
+        if (FUSED) {
+            if (active) {
+                v.x -= up.eta * (g.x * inv + up.regv * v.x);
+                v.y -= up.eta * (g.y * inv + up.regv * v.y);
+                v.z -= up.eta * (g.z * inv + up.regv * v.z);
+                v.w -= up.eta * (g.w * inv + up.regv * v.w);
+                V4[i * LPR + fq] = v;
+                if (fq == 0 && k1) {
+                    const float w = W[i];
+                    W[i] = w - up.eta * (C * inv + up.regw * w);
+                }
+            }
+        } else {
+            G4[i * LPR + fq] = g;
+            if (fq == 0) Gw[i] = k1 ? C : 0.f;
+        }
+    }
+}
+
+template <int LPR>
+static cudaError_t pull_dispatch(const ModelView& m, const int32_t* seg, const uint2* pay,
+                                 const float* S, const float* mult, const double* d_scal,
+                                 const int32_t* d_err, UpdateParams up, bool fused, float* grad,
+                                 int sm_count, cudaStream_t st) {
+    const int64_t threads = m.n_slots * LPR;
+    int64_t blocks = (threads + 255) / 256;
+    const int64_t cap = (int64_t)sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    float* gw = grad ? grad + m.n_slots * m.kp : nullptr;
+    float* gw0 = grad ? gw + m.n_slots : nullptr;
+    if (fused)
+        fm_pull_kernel<LPR, true><<<(unsigned)blocks, 256, 0, st>>>(
+            (float4*)m.v, m.w, m.w0, m.n_slots, m.k0, m.k1, seg, pay, (const float4*)S, mult,
+            d_scal, d_err, up, nullptr, nullptr, nullptr);
+    else
+        fm_pull_kernel<LPR, false><<<(unsigned)blocks, 256, 0, st>>>(
+            (float4*)m.v, m.w, m.w0, m.n_slots, m.k0, m.k1, seg, pay, (const float4*)S, mult,
+            d_scal, d_err, up, (float4*)grad, gw, gw0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pull(const ModelView& m, const int32_t* seg, const uint2* pay, const float* S,
+                        const float* mult, const double* d_scal, const int32_t* d_err,
+                        UpdateParams up, bool fused, float* grad, int sm_count, cudaStream_t st,
+                        int64_t* launches) {
+    ++*launches;
+    switch (m.lpr) {
+        case 1: return pull_dispatch<1>(m, seg, pay, S, mult, d_scal, d_err, up, fused, grad, sm_count, st);
+        case 2: return pull_dispatch<2>(m, seg, pay, S, mult, d_scal, d_err, up, fused, grad, sm_count, st);
+        case 4: return pull_dispatch<4>(m, seg, pay, S, mult, d_scal, d_err, up, fused, grad, sm_count, st);
+        case 8: return pull_dispatch<8>(m, seg, pay, S, mult, d_scal, d_err, up, fused, grad, sm_count, st);
+        case 16: return pull_dispatch<16>(m, seg, pay, S, mult, d_scal, d_err, up, fused, grad, sm_count, st);
+        case 32: return pull_dispatch<32>(m, seg, pay, S, mult, d_scal, d_err, up, fused, grad, sm_count, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------------
+// Dense update from the all-reduced gradient [gV | gw | gw0]  (DESIGN.md 2.3).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fm_update_kernel(float4* __restrict__ V4, float* __restrict__ W, float* __restrict__ W0,
+                 int64_t nv4, int64_t n_slots, int k0, int k1, const float4* __restrict__ G4,
+                 const float* __restrict__ Gw, const float* __restrict__ Gw0,
+                 const double* __restrict__ d_scal, const int32_t* __restrict__ err,
+                 UpdateParams up) {
+    if (*err) return;
+    const double count = d_scal[SC_COUNT];
+    if (!(count > 0.0)) return;
+    const float inv = (float)(1.0 / count);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = tid; i < nv4; i += stride) {
+        float4 v = V4[i];
+        const float4 g = __ldg(G4 + i);
+        v.x -= up.eta * (g.x * inv + up.regv * v.x);
+        v.y -= up.eta * (g.y * inv + up.regv * v.y);
+        v.z -= up.eta * (g.z * inv + up.regv * v.z);
+        v.w -= up.eta * (g.w * inv + up.regv * v.w);
+        V4[i] = v;
+    }
+    if (k1)
+        for (int64_t i = tid; i < n_slots; i += stride) {
+            const float w = W[i];
+            W[i] = w - up.eta * (__ldg(Gw + i) * inv + up.regw * w);
+        }
+    if (k0 && tid == 0) {
+        const float w0 = *W0;
+        *W0 = w0 - up.eta * (*Gw0 * inv + up.reg0 * w0);
+    }
+}
+
+cudaError_t launch_update(const ModelView& m, const float* grad, const double* d_scal,
+                          const int32_t* d_err, UpdateParams up, cudaStream_t st,
+                          int64_t* launches) {
+    ++*launches;
+    const int64_t nv4 = m.n_slots * m.lpr;
+    int64_t blocks = (nv4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    const float* gw = grad + m.n_slots * m.kp;
+    fm_update_kernel<<<(unsigned)blocks, 256, 0, st>>>((float4*)m.v, m.w, m.w0, nv4, m.n_slots,
+                                                       m.k0, m.k1, (const float4*)grad, gw,
+                                                       gw + m.n_slots, d_scal, d_err, up);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Small utilities.
+// ------------------------------------------------------------------------------------------
+__global__ void row_lens_kernel(const int64_t* __restrict__ row_ptr,
+                                const int32_t* __restrict__ row_ids, int64_t n,
+                                int64_t* __restrict__ lens) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t r = row_ids[i];
+        lens[i] = row_ptr[r + 1] - row_ptr[r];
+    }
+}
+
+cudaError_t launch_row_lens(const int64_t* row_ptr, const int32_t* row_ids, int64_t n,
+                            int64_t* lens, cudaStream_t st, int64_t* launches) {
+    if (n <= 0) return cudaSuccess;
+    ++*launches;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    row_lens_kernel<<<(unsigned)blocks, 256, 0, st>>>(row_ptr, row_ids, n, lens);
+    return cudaGetLastError();
+}
+
+__global__ void idx_range_kernel(const int32_t* __restrict__ idx, int64_t nnz,
+                                 int32_t* __restrict__ minmax) {
+    int lo = INT32_MAX, hi = INT32_MIN;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) {
+        const int v = idx[i];
+        lo = min(lo, v);
+        hi = max(hi, v);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        lo = min(lo, __shfl_xor_sync(FULL, lo, off));
+        hi = max(hi, __shfl_xor_sync(FULL, hi, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(minmax, lo);  // integer atomics: order-independent result
+        atomicMax(minmax + 1, hi);
+    }
+}
+
+cudaError_t launch_idx_range(const int32_t* idx, int64_t nnz, int32_t* d_minmax, cudaStream_t st,
+                             int64_t* launches) {
+    if (nnz <= 0) return cudaSuccess;
+    ++*launches;
+    int64_t blocks = (nnz + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    idx_range_kernel<<<(unsigned)blocks, 256, 0, st>>>(idx, nnz, d_minmax);
+    return cudaGetLastError();
+}
+
+// [n_slots][k] <-> [n_slots][kp] (zero padded)
+__global__ void pad_v_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                             int64_t n_slots, int k, int kp, int unpad) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t total = n_slots * (unpad ? k : kp);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        if (unpad) {
+            const int64_t i = e / k;
+            const int f = (int)(e % k);
+            dst[e] = src[i * kp + f];
+        } else {
+            const int64_t i = e / kp;
+            const int f = (int)(e % kp);
+            dst[e] = f < k ? src[i * k + f] : 0.f;
+        }
+    }
+}
+
+cudaError_t launch_pad_v(const float* src, float* dst, int64_t n_slots, int k, int kp, bool unpad,
+                         cudaStream_t st, int64_t* launches) {
+    const int64_t total = n_slots * (unpad ? k : kp);
+    if (total <= 0) return cudaSuccess;
+    ++*launches;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pad_v_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, n_slots, k, kp, unpad ? 1 : 0);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Synthetic CTR rows (numpy twin: sparkfm_b200/synth.py ctr_rows).  Integer
+// arithmetic only, so host and device agree bit for bit.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t mix64_dev(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+constexpr uint64_t SALT_FEATURE = 0x5fe14bd7a3c1e5b3ULL;
+constexpr uint64_t SALT_A = 0x1b873593cc9e2d51ULL;
+constexpr uint64_t SALT_B = 0x85ebca6bc2b2ae35ULL;
+constexpr uint64_t SALT_NOISE = 0x27d4eb2f165667c5ULL;
+constexpr int64_t LABEL_THRESHOLD = 110000;  // ~25 % positives (synth.py)
+
+__global__ void __launch_bounds__(256)
+synth_ctr_kernel(int64_t n_rows, int64_t row_off, int n_fields,
+                 const int32_t* __restrict__ log2card, const uint32_t* __restrict__ cdf,
+                 const int64_t* __restrict__ cdf_off, uint64_t seed_key, int64_t n_slots,
+                 int32_t* __restrict__ idx, float* __restrict__ label,
+                 int64_t* __restrict__ row_ptr) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+        const uint64_t gr = (uint64_t)(row_off + r);
+        int64_t lin = 0, sb = 0, sb2 = 0;
+        for (int f = 0; f < n_fields; ++f) {
+            const uint64_t h = mix64_dev(seed_key + gr * (uint64_t)n_fields + (uint64_t)f);
+            const uint32_t u = (uint32_t)(h >> 32);
+            const uint32_t* tab = cdf + cdf_off[f];
+            int lo = 0, hi = (1 << log2card[f]) - 1;  // first j with u <= tab[j]
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (u <= tab[mid]) hi = mid; else lo = mid + 1;
+            }
+            const uint64_t fid =
+                mix64_dev((((uint64_t)f) << 40) ^ (uint64_t)lo ^ SALT_FEATURE) % (uint64_t)n_slots;
+            idx[r * n_fields + f] = (int32_t)fid;
+            const int64_t a = (int64_t)(mix64_dev(fid ^ SALT_A) & 0xFFFF) - 32768;
+            const int64_t b = (int64_t)(mix64_dev(fid ^ SALT_B) & 0xFF) - 128;
+            lin += a;
+            sb += b;
+            sb2 += b * b;
+        }
+        const int64_t noise =
+            (int64_t)(mix64_dev(seed_key ^ mix64_dev(gr ^ SALT_NOISE)) & 0x7FFFF) - 262144;
+        const int64_t score = lin + (sb * sb - sb2) / 2 + noise;  // (sb^2 - sb2) is always even
+        label[r] = score > LABEL_THRESHOLD ? 1.f : 0.f;
+        row_ptr[r] = r * n_fields;
+        if (r == n_rows - 1) row_ptr[n_rows] = n_rows * n_fields;
+    }
+}
+
+cudaError_t launch_synth_ctr(int64_t n_rows, int64_t row_off, int n_fields,
+                             const int32_t* d_log2card, const uint32_t* d_cdf,
+                             const int64_t* d_cdf_off, uint64_t seed, int64_t n_slots,
+                             int32_t* idx, float* label, int64_t* row_ptr, cudaStream_t st,
+                             int64_t* launches) {
+    if (n_rows <= 0) return cudaSuccess;
+    ++*launches;
+    int64_t blocks = (n_rows + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    synth_ctr_kernel<<<(unsigned)blocks, 256, 0, st>>>(n_rows, row_off, n_fields, d_log2card,
+                                                       d_cdf, d_cdf_off, mix64_dev(seed), n_slots,
+                                                       idx, label, row_ptr);
+    return cudaGetLastError();
+}
+
+}  // namespace sfm

@@ -1,0 +1,137 @@
+// sfm_nccl.cpp -- NCCL bound at run time with dlopen, so libsparkfm_b200.so loads on machines
+// without NCCL (and, inside a torch process, shares the libnccl.so.2 torch already mapped).
+// The collective replaces Spark's driver-side combination of partition results
+// (Model.scala:14 `.sum()`, fm/lib/ALS.scala:153 `.reduce(_+_)`; treeAggregate in north_star).
+#include <dlfcn.h>
+#include <string.h>
+
+#include <string>
+
+#include "sfm_common.h"
+
+namespace sfm {
+
+// Minimal NCCL declarations (ABI-stable across NCCL 2.x).
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclFloat32 = 7, ncclFloat64 = 8 };  // ncclDataType_t
+enum { ncclSum = 0 };                      // ncclRedOp_t
+
+struct Nccl {
+    void* dl = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+static std::string nerr(Nccl* n, const char* what, int rc) {
+    std::string s = what;
+    s += ": ";
+    s += n->GetErrorString ? n->GetErrorString(rc) : "nccl error";
+    return s;
+}
+
+Nccl* nccl_load(std::string* err) {
+    static Nccl* inst = nullptr;
+    if (inst) return inst;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* dl = nullptr;
+    for (const char* nm : names) {
+        dl = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (dl) break;
+    }
+    if (!dl) {
+        if (err) *err = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+        return nullptr;
+    }
+    Nccl* n = new Nccl;
+    n->dl = dl;
+#define SYM(field, name)                                                  \
+    *(void**)(&n->field) = dlsym(dl, name);                               \
+    if (!n->field) {                                                      \
+        if (err) *err = std::string("libnccl is missing symbol ") + name; \
+        delete n;                                                         \
+        return nullptr;                                                   \
+    }
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(AllReduce, "ncclAllReduce")
+    SYM(Broadcast, "ncclBroadcast")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    inst = n;
+    return n;
+}
+
+int nccl_unique_id(Nccl* n, uint8_t* id128, std::string* err) {
+    ncclUniqueId id;
+    const int rc = n->GetUniqueId(&id);
+    if (rc != ncclSuccess) {
+        if (err) *err = nerr(n, "ncclGetUniqueId", rc);
+        return SFM_ERR_NCCL;
+    }
+    memcpy(id128, id.internal, 128);
+    return SFM_OK;
+}
+
+int nccl_init(Nccl* n, void** comm, const uint8_t* id128, int rank, int world, std::string* err) {
+    ncclUniqueId id;
+    memcpy(id.internal, id128, 128);
+    ncclComm_t c = nullptr;
+    const int rc = n->CommInitRank(&c, world, id, rank);
+    if (rc != ncclSuccess) {
+        if (err) *err = nerr(n, "ncclCommInitRank", rc);
+        return SFM_ERR_NCCL;
+    }
+    *comm = c;
+    return SFM_OK;
+}
+
+int nccl_destroy(Nccl* n, void* comm) {
+    if (n && comm) n->CommDestroy((ncclComm_t)comm);
+    return SFM_OK;
+}
+
+int nccl_allreduce_f32(Nccl* n, void* comm, float* buf, size_t count, cudaStream_t st,
+                       std::string* err) {
+    const int rc = n->AllReduce(buf, buf, count, ncclFloat32, ncclSum, (ncclComm_t)comm, st);
+    if (rc != ncclSuccess) {
+        if (err) *err = nerr(n, "ncclAllReduce(f32)", rc);
+        return SFM_ERR_NCCL;
+    }
+    return SFM_OK;
+}
+
+int nccl_allreduce_f64(Nccl* n, void* comm, double* buf, size_t count, cudaStream_t st,
+                       std::string* err) {
+    const int rc = n->AllReduce(buf, buf, count, ncclFloat64, ncclSum, (ncclComm_t)comm, st);
+    if (rc != ncclSuccess) {
+        if (err) *err = nerr(n, "ncclAllReduce(f64)", rc);
+        return SFM_ERR_NCCL;
+    }
+    return SFM_OK;
+}
+
+int nccl_bcast_f32(Nccl* n, void* comm, float* buf, size_t count, int root, cudaStream_t st,
+                   std::string* err) {
+    const int rc = n->Broadcast(buf, buf, count, ncclFloat32, root, (ncclComm_t)comm, st);
+    if (rc != ncclSuccess) {
+        if (err) *err = nerr(n, "ncclBroadcast", rc);
+        return SFM_ERR_NCCL;
+    }
+    return SFM_OK;
+}
+
+int nccl_group_start(Nccl* n) { return n->GroupStart(); }
+int nccl_group_end(Nccl* n) { return n->GroupEnd(); }
+
+}  // namespace sfm

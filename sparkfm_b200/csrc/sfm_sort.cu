@@ -1,0 +1,76 @@
+// sfm_sort.cu -- CUB-backed helpers (library calls, kept in their own translation unit):
+//   * stable radix sort of the batch's (feature id, {row, x}) entries -- the transposition the
+//     deterministic reduce-by-feature needs.  It is overhead, not counted in
+//     the algorithmic bytes.
+//   * exclusive scan of row lengths, Bernoulli row sampler (stream compaction).
+#include <cub/cub.cuh>
+
+#include "sfm_common.h"
+
+namespace sfm {
+
+typedef unsigned long long pay_t;  // uint2 payload moved as one 8-byte word
+
+size_t sort_pairs_temp_bytes(int64_t n, int end_bit) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (const pay_t*)nullptr, (pay_t*)nullptr, n, 0, end_bit);
+    return bytes;
+}
+
+cudaError_t sort_pairs(void* tmp, size_t tmp_bytes, const uint32_t* keys_in, uint32_t* keys_out,
+                       const uint2* pay_in, uint2* pay_out, int64_t n, int end_bit,
+                       cudaStream_t st, int64_t* launches) {
+    // onesweep: 1 histogram + 1 scan + ceil(end_bit/8) passes
+    *launches += 2 + (end_bit + 7) / 8;
+    return cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out,
+                                           reinterpret_cast<const pay_t*>(pay_in),
+                                           reinterpret_cast<pay_t*>(pay_out), n, 0, end_bit, st);
+}
+
+size_t scan_temp_bytes(int64_t n) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int64_t*)nullptr, (int64_t*)nullptr, n);
+    return bytes;
+}
+
+cudaError_t exclusive_scan_i64(void* tmp, size_t tmp_bytes, const int64_t* in, int64_t* out,
+                               int64_t n, cudaStream_t st, int64_t* launches) {
+    *launches += 2;
+    return cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, n, st);
+}
+
+__host__ __device__ __forceinline__ uint64_t mix64_s(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+// row r (global) is in the batch iff (mix64(key ^ mix64(r)) >> 11) < thr.
+struct InBatch {
+    uint64_t key, thr;
+    int64_t off;
+    __host__ __device__ bool operator()(const int32_t& r) const {
+        return (mix64_s(key ^ mix64_s((uint64_t)(off + r))) >> 11) < thr;
+    }
+};
+
+size_t select_temp_bytes(int64_t n) {
+    size_t bytes = 0;
+    cub::CountingInputIterator<int32_t> it(0);
+    cub::DeviceSelect::If(nullptr, bytes, it, (int32_t*)nullptr, (int32_t*)nullptr, (int)n,
+                          InBatch{0, 0, 0});
+    return bytes;
+}
+
+cudaError_t sample_rows_device(void* tmp, size_t tmp_bytes, int64_t n, int64_t global_off,
+                               uint64_t key, uint64_t thr, int32_t* out_rows, int32_t* d_count,
+                               cudaStream_t st, int64_t* launches) {
+    *launches += 2;
+    cub::CountingInputIterator<int32_t> it(0);
+    return cub::DeviceSelect::If(tmp, tmp_bytes, it, out_rows, d_count, (int)n,
+                                 InBatch{key, thr, global_off}, st);
+}
+
+}  // namespace sfm

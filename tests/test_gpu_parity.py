@@ -1,0 +1,388 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the fp64 CPU oracle on the
+same seeded inputs.  The oracle is PARITY UNPINNED (no runnable reference, no reference golden
+vectors -- see oracle/fm_oracle.h); `predict` follows FMModel.scala:34-63, training follows the
+spec in DESIGN.md section 2.
+
+Tolerances (BASELINE.json north_star): predictions 1e-5 relative, per-iteration training loss
+1e-4 relative, CSR packing / indexing / sampling bit-exact.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import capi as ocapi
+from oracle.capi import OracleFM
+from sparkfm_b200 import Handle, synth
+from sparkfm_b200._lib import SFM_ERR_INDEX, SFM_ERR_STATE, SfmError
+
+pytestmark = pytest.mark.gpu
+
+PRED_RTOL = 1e-5   # relative, with an absolute floor of PRED_RTOL * PRED_SCALE
+LOSS_RTOL = 1e-4
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "predict_kat.json")
+
+
+def rel_err(got, want, floor):
+    want = np.asarray(want, dtype=np.float64)
+    return np.max(np.abs(np.asarray(got, dtype=np.float64) - want) / np.maximum(np.abs(want), floor)) \
+        if len(want) else 0.0
+
+
+def make_model(rng, n_slots, k, w_std=0.1, v_std=0.1):
+    return (float(rng.normal(0, 0.1)), rng.normal(0, w_std, n_slots).astype(np.float32),
+            rng.normal(0, v_std, (n_slots, k)).astype(np.float32))
+
+
+# ------------------------------------------------------------------------------ predict
+def test_predict_known_answers():
+    """Builder-authored exact vectors (tests/golden/make_predict_kat.py)."""
+    cases = json.load(open(GOLDEN))["cases"]
+    for c in cases:
+        n, k = c["n_slots"], c["k"]
+        hd = Handle(n, k, k0=c["k0"], k1=c["k1"])
+        hd.set_model(c["w0"], np.array(c["w"], np.float32),
+                     np.array(c["v"], np.float32).reshape(n, k) if k else None)
+        rp, idx, val = [0], [], []
+        for r in c["rows"]:
+            idx += r["idx"]
+            val += r["val"]
+            rp.append(len(idx))
+        got = hd.predict(rp, np.array(idx, np.int32), np.array(val, np.float32))
+        # all inputs are small dyadic rationals: fp32 evaluates them exactly
+        assert got.tolist() == [float(np.float32(x)) for x in c["predict"]], c["name"]
+        hd.close()
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 8, 12, 16, 32, 64, 100, 128])
+def test_predict_matches_oracle_all_k(k):
+    rng = np.random.default_rng(100 + k)
+    n_slots, n_rows = 3000, 2500
+    row_ptr, idx, val = synth.ragged_rows(n_rows, n_slots, 24, seed=k, max_nnz=90, values="normal")
+    w0, w, v = make_model(rng, n_slots, k)
+    hd = Handle(n_slots, k)
+    hd.set_model(w0, w, v)
+    orc = OracleFM(n_slots, k)
+    orc.set_model(w0, w, v)
+    got = hd.predict(row_ptr, idx, val)
+    want = orc.predict(row_ptr, idx, val.astype(np.float64))
+    assert rel_err(got, want, 1e-2) < PRED_RTOL
+    hd.close()
+
+
+def test_predict_edge_rows():
+    """Empty rows (-> w0, FMModel.scala:42), duplicate indices, explicit zeros, unsorted indices,
+    a 1000-entry row, feature 0 and the last slot; with and without values."""
+    rng = np.random.default_rng(5)
+    n_slots, k = 2048, 16
+    w0, w, v = make_model(rng, n_slots, k)
+    rows = [[], [0], [n_slots - 1], [7, 7, 7], [5, 3, 9, 3], list(rng.integers(0, n_slots, 1000)),
+            [], list(range(33)), list(range(32)), list(range(31)), []]
+    rp = np.cumsum([0] + [len(r) for r in rows]).astype(np.int64)
+    idx = np.array([i for r in rows for i in r], np.int32)
+    val = rng.normal(0, 1, len(idx)).astype(np.float32)
+    val[rp[4] + 1] = 0.0  # explicit zero
+    hd = Handle(n_slots, k)
+    hd.set_model(w0, w, v)
+    orc = OracleFM(n_slots, k)
+    orc.set_model(w0, w, v)
+    got = hd.predict(rp, idx, val)
+    want = orc.predict(rp, idx, val.astype(np.float64))
+    assert rel_err(got, want, 1e-2) < PRED_RTOL
+    assert got[0] == np.float32(w0) and got[6] == np.float32(w0)
+    got1 = hd.predict(rp, idx, None)  # val == NULL means all ones
+    want1 = orc.predict(rp, idx, np.ones(len(idx)))
+    assert rel_err(got1, want1, 1e-2) < PRED_RTOL
+    assert hd.predict([0], np.zeros(0, np.int32), None).shape == (0,)  # empty batch
+    hd.close()
+
+
+def test_predict_dominant_feature_no_cancellation():
+    """one huge entry makes 0.5*(s^2 - q) cancel catastrophically in fp32; the
+    kernel's sum_{i<j} form must still hold 1e-5 against the fp64 oracle."""
+    rng = np.random.default_rng(9)
+    n_slots, k, n_rows = 500, 16, 256
+    row_ptr, idx, val = synth.ragged_rows(n_rows, n_slots, 30, seed=3, values="uniform")
+    val[row_ptr[:-1]] = 1000.0
+    w0, w, v = make_model(rng, n_slots, k, v_std=0.01)
+    hd = Handle(n_slots, k)
+    hd.set_model(w0, w, v)
+    orc = OracleFM(n_slots, k)
+    orc.set_model(w0, w, v)
+    got = hd.predict(row_ptr, idx, val)
+    want = orc.predict(row_ptr, idx, val.astype(np.float64))
+    assert rel_err(got, want, 1e-2) < PRED_RTOL
+    hd.close()
+
+
+def test_predict_flags_k0_k1():
+    rng = np.random.default_rng(2)
+    n_slots, k = 700, 8
+    row_ptr, idx, val = synth.ragged_rows(300, n_slots, 10, seed=4, values="normal")
+    w0, w, v = make_model(rng, n_slots, k)
+    for k0, k1 in ((0, 0), (1, 0), (0, 1)):
+        hd = Handle(n_slots, k, k0=k0, k1=k1)
+        hd.set_model(w0, w, v)
+        orc = OracleFM(n_slots, k, k0=k0, k1=k1)
+        orc.set_model(w0, w, v)
+        assert rel_err(hd.predict(row_ptr, idx, val),
+                       orc.predict(row_ptr, idx, val.astype(np.float64)), 1e-2) < PRED_RTOL
+        hd.close()
+
+
+def test_index_out_of_range_is_reported_error():
+    hd = Handle(100, 8)
+    hd.init_model(0.0, 0.01, 1)
+    for bad in (100, -1, 2 ** 31 - 1):
+        with pytest.raises(SfmError) as ei:
+            hd.predict([0, 2], np.array([3, bad], np.int32), np.ones(2, np.float32))
+        assert ei.value.status == SFM_ERR_INDEX
+    with pytest.raises(SfmError) as ei:
+        hd.load_dataset([0, 1], np.array([100], np.int32), None, np.ones(1, np.float32))
+    assert ei.value.status == SFM_ERR_INDEX
+    with pytest.raises(SfmError) as ei:
+        hd.train_step(1)
+    assert ei.value.status == SFM_ERR_STATE
+    before = hd.get_model()
+    with pytest.raises(SfmError):
+        hd.train_step_csr(1, [0, 1], np.array([500], np.int32), None, np.ones(1, np.float32))
+    after = hd.get_model()
+    assert before[0] == after[0] and np.array_equal(before[1], after[1]) \
+        and np.array_equal(before[2], after[2]), "a failed step must not touch the model"
+    hd.close()
+
+
+def test_model_roundtrip_and_save_load(tmp_path):
+    rng = np.random.default_rng(1)
+    for k in (3, 16):
+        n_slots = 321
+        w0, w, v = make_model(rng, n_slots, k)
+        hd = Handle(n_slots, k, task=1, reg=(0.1, 0.2, 0.3), step_size=0.7,
+                    mini_batch_fraction=0.25, sampler_seed=99)
+        hd.set_model(w0, w, v)
+        g0, gw, gv = hd.get_model()
+        assert g0 == np.float32(w0) and np.array_equal(gw, w) and np.array_equal(gv, v)
+        d0, dw, dv = hd.get_model_f64()
+        assert np.array_equal(dw, w.astype(np.float64)) and np.array_equal(dv, v.astype(np.float64))
+        path = tmp_path / f"m{k}.sfm"
+        hd.save(path)
+        h2 = Handle.load(path)
+        l0, lw, lv = h2.get_model()
+        assert l0 == g0 and np.array_equal(lw, w) and np.array_equal(lv, v)
+        c = h2.config()
+        assert (c.task, c.k, c.n_slots, c.sampler_seed) == (1, k, n_slots, 99)
+        assert np.float32(c.regv) == np.float32(0.3) and np.float32(c.step_size) == np.float32(0.7)
+        hd.close()
+        h2.close()
+
+
+def test_init_model_matches_oracle_generator():
+    """sfm_init_model and the oracle's fmo_init_v share the documented generator: identical."""
+    n_slots, k = 1000, 16
+    hd = Handle(n_slots, k)
+    hd.init_model(0.0, 0.01, 12345)
+    w0, w, v = hd.get_model()
+    orc = OracleFM(n_slots, k)
+    orc.init_v(0.0, 0.01, 12345)
+    assert w0 == 0.0 and not w.any()
+    assert np.array_equal(v.astype(np.float64), orc.v)
+    assert abs(v.std() - 0.01) < 5e-4 and abs(v.mean()) < 5e-4
+    hd.close()
+
+
+# ------------------------------------------------------------------------------ training
+def _train_case(task, k, n_slots, n_rows, mean_nnz, values, reg, step, frac, iters, seed,
+                k0=1, k1=1):
+    rng = np.random.default_rng(seed)
+    row_ptr, idx, val = synth.ragged_rows(n_rows, n_slots, mean_nnz, seed=seed, values=values)
+    if task == 1:
+        label = np.where(rng.random(n_rows) < 0.35, 1.0, -1.0).astype(np.float32)
+    else:
+        label = rng.normal(0, 1, n_rows).astype(np.float32)
+    w0, w, v = make_model(rng, n_slots, k, 0.05, 0.05)
+    hd = Handle(n_slots, k, task=task, k0=k0, k1=k1, reg=reg, step_size=step,
+                mini_batch_fraction=frac, sampler_seed=42)
+    hd.set_model(w0, w, v)
+    hd.load_dataset(row_ptr, idx, val, label)
+    orc = OracleFM(n_slots, k, task=task, k0=k0, k1=k1,
+                   reg=tuple(float(np.float32(r)) for r in reg))
+    orc.set_model(w0, w, v)
+    frac32 = float(np.float32(frac))
+    step32 = float(np.float32(step))
+    for it in range(1, iters + 1):
+        ids = ocapi.sample_rows(42, it, frac32, 0, n_rows)
+        lo = orc.train_step(row_ptr, idx, val.astype(np.float64), label, ids, it, step32)
+        lo = lo / len(ids) if len(ids) else 0.0
+        lg, batch = hd.train_step(it)
+        assert batch == len(ids)                       # sampler parity is exact
+        assert abs(lg - lo) <= LOSS_RTOL * abs(lo), (it, lg, lo)
+    g0, gw, gv = hd.get_model()
+    scale = max(np.abs(orc.v).max(), 1e-3)
+    assert np.max(np.abs(gv - orc.v)) / scale < 1e-3
+    assert np.max(np.abs(gw - orc.w)) / max(np.abs(orc.w).max(), 1e-3) < 1e-3
+    assert abs(g0 - orc.w0.value) < 1e-3 * max(abs(orc.w0.value), 1e-2)
+    hd.close()
+
+
+def test_train_loss_curve_classification():
+    _train_case(task=1, k=8, n_slots=2000, n_rows=6000, mean_nnz=20, values="ones",
+                reg=(0.0, 1e-4, 1e-3), step=0.5, frac=0.3, iters=12, seed=21)
+
+
+def test_train_loss_curve_regression():
+    _train_case(task=0, k=16, n_slots=3000, n_rows=5000, mean_nnz=30, values="normal",
+                reg=(1e-3, 1e-3, 1e-2), step=0.02, frac=0.1, iters=12, seed=22)
+
+
+def test_train_full_batch_and_padded_k():
+    _train_case(task=0, k=5, n_slots=800, n_rows=1500, mean_nnz=12, values="uniform",
+                reg=(0.0, 0.0, 0.0), step=0.05, frac=1.0, iters=6, seed=23)
+
+
+def test_train_flags_no_bias_no_linear():
+    _train_case(task=1, k=4, n_slots=600, n_rows=1200, mean_nnz=10, values="ones",
+                reg=(0.0, 0.0, 1e-3), step=0.3, frac=0.5, iters=5, seed=24, k0=0, k1=0)
+
+
+def test_gradient_matches_oracle():
+    rng = np.random.default_rng(31)
+    n_slots, k, n_rows = 1500, 16, 3000
+    row_ptr, idx, val = synth.ragged_rows(n_rows, n_slots, 25, seed=31, values="normal")
+    label = np.where(rng.random(n_rows) < 0.5, 1.0, 0.0).astype(np.float32)
+    w0, w, v = make_model(rng, n_slots, k)
+    for task in (0, 1):
+        hd = Handle(n_slots, k, task=task)
+        hd.set_model(w0, w, v)
+        hd.load_dataset(row_ptr, idx, val, label)
+        orc = OracleFM(n_slots, k, task=task)
+        orc.set_model(w0, w, v)
+        ids = np.arange(0, n_rows, 3, dtype=np.int64)
+        gv, gw, gw0, loss, batch = hd.gradient(ids)
+        ov, ow, ow0, oloss = orc.gradient(row_ptr, idx, val.astype(np.float64), label, ids)
+        assert batch == len(ids)
+        assert abs(loss - oloss) <= LOSS_RTOL * abs(oloss)
+        assert np.max(np.abs(gv - ov)) <= 2e-5 * np.abs(ov).max()
+        assert np.max(np.abs(gw - ow)) <= 2e-5 * np.abs(ow).max()
+        assert abs(gw0 - ow0) <= 2e-5 * max(abs(ow0), 1.0)
+        hd.close()
+
+
+def test_training_is_bitwise_deterministic_and_csr_path_agrees():
+    """No float atomics: two runs give identical bits; the host-CSR entry point
+    (sfm_train_step_csr) gives the same bits as the resident path on the same rows."""
+    rng = np.random.default_rng(41)
+    n_slots, k, n_rows = 1200, 16, 4000
+    card = synth.ctr_field_log2_cards(13)
+    cdf, off = synth.zipf_tables(card)
+    idx2, label = synth.ctr_rows(0, n_rows, card, cdf, off, n_slots, 5)  # Zipf-hot features
+    row_ptr = np.arange(n_rows + 1, dtype=np.int64) * 13
+    idx = idx2.reshape(-1)
+    w0, w, v = make_model(rng, n_slots, k)
+    models, losses = [], []
+    for run in range(3):
+        hd = Handle(n_slots, k, task=1, reg=(0, 1e-4, 1e-4), step_size=0.3,
+                    mini_batch_fraction=0.5, sampler_seed=7)
+        hd.set_model(w0, w, v)
+        ls = []
+        if run < 2:
+            hd.load_dataset(row_ptr, idx, None, label)
+            for it in range(1, 6):
+                ls.append(hd.train_step(it)[0])
+        else:
+            for it in range(1, 6):
+                ids = ocapi.sample_rows(7, it, 0.5, 0, n_rows)
+                sub = (ids[:, None] * 13 + np.arange(13)[None, :]).reshape(-1)
+                ls.append(hd.train_step_csr(it, np.arange(len(ids) + 1, dtype=np.int64) * 13,
+                                            idx[sub], None, label[ids])[0])
+        models.append(hd.get_model())
+        losses.append(ls)
+        hd.close()
+    for other in (1, 2):
+        assert losses[0] == losses[other]
+        assert models[0][0] == models[other][0]
+        assert np.array_equal(models[0][1], models[other][1])
+        assert np.array_equal(models[0][2], models[other][2])
+
+
+def test_explicit_row_ids_and_sfm_train_loop():
+    rng = np.random.default_rng(51)
+    n_slots, k, n_rows = 900, 8, 2000
+    row_ptr, idx, val = synth.ragged_rows(n_rows, n_slots, 15, seed=51, values="uniform")
+    label = rng.normal(0, 1, n_rows).astype(np.float32)
+    w0, w, v = make_model(rng, n_slots, k)
+    kw = dict(task=0, reg=(0, 1e-3, 1e-3), step_size=0.05, mini_batch_fraction=0.25, sampler_seed=42)
+    a = Handle(n_slots, k, **kw)
+    b = Handle(n_slots, k, **kw)
+    for h in (a, b):
+        h.set_model(w0, w, v)
+        h.load_dataset(row_ptr, idx, val, label)
+    hist = a.train(1, 7)                                   # device loop, built-in sampler
+    for it in range(1, 8):
+        ids = ocapi.sample_rows(42, it, 0.25, 0, n_rows)   # same rows, passed explicitly
+        lb, nb = b.train_step(it, ids)
+        assert nb == len(ids) and lb == hist[it - 1]
+    ma, mb = a.get_model(), b.get_model()
+    assert ma[0] == mb[0] and np.array_equal(ma[1], mb[1]) and np.array_equal(ma[2], mb[2])
+    a.close()
+    b.close()
+
+
+def test_evaluate_matches_oracle_metrics():
+    rng = np.random.default_rng(61)
+    n_slots, k, n_rows = 1000, 8, 5000
+    row_ptr, idx, val = synth.ragged_rows(n_rows, n_slots, 12, seed=61, values="normal")
+    label = np.where(rng.random(n_rows) < 0.5, 1.0, -1.0).astype(np.float32)
+    w0, w, v = make_model(rng, n_slots, k)
+    hd = Handle(n_slots, k, task=1)
+    hd.set_model(w0, w, v)
+    hd.load_dataset(row_ptr, idx, val, label)
+    orc = OracleFM(n_slots, k, task=1)
+    orc.set_model(w0, w, v)
+    p = orc.predict(row_ptr, idx, val.astype(np.float64))
+    y = label.astype(np.float64)
+    m = hd.evaluate()
+    assert abs(m["rmse"] - np.sqrt(np.mean((y - p) ** 2))) < 1e-5          # Model.scala:14-15
+    assert abs(m["mean_error"] - np.mean(y - p)) < 1e-5                    # Model.scala:22
+    agree = np.mean(((y >= 0) & (p >= 0)) | ((y < 0) & (p < 0)))           # Model.scala:29
+    assert abs(m["accuracy"] - agree) < 2e-4  # sign flips of |p| ~ 1e-7 are allowed
+    assert m["n"] == n_rows
+    assert rel_err(hd.predict_resident(100, 900), p[100:900], 1e-2) < PRED_RTOL
+    hd.close()
+
+
+def test_device_synth_is_bit_identical_to_numpy_twin():
+    n_slots, n_fields, n_rows, off0 = 100_000, 39, 20_000, 12_345
+    card = synth.ctr_field_log2_cards(n_fields)
+    cdf, off = synth.zipf_tables(card)
+    hd = Handle(n_slots, 4)
+    hd.synth_ctr_dataset(n_rows, off0, card, cdf, off, seed=20260103)
+    rp, idx, val, label = hd.get_dataset_rows(0, n_rows)
+    widx, wlabel = synth.ctr_rows(off0, off0 + n_rows, card, cdf, off, n_slots, 20260103)
+    assert np.array_equal(rp, np.arange(n_rows + 1) * n_fields)
+    assert np.array_equal(idx, widx.reshape(-1))
+    assert np.array_equal(label, wlabel)
+    assert np.all(val == 1.0)
+    assert hd.dataset_info() == (n_rows, n_rows * n_fields, int(widx.max()))
+    hd.close()
+
+
+def test_criteo_shaped_small_slice_trains_like_oracle():
+    """Config 3 in miniature (39 one-hot fields, Zipf, k=16, logistic)."""
+    n_slots, k, n_rows = 20_000, 16, 30_000
+    rp, idx, _, label = synth.ctr_csr(0, n_rows, 39, n_slots, 20260103)
+    hd = Handle(n_slots, k, task=1, reg=(0, 0, 1e-4), step_size=0.2, mini_batch_fraction=0.2,
+                sampler_seed=42)
+    hd.init_model(0.0, 0.01, 1)
+    w0, w, v = hd.get_model()
+    hd.load_dataset(rp, idx, None, label)
+    orc = OracleFM(n_slots, k, task=1, reg=(0.0, 0.0, float(np.float32(1e-4))))
+    orc.set_model(w0, w, v)
+    ones = np.ones(len(idx))
+    frac32, step32 = float(np.float32(0.2)), float(np.float32(0.2))
+    for it in range(1, 9):
+        ids = ocapi.sample_rows(42, it, frac32, 0, n_rows)
+        lo = orc.train_step(rp, idx, ones, label, ids, it, step32) / len(ids)
+        lg, batch = hd.train_step(it)
+        assert batch == len(ids) and abs(lg - lo) <= LOSS_RTOL * lo, (it, lg, lo)
+    hd.close()

@@ -1,0 +1,176 @@
+"""CPU tests of the oracle itself (no GPU): the C oracle (oracle/fm_oracle.c) and the independent
+numpy restatement (oracle/fm_numpy.py) against the builder-authored exact known answers
+(tests/golden/predict_kat.json -- the reference has no golden vectors), against
+each other, and against first principles (finite differences for the gradient spec)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import capi, fm_numpy as fn
+from oracle.capi import OracleFM
+from sparkfm_b200 import synth
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "predict_kat.json")
+
+
+def _case_arrays(c):
+    rp, idx, val = [0], [], []
+    for r in c["rows"]:
+        idx += r["idx"]
+        val += r["val"]
+        rp.append(len(idx))
+    n, k = c["n_slots"], c["k"]
+    return (np.array(rp, np.int64), np.array(idx, np.int32), np.array(val, np.float64),
+            np.array(c["w"]), np.array(c["v"], np.float64).reshape(n, k))
+
+
+def test_golden_file_is_reproducible():
+    from tests.golden import make_predict_kat as mk  # noqa: F401  (regenerates CASES on import)
+    disk = json.load(open(GOLDEN))["cases"]
+    assert [c["name"] for c in disk] == [c["name"] for c in mk.CASES]
+    for a, b in zip(disk, mk.CASES):
+        assert a["predict"] == b["predict"] and a["predict_exact"] == b["predict_exact"]
+
+
+def test_predict_known_answers_both_oracles():
+    for c in json.load(open(GOLDEN))["cases"]:
+        rp, idx, val, w, v = _case_arrays(c)
+        o = OracleFM(c["n_slots"], c["k"], k0=c["k0"], k1=c["k1"])
+        o.set_model(c["w0"], w, v)
+        assert o.predict(rp, idx, val).tolist() == c["predict"], c["name"]
+        assert o.predict(rp, idx, val, fast=True).tolist() == c["predict"], c["name"]
+        assert fn.predict(c["w0"], w, v, rp, idx, val, c["k0"], c["k1"]).tolist() == c["predict"]
+        assert fn.predict_vec(c["w0"], w, v, rp, idx, val, c["k0"], c["k1"]).tolist() == c["predict"]
+
+
+def test_hand_computed_two_feature_case():
+    """yhat = w0 + w1 x1 + w2 x2 + <v1, v2> x1 x2, worked by hand: 1/4 + 1/2 - 1/4 + (1/16 - 3/16)."""
+    w = np.array([0, 0.5, -0.25, 0.375])
+    v = np.array([[0, 0], [0.5, -0.25], [0.125, 0.75], [-0.5, 0.5]])
+    o = OracleFM(4, 2)
+    o.set_model(0.25, w, v)
+    assert o.predict([0, 2], np.array([1, 2], np.int32), np.array([1.0, 1.0]))[0] == 0.375
+
+
+@pytest.mark.parametrize("k", [1, 5, 16])
+def test_c_oracle_matches_numpy_restatement(k):
+    rng = np.random.default_rng(k)
+    n_slots, n_rows = 400, 300
+    row_ptr, idx, val = synth.ragged_rows(n_rows, n_slots, 9, seed=k, values="normal")
+    row_ptr = row_ptr.copy()
+    w0, w, v = 0.3, rng.normal(0, 1, n_slots), rng.normal(0, 0.5, (n_slots, k))
+    o = OracleFM(n_slots, k)
+    o.set_model(w0, w, v)
+    a = o.predict(row_ptr, idx, val.astype(np.float64))
+    b = fn.predict(w0, w, v, row_ptr, idx, val.astype(np.float64))
+    assert np.array_equal(a, b)            # same fold order -> same bits
+    c = o.predict(row_ptr, idx, val.astype(np.float64), fast=True, threads=2)
+    assert np.allclose(a, c, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("task", [0, 1])
+def test_gradient_is_the_derivative_of_the_loss(task):
+    """The written spec against central finite differences of the loss; for
+    regression the reported loss is (yhat-y)^2 and the gradient is that of HALF of it."""
+    rng = np.random.default_rng(7 + task)
+    n_slots, k, n_rows = 12, 3, 9
+    row_ptr, idx, val = synth.ragged_rows(n_rows, n_slots, 4, seed=3, values="normal")
+    val = val.astype(np.float64)
+    label = np.where(rng.random(n_rows) < 0.5, 1.0, -1.0) if task else rng.normal(0, 1, n_rows)
+    w0, w, v = 0.2, rng.normal(0, 0.5, n_slots), rng.normal(0, 0.5, (n_slots, k))
+    ids = np.arange(n_rows)
+
+    def loss_at(w0_, w_, v_):
+        o = OracleFM(n_slots, k, task=task)
+        o.set_model(w0_, w_, v_)
+        tot = o.gradient(row_ptr, idx, val, label, ids)[3]
+        return tot * (1.0 if task else 0.5)
+
+    o = OracleFM(n_slots, k, task=task)
+    o.set_model(w0, w, v)
+    gv, gw, gw0, _ = o.gradient(row_ptr, idx, val, label, ids)
+    nv, nw, nw0, _ = fn.gradient(task, w0, w, v, row_ptr, idx, val, label, ids)
+    assert np.allclose(gv, nv, rtol=1e-12, atol=1e-13) and np.allclose(gw, nw, rtol=1e-12, atol=1e-13)
+    assert math.isclose(gw0, nw0, rel_tol=1e-12)
+    eps = 1e-6
+    assert abs((loss_at(w0 + eps, w, v) - loss_at(w0 - eps, w, v)) / (2 * eps) - gw0) < 1e-6
+    for i in range(n_slots):
+        wp, wm = w.copy(), w.copy()
+        wp[i] += eps
+        wm[i] -= eps
+        assert abs((loss_at(w0, wp, v) - loss_at(w0, wm, v)) / (2 * eps) - gw[i]) < 1e-6
+        for f in range(k):
+            vp, vm = v.copy(), v.copy()
+            vp[i, f] += eps
+            vm[i, f] -= eps
+            assert abs((loss_at(w0, w, vp) - loss_at(w0, w, vm)) / (2 * eps) - gv[i, f]) < 1e-6
+
+
+def test_loss_mult_extremes_are_finite():
+    for yhat in (-800.0, -30.0, 0.0, 30.0, 800.0):
+        for lab in (1.0, 0.0, -1.0):
+            ls, mu = fn.loss_mult(1, yhat, lab)
+            assert math.isfinite(ls) and math.isfinite(mu) and ls >= 0.0 and abs(mu) <= 1.0
+
+
+def test_update_rule_by_hand():
+    """theta <- theta - (step/sqrt(t)) * (g/|B| + lambda*theta), all slots, t = 4 -> eta = step/2."""
+    o = OracleFM(2, 1, task=0, reg=(0.5, 0.25, 0.125))
+    o.set_model(1.0, np.array([2.0, -4.0]), np.array([[8.0], [16.0]]))
+    # one row: feature 0, x = 1, label 0  ->  yhat = w0 + w_0 = 3, mult = 3 (pair term is 0)
+    loss = o.train_step([0, 1], np.array([0], np.int32), np.array([1.0]), np.array([0.0]),
+                        np.array([0]), it=4, step_size=1.0, batch_count=1)
+    assert loss == 9.0
+    eta = 0.5
+    assert o.w0.value == 1.0 - eta * (3.0 + 0.5 * 1.0)
+    assert o.w.tolist() == [2.0 - eta * (3.0 + 0.25 * 2.0), -4.0 - eta * (0.25 * -4.0)]
+    # dV_00 = (x*s - v*x^2)*mult = 0 for a single-feature row; only the L2 decay moves V
+    assert o.v.reshape(-1).tolist() == [8.0 - eta * 0.125 * 8.0, 16.0 - eta * 0.125 * 16.0]
+
+
+def test_mt_step_matches_single_thread():
+    rng = np.random.default_rng(3)
+    n_slots, k, n_rows = 300, 4, 500
+    row_ptr, idx, val = synth.ragged_rows(n_rows, n_slots, 8, seed=9, values="normal")
+    label = rng.normal(0, 1, n_rows)
+    w0, w, v = 0.1, rng.normal(0, 0.1, n_slots), rng.normal(0, 0.1, (n_slots, k))
+    a = OracleFM(n_slots, k, reg=(0.0, 0.01, 0.01))
+    b = OracleFM(n_slots, k, reg=(0.0, 0.01, 0.01))
+    ids = np.arange(0, n_rows, 2)
+    for o in (a, b):
+        o.set_model(w0, w, v)
+    la = a.train_step(row_ptr, idx, val, label, ids, 2, 0.1)
+    lb = b.train_step(row_ptr, idx, val, label, ids, 2, 0.1, threads=3)
+    assert math.isclose(la, lb, rel_tol=1e-12)
+    assert np.allclose(a.v, b.v, rtol=1e-12, atol=1e-14) and np.allclose(a.w, b.w, rtol=1e-12, atol=1e-14)
+
+
+def test_sampler_c_vs_numpy_and_shard_union():
+    for frac in (0.0, 0.01, 0.3, float(np.float32(0.1)), 1.0, 1.5):
+        for it in (1, 2, 50):
+            a = capi.sample_rows(42, it, frac, 0, 5000)
+            b = fn.sample_rows(42, it, frac, 0, 5000)
+            assert np.array_equal(a, b)
+            # shards sample GLOBAL row numbers: the union over ranks is the single-node batch
+            parts = [capi.sample_rows(42, it, frac, lo, hi) for lo, hi in ((0, 1234), (1234, 3000), (3000, 5000))]
+            assert np.array_equal(np.concatenate(parts), a)
+    assert len(capi.sample_rows(42, 1, 1.0, 0, 100)) == 100
+    n = len(capi.sample_rows(42, 3, 0.25, 0, 200_000))
+    assert abs(n / 200_000 - 0.25) < 0.005
+    assert not np.array_equal(capi.sample_rows(42, 1, 0.5, 0, 1000), capi.sample_rows(42, 2, 0.5, 0, 1000))
+    assert capi.lib().fmo_mix64(0) == fn.mix64(0) == 0xE220A8397B1DCDAF  # splitmix64 first output
+
+
+def test_init_v_statistics_and_determinism():
+    o = OracleFM(2000, 8)
+    o.init_v(0.0, 0.01, 5)
+    a = o.v.copy()
+    o.init_v(0.0, 0.01, 5)
+    assert np.array_equal(a, o.v)
+    assert abs(a.mean()) < 3e-4 and abs(a.std() - 0.01) < 3e-4
+    assert np.array_equal(a, a.astype(np.float32).astype(np.float64))  # fp32-representable
+    o.init_v(0.0, 0.01, 6)
+    assert not np.array_equal(a, o.v)
