@@ -19,15 +19,19 @@ from sparkfm_b200._lib import SFM_ERR_INDEX, SFM_ERR_STATE, SfmError
 
 pytestmark = pytest.mark.gpu
 
-PRED_RTOL = 1e-5   # relative, with an absolute floor of PRED_RTOL * PRED_SCALE
+PRED_RTOL = 1e-5   # |got - want| <= 1e-5 * max(|want|, mean |want| of the batch): fp32 cannot
+                   # hold a RELATIVE bound on predictions that cancel to ~0, so values below the
+                   # batch's typical magnitude are held to the same absolute error instead
 LOSS_RTOL = 1e-4
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "predict_kat.json")
 
 
-def rel_err(got, want, floor):
+def rel_err(got, want, floor=None):
     want = np.asarray(want, dtype=np.float64)
-    return np.max(np.abs(np.asarray(got, dtype=np.float64) - want) / np.maximum(np.abs(want), floor)) \
-        if len(want) else 0.0
+    if not len(want):
+        return 0.0
+    floor = max(float(np.mean(np.abs(want))), 1e-30)
+    return np.max(np.abs(np.asarray(got, dtype=np.float64) - want) / np.maximum(np.abs(want), floor))
 
 
 def make_model(rng, n_slots, k, w_std=0.1, v_std=0.1):

@@ -1,0 +1,172 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol include/sparkfm_b200.h
+declares; host-side logic of the boundary (LibFM text ingest/export, CSR packing, sampler,
+synthetic generators, the Python mirror's DataSet) -- bit-exact against the oracle's pure-Python
+restatement of the Scala (fm/FMUtils.scala:23-74, DataSet.scala:23-29)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import capi as ocapi, fm_numpy as fn
+from sparkfm_b200 import DataSet, LabeledPoint, SparseVector, _lib, format_libfm, parse_libfm, \
+    sample_rows, synth
+from sparkfm_b200._lib import SFM_ERR_CUDA, SfmConfig
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "sparkfm_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(sfm_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 40
+    L = ctypes.CDLL(_lib.SO_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} is declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes table and header disagree"
+    assert _lib.load().sfm_abi_version() == 1
+    assert _lib.load().sfm_status_string(-5).decode().startswith("feature index")
+
+
+def test_config_struct_layout_matches_header():
+    # int32 x6, int64, float x5, int32, uint64  -> 64 bytes, n_slots at 24, seed at 56
+    assert ctypes.sizeof(SfmConfig) == 64
+    assert SfmConfig.n_slots.offset == 24 and SfmConfig.sampler_seed.offset == 56
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    L = _lib.load()
+    if L.sfm_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    cfg = SfmConfig(1, 0, 8, 1, 1, 0, 100, 0, 0, 0, 0.1, 1.0, 0, 42)
+    h = ctypes.c_void_p()
+    assert L.sfm_create(ctypes.byref(cfg), ctypes.byref(h)) == SFM_ERR_CUDA
+    assert not h.value
+    from sparkfm_b200 import Handle
+    with pytest.raises(_lib.SfmError):
+        Handle(100, 8)
+
+
+# ------------------------------------------------------------------------------ LibFM text
+TEXT = b"""# a comment line
+1 3:1.5 7:2 1:0.25
+
+   -1 0:1   5:1e-2  5:3
+0.5
++2.5e0 2147483647:1 4:-0d 9:7f\r
+\t 3 1:1 \t
+"""
+
+
+def test_parser_matches_scala_rules_bit_exact():
+    """Index verbatim (no shift, FMUtils:32), order + duplicates kept, trim, '#', repeated spaces,
+    CRLF, Java number grammar (d/f suffix), a row without features when numFeatures is given."""
+    lab, rp, idx, val, d = parse_libfm(TEXT, num_features=100)
+    olab, orp, oidx, oval, od = fn.parse_libfm_lines(TEXT.decode().split("\n"), 100)
+    assert d == od == 100
+    assert lab.tolist() == olab.tolist() == [1.0, -1.0, 0.5, 2.5, 3.0]
+    assert rp.tolist() == orp.tolist() == [0, 3, 6, 6, 9, 10]
+    assert idx.tolist() == oidx.tolist() == [3, 7, 1, 0, 5, 5, 2147483647, 4, 9, 1]
+    assert val.tobytes() == oval.tobytes()
+    assert val.tolist()[:6] == [1.5, 2.0, 0.25, 1.0, 0.01, 3.0] and np.signbit(val[7])
+
+
+def test_parser_dimension_inference_and_errors():
+    lab, rp, idx, val, d = parse_libfm(b"1 4:1 9:2\n0 2:1\n")
+    assert d == 9                                    # max index; vector length is d+1 (:50)
+    for bad, line in ((b"1 4:1\n0\n", 0),            # indices.max on an empty row (:45)
+                      (b"", 0),                      # reduce on an empty collection
+                      (b"1 4:1\nx 2:1\n", 2),        # label.toDouble
+                      (b"1 4\n", 1),                 # indexAndValue(1) missing
+                      (b"1 4:\n", 1),                # "4:".split(':') has one element
+                      (b"1 4.0:1\n", 1),             # toInt
+                      (b"1 :3\n", 1),
+                      (b"1 4:1_0\n", 1),
+                      (b"1\t4:1\n", 1),              # only ' ' separates tokens (:28)
+                      (b"1 99999999999:1\n", 1)):
+        with pytest.raises(ValueError) as ei:
+            parse_libfm(bad)
+        assert f"line {line}" in str(ei.value), bad
+        with pytest.raises(ValueError):
+            fn.parse_libfm_lines(bad.decode().split("\n"))
+    # "3:4:5" -> split(':') -> (3, 4): extra parts ignored, like the Scala
+    _, _, idx, val, _ = parse_libfm(b"1 3:4:5\n")
+    assert idx.tolist() == [3] and val.tolist() == [4.0]
+    _, _, oidx, oval, _ = fn.parse_libfm_lines(["1 3:4:5"])
+    assert oidx.tolist() == [3] and oval.tolist() == [4.0]
+
+
+def test_parser_config1_text_roundtrip_is_bit_exact():
+    """BASELINE config 1 is LIBSVM-format: generator -> text -> C++ parser == generator arrays
+    == pure-Python parser, bit for bit (labels, row_ptr, indices, values)."""
+    row_ptr, idx, val, label = synth.classification_c1(3000, 10_000, 20, 8)
+    text = synth.to_libfm_text(row_ptr, idx, val, label).encode()
+    lab, rp, i2, v2, d = parse_libfm(text)
+    assert np.array_equal(rp, row_ptr) and np.array_equal(i2, idx)
+    assert np.array_equal(v2, val.astype(np.float64)) and np.array_equal(lab, label.astype(np.float64))
+    assert d == int(idx.max())
+    olab, orp, oidx, oval, od = fn.parse_libfm_lines(text.decode().split("\n"))
+    assert np.array_equal(orp, rp) and np.array_equal(oidx, i2) and oval.tobytes() == v2.tobytes()
+    assert od == d and olab.tobytes() == lab.tobytes()
+
+
+def test_formatter_matches_decimalformat_rules():
+    """fm/FMUtils.scala:58-74: index + 1, "#" for integral values, "#.###" HALF_EVEN otherwise
+    (no leading zero: 0.5 -> ".5")."""
+    out = format_libfm([1.0, -0.5, 2.0], [0, 3, 4, 4], np.array([0, 9, 4, 2], np.int32),
+                       [1.0, 0.12345, -2.5, 0.0625]).decode()
+    assert out == "1 1:1 10:.123 5:-2.5\n-.5 3:.062\n2\n"
+    out = format_libfm([1234567.0], [0, 2], np.array([0, 1], np.int32), [0.0004, 1e3]).decode()
+    assert out == "1234567 1:0 2:1000\n"
+
+
+# ------------------------------------------------------------------------------ sampler
+def test_c_abi_sampler_equals_oracle_sampler():
+    for frac in (0.0, 0.05, float(np.float32(0.1)), 0.5, 1.0):
+        for it in (1, 7):
+            a = sample_rows(42, it, frac, 100, 9000)
+            assert np.array_equal(a, ocapi.sample_rows(42, it, frac, 100, 9000))
+            assert np.array_equal(a, fn.sample_rows(42, it, frac, 100, 9000))
+
+
+# ------------------------------------------------------------------------------ generators
+def test_ctr_generator_shape_and_determinism():
+    card = synth.ctr_field_log2_cards(39)
+    assert len(card) == 39 and card.max() == 20 and card.min() == 4
+    cdf, off = synth.zipf_tables(card)
+    assert cdf.dtype == np.uint32 and all(cdf[o + (1 << c) - 1] == 2 ** 32 - 1 for o, c in zip(off, card))
+    a, la = synth.ctr_rows(1000, 3000, card, cdf, off, 1_000_000, 20260103)
+    b, lb = synth.ctr_rows(0, 3000, card, cdf, off, 1_000_000, 20260103)
+    assert np.array_equal(a, b[1000:]) and np.array_equal(la, lb[1000:])   # counter-based
+    assert a.min() >= 0 and a.max() < 1_000_000
+    assert 0.2 < lb.mean() < 0.3
+    # Zipf: the most frequent id of a wide field covers far more than a uniform share
+    col = b[:, 38]
+    assert np.bincount(col).max() / len(col) > 0.05
+
+
+def test_ragged_generator_has_no_duplicates_and_is_sorted():
+    rp, idx, val = synth.ragged_rows(500, 50, 20, seed=1, max_nnz=40)
+    for r in range(500):
+        seg = idx[rp[r]:rp[r + 1]]
+        assert len(seg) >= 1 and np.all(np.diff(seg) > 0)
+
+
+# ------------------------------------------------------------------------------ DataSet
+def test_dataset_size_dimension_and_packing():
+    rows = [(1.0, SparseVector([5, 2, 2], [1.0, 0.0, 3.0], 10)),
+            LabeledPoint(0.0, SparseVector([7], [2.0], 10))]
+    ds = DataSet.from_rows(rows, "t")
+    assert ds.size == 2 and not ds.isEmpty
+    assert ds.dimension == 7                       # max index, not max+1 (DataSet.scala:27-29)
+    assert ds.row_ptr.tolist() == [0, 3, 4]
+    assert ds.idx.tolist() == [5, 2, 2, 7]         # stored order and duplicates preserved
+    assert ds.val.tolist() == [1.0, 0.0, 3.0, 2.0] and ds.targets.tolist() == [1.0, 0.0]
+    sv = ds.inputs(0)
+    assert sv.index.tolist() == [5, 2, 2] and sv.used == 3 and sv.length == 10
+    empty = DataSet([], [0], [], [])
+    assert empty.isEmpty and empty.size == 0 and empty.dimension == 0
+    with pytest.raises(ValueError):
+        DataSet([1.0], [0, 0], [], []).dimension   # `_.index.max` on an empty row throws
