@@ -195,9 +195,7 @@ static int stage_csr(sfm_handle* h, const int64_t* row_ptr, const int32_t* idx, 
             h->stats.h2d_bytes += (int64_t)sizeof(float) * nnz;
         }
     }
-    // row_ptr monotonicity is checked on the host (cheap, sequential): malformed CSR is an error
-    for (int64_t r = 0; r < n_rows; ++r)
-        if (row_ptr[r + 1] < row_ptr[r]) return set_err(h, SFM_ERR_INDEX, "row_ptr is not non-decreasing");
+    // row_ptr monotonicity is checked by the forward kernel (end < beg sets the error flag)
     out->row_ptr = (const int64_t*)h->b_stage_rowptr.p;
     out->idx = (const int32_t*)h->b_stage_idx.p;
     out->val = val ? (const float*)h->b_stage_val.p : nullptr;
@@ -206,6 +204,7 @@ static int stage_csr(sfm_handle* h, const int64_t* row_ptr, const int32_t* idx, 
     out->row_lo = 0;
     out->n_rows = n_rows;
     out->nnz = nnz;
+    out->idx_len = nnz;
     out->out_ptr = (const int64_t*)h->b_stage_rowptr.p;
     out->out_base = 0;
     out->uniform_m = -1;
@@ -236,6 +235,7 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     }
     RC(ensure(h, h->b_seg, sizeof(int32_t) * (size_t)(m.n_slots + 1)));
     RC(ensure(h, h->b_partials, sizeof(double) * 4 * 512));
+    RC(ensure(h, h->b_pull, pull_scratch_bytes(m, nnz)));
     const int end_bit = bits_for(m.n_slots);
     size_t sort_bytes = 0;
     if (nnz > 0) {
@@ -270,8 +270,9 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     CU(launch_segments(keys_sorted, nnz, m.n_slots, (int32_t*)h->b_seg.p, h->stream, L));
     pt.lap(&h->stats.ms_sort);
     const UpdateParams up = update_params(h, iter);
-    CU(launch_pull(m, (const int32_t*)h->b_seg.p, pay_sorted, o.S, o.mult, h->d_scal, h->d_err, up,
-                   fused, fused ? nullptr : (float*)h->b_grad.p, h->sm_count, h->stream, L));
+    CU(launch_pull(m, (const int32_t*)h->b_seg.p, keys_sorted, pay_sorted, nnz, b.val == nullptr,
+                   o.S, o.mult, (float*)h->b_pull.p, h->d_scal, h->d_err, up, fused,
+                   fused ? nullptr : (float*)h->b_grad.p, h->sm_count, h->stream, L));
     pt.lap(&h->stats.ms_reduce);
     if (multi) {
         RC(nccl_allreduce_f32(h->nccl, h->comm, (float*)h->b_grad.p, grad_len(h), h->stream,
@@ -297,6 +298,7 @@ static int resident_batch(sfm_handle* h, const int32_t* ids_dev, int64_t n_ids, 
     b->label = ds.label;
     b->row_ids = ids_dev;
     b->row_lo = 0;
+    b->idx_len = ds.nnz;
     b->uniform_m = ds.uniform_m;
     b->out_base = 0;
     if (!ids_dev) {
@@ -507,7 +509,8 @@ int32_t sfm_destroy(sfm_handle* h) {
     Buf* bufs[] = {&h->b_row_ids, &h->b_out_ptr, &h->b_S, &h->b_mult, &h->b_loss, &h->b_yhat,
                    &h->b_keys[0], &h->b_keys[1], &h->b_pay[0], &h->b_pay[1], &h->b_seg,
                    &h->b_sort_tmp, &h->b_grad, &h->b_partials, &h->b_stage_rowptr,
-                   &h->b_stage_idx, &h->b_stage_val, &h->b_stage_label, &h->b_sel_tmp, &h->b_lens};
+                   &h->b_stage_idx, &h->b_stage_val, &h->b_stage_label, &h->b_sel_tmp, &h->b_lens,
+                   &h->b_pull};
     for (Buf* b : bufs) free_buf(*b);
     if (h->m.v) cudaFree(h->m.v);
     if (h->m.w) cudaFree(h->m.w);

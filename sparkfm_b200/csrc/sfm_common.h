@@ -40,6 +40,7 @@ struct BatchView {
     int64_t row_lo;
     int64_t n_rows;          // batch rows on this rank
     int64_t nnz;             // batch entries on this rank
+    int64_t idx_len;         // length of idx / val (row_ptr values outside [0, idx_len] are errors)
     const int64_t* out_ptr;  // batch position -> first output slot (+out_base), nullptr = pos*m
     int64_t out_base;
     int32_t uniform_m;
@@ -70,7 +71,7 @@ struct sfm_handle {
     // batch scratch (all growable)
     sfm::Buf b_row_ids, b_out_ptr, b_S, b_mult, b_loss, b_yhat, b_keys[2], b_pay[2], b_seg,
         b_sort_tmp, b_grad, b_partials, b_stage_rowptr, b_stage_idx, b_stage_val, b_stage_label,
-        b_sel_tmp, b_lens;
+        b_sel_tmp, b_lens, b_pull;
     double* d_scal = nullptr;  // [SC_N] device
     int32_t* d_err = nullptr;  // device error flag
     int32_t* d_count = nullptr;  // device int (sampler count)
@@ -115,10 +116,12 @@ struct UpdateParams {
 };
 // reduce-by-feature over the sorted entries.  fused: apply the SGD update in place (one GPU);
 // else write the dense gradient grad = [gV n_slots*kp | gw n_slots | gw0].
-cudaError_t launch_pull(const ModelView& m, const int32_t* seg, const uint2* pay, const float* S,
-                        const float* mult, const double* d_scal, const int32_t* d_err,
-                        UpdateParams up, bool fused, float* grad, int sm_count, cudaStream_t st,
-                        int64_t* launches);
+cudaError_t launch_pull(const ModelView& m, const int32_t* seg, const uint32_t* keys,
+                        const uint2* pay, int64_t nnz, bool binary, const float* S,
+                        const float* mult, float* scratch, const double* d_scal,
+                        const int32_t* d_err, UpdateParams up, bool fused, float* grad,
+                        int sm_count, cudaStream_t st, int64_t* launches);
+size_t pull_scratch_bytes(const ModelView& m, int64_t nnz);
 // dense update from an (all-reduced) gradient buffer
 cudaError_t launch_update(const ModelView& m, const float* grad, const double* d_scal,
                           const int32_t* d_err, UpdateParams up, cudaStream_t st,

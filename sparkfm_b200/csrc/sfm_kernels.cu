@@ -70,7 +70,7 @@ fm_forward_kernel(const float4* __restrict__ V4, const float* __restrict__ W,
                   const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ idx,
                   const float* __restrict__ val, const float* __restrict__ label,
                   const int32_t* __restrict__ row_ids, int64_t row_lo, int64_t n_rows,
-                  const int64_t* __restrict__ out_ptr, int64_t out_base, int uniform_m,
+                  int64_t idx_len, const int64_t* __restrict__ out_ptr, int64_t out_base, int uniform_m,
                   float4* __restrict__ S4, float* __restrict__ mult_out,
                   float* __restrict__ loss_out, float* __restrict__ yhat_out,
                   uint32_t* __restrict__ keys, uint2* __restrict__ pay, int32_t* __restrict__ err) {
@@ -85,7 +85,11 @@ fm_forward_kernel(const float4* __restrict__ V4, const float* __restrict__ W,
     for (int64_t pos = warp0; pos < n_rows; pos += nwarps) {
         const int64_t r = row_ids ? (int64_t)__ldg(row_ids + pos) : row_lo + pos;
         const int64_t beg = __ldg(row_ptr + r);
-        const int64_t end = __ldg(row_ptr + r + 1);
+        int64_t end = __ldg(row_ptr + r + 1);
+        if (end < beg || beg < 0 || end > idx_len) {  // malformed CSR: reported, row treated as empty
+            if (lane == 0) atomicExch(err, 1);
+            end = beg;
+        }
         int64_t obase = 0;
         if (TRAIN) obase = out_ptr ? __ldg(out_ptr + pos) - out_base : pos * (int64_t)uniform_m;
 
@@ -102,7 +106,7 @@ fm_forward_kernel(const float4* __restrict__ V4, const float* __restrict__ W,
                     atomicExch(err, 1);
                     id = -1;
                 }
-                if (TRAIN) {
+                if (TRAIN && HAS_VAL) {  // entry list for the reduce-by-feature: {row, x}
                     keys[obase + (j - beg)] = id < 0 ? 0u : (uint32_t)id;
                     pay[obase + (j - beg)] =
                         make_uint2((uint32_t)pos, id < 0 ? 0u : __float_as_uint(x));
@@ -180,11 +184,23 @@ fm_forward_kernel(const float4* __restrict__ V4, const float* __restrict__ W,
         yhat += pair;
         if (TRAIN) {
             if (lane < LPR) S4[pos * LPR + fq] = s;
+            float ls = 0.f, mu = 0.f;
             if (lane == 0) {
-                float ls, mu;
                 loss_mult(task, yhat, __ldg(label + r), ls, mu);
                 loss_out[pos] = ls;
                 mult_out[pos] = mu;
+            }
+            if (!HAS_VAL) {
+                // all-ones data: the entry list carries {row, mult_r} so that the reduce needs
+                // one gather per entry; the indices were just read, this pass hits L1
+                mu = __shfl_sync(FULL, mu, 0);
+                for (int64_t j = beg + lane; j < end; j += 32) {
+                    const int id = __ldg(idx + j);
+                    const bool ok = (uint32_t)id < (uint64_t)n_slots;
+                    keys[obase + (j - beg)] = ok ? (uint32_t)id : 0u;
+                    pay[obase + (j - beg)] =
+                        make_uint2((uint32_t)pos, ok ? __float_as_uint(mu) : 0u);
+                }
             }
         } else {
             if (lane == 0) yhat_out[pos] = yhat;
@@ -202,7 +218,7 @@ static cudaError_t forward_dispatch(const ModelView& m, const BatchView& b, cons
     if (blocks > cap) blocks = cap;
 #define FWD_ARGS                                                                              \
     (const float4*)m.v, m.w, m.w0, m.n_slots, m.k0, m.k1, m.task, b.row_ptr, b.idx, b.val,    \
-        b.label, b.row_ids, b.row_lo, b.n_rows, b.out_ptr, b.out_base, b.uniform_m,           \
+        b.label, b.row_ids, b.row_lo, b.n_rows, b.idx_len, b.out_ptr, b.out_base, b.uniform_m,           \
         (float4*)o.S, o.mult, o.loss, o.yhat, o.keys, o.pay, d_err
     const dim3 g((unsigned)blocks), t(256);
     if (train) {
@@ -367,20 +383,149 @@ cudaError_t launch_segments(const uint32_t* keys, int64_t nnz, int64_t n_slots, 
 // ------------------------------------------------------------------------------------------
 // Reduce-by-feature, pull form.  With c = mult_r * x_ri:
 //     gV_if = sum_r c * S_rf  -  v_if * sum_r c * x_ri        gw_i = sum_r c
-// so a feature needs only the rows' factor sums S_r (kp floats) and multipliers, gathered in
-// the sorted (feature, batch position) order.  A group of LPR lanes owns one feature and walks
-// its segment; the running sums are in registers, the order is fixed -> bitwise reproducible.
-// FUSED: theta <- theta - eta*(g/B + lambda*theta) applied on the spot (every feature is
-// visited, so untouched slots get their L2 decay too).
+// so a feature needs only the factor sums S_r (kp floats) and multipliers of the rows that
+// contain it -- no per-entry gradient is ever materialised.  The entries arrive sorted by
+// (feature, batch position); the reduction tree over them depends on POSITIONS only:
+//
+//   level 0  a group of LPR lanes walks SUB consecutive sorted entries, adding in order;
+//   level 1  a CTA covers G*SUB consecutive entries; a run that spans several groups is summed
+//            by the group where it starts, over the following groups' "head" partials, in order;
+//   level 2  a run that spans several CTA chunks leaves one record per chunk (R2[chunk]); the
+//            finalize kernel adds them in chunk order to the record of the run's start (R1[i]).
+//
+// Work is therefore balanced by construction (every CTA gets the same number of entries, however
+// skewed the feature frequencies are) and the result is bitwise reproducible -- no float atomics.
+// Records are REC = kp + 4 floats: [A (kp) | D | C | 0 | 0].
+// BINARY (data set without a value array): payload = {row, mult_r}, x = 1, D = C, one gather
+// (the S row) per entry; otherwise payload = {row, x} and mult_r is gathered too.
 // ------------------------------------------------------------------------------------------
-template <int LPR, bool FUSED>
+constexpr int PULL_SUB = 32;
+
+template <int LPR>
+__device__ __forceinline__ void store_rec(float* __restrict__ rec, int fq, const float4& A,
+                                          float D, float C) {
+    reinterpret_cast<float4*>(rec)[fq] = A;
+    if (fq == 0) reinterpret_cast<float4*>(rec)[LPR] = make_float4(D, C, 0.f, 0.f);
+}
+
+template <int LPR, bool BINARY>
 __global__ void __launch_bounds__(256)
-fm_pull_kernel(float4* __restrict__ V4, float* __restrict__ W, float* __restrict__ W0,
-               int64_t n_slots, int k0, int k1, const int32_t* __restrict__ seg,
-               const uint2* __restrict__ pay, const float4* __restrict__ S4,
-               const float* __restrict__ mult, const double* __restrict__ d_scal,
-               const int32_t* __restrict__ err, UpdateParams up, float4* __restrict__ G4,
-               float* __restrict__ Gw, float* __restrict__ Gw0) {
+fm_pull_chunks_kernel(const uint32_t* __restrict__ keys, const uint2* __restrict__ pay,
+                      const float4* __restrict__ S4, const float* __restrict__ mult,
+                      const int32_t* __restrict__ seg, int nnz, float* __restrict__ R1,
+                      float* __restrict__ R2) {
+    constexpr int G = 256 / LPR;
+    constexpr int CHB = G * PULL_SUB;
+    constexpr int REC = LPR * 4 + 4;
+    constexpr int U = 4;
+    __shared__ float4 headA[G][LPR];
+    __shared__ float2 headDC[G];
+
+    const int g = threadIdx.x / LPR;
+    const int fq = threadIdx.x % LPR;
+    const int cstart = blockIdx.x * CHB;
+    const int p0 = cstart + g * PULL_SUB;
+    const int p1 = min(p0 + PULL_SUB, nnz);
+
+    float4 A = f4_zero();
+    float D = 0.f, C = 0.f;
+    int cur = -1;
+    bool cur_is_head = false;
+
+    if (p0 < nnz) {
+        cur = (int)__ldg(keys + p0);
+        cur_is_head = p0 > __ldg(seg + cur);
+        for (int base = p0; base < p1; base += U) {
+            int kk[U];
+            float cc[U], xx[U];
+            float4 sv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int p = base + u;
+                const bool ok = p < p1;
+                kk[u] = ok ? (int)__ldg(keys + p) : cur;
+                uint2 pl = ok ? __ldg(pay + p) : make_uint2(0u, 0u);
+                const float second = __uint_as_float(pl.y);
+                if (BINARY) {
+                    cc[u] = second;
+                    xx[u] = 1.f;
+                } else {
+                    xx[u] = second;
+                    cc[u] = ok ? __ldg(mult + pl.x) * second : 0.f;
+                }
+                sv[u] = __ldg(S4 + (int64_t)pl.x * LPR + fq);
+                if (!ok) { cc[u] = 0.f; kk[u] = -2; }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (kk[u] == -2) continue;
+                if (kk[u] != cur) {
+                    // the run of `cur` ended inside this sub-chunk
+                    if (cur_is_head) {
+                        if (g == 0) store_rec<LPR>(R2 + (int64_t)blockIdx.x * REC, fq, A, D, C);
+                        else { headA[g][fq] = A; if (fq == 0) headDC[g] = make_float2(D, C); }
+                    } else {
+                        store_rec<LPR>(R1 + (int64_t)cur * REC, fq, A, D, C);
+                    }
+                    cur = kk[u];
+                    cur_is_head = false;
+                    A = f4_zero();
+                    D = 0.f;
+                    C = 0.f;
+                }
+                const float c = cc[u];
+                A.x = fmaf(c, sv[u].x, A.x);
+                A.y = fmaf(c, sv[u].y, A.y);
+                A.z = fmaf(c, sv[u].z, A.z);
+                A.w = fmaf(c, sv[u].w, A.w);
+                D = BINARY ? D : fmaf(c, xx[u], D);
+                C += c;
+            }
+        }
+    }
+    // the run still open at the end of the sub-chunk
+    const bool open = p0 < nnz;
+    bool owner = false;
+    int run_end = 0;
+    if (open) {
+        run_end = __ldg(seg + cur + 1);
+        if (cur_is_head && g != 0) {
+            headA[g][fq] = A;               // a middle / final piece of somebody else's run
+            if (fq == 0) headDC[g] = make_float2(D, C);
+        } else {
+            owner = true;                   // starts here (R1) or is the chunk's inherited run (R2)
+        }
+    }
+    __syncthreads();
+    if (owner) {
+        if (run_end > p1) {                 // extends into following groups of this CTA chunk
+            const int last = min(run_end, cstart + CHB) - 1;
+            const int gl = (last - cstart) / PULL_SUB;
+            for (int g2 = g + 1; g2 <= gl; ++g2) {
+                const float4 a = headA[g2][fq];
+                const float2 dc = headDC[g2];
+                A.x += a.x; A.y += a.y; A.z += a.z; A.w += a.w;
+                D += dc.x;
+                C += dc.y;
+            }
+        }
+        float* dst = cur_is_head ? R2 + (int64_t)blockIdx.x * REC : R1 + (int64_t)cur * REC;
+        store_rec<LPR>(dst, fq, A, D, C);
+    }
+}
+
+// Level 2 + gradient / update.  One group of LPR lanes per feature, every feature visited (so
+// untouched slots receive their L2 decay).
+template <int LPR, bool FUSED, bool BINARY>
+__global__ void __launch_bounds__(256)
+fm_pull_finalize_kernel(float4* __restrict__ V4, float* __restrict__ W, float* __restrict__ W0,
+                        int64_t n_slots, int k0, int k1, const int32_t* __restrict__ seg,
+                        const float* __restrict__ R1, const float* __restrict__ R2,
+                        const double* __restrict__ d_scal, const int32_t* __restrict__ err,
+                        UpdateParams up, float4* __restrict__ G4, float* __restrict__ Gw,
+                        float* __restrict__ Gw0) {
+    constexpr int CHB = (256 / LPR) * PULL_SUB;
+    constexpr int REC = LPR * 4 + 4;
     if (FUSED && *err) return;  // a bad index was seen: leave the model untouched
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / LPR;
@@ -401,20 +546,25 @@ fm_pull_kernel(float4* __restrict__ V4, float* __restrict__ W, float* __restrict
         }
     }
     for (int64_t i = tid / LPR; i < n_slots; i += ngroups) {
-        const int b = seg[i], e = seg[i + 1];
+        const int s = __ldg(seg + i), e = __ldg(seg + i + 1);
         float4 A = f4_zero();
         float D = 0.f, C = 0.f;
-        for (int p = b; p < e; ++p) {
-            const uint2 pl = __ldg(pay + p);
-            const float x = __uint_as_float(pl.y);
-            const float c = __ldg(mult + pl.x) * x;
-            const float4 sv = __ldg(S4 + (int64_t)pl.x * LPR + fq);
-            A.x = fmaf(c, sv.x, A.x);
-            A.y = fmaf(c, sv.y, A.y);
-            A.z = fmaf(c, sv.z, A.z);
-            A.w = fmaf(c, sv.w, A.w);
-            D = fmaf(c, x, D);
-            C += c;
+        if (e > s) {
+            const float* r = R1 + i * REC;
+            A = __ldg(reinterpret_cast<const float4*>(r) + fq);
+            float4 dc = __ldg(reinterpret_cast<const float4*>(r) + LPR);
+            D = dc.x;
+            C = dc.y;
+            const int c1 = (e - 1) / CHB;
+            for (int c = s / CHB + 1; c <= c1; ++c) {
+                const float* r2 = R2 + (int64_t)c * REC;
+                const float4 a = __ldg(reinterpret_cast<const float4*>(r2) + fq);
+                dc = __ldg(reinterpret_cast<const float4*>(r2) + LPR);
+                A.x += a.x; A.y += a.y; A.z += a.z; A.w += a.w;
+                D += dc.x;
+                C += dc.y;
+            }
+            if (BINARY) D = C;
         }
         float4 v = V4[i * LPR + fq];
         float4 g;
@@ -441,11 +591,31 @@ fm_pull_kernel(float4* __restrict__ V4, float* __restrict__ W, float* __restrict
     }
 }
 
+size_t pull_scratch_bytes(const ModelView& m, int64_t nnz) {
+    const int64_t chb = (256 / m.lpr) * PULL_SUB;
+    const int64_t rec = m.kp + 4;
+    return sizeof(float) * (size_t)rec * (size_t)(m.n_slots + (nnz + chb - 1) / chb + 1);
+}
+
 template <int LPR>
-static cudaError_t pull_dispatch(const ModelView& m, const int32_t* seg, const uint2* pay,
-                                 const float* S, const float* mult, const double* d_scal,
+static cudaError_t pull_dispatch(const ModelView& m, const int32_t* seg, const uint32_t* keys,
+                                 const uint2* pay, int64_t nnz, bool binary, const float* S,
+                                 const float* mult, float* scratch, const double* d_scal,
                                  const int32_t* d_err, UpdateParams up, bool fused, float* grad,
                                  int sm_count, cudaStream_t st) {
+    constexpr int CHB = (256 / LPR) * PULL_SUB;
+    constexpr int REC = LPR * 4 + 4;
+    float* R1 = scratch;
+    float* R2 = scratch + (size_t)m.n_slots * REC;
+    const int64_t nchunks = (nnz + CHB - 1) / CHB;
+    if (nchunks > 0) {
+        if (binary)
+            fm_pull_chunks_kernel<LPR, true><<<(unsigned)nchunks, 256, 0, st>>>(
+                keys, pay, (const float4*)S, mult, seg, (int)nnz, R1, R2);
+        else
+            fm_pull_chunks_kernel<LPR, false><<<(unsigned)nchunks, 256, 0, st>>>(
+                keys, pay, (const float4*)S, mult, seg, (int)nnz, R1, R2);
+    }
     const int64_t threads = m.n_slots * LPR;
     int64_t blocks = (threads + 255) / 256;
     const int64_t cap = (int64_t)sm_count * 32;
@@ -453,30 +623,37 @@ static cudaError_t pull_dispatch(const ModelView& m, const int32_t* seg, const u
     if (blocks < 1) blocks = 1;
     float* gw = grad ? grad + m.n_slots * m.kp : nullptr;
     float* gw0 = grad ? gw + m.n_slots : nullptr;
-    if (fused)
-        fm_pull_kernel<LPR, true><<<(unsigned)blocks, 256, 0, st>>>(
-            (float4*)m.v, m.w, m.w0, m.n_slots, m.k0, m.k1, seg, pay, (const float4*)S, mult,
-            d_scal, d_err, up, nullptr, nullptr, nullptr);
-    else
-        fm_pull_kernel<LPR, false><<<(unsigned)blocks, 256, 0, st>>>(
-            (float4*)m.v, m.w, m.w0, m.n_slots, m.k0, m.k1, seg, pay, (const float4*)S, mult,
-            d_scal, d_err, up, (float4*)grad, gw, gw0);
+#define FIN_ARGS                                                                              \
+    (float4*)m.v, m.w, m.w0, m.n_slots, m.k0, m.k1, seg, R1, R2, d_scal, d_err, up,           \
+        (float4*)grad, gw, gw0
+    const dim3 gd((unsigned)blocks), bd(256);
+    if (fused) {
+        if (binary) fm_pull_finalize_kernel<LPR, true, true><<<gd, bd, 0, st>>>(FIN_ARGS);
+        else        fm_pull_finalize_kernel<LPR, true, false><<<gd, bd, 0, st>>>(FIN_ARGS);
+    } else {
+        if (binary) fm_pull_finalize_kernel<LPR, false, true><<<gd, bd, 0, st>>>(FIN_ARGS);
+        else        fm_pull_finalize_kernel<LPR, false, false><<<gd, bd, 0, st>>>(FIN_ARGS);
+    }
+#undef FIN_ARGS
     return cudaGetLastError();
 }
 
-cudaError_t launch_pull(const ModelView& m, const int32_t* seg, const uint2* pay, const float* S,
-                        const float* mult, const double* d_scal, const int32_t* d_err,
-                        UpdateParams up, bool fused, float* grad, int sm_count, cudaStream_t st,
-                        int64_t* launches) {
-    ++*launches;
+cudaError_t launch_pull(const ModelView& m, const int32_t* seg, const uint32_t* keys,
+                        const uint2* pay, int64_t nnz, bool binary, const float* S,
+                        const float* mult, float* scratch, const double* d_scal,
+                        const int32_t* d_err, UpdateParams up, bool fused, float* grad,
+                        int sm_count, cudaStream_t st, int64_t* launches) {
+    *launches += nnz > 0 ? 2 : 1;
+#define PD(L) pull_dispatch<L>(m, seg, keys, pay, nnz, binary, S, mult, scratch, d_scal, d_err, up, fused, grad, sm_count, st)
     switch (m.lpr) {
-        case 1: return pull_dispatch<1>(m, seg, pay, S, mult, d_scal, d_err, up, fused, grad, sm_count, st);
-        case 2: return pull_dispatch<2>(m, seg, pay, S, mult, d_scal, d_err, up, fused, grad, sm_count, st);
-        case 4: return pull_dispatch<4>(m, seg, pay, S, mult, d_scal, d_err, up, fused, grad, sm_count, st);
-        case 8: return pull_dispatch<8>(m, seg, pay, S, mult, d_scal, d_err, up, fused, grad, sm_count, st);
-        case 16: return pull_dispatch<16>(m, seg, pay, S, mult, d_scal, d_err, up, fused, grad, sm_count, st);
-        case 32: return pull_dispatch<32>(m, seg, pay, S, mult, d_scal, d_err, up, fused, grad, sm_count, st);
+        case 1: return PD(1);
+        case 2: return PD(2);
+        case 4: return PD(4);
+        case 8: return PD(8);
+        case 16: return PD(16);
+        case 32: return PD(32);
     }
+#undef PD
     return cudaErrorInvalidValue;
 }
 
