@@ -304,8 +304,8 @@ static int resident_batch(sfm_handle* h, const int32_t* ids_dev, int64_t n_ids, 
     if (!ids_dev) {
         b->n_rows = ds.n_rows;
         b->nnz = ds.nnz;
-        b->out_ptr = ds.row_ptr;  // identity batch: output slot = CSR position
-        b->uniform_m = -1;
+        // identity batch: output slot = CSR position (= pos * m when the rows are uniform)
+        b->out_ptr = ds.uniform_m >= 0 ? nullptr : ds.row_ptr;
         return SFM_OK;
     }
     b->n_rows = n_ids;

@@ -53,28 +53,96 @@ __device__ __forceinline__ void loss_mult(int task, float yhat, float label, flo
 
 // ------------------------------------------------------------------------------------------
 // Forward.  One warp per row.  A V row is kp floats = LPR float4; the warp's 32 lanes are
-// NPP = 32/LPR "entry slots" x LPR "factor quads": lane = slot*LPR + fq.  A tile of 32 CSR
-// entries is read coalesced (one idx + one val per lane) and kept in registers; each pass
-// broadcasts NPP of them with shuffles and every lane gathers ONE float4 of the entry's V row,
-// so a pass issues NPP fully-used 16*LPR-byte row reads per warp.
+// NPP = 32/LPR "entry slots" x LPR "factor quads": lane = slot*LPR + fq.  Up to 64 CSR entries
+// of the row (two tiles of 32) are read coalesced, one idx (+ one val) per lane per tile, and
+// kept in registers; each pass broadcasts NPP of them with shuffles and every lane gathers ONE
+// float4 of the entry's V row, so a pass issues NPP fully-used 16*LPR-byte row reads per warp.
 //
 // The pairwise term is accumulated as  P <- P + a*S; S <- S + a  (a = v_if * x_i), i.e.
 // sum_{i<j} a_i a_j, which equals the reference's 0.5*(S^2 - sum a^2) (FMModel.scala:50) exactly
 // in real arithmetic but has no cancellation in fp32; partial (S, P) pairs of different lanes
-// merge with P = P1 + P2 + S1*S2.
+// merge with P = P1 + P2 + S1*S2.  The cross-slot merge halves the components a lane carries at
+// each of the first two levels (4 -> 2 -> 1), so it costs 4+2+2.. shuffles instead of 8 per level.
+//
+// The kernel is instruction-issue bound (ncu: ~60 % issue-active, L2 ~21 %), hence the
+// specialisations: HAS_VAL = false drops every multiply by x; UNIFORM rows need no row_ptr.
 // ------------------------------------------------------------------------------------------
-template <int LPR, bool TRAIN, bool HAS_VAL>
+__device__ __forceinline__ void acc_entry(float4& s, float4& p, const float4& a) {
+    p.x = fmaf(a.x, s.x, p.x); s.x += a.x;
+    p.y = fmaf(a.y, s.y, p.y); s.y += a.y;
+    p.z = fmaf(a.z, s.z, p.z); s.z += a.z;
+    p.w = fmaf(a.w, s.w, p.w); s.w += a.w;
+}
+
+// Per-sample loss and dLoss/dyhat, DESIGN.md 2.2 (oracle: fmo_loss_mult).  Fast intrinsics:
+// relative error ~1e-6, far inside the 1e-4 loss tolerance.
+__device__ __forceinline__ void loss_mult_fast(int task, float yhat, float label, float& loss,
+                                               float& mult) {
+    if (task == SFM_TASK_CLASSIFICATION) {
+        const float y = label > 0.f ? 1.f : -1.f;
+        const float m = y * yhat;
+        const float e = __expf(-fabsf(m));
+        const float r = __fdividef(1.f, 1.f + e);
+        loss = fmaxf(-m, 0.f) + (e > 1e-4f ? __logf(1.f + e) : e * (1.f - 0.5f * e));
+        mult = -y * (m > 0.f ? e * r : r);
+    } else {
+        const float d = yhat - label;
+        loss = d * d;
+        mult = d;
+    }
+}
+
+template <int LPR, bool HAS_VAL>
+__device__ __forceinline__ void forward_tile(const float4* __restrict__ V4,
+                                             const float* __restrict__ W, int id, float x, int cnt,
+                                             int slot, int fq, float4& s, float4& p, float& lin) {
+    constexpr int NPP = 32 / LPR;
+    constexpr int PCH = LPR < 8 ? LPR : 8;  // passes whose gathers are in flight together
+#pragma unroll
+    for (int t0 = 0; t0 < LPR; t0 += PCH) {
+        if (t0 * NPP >= cnt) break;         // warp-uniform
+        float4 vv[PCH];
+        float ww[PCH], xx[PCH];
+#pragma unroll
+        for (int t = 0; t < PCH; ++t) {
+            const int pid = __shfl_sync(FULL, id, (t0 + t) * NPP + slot);
+            if (HAS_VAL) xx[t] = __shfl_sync(FULL, x, (t0 + t) * NPP + slot);
+            const bool ok = pid >= 0;
+            const int64_t row = ok ? pid : 0;
+            vv[t] = __ldg(V4 + row * LPR + fq);
+            ww[t] = (fq == 0) ? __ldg(W + row) : 0.f;
+            if (!ok) {  // past the end of the row, or an out-of-range index (reported)
+                vv[t] = f4_zero();
+                ww[t] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < PCH; ++t) {
+            float4 a = vv[t];
+            if (HAS_VAL) {
+                const float px = xx[t];
+                a.x *= px; a.y *= px; a.z *= px; a.w *= px;
+                lin = fmaf(ww[t], px, lin);
+            } else {
+                lin += ww[t];
+            }
+            acc_entry(s, p, a);
+        }
+    }
+}
+
+template <int LPR, bool TRAIN, bool HAS_VAL, bool UNIFORM>
 __global__ void __launch_bounds__(256)
 fm_forward_kernel(const float4* __restrict__ V4, const float* __restrict__ W,
                   const float* __restrict__ W0, int64_t n_slots, int k0, int k1, int task,
                   const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ idx,
                   const float* __restrict__ val, const float* __restrict__ label,
                   const int32_t* __restrict__ row_ids, int64_t row_lo, int64_t n_rows,
-                  int64_t idx_len, const int64_t* __restrict__ out_ptr, int64_t out_base, int uniform_m,
-                  float4* __restrict__ S4, float* __restrict__ mult_out,
+                  int64_t idx_len, const int64_t* __restrict__ out_ptr, int64_t out_base,
+                  int uniform_m, float* __restrict__ S, float* __restrict__ mult_out,
                   float* __restrict__ loss_out, float* __restrict__ yhat_out,
                   uint32_t* __restrict__ keys, uint2* __restrict__ pay, int32_t* __restrict__ err) {
-    constexpr int NPP = 32 / LPR;
+    constexpr int KP = LPR * 4;
     const int lane = threadIdx.x & 31;
     const int slot = lane / LPR;
     const int fq = lane % LPR;
@@ -84,122 +152,133 @@ fm_forward_kernel(const float4* __restrict__ V4, const float* __restrict__ W,
 
     for (int64_t pos = warp0; pos < n_rows; pos += nwarps) {
         const int64_t r = row_ids ? (int64_t)__ldg(row_ids + pos) : row_lo + pos;
-        const int64_t beg = __ldg(row_ptr + r);
-        int64_t end = __ldg(row_ptr + r + 1);
-        if (end < beg || beg < 0 || end > idx_len) {  // malformed CSR: reported, row treated as empty
-            if (lane == 0) atomicExch(err, 1);
-            end = beg;
+        int64_t beg, end;
+        if (UNIFORM) {
+            beg = r * uniform_m;
+            end = beg + uniform_m;
+        } else {
+            beg = __ldg(row_ptr + r);
+            end = __ldg(row_ptr + r + 1);
+            if (end < beg || beg < 0 || end > idx_len) {  // malformed CSR: reported, row = empty
+                if (lane == 0) atomicExch(err, 1);
+                end = beg;
+            }
         }
         int64_t obase = 0;
         if (TRAIN) obase = out_ptr ? __ldg(out_ptr + pos) - out_base : pos * (int64_t)uniform_m;
 
         float4 s = f4_zero(), p = f4_zero();
         float lin = 0.f;
-        for (int64_t tile = beg; tile < end; tile += 32) {
-            const int64_t j = tile + lane;
-            int id = -1;
-            float x = 0.f;
-            if (j < end) {
-                id = __ldg(idx + j);
-                x = HAS_VAL ? __ldg(val + j) : 1.f;
-                if ((uint32_t)id >= (uint64_t)n_slots) {  // reported, never dereferenced
-                    atomicExch(err, 1);
-                    id = -1;
+        int id0 = -1, id1 = -1;  // the first 64 entries stay in registers for the emission
+        for (int64_t tile = beg; tile < end; tile += 64) {
+            const int64_t j0 = tile + lane, j1 = j0 + 32;
+            int ia = -1, ib = -1;
+            float xa = 0.f, xb = 0.f;
+            if (j0 < end) {
+                ia = __ldg(idx + j0);
+                if (HAS_VAL) xa = __ldg(val + j0);
+            }
+            if (j1 < end) {
+                ib = __ldg(idx + j1);
+                if (HAS_VAL) xb = __ldg(val + j1);
+            }
+            if ((j0 < end && (uint32_t)ia >= (uint64_t)n_slots) ||
+                (j1 < end && (uint32_t)ib >= (uint64_t)n_slots)) {
+                atomicExch(err, 1);  // reported, never dereferenced
+                if ((uint32_t)ia >= (uint64_t)n_slots) ia = -1;
+                if ((uint32_t)ib >= (uint64_t)n_slots) ib = -1;
+            }
+            if (TRAIN && HAS_VAL) {  // entry list for the reduce-by-feature: {row, x}
+                if (j0 < end) {
+                    keys[obase + (j0 - beg)] = ia < 0 ? 0u : (uint32_t)ia;
+                    pay[obase + (j0 - beg)] = make_uint2((uint32_t)pos, ia < 0 ? 0u : __float_as_uint(xa));
                 }
-                if (TRAIN && HAS_VAL) {  // entry list for the reduce-by-feature: {row, x}
-                    keys[obase + (j - beg)] = id < 0 ? 0u : (uint32_t)id;
-                    pay[obase + (j - beg)] =
-                        make_uint2((uint32_t)pos, id < 0 ? 0u : __float_as_uint(x));
+                if (j1 < end) {
+                    keys[obase + (j1 - beg)] = ib < 0 ? 0u : (uint32_t)ib;
+                    pay[obase + (j1 - beg)] = make_uint2((uint32_t)pos, ib < 0 ? 0u : __float_as_uint(xb));
                 }
             }
-            const int cnt = (int)min((int64_t)32, end - tile);
-            if (cnt == 32) {
-                // full tile: LPR passes, all gathers independent -> issued back to back
-                constexpr int PCH = LPR < 8 ? LPR : 8;  // passes in flight (bounds registers)
+            if (tile == beg) { id0 = ia; id1 = ib; }
+            const int cnt = (int)min((int64_t)64, end - tile);
+            forward_tile<LPR, HAS_VAL>(V4, W, ia, xa, min(cnt, 32), slot, fq, s, p, lin);
+            if (cnt > 32) forward_tile<LPR, HAS_VAL>(V4, W, ib, xb, cnt - 32, slot, fq, s, p, lin);
+        }
+
+        // ---- merge the NPP entry slots; components carried per lane: 4 -> 2 -> 1
+        float sv[4] = {s.x, s.y, s.z, s.w};
+        float pv[4] = {p.x, p.y, p.z, p.w};
+        int ncomp = 4;
 #pragma unroll
-                for (int t0 = 0; t0 < LPR; t0 += PCH) {
-                float4 vv[PCH];
-                float xx[PCH], ww[PCH];
+        for (int off = 16; off >= LPR; off >>= 1) {
+            if (ncomp > 1) {
+                const int half = ncomp >> 1;
+                const bool up = (lane & off) != 0;
 #pragma unroll
-                for (int t = 0; t < PCH; ++t) {
-                    const int pid = __shfl_sync(FULL, id, (t0 + t) * NPP + slot);
-                    xx[t] = __shfl_sync(FULL, x, (t0 + t) * NPP + slot);
-                    const int64_t row = pid < 0 ? 0 : pid;
-                    if (pid < 0) xx[t] = 0.f;
-                    vv[t] = __ldg(V4 + row * LPR + fq);
-                    ww[t] = (fq == 0) ? __ldg(W + row) : 0.f;
+                for (int c = 0; c < 2; ++c) {
+                    if (c < half) {
+                        const float ss = __shfl_xor_sync(FULL, up ? sv[c] : sv[c + half], off);
+                        const float ps = __shfl_xor_sync(FULL, up ? pv[c] : pv[c + half], off);
+                        const float sk = up ? sv[c + half] : sv[c];
+                        const float pk = up ? pv[c + half] : pv[c];
+                        pv[c] = (pk + ps) + sk * ss;
+                        sv[c] = sk + ss;
+                    }
                 }
-#pragma unroll
-                for (int t = 0; t < PCH; ++t) {
-                    const float px = xx[t];
-                    const float ax = px != 0.f ? vv[t].x * px : 0.f;
-                    const float ay = px != 0.f ? vv[t].y * px : 0.f;
-                    const float az = px != 0.f ? vv[t].z * px : 0.f;
-                    const float aw = px != 0.f ? vv[t].w * px : 0.f;
-                    p.x = fmaf(ax, s.x, p.x); s.x += ax;
-                    p.y = fmaf(ay, s.y, p.y); s.y += ay;
-                    p.z = fmaf(az, s.z, p.z); s.z += az;
-                    p.w = fmaf(aw, s.w, p.w); s.w += aw;
-                    lin = px != 0.f ? fmaf(ww[t], px, lin) : lin;
-                }
-                }
+                ncomp = half;
             } else {
-                for (int t = 0; t * NPP < cnt; ++t) {
-                    const int pid = __shfl_sync(FULL, id, t * NPP + slot);
-                    float px = __shfl_sync(FULL, x, t * NPP + slot);
-                    const int64_t row = pid < 0 ? 0 : pid;
-                    if (pid < 0) px = 0.f;
-                    const float4 v = __ldg(V4 + row * LPR + fq);
-                    const float wv = (fq == 0) ? __ldg(W + row) : 0.f;
-                    const float ax = px != 0.f ? v.x * px : 0.f;
-                    const float ay = px != 0.f ? v.y * px : 0.f;
-                    const float az = px != 0.f ? v.z * px : 0.f;
-                    const float aw = px != 0.f ? v.w * px : 0.f;
-                    p.x = fmaf(ax, s.x, p.x); s.x += ax;
-                    p.y = fmaf(ay, s.y, p.y); s.y += ay;
-                    p.z = fmaf(az, s.z, p.z); s.z += az;
-                    p.w = fmaf(aw, s.w, p.w); s.w += aw;
-                    lin = px != 0.f ? fmaf(wv, px, lin) : lin;
-                }
+                const float ss = __shfl_xor_sync(FULL, sv[0], off);
+                const float ps = __shfl_xor_sync(FULL, pv[0], off);
+                pv[0] = (pv[0] + ps) + sv[0] * ss;
+                sv[0] += ss;
             }
         }
-        // merge the NPP entry slots (lanes that differ in `slot`, same fq)
+        // which factors this lane now holds: quad fq, component offset from the two halvings
+        constexpr int LV = (LPR == 32) ? 0 : (LPR == 16) ? 1 : (LPR == 8) ? 2 : (LPR == 4) ? 3
+                         : (LPR == 2) ? 4 : 5;
+        constexpr int NFIN = LV == 0 ? 4 : (LV == 1 ? 2 : 1);
+        constexpr int DUPMASK = (LPR <= 4) ? (7 & ~(LPR - 1)) : 0;  // lanes holding duplicates
+        int cbase = 0;
+        if (LV >= 1) cbase += (lane & 16) ? 2 : 0;
+        if (LV >= 2) cbase += (lane & 8) ? 1 : 0;
+        const bool canon = (lane & DUPMASK) == 0;
+        float tot = 0.f;
+        if (canon) {
 #pragma unroll
-        for (int off = LPR; off < 32; off <<= 1) {
-            const float4 so = shfl_xor4(s, off);
-            const float4 po = shfl_xor4(p, off);
-            p.x = (p.x + po.x) + s.x * so.x; s.x += so.x;
-            p.y = (p.y + po.y) + s.y * so.y; s.y += so.y;
-            p.z = (p.z + po.z) + s.z * so.z; s.z += so.z;
-            p.w = (p.w + po.w) + s.w * so.w; s.w += so.w;
-            lin += __shfl_xor_sync(FULL, lin, off);
+            for (int c = 0; c < NFIN; ++c) tot += pv[c];
         }
-        float pair = (p.x + p.y) + (p.z + p.w);
+        if (k1) tot += lin;  // lin is non-zero on fq == 0 lanes only, one partial per slot
 #pragma unroll
-        for (int off = 1; off < LPR; off <<= 1) pair += __shfl_xor_sync(FULL, pair, off);
-        // lin lives in fq == 0 lanes only (already merged over slots)
-        const float lin0 = __shfl_sync(FULL, lin, 0);
-        float yhat = w0;
-        if (k1) yhat += lin0;
-        yhat += pair;
+        for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(FULL, tot, off);
+        const float yhat = w0 + tot;
+
         if (TRAIN) {
-            if (lane < LPR) S4[pos * LPR + fq] = s;
+            if (canon) {
+#pragma unroll
+                for (int c = 0; c < NFIN; ++c) S[pos * KP + fq * 4 + cbase + c] = sv[c];
+            }
             float ls = 0.f, mu = 0.f;
+            loss_mult_fast(task, yhat, __ldg(label + r), ls, mu);  // uniform across the warp
             if (lane == 0) {
-                loss_mult(task, yhat, __ldg(label + r), ls, mu);
                 loss_out[pos] = ls;
                 mult_out[pos] = mu;
             }
             if (!HAS_VAL) {
-                // all-ones data: the entry list carries {row, mult_r} so that the reduce needs
-                // one gather per entry; the indices were just read, this pass hits L1
-                mu = __shfl_sync(FULL, mu, 0);
-                for (int64_t j = beg + lane; j < end; j += 32) {
+                // all-ones data: the entry list carries {row, mult_r}, so the reduce needs one
+                // gather per entry
+                const int64_t n = end - beg;
+                if (lane < n) {
+                    keys[obase + lane] = id0 < 0 ? 0u : (uint32_t)id0;
+                    pay[obase + lane] = make_uint2((uint32_t)pos, id0 < 0 ? 0u : __float_as_uint(mu));
+                }
+                if (lane + 32 < n) {
+                    keys[obase + lane + 32] = id1 < 0 ? 0u : (uint32_t)id1;
+                    pay[obase + lane + 32] = make_uint2((uint32_t)pos, id1 < 0 ? 0u : __float_as_uint(mu));
+                }
+                for (int64_t j = beg + 64 + lane; j < end; j += 32) {  // rows longer than 64
                     const int id = __ldg(idx + j);
                     const bool ok = (uint32_t)id < (uint64_t)n_slots;
                     keys[obase + (j - beg)] = ok ? (uint32_t)id : 0u;
-                    pay[obase + (j - beg)] =
-                        make_uint2((uint32_t)pos, ok ? __float_as_uint(mu) : 0u);
+                    pay[obase + (j - beg)] = make_uint2((uint32_t)pos, ok ? __float_as_uint(mu) : 0u);
                 }
             }
         } else {
@@ -218,16 +297,19 @@ static cudaError_t forward_dispatch(const ModelView& m, const BatchView& b, cons
     if (blocks > cap) blocks = cap;
 #define FWD_ARGS                                                                              \
     (const float4*)m.v, m.w, m.w0, m.n_slots, m.k0, m.k1, m.task, b.row_ptr, b.idx, b.val,    \
-        b.label, b.row_ids, b.row_lo, b.n_rows, b.idx_len, b.out_ptr, b.out_base, b.uniform_m,           \
-        (float4*)o.S, o.mult, o.loss, o.yhat, o.keys, o.pay, d_err
+        b.label, b.row_ids, b.row_lo, b.n_rows, b.idx_len, b.out_ptr, b.out_base,             \
+        b.uniform_m, o.S, o.mult, o.loss, o.yhat, o.keys, o.pay, d_err
+#define FWD_LAUNCH(T, HV, UN) fm_forward_kernel<LPR, T, HV, UN><<<g, t, 0, st>>>(FWD_ARGS)
     const dim3 g((unsigned)blocks), t(256);
+    const bool un = b.uniform_m >= 0;
     if (train) {
-        if (b.val) fm_forward_kernel<LPR, true, true><<<g, t, 0, st>>>(FWD_ARGS);
-        else       fm_forward_kernel<LPR, true, false><<<g, t, 0, st>>>(FWD_ARGS);
+        if (b.val) { if (un) FWD_LAUNCH(true, true, true); else FWD_LAUNCH(true, true, false); }
+        else       { if (un) FWD_LAUNCH(true, false, true); else FWD_LAUNCH(true, false, false); }
     } else {
-        if (b.val) fm_forward_kernel<LPR, false, true><<<g, t, 0, st>>>(FWD_ARGS);
-        else       fm_forward_kernel<LPR, false, false><<<g, t, 0, st>>>(FWD_ARGS);
+        if (b.val) { if (un) FWD_LAUNCH(false, true, true); else FWD_LAUNCH(false, true, false); }
+        else       { if (un) FWD_LAUNCH(false, false, true); else FWD_LAUNCH(false, false, false); }
     }
+#undef FWD_LAUNCH
 #undef FWD_ARGS
     return cudaGetLastError();
 }
