@@ -233,7 +233,7 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
         RC(ensure(h, h->b_keys[i], sizeof(uint32_t) * (size_t)(nnz > 0 ? nnz : 1)));
         RC(ensure(h, h->b_pay[i], sizeof(uint2) * (size_t)(nnz > 0 ? nnz : 1)));
     }
-    RC(ensure(h, h->b_seg, sizeof(int32_t) * (size_t)(m.n_slots + 1)));
+    RC(ensure(h, h->b_seg, sizeof(int32_t) * 2 * (size_t)m.n_slots));  // seg_lo | seg_hi
     RC(ensure(h, h->b_partials, sizeof(double) * 4 * 512));
     RC(ensure(h, h->b_pull, pull_scratch_bytes(m, nnz)));
     const int end_bit = bits_for(m.n_slots);
@@ -246,6 +246,8 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     const bool fused = !multi && !grad_keep;
     if (!fused) RC(ensure(h, h->b_grad, sizeof(float) * grad_len(h)));
 
+    if ((n + 1) * (int64_t)m.lpr >= 4294967296LL)
+        return set_err(h, SFM_ERR_ARG, "batch too large: rows * kp/4 must stay below 2^32");
     PhaseTimer pt(h);
     CU(cudaMemsetAsync(h->d_err, 0, sizeof(int32_t), h->stream));
     FwdOut o;
@@ -267,10 +269,9 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     if (nnz > 0)
         CU(sort_pairs(h->b_sort_tmp.p, sort_bytes, o.keys, (uint32_t*)h->b_keys[1].p, o.pay,
                       (uint2*)h->b_pay[1].p, nnz, end_bit, h->stream, L));
-    CU(launch_segments(keys_sorted, nnz, m.n_slots, (int32_t*)h->b_seg.p, h->stream, L));
     pt.lap(&h->stats.ms_sort);
     const UpdateParams up = update_params(h, iter);
-    CU(launch_pull(m, (const int32_t*)h->b_seg.p, keys_sorted, pay_sorted, nnz, b.val == nullptr,
+    CU(launch_pull(m, (int32_t*)h->b_seg.p, keys_sorted, pay_sorted, nnz, b.val == nullptr,
                    o.S, o.mult, (float*)h->b_pull.p, h->d_scal, h->d_err, up, fused,
                    fused ? nullptr : (float*)h->b_grad.p, h->sm_count, h->stream, L));
     pt.lap(&h->stats.ms_reduce);
@@ -442,8 +443,10 @@ int32_t sfm_create(const sfm_config* cfg, sfm_handle** out) {
     if (!cfg || !out) return SFM_ERR_ARG;
     *out = nullptr;
     if (cfg->abi_version != SFM_ABI_VERSION) return SFM_ERR_ARG;
-    if (cfg->k < 0 || cfg->k > 128 || cfg->n_slots < 1 || cfg->n_slots > 2147483647LL)
+    if (cfg->k < 0 || cfg->k > 128 || cfg->n_slots < 1 || cfg->n_slots >= 2147483647LL)
         return SFM_ERR_ARG;
+    if ((cfg->n_slots + 1) * (int64_t)(kp_for(cfg->k) / 4) >= 4294967296LL)
+        return SFM_ERR_ARG;  // V row offsets are 32-bit float4 indices in the kernels
     if (cfg->task != SFM_TASK_REGRESSION && cfg->task != SFM_TASK_CLASSIFICATION) return SFM_ERR_ARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -481,16 +484,17 @@ int32_t sfm_create(const sfm_config* cfg, sfm_handle** out) {
     CK(cudaEventCreate(&h->ev_t0));
     CK(cudaEventCreate(&h->ev_t1));
     CK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
-    CK(cudaMalloc(&m.v, sizeof(float) * (size_t)m.n_slots * m.kp));
-    CK(cudaMalloc(&m.w, sizeof(float) * (size_t)m.n_slots));
+    // one extra, always-zero row at index n_slots: the target of padded / rejected entries
+    CK(cudaMalloc(&m.v, sizeof(float) * (size_t)(m.n_slots + 1) * m.kp));
+    CK(cudaMalloc(&m.w, sizeof(float) * (size_t)(m.n_slots + 1)));
     CK(cudaMalloc(&m.w0, sizeof(float) * 4));
     CK(cudaMalloc(&h->d_scal, sizeof(double) * 8));
     CK(cudaMalloc(&h->d_err, sizeof(int32_t) * 4));
     CK(cudaMalloc(&h->d_count, sizeof(int32_t) * 4));
     CK(cudaMallocHost(&h->h_scal, sizeof(double) * 8));
     CK(cudaMallocHost(&h->h_flags, sizeof(int32_t) * 8));
-    CK(cudaMemsetAsync(m.v, 0, sizeof(float) * (size_t)m.n_slots * m.kp, h->stream));
-    CK(cudaMemsetAsync(m.w, 0, sizeof(float) * (size_t)m.n_slots, h->stream));
+    CK(cudaMemsetAsync(m.v, 0, sizeof(float) * (size_t)(m.n_slots + 1) * m.kp, h->stream));
+    CK(cudaMemsetAsync(m.w, 0, sizeof(float) * (size_t)(m.n_slots + 1), h->stream));
     CK(cudaMemsetAsync(m.w0, 0, sizeof(float) * 4, h->stream));
     CK(cudaMemsetAsync(h->d_scal, 0, sizeof(double) * 8, h->stream));
     CK(cudaMemsetAsync(h->d_err, 0, sizeof(int32_t) * 4, h->stream));

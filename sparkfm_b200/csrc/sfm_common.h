@@ -108,15 +108,12 @@ cudaError_t launch_forward(const ModelView& m, const BatchView& b, const FwdOut&
 // loss / mult -> d_scal[SC_LOSS], [SC_GW0], [SC_COUNT] (fixed-shape fp64 tree, deterministic)
 cudaError_t launch_scalar_reduce(const float* loss, const float* mult, int64_t n, double* partials,
                                  double* d_scal, cudaStream_t st, int64_t* launches);
-// sorted keys -> seg[f] = first position with key >= f, f in [0, n_slots]
-cudaError_t launch_segments(const uint32_t* keys, int64_t nnz, int64_t n_slots, int32_t* seg,
-                            cudaStream_t st, int64_t* launches);
 struct UpdateParams {
     float eta, reg0, regw, regv;
 };
 // reduce-by-feature over the sorted entries.  fused: apply the SGD update in place (one GPU);
 // else write the dense gradient grad = [gV n_slots*kp | gw n_slots | gw0].
-cudaError_t launch_pull(const ModelView& m, const int32_t* seg, const uint32_t* keys,
+cudaError_t launch_pull(const ModelView& m, int32_t* seg, const uint32_t* keys,
                         const uint2* pay, int64_t nnz, bool binary, const float* S,
                         const float* mult, float* scratch, const double* d_scal,
                         const int32_t* d_err, UpdateParams up, bool fused, float* grad,

@@ -92,39 +92,54 @@ __device__ __forceinline__ void loss_mult_fast(int task, float yhat, float label
     }
 }
 
+// `id` is a valid row of V for every lane: entries past the end of the CSR row (and reported
+// out-of-range indices) point at the all-zero row n_slots that sfm_create appends to V and w, so
+// the pass loop needs no validity selects.  Row offsets are 32-bit (sfm_create bounds
+// n_slots * LPR below 2^32).
 template <int LPR, bool HAS_VAL>
 __device__ __forceinline__ void forward_tile(const float4* __restrict__ V4,
                                              const float* __restrict__ W, int id, float x, int cnt,
                                              int slot, int fq, float4& s, float4& p, float& lin) {
     constexpr int NPP = 32 / LPR;
     constexpr int PCH = LPR < 8 ? LPR : 8;  // passes whose gathers are in flight together
+    if (cnt == 32) {
 #pragma unroll
-    for (int t0 = 0; t0 < LPR; t0 += PCH) {
-        if (t0 * NPP >= cnt) break;         // warp-uniform
-        float4 vv[PCH];
-        float ww[PCH], xx[PCH];
+        for (int t0 = 0; t0 < LPR; t0 += PCH) {
+            float4 vv[PCH];
+            float ww[PCH], xx[PCH];
 #pragma unroll
-        for (int t = 0; t < PCH; ++t) {
-            const int pid = __shfl_sync(FULL, id, (t0 + t) * NPP + slot);
-            if (HAS_VAL) xx[t] = __shfl_sync(FULL, x, (t0 + t) * NPP + slot);
-            const bool ok = pid >= 0;
-            const int64_t row = ok ? pid : 0;
-            vv[t] = __ldg(V4 + row * LPR + fq);
-            ww[t] = (fq == 0) ? __ldg(W + row) : 0.f;
-            if (!ok) {  // past the end of the row, or an out-of-range index (reported)
-                vv[t] = f4_zero();
-                ww[t] = 0.f;
+            for (int t = 0; t < PCH; ++t) {
+                const uint32_t row = (uint32_t)__shfl_sync(FULL, id, (t0 + t) * NPP + slot);
+                if (HAS_VAL) xx[t] = __shfl_sync(FULL, x, (t0 + t) * NPP + slot);
+                vv[t] = __ldg(V4 + (row * LPR + fq));
+                ww[t] = (fq == 0) ? __ldg(W + row) : 0.f;
+            }
+#pragma unroll
+            for (int t = 0; t < PCH; ++t) {
+                float4 a = vv[t];
+                if (HAS_VAL) {
+                    const float px = xx[t];
+                    a.x *= px; a.y *= px; a.z *= px; a.w *= px;
+                    lin = fmaf(ww[t], px, lin);
+                } else {
+                    lin += ww[t];
+                }
+                acc_entry(s, p, a);
             }
         }
-#pragma unroll
-        for (int t = 0; t < PCH; ++t) {
-            float4 a = vv[t];
+    } else {
+        // partial tile: only the passes that hold entries (warp-uniform trip count)
+        const int npass = (cnt + NPP - 1) / NPP;
+        for (int t = 0; t < npass; ++t) {
+            const uint32_t row = (uint32_t)__shfl_sync(FULL, id, t * NPP + slot);
+            float4 a = __ldg(V4 + (row * LPR + fq));
+            const float wv = (fq == 0) ? __ldg(W + row) : 0.f;
             if (HAS_VAL) {
-                const float px = xx[t];
+                const float px = __shfl_sync(FULL, x, t * NPP + slot);
                 a.x *= px; a.y *= px; a.z *= px; a.w *= px;
-                lin = fmaf(ww[t], px, lin);
+                lin = fmaf(wv, px, lin);
             } else {
-                lin += ww[t];
+                lin += wv;
             }
             acc_entry(s, p, a);
         }
@@ -169,10 +184,11 @@ fm_forward_kernel(const float4* __restrict__ V4, const float* __restrict__ W,
 
         float4 s = f4_zero(), p = f4_zero();
         float lin = 0.f;
-        int id0 = -1, id1 = -1;  // the first 64 entries stay in registers for the emission
+        const int zrow = (int)n_slots;  // the appended all-zero row
+        int id0 = zrow, id1 = zrow;     // the first 64 entries stay in registers for the emission
         for (int64_t tile = beg; tile < end; tile += 64) {
             const int64_t j0 = tile + lane, j1 = j0 + 32;
-            int ia = -1, ib = -1;
+            int ia = zrow, ib = zrow;
             float xa = 0.f, xb = 0.f;
             if (j0 < end) {
                 ia = __ldg(idx + j0);
@@ -182,20 +198,20 @@ fm_forward_kernel(const float4* __restrict__ V4, const float* __restrict__ W,
                 ib = __ldg(idx + j1);
                 if (HAS_VAL) xb = __ldg(val + j1);
             }
-            if ((j0 < end && (uint32_t)ia >= (uint64_t)n_slots) ||
-                (j1 < end && (uint32_t)ib >= (uint64_t)n_slots)) {
-                atomicExch(err, 1);  // reported, never dereferenced
-                if ((uint32_t)ia >= (uint64_t)n_slots) ia = -1;
-                if ((uint32_t)ib >= (uint64_t)n_slots) ib = -1;
+            if ((uint32_t)ia > (uint32_t)zrow || (uint32_t)ib > (uint32_t)zrow ||
+                (j0 < end && ia == zrow) || (j1 < end && ib == zrow)) {
+                atomicExch(err, 1);  // out-of-range index: reported, never dereferenced
+                if ((uint32_t)ia > (uint32_t)zrow) ia = zrow;
+                if ((uint32_t)ib > (uint32_t)zrow) ib = zrow;
             }
             if (TRAIN && HAS_VAL) {  // entry list for the reduce-by-feature: {row, x}
                 if (j0 < end) {
-                    keys[obase + (j0 - beg)] = ia < 0 ? 0u : (uint32_t)ia;
-                    pay[obase + (j0 - beg)] = make_uint2((uint32_t)pos, ia < 0 ? 0u : __float_as_uint(xa));
+                    keys[obase + (j0 - beg)] = ia == zrow ? 0u : (uint32_t)ia;
+                    pay[obase + (j0 - beg)] = make_uint2((uint32_t)pos, ia == zrow ? 0u : __float_as_uint(xa));
                 }
                 if (j1 < end) {
-                    keys[obase + (j1 - beg)] = ib < 0 ? 0u : (uint32_t)ib;
-                    pay[obase + (j1 - beg)] = make_uint2((uint32_t)pos, ib < 0 ? 0u : __float_as_uint(xb));
+                    keys[obase + (j1 - beg)] = ib == zrow ? 0u : (uint32_t)ib;
+                    pay[obase + (j1 - beg)] = make_uint2((uint32_t)pos, ib == zrow ? 0u : __float_as_uint(xb));
                 }
             }
             if (tile == beg) { id0 = ia; id1 = ib; }
@@ -267,12 +283,12 @@ fm_forward_kernel(const float4* __restrict__ V4, const float* __restrict__ W,
                 // gather per entry
                 const int64_t n = end - beg;
                 if (lane < n) {
-                    keys[obase + lane] = id0 < 0 ? 0u : (uint32_t)id0;
-                    pay[obase + lane] = make_uint2((uint32_t)pos, id0 < 0 ? 0u : __float_as_uint(mu));
+                    keys[obase + lane] = id0 == zrow ? 0u : (uint32_t)id0;
+                    pay[obase + lane] = make_uint2((uint32_t)pos, id0 == zrow ? 0u : __float_as_uint(mu));
                 }
                 if (lane + 32 < n) {
-                    keys[obase + lane + 32] = id1 < 0 ? 0u : (uint32_t)id1;
-                    pay[obase + lane + 32] = make_uint2((uint32_t)pos, id1 < 0 ? 0u : __float_as_uint(mu));
+                    keys[obase + lane + 32] = id1 == zrow ? 0u : (uint32_t)id1;
+                    pay[obase + lane + 32] = make_uint2((uint32_t)pos, id1 == zrow ? 0u : __float_as_uint(mu));
                 }
                 for (int64_t j = beg + 64 + lane; j < end; j += 32) {  // rows longer than 64
                     const int id = __ldg(idx + j);
@@ -440,29 +456,6 @@ cudaError_t launch_metrics(const float* yhat, const float* label, int64_t n, dou
 }
 
 // ------------------------------------------------------------------------------------------
-// seg[f] = first sorted position whose key >= f  (f in [0, n_slots]).
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-segments_kernel(const uint32_t* __restrict__ keys, int64_t nnz, int64_t n_slots,
-                int32_t* __restrict__ seg) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p <= nnz; p += stride) {
-        const int64_t prev = p == 0 ? -1 : (int64_t)keys[p - 1];
-        const int64_t cur = p == nnz ? n_slots : (int64_t)keys[p];
-        for (int64_t f = prev + 1; f <= cur; ++f) seg[f] = (int32_t)p;
-    }
-}
-
-cudaError_t launch_segments(const uint32_t* keys, int64_t nnz, int64_t n_slots, int32_t* seg,
-                            cudaStream_t st, int64_t* launches) {
-    ++*launches;
-    int64_t blocks = (nnz + 1 + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    segments_kernel<<<(unsigned)blocks, 256, 0, st>>>(keys, nnz, n_slots, seg);
-    return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------
 // Reduce-by-feature, pull form.  With c = mult_r * x_ri:
 //     gV_if = sum_r c * S_rf  -  v_if * sum_r c * x_ri        gw_i = sum_r c
 // so a feature needs only the factor sums S_r (kp floats) and multipliers of the rows that
@@ -477,11 +470,24 @@ cudaError_t launch_segments(const uint32_t* keys, int64_t nnz, int64_t n_slots, 
 //
 // Work is therefore balanced by construction (every CTA gets the same number of entries, however
 // skewed the feature frequencies are) and the result is bitwise reproducible -- no float atomics.
+// The CTA's tile of sorted (key, payload) entries is staged in shared memory with coalesced
+// 128-bit loads, stored transposed ([entry][group], +1 padding) so that the walk is
+// bank-conflict free; the only gathers left are the S rows.  The kernel also records where every
+// feature's run starts and ends (seg_lo / seg_hi, zeroed per step) for the finalize pass.
 // Records are REC = kp + 4 floats: [A (kp) | D | C | 0 | 0].
 // BINARY (data set without a value array): payload = {row, mult_r}, x = 1, D = C, one gather
 // (the S row) per entry; otherwise payload = {row, x} and mult_r is gathered too.
 // ------------------------------------------------------------------------------------------
 constexpr int PULL_SUB = 32;
+constexpr uint32_t PULL_SENTINEL = 0xFFFFFFFFu;
+
+template <int LPR>
+struct PullCfg {
+    static constexpr int THREADS = LPR >= 4 ? 256 : 64 * LPR;
+    static constexpr int G = THREADS / LPR;        // groups per CTA (<= 64)
+    static constexpr int CHB = G * PULL_SUB;       // sorted entries per CTA
+    static constexpr int REC = LPR * 4 + 4;
+};
 
 template <int LPR>
 __device__ __forceinline__ void store_rec(float* __restrict__ rec, int fq, const float4& A,
@@ -491,86 +497,123 @@ __device__ __forceinline__ void store_rec(float* __restrict__ rec, int fq, const
 }
 
 template <int LPR, bool BINARY>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PullCfg<LPR>::THREADS)
 fm_pull_chunks_kernel(const uint32_t* __restrict__ keys, const uint2* __restrict__ pay,
-                      const float4* __restrict__ S4, const float* __restrict__ mult,
-                      const int32_t* __restrict__ seg, int nnz, float* __restrict__ R1,
-                      float* __restrict__ R2) {
-    constexpr int G = 256 / LPR;
-    constexpr int CHB = G * PULL_SUB;
-    constexpr int REC = LPR * 4 + 4;
-    constexpr int U = 4;
+                      const float4* __restrict__ S4, const float* __restrict__ mult, int nnz,
+                      float* __restrict__ R1, float* __restrict__ R2,
+                      int32_t* __restrict__ seg_lo, int32_t* __restrict__ seg_hi) {
+    using Cfg = PullCfg<LPR>;
+    constexpr int G = Cfg::G, CHB = Cfg::CHB, REC = Cfg::REC, SUB = PULL_SUB, U = 4;
+    __shared__ uint32_t key_s[SUB][G + 1];
+    __shared__ uint32_t row_s[SUB][G + 1];
+    __shared__ float val_s[SUB][G + 1];   // BINARY: mult_r; else: x
     __shared__ float4 headA[G][LPR];
     __shared__ float2 headDC[G];
+    __shared__ uint32_t edge[2];           // key before / after this chunk
 
-    const int g = threadIdx.x / LPR;
-    const int fq = threadIdx.x % LPR;
+    const int tid = threadIdx.x;
+    const int g = tid / LPR;
+    const int fq = tid % LPR;
     const int cstart = blockIdx.x * CHB;
-    const int p0 = cstart + g * PULL_SUB;
-    const int p1 = min(p0 + PULL_SUB, nnz);
 
+    // ---- stage the tile: thread -> 4 consecutive entries (one 16-byte + two 16-byte loads)
+    for (int q = tid; q < CHB / 4; q += Cfg::THREADS) {
+        const int e0 = q * 4;
+        const int p = cstart + e0;
+        uint32_t k4[4];
+        uint2 p4[4];
+        if (p + 3 < nnz) {
+            const uint4 kk = __ldg(reinterpret_cast<const uint4*>(keys + p));
+            const uint4 pa = __ldg(reinterpret_cast<const uint4*>(pay + p));
+            const uint4 pb = __ldg(reinterpret_cast<const uint4*>(pay + p) + 1);
+            k4[0] = kk.x; k4[1] = kk.y; k4[2] = kk.z; k4[3] = kk.w;
+            p4[0] = make_uint2(pa.x, pa.y); p4[1] = make_uint2(pa.z, pa.w);
+            p4[2] = make_uint2(pb.x, pb.y); p4[3] = make_uint2(pb.z, pb.w);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool ok = p + u < nnz;
+                k4[u] = ok ? __ldg(keys + p + u) : PULL_SENTINEL;
+                p4[u] = ok ? __ldg(pay + p + u) : make_uint2(0u, 0u);
+            }
+        }
+        const int gg = e0 / SUB, ee = e0 % SUB;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            key_s[ee + u][gg] = k4[u];
+            row_s[ee + u][gg] = p4[u].x;
+            val_s[ee + u][gg] = __uint_as_float(p4[u].y);
+        }
+    }
+    if (tid == 0) {
+        edge[0] = cstart > 0 ? __ldg(keys + cstart - 1) : PULL_SENTINEL;
+        edge[1] = cstart + CHB < nnz ? __ldg(keys + cstart + CHB) : PULL_SENTINEL;
+    }
+    __syncthreads();
+
+    // ---- level 0: walk my SUB entries
+    const int p0 = cstart + g * SUB;
+    uint32_t cur = key_s[0][g];
+    const uint32_t before = g > 0 ? key_s[SUB - 1][g - 1] : edge[0];
+    bool cur_is_head = cur != PULL_SENTINEL && before == cur;
+    if (cur != PULL_SENTINEL && !cur_is_head && fq == 0) seg_lo[cur] = p0;
     float4 A = f4_zero();
     float D = 0.f, C = 0.f;
-    int cur = -1;
-    bool cur_is_head = false;
-
-    if (p0 < nnz) {
-        cur = (int)__ldg(keys + p0);
-        cur_is_head = p0 > __ldg(seg + cur);
-        for (int base = p0; base < p1; base += U) {
-            int kk[U];
-            float cc[U], xx[U];
-            float4 sv[U];
+#pragma unroll 1
+    for (int base = 0; base < SUB; base += U) {
+        uint32_t kk[U];
+        float cc[U], xx[U];
+        float4 sv[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int p = base + u;
-                const bool ok = p < p1;
-                kk[u] = ok ? (int)__ldg(keys + p) : cur;
-                uint2 pl = ok ? __ldg(pay + p) : make_uint2(0u, 0u);
-                const float second = __uint_as_float(pl.y);
-                if (BINARY) {
-                    cc[u] = second;
-                    xx[u] = 1.f;
-                } else {
-                    xx[u] = second;
-                    cc[u] = ok ? __ldg(mult + pl.x) * second : 0.f;
-                }
-                sv[u] = __ldg(S4 + (int64_t)pl.x * LPR + fq);
-                if (!ok) { cc[u] = 0.f; kk[u] = -2; }
+        for (int u = 0; u < U; ++u) {
+            kk[u] = key_s[base + u][g];
+            const uint32_t row = row_s[base + u][g];
+            const float second = val_s[base + u][g];
+            if (BINARY) {
+                cc[u] = second;
+                xx[u] = 1.f;
+            } else {
+                xx[u] = second;
+                cc[u] = __ldg(mult + row) * second;
             }
+            sv[u] = __ldg(S4 + (row * LPR + fq));
+        }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (kk[u] == -2) continue;
-                if (kk[u] != cur) {
-                    // the run of `cur` ended inside this sub-chunk
+        for (int u = 0; u < U; ++u) {
+            if (kk[u] != cur) {
+                // the run of `cur` ended at position p0 + base + u
+                if (cur != PULL_SENTINEL) {
                     if (cur_is_head) {
                         if (g == 0) store_rec<LPR>(R2 + (int64_t)blockIdx.x * REC, fq, A, D, C);
                         else { headA[g][fq] = A; if (fq == 0) headDC[g] = make_float2(D, C); }
                     } else {
                         store_rec<LPR>(R1 + (int64_t)cur * REC, fq, A, D, C);
                     }
-                    cur = kk[u];
-                    cur_is_head = false;
-                    A = f4_zero();
-                    D = 0.f;
-                    C = 0.f;
+                    if (fq == 0) seg_hi[cur] = p0 + base + u;
                 }
-                const float c = cc[u];
-                A.x = fmaf(c, sv[u].x, A.x);
-                A.y = fmaf(c, sv[u].y, A.y);
-                A.z = fmaf(c, sv[u].z, A.z);
-                A.w = fmaf(c, sv[u].w, A.w);
-                D = BINARY ? D : fmaf(c, xx[u], D);
-                C += c;
+                cur = kk[u];
+                cur_is_head = false;
+                if (cur != PULL_SENTINEL && fq == 0) seg_lo[cur] = p0 + base + u;
+                A = f4_zero();
+                D = 0.f;
+                C = 0.f;
             }
+            const float c = kk[u] == PULL_SENTINEL ? 0.f : cc[u];
+            A.x = fmaf(c, sv[u].x, A.x);
+            A.y = fmaf(c, sv[u].y, A.y);
+            A.z = fmaf(c, sv[u].z, A.z);
+            A.w = fmaf(c, sv[u].w, A.w);
+            D = BINARY ? D : fmaf(c, xx[u], D);
+            C += c;
         }
     }
-    // the run still open at the end of the sub-chunk
-    const bool open = p0 < nnz;
+    // ---- level 1: the run still open at the end of my sub-chunk
+    const uint32_t after = g < G - 1 ? key_s[0][g + 1] : edge[1];
+    const bool open = cur != PULL_SENTINEL;
+    const bool continues = open && after == cur;
     bool owner = false;
-    int run_end = 0;
     if (open) {
-        run_end = __ldg(seg + cur + 1);
+        if (!continues && fq == 0) seg_hi[cur] = p0 + SUB < nnz ? p0 + SUB : nnz;
         if (cur_is_head && g != 0) {
             headA[g][fq] = A;               // a middle / final piece of somebody else's run
             if (fq == 0) headDC[g] = make_float2(D, C);
@@ -580,15 +623,15 @@ fm_pull_chunks_kernel(const uint32_t* __restrict__ keys, const uint2* __restrict
     }
     __syncthreads();
     if (owner) {
-        if (run_end > p1) {                 // extends into following groups of this CTA chunk
-            const int last = min(run_end, cstart + CHB) - 1;
-            const int gl = (last - cstart) / PULL_SUB;
-            for (int g2 = g + 1; g2 <= gl; ++g2) {
+        if (continues) {
+            for (int g2 = g + 1; g2 < G; ++g2) {
+                if (key_s[0][g2] != cur) break;
                 const float4 a = headA[g2][fq];
                 const float2 dc = headDC[g2];
                 A.x += a.x; A.y += a.y; A.z += a.z; A.w += a.w;
                 D += dc.x;
                 C += dc.y;
+                if (key_s[SUB - 1][g2] != cur) break;   // the run ended inside g2
             }
         }
         float* dst = cur_is_head ? R2 + (int64_t)blockIdx.x * REC : R1 + (int64_t)cur * REC;
@@ -601,13 +644,13 @@ fm_pull_chunks_kernel(const uint32_t* __restrict__ keys, const uint2* __restrict
 template <int LPR, bool FUSED, bool BINARY>
 __global__ void __launch_bounds__(256)
 fm_pull_finalize_kernel(float4* __restrict__ V4, float* __restrict__ W, float* __restrict__ W0,
-                        int64_t n_slots, int k0, int k1, const int32_t* __restrict__ seg,
-                        const float* __restrict__ R1, const float* __restrict__ R2,
-                        const double* __restrict__ d_scal, const int32_t* __restrict__ err,
-                        UpdateParams up, float4* __restrict__ G4, float* __restrict__ Gw,
-                        float* __restrict__ Gw0) {
-    constexpr int CHB = (256 / LPR) * PULL_SUB;
-    constexpr int REC = LPR * 4 + 4;
+                        int64_t n_slots, int k0, int k1, const int32_t* __restrict__ seg_lo,
+                        const int32_t* __restrict__ seg_hi, const float* __restrict__ R1,
+                        const float* __restrict__ R2, const double* __restrict__ d_scal,
+                        const int32_t* __restrict__ err, UpdateParams up, float4* __restrict__ G4,
+                        float* __restrict__ Gw, float* __restrict__ Gw0) {
+    constexpr int CHB = PullCfg<LPR>::CHB;
+    constexpr int REC = PullCfg<LPR>::REC;
     if (FUSED && *err) return;  // a bad index was seen: leave the model untouched
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / LPR;
@@ -628,7 +671,7 @@ fm_pull_finalize_kernel(float4* __restrict__ V4, float* __restrict__ W, float* _
         }
     }
     for (int64_t i = tid / LPR; i < n_slots; i += ngroups) {
-        const int s = __ldg(seg + i), e = __ldg(seg + i + 1);
+        const int s = __ldg(seg_lo + i), e = __ldg(seg_hi + i);
         float4 A = f4_zero();
         float D = 0.f, C = 0.f;
         if (e > s) {
@@ -673,30 +716,39 @@ fm_pull_finalize_kernel(float4* __restrict__ V4, float* __restrict__ W, float* _
     }
 }
 
+template <int LPR>
+static int64_t pull_chunks_for(int64_t nnz) {
+    return (nnz + PullCfg<LPR>::CHB - 1) / PullCfg<LPR>::CHB;
+}
+
 size_t pull_scratch_bytes(const ModelView& m, int64_t nnz) {
-    const int64_t chb = (256 / m.lpr) * PULL_SUB;
+    const int threads = m.lpr >= 4 ? 256 : 64 * m.lpr;
+    const int64_t chb = (threads / m.lpr) * PULL_SUB;
     const int64_t rec = m.kp + 4;
     return sizeof(float) * (size_t)rec * (size_t)(m.n_slots + (nnz + chb - 1) / chb + 1);
 }
 
 template <int LPR>
-static cudaError_t pull_dispatch(const ModelView& m, const int32_t* seg, const uint32_t* keys,
+static cudaError_t pull_dispatch(const ModelView& m, int32_t* seg, const uint32_t* keys,
                                  const uint2* pay, int64_t nnz, bool binary, const float* S,
                                  const float* mult, float* scratch, const double* d_scal,
                                  const int32_t* d_err, UpdateParams up, bool fused, float* grad,
                                  int sm_count, cudaStream_t st) {
-    constexpr int CHB = (256 / LPR) * PULL_SUB;
-    constexpr int REC = LPR * 4 + 4;
+    using Cfg = PullCfg<LPR>;
     float* R1 = scratch;
-    float* R2 = scratch + (size_t)m.n_slots * REC;
-    const int64_t nchunks = (nnz + CHB - 1) / CHB;
+    float* R2 = scratch + (size_t)m.n_slots * Cfg::REC;
+    int32_t* seg_lo = seg;
+    int32_t* seg_hi = seg + m.n_slots;
+    cudaError_t e = cudaMemsetAsync(seg, 0, sizeof(int32_t) * 2 * (size_t)m.n_slots, st);
+    if (e != cudaSuccess) return e;
+    const int64_t nchunks = pull_chunks_for<LPR>(nnz);
     if (nchunks > 0) {
         if (binary)
-            fm_pull_chunks_kernel<LPR, true><<<(unsigned)nchunks, 256, 0, st>>>(
-                keys, pay, (const float4*)S, mult, seg, (int)nnz, R1, R2);
+            fm_pull_chunks_kernel<LPR, true><<<(unsigned)nchunks, Cfg::THREADS, 0, st>>>(
+                keys, pay, (const float4*)S, mult, (int)nnz, R1, R2, seg_lo, seg_hi);
         else
-            fm_pull_chunks_kernel<LPR, false><<<(unsigned)nchunks, 256, 0, st>>>(
-                keys, pay, (const float4*)S, mult, seg, (int)nnz, R1, R2);
+            fm_pull_chunks_kernel<LPR, false><<<(unsigned)nchunks, Cfg::THREADS, 0, st>>>(
+                keys, pay, (const float4*)S, mult, (int)nnz, R1, R2, seg_lo, seg_hi);
     }
     const int64_t threads = m.n_slots * LPR;
     int64_t blocks = (threads + 255) / 256;
@@ -706,8 +758,8 @@ static cudaError_t pull_dispatch(const ModelView& m, const int32_t* seg, const u
     float* gw = grad ? grad + m.n_slots * m.kp : nullptr;
     float* gw0 = grad ? gw + m.n_slots : nullptr;
 #define FIN_ARGS                                                                              \
-    (float4*)m.v, m.w, m.w0, m.n_slots, m.k0, m.k1, seg, R1, R2, d_scal, d_err, up,           \
-        (float4*)grad, gw, gw0
+    (float4*)m.v, m.w, m.w0, m.n_slots, m.k0, m.k1, seg_lo, seg_hi, R1, R2, d_scal, d_err,    \
+        up, (float4*)grad, gw, gw0
     const dim3 gd((unsigned)blocks), bd(256);
     if (fused) {
         if (binary) fm_pull_finalize_kernel<LPR, true, true><<<gd, bd, 0, st>>>(FIN_ARGS);
@@ -720,7 +772,7 @@ static cudaError_t pull_dispatch(const ModelView& m, const int32_t* seg, const u
     return cudaGetLastError();
 }
 
-cudaError_t launch_pull(const ModelView& m, const int32_t* seg, const uint32_t* keys,
+cudaError_t launch_pull(const ModelView& m, int32_t* seg, const uint32_t* keys,
                         const uint2* pay, int64_t nnz, bool binary, const float* S,
                         const float* mult, float* scratch, const double* d_scal,
                         const int32_t* d_err, UpdateParams up, bool fused, float* grad,
