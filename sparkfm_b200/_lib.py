@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libsparkfm_b200.so")
+SO_PATH = os.environ.get("SFM_LIB") or os.path.join(_HERE, "libsparkfm_b200.so")  # SFM_LIB: A/B builds
 
 SFM_ABI_VERSION = 1
 SFM_OK = 0

@@ -233,10 +233,16 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
         RC(ensure(h, h->b_keys[i], sizeof(uint32_t) * (size_t)(nnz > 0 ? nnz : 1)));
         RC(ensure(h, h->b_pay[i], sizeof(uint2) * (size_t)(nnz > 0 ? nnz : 1)));
     }
-    RC(ensure(h, h->b_seg, sizeof(int32_t) * 2 * (size_t)m.n_slots));  // seg_lo | seg_hi
+    int blk_shift = 30, n_blocks = 1;
+    pull_plan(m, n, &blk_shift, &n_blocks);
+    const int key_bits = bits_for(m.n_slots);
+    int blk_bits = 0;
+    while (((int64_t)1 << blk_bits) < n_blocks) ++blk_bits;
+    if (key_bits + blk_bits > 32) return set_err(h, SFM_ERR_ARG, "sort key does not fit 32 bits");
+    RC(ensure(h, h->b_seg, sizeof(int32_t) * 2 * (size_t)m.n_slots * n_blocks));  // seg_lo | seg_hi
     RC(ensure(h, h->b_partials, sizeof(double) * 4 * 512));
-    RC(ensure(h, h->b_pull, pull_scratch_bytes(m, nnz)));
-    const int end_bit = bits_for(m.n_slots);
+    RC(ensure(h, h->b_pull, pull_scratch_bytes(m, nnz, n_blocks)));
+    const int end_bit = key_bits + blk_bits;
     size_t sort_bytes = 0;
     if (nnz > 0) {
         sort_bytes = sort_pairs_temp_bytes(nnz, end_bit);
@@ -257,6 +263,8 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     o.yhat = nullptr;
     o.keys = (uint32_t*)h->b_keys[0].p;
     o.pay = (uint2*)h->b_pay[0].p;
+    o.key_bits = key_bits;
+    o.blk_shift = blk_shift;
     CU(launch_forward(m, b, o, true, h->d_err, h->sm_count, h->stream, L));
     CU(launch_scalar_reduce(o.loss, o.mult, n, (double*)h->b_partials.p, h->d_scal, h->stream, L));
     pt.lap(&h->stats.ms_forward);
@@ -271,7 +279,7 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
                       (uint2*)h->b_pay[1].p, nnz, end_bit, h->stream, L));
     pt.lap(&h->stats.ms_sort);
     const UpdateParams up = update_params(h, iter);
-    CU(launch_pull(m, (int32_t*)h->b_seg.p, keys_sorted, pay_sorted, nnz, b.val == nullptr,
+    CU(launch_pull(m, (int32_t*)h->b_seg.p, key_bits, n_blocks, keys_sorted, pay_sorted, nnz, b.val == nullptr,
                    o.S, o.mult, (float*)h->b_pull.p, h->d_scal, h->d_err, up, fused,
                    fused ? nullptr : (float*)h->b_grad.p, h->sm_count, h->stream, L));
     pt.lap(&h->stats.ms_reduce);

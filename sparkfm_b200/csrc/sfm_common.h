@@ -101,7 +101,9 @@ struct FwdOut {
     float* loss;     // [n_rows]       per-row loss (train)
     float* yhat;     // [n_rows]       predictions (predict) or nullptr
     uint32_t* keys;  // [nnz]          feature id of every batch entry (train)
-    uint2* pay;      // [nnz]          {batch row, x bits} (train)
+    uint2* pay;      // [nnz]          {batch row, x bits | mult bits} (train)
+    int key_bits;    // bits of the feature id inside a sort key
+    int blk_shift;   // batch row >> blk_shift = row block, the key's prefix
 };
 cudaError_t launch_forward(const ModelView& m, const BatchView& b, const FwdOut& o, bool train,
                            int32_t* d_err, int sm_count, cudaStream_t st, int64_t* launches);
@@ -113,12 +115,14 @@ struct UpdateParams {
 };
 // reduce-by-feature over the sorted entries.  fused: apply the SGD update in place (one GPU);
 // else write the dense gradient grad = [gV n_slots*kp | gw n_slots | gw0].
-cudaError_t launch_pull(const ModelView& m, int32_t* seg, const uint32_t* keys,
-                        const uint2* pay, int64_t nnz, bool binary, const float* S,
+cudaError_t launch_pull(const ModelView& m, int32_t* seg, int key_bits, int n_blocks,
+                        const uint32_t* keys, const uint2* pay, int64_t nnz, bool binary,
+                        const float* S,
                         const float* mult, float* scratch, const double* d_scal,
                         const int32_t* d_err, UpdateParams up, bool fused, float* grad,
                         int sm_count, cudaStream_t st, int64_t* launches);
-size_t pull_scratch_bytes(const ModelView& m, int64_t nnz);
+size_t pull_scratch_bytes(const ModelView& m, int64_t nnz, int n_blocks);
+void pull_plan(const ModelView& m, int64_t n_rows, int* blk_shift, int* n_blocks);
 // dense update from an (all-reduced) gradient buffer
 cudaError_t launch_update(const ModelView& m, const float* grad, const double* d_scal,
                           const int32_t* d_err, UpdateParams up, cudaStream_t st,

@@ -16,6 +16,7 @@
 // All of it is HBM / L2 bound gather + reduction work: tensor cores do not apply.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "sfm_common.h"
 
@@ -154,7 +155,8 @@ fm_forward_kernel(const float4* __restrict__ V4, const float* __restrict__ W,
                   const float* __restrict__ val, const float* __restrict__ label,
                   const int32_t* __restrict__ row_ids, int64_t row_lo, int64_t n_rows,
                   int64_t idx_len, const int64_t* __restrict__ out_ptr, int64_t out_base,
-                  int uniform_m, float* __restrict__ S, float* __restrict__ mult_out,
+                  int uniform_m, int key_bits, int blk_shift, float* __restrict__ S,
+                  float* __restrict__ mult_out,
                   float* __restrict__ loss_out, float* __restrict__ yhat_out,
                   uint32_t* __restrict__ keys, uint2* __restrict__ pay, int32_t* __restrict__ err) {
     constexpr int KP = LPR * 4;
@@ -181,6 +183,9 @@ fm_forward_kernel(const float4* __restrict__ V4, const float* __restrict__ W,
         }
         int64_t obase = 0;
         if (TRAIN) obase = out_ptr ? __ldg(out_ptr + pos) - out_base : pos * (int64_t)uniform_m;
+        // sort key = (row block << key_bits) | feature: the reduce then sweeps one L2-sized block
+        // of S rows at a time
+        const uint32_t kpre = TRAIN ? (uint32_t)(pos >> blk_shift) << key_bits : 0u;
 
         float4 s = f4_zero(), p = f4_zero();
         float lin = 0.f;
@@ -206,11 +211,11 @@ fm_forward_kernel(const float4* __restrict__ V4, const float* __restrict__ W,
             }
             if (TRAIN && HAS_VAL) {  // entry list for the reduce-by-feature: {row, x}
                 if (j0 < end) {
-                    keys[obase + (j0 - beg)] = ia == zrow ? 0u : (uint32_t)ia;
+                    keys[obase + (j0 - beg)] = kpre | (ia == zrow ? 0u : (uint32_t)ia);
                     pay[obase + (j0 - beg)] = make_uint2((uint32_t)pos, ia == zrow ? 0u : __float_as_uint(xa));
                 }
                 if (j1 < end) {
-                    keys[obase + (j1 - beg)] = ib == zrow ? 0u : (uint32_t)ib;
+                    keys[obase + (j1 - beg)] = kpre | (ib == zrow ? 0u : (uint32_t)ib);
                     pay[obase + (j1 - beg)] = make_uint2((uint32_t)pos, ib == zrow ? 0u : __float_as_uint(xb));
                 }
             }
@@ -283,17 +288,17 @@ fm_forward_kernel(const float4* __restrict__ V4, const float* __restrict__ W,
                 // gather per entry
                 const int64_t n = end - beg;
                 if (lane < n) {
-                    keys[obase + lane] = id0 == zrow ? 0u : (uint32_t)id0;
+                    keys[obase + lane] = kpre | (id0 == zrow ? 0u : (uint32_t)id0);
                     pay[obase + lane] = make_uint2((uint32_t)pos, id0 == zrow ? 0u : __float_as_uint(mu));
                 }
                 if (lane + 32 < n) {
-                    keys[obase + lane + 32] = id1 == zrow ? 0u : (uint32_t)id1;
+                    keys[obase + lane + 32] = kpre | (id1 == zrow ? 0u : (uint32_t)id1);
                     pay[obase + lane + 32] = make_uint2((uint32_t)pos, id1 == zrow ? 0u : __float_as_uint(mu));
                 }
                 for (int64_t j = beg + 64 + lane; j < end; j += 32) {  // rows longer than 64
                     const int id = __ldg(idx + j);
                     const bool ok = (uint32_t)id < (uint64_t)n_slots;
-                    keys[obase + (j - beg)] = ok ? (uint32_t)id : 0u;
+                    keys[obase + (j - beg)] = kpre | (ok ? (uint32_t)id : 0u);
                     pay[obase + (j - beg)] = make_uint2((uint32_t)pos, ok ? __float_as_uint(mu) : 0u);
                 }
             }
@@ -314,7 +319,7 @@ static cudaError_t forward_dispatch(const ModelView& m, const BatchView& b, cons
 #define FWD_ARGS                                                                              \
     (const float4*)m.v, m.w, m.w0, m.n_slots, m.k0, m.k1, m.task, b.row_ptr, b.idx, b.val,    \
         b.label, b.row_ids, b.row_lo, b.n_rows, b.idx_len, b.out_ptr, b.out_base,             \
-        b.uniform_m, o.S, o.mult, o.loss, o.yhat, o.keys, o.pay, d_err
+        b.uniform_m, o.key_bits, o.blk_shift, o.S, o.mult, o.loss, o.yhat, o.keys, o.pay, d_err
 #define FWD_LAUNCH(T, HV, UN) fm_forward_kernel<LPR, T, HV, UN><<<g, t, 0, st>>>(FWD_ARGS)
     const dim3 g((unsigned)blocks), t(256);
     const bool un = b.uniform_m >= 0;
@@ -479,6 +484,9 @@ cudaError_t launch_metrics(const float* yhat, const float* label, int64_t n, dou
 // (the S row) per entry; otherwise payload = {row, x} and mult_r is gathered too.
 // ------------------------------------------------------------------------------------------
 constexpr int PULL_SUB = 32;
+#ifndef PULL_U
+#define PULL_U 4
+#endif
 constexpr uint32_t PULL_SENTINEL = 0xFFFFFFFFu;
 
 template <int LPR>
@@ -501,9 +509,15 @@ __global__ void __launch_bounds__(PullCfg<LPR>::THREADS)
 fm_pull_chunks_kernel(const uint32_t* __restrict__ keys, const uint2* __restrict__ pay,
                       const float4* __restrict__ S4, const float* __restrict__ mult, int nnz,
                       float* __restrict__ R1, float* __restrict__ R2,
-                      int32_t* __restrict__ seg_lo, int32_t* __restrict__ seg_hi) {
+                      int32_t* __restrict__ seg_lo, int32_t* __restrict__ seg_hi, int key_bits,
+                      int64_t n_slots) {
     using Cfg = PullCfg<LPR>;
-    constexpr int G = Cfg::G, CHB = Cfg::CHB, REC = Cfg::REC, SUB = PULL_SUB, U = 4;
+    const uint32_t kmask = (1u << key_bits) - 1u;
+    // key = (row block << key_bits) | feature  ->  slot block * n_slots + feature
+    auto slot_of = [=](uint32_t key) -> int64_t {
+        return (int64_t)(key >> key_bits) * n_slots + (int64_t)(key & kmask);
+    };
+    constexpr int G = Cfg::G, CHB = Cfg::CHB, REC = Cfg::REC, SUB = PULL_SUB, U = PULL_U;
     __shared__ uint32_t key_s[SUB][G + 1];
     __shared__ uint32_t row_s[SUB][G + 1];
     __shared__ float val_s[SUB][G + 1];   // BINARY: mult_r; else: x
@@ -556,7 +570,7 @@ fm_pull_chunks_kernel(const uint32_t* __restrict__ keys, const uint2* __restrict
     uint32_t cur = key_s[0][g];
     const uint32_t before = g > 0 ? key_s[SUB - 1][g - 1] : edge[0];
     bool cur_is_head = cur != PULL_SENTINEL && before == cur;
-    if (cur != PULL_SENTINEL && !cur_is_head && fq == 0) seg_lo[cur] = p0;
+    if (cur != PULL_SENTINEL && !cur_is_head && fq == 0) seg_lo[slot_of(cur)] = p0;
     float4 A = f4_zero();
     float D = 0.f, C = 0.f;
 #pragma unroll 1
@@ -587,13 +601,13 @@ fm_pull_chunks_kernel(const uint32_t* __restrict__ keys, const uint2* __restrict
                         if (g == 0) store_rec<LPR>(R2 + (int64_t)blockIdx.x * REC, fq, A, D, C);
                         else { headA[g][fq] = A; if (fq == 0) headDC[g] = make_float2(D, C); }
                     } else {
-                        store_rec<LPR>(R1 + (int64_t)cur * REC, fq, A, D, C);
+                        store_rec<LPR>(R1 + slot_of(cur) * REC, fq, A, D, C);
                     }
-                    if (fq == 0) seg_hi[cur] = p0 + base + u;
+                    if (fq == 0) seg_hi[slot_of(cur)] = p0 + base + u;
                 }
                 cur = kk[u];
                 cur_is_head = false;
-                if (cur != PULL_SENTINEL && fq == 0) seg_lo[cur] = p0 + base + u;
+                if (cur != PULL_SENTINEL && fq == 0) seg_lo[slot_of(cur)] = p0 + base + u;
                 A = f4_zero();
                 D = 0.f;
                 C = 0.f;
@@ -613,7 +627,7 @@ fm_pull_chunks_kernel(const uint32_t* __restrict__ keys, const uint2* __restrict
     const bool continues = open && after == cur;
     bool owner = false;
     if (open) {
-        if (!continues && fq == 0) seg_hi[cur] = p0 + SUB < nnz ? p0 + SUB : nnz;
+        if (!continues && fq == 0) seg_hi[slot_of(cur)] = p0 + SUB < nnz ? p0 + SUB : nnz;
         if (cur_is_head && g != 0) {
             headA[g][fq] = A;               // a middle / final piece of somebody else's run
             if (fq == 0) headDC[g] = make_float2(D, C);
@@ -634,7 +648,7 @@ fm_pull_chunks_kernel(const uint32_t* __restrict__ keys, const uint2* __restrict
                 if (key_s[SUB - 1][g2] != cur) break;   // the run ended inside g2
             }
         }
-        float* dst = cur_is_head ? R2 + (int64_t)blockIdx.x * REC : R1 + (int64_t)cur * REC;
+        float* dst = cur_is_head ? R2 + (int64_t)blockIdx.x * REC : R1 + slot_of(cur) * REC;
         store_rec<LPR>(dst, fq, A, D, C);
     }
 }
@@ -646,9 +660,10 @@ __global__ void __launch_bounds__(256)
 fm_pull_finalize_kernel(float4* __restrict__ V4, float* __restrict__ W, float* __restrict__ W0,
                         int64_t n_slots, int k0, int k1, const int32_t* __restrict__ seg_lo,
                         const int32_t* __restrict__ seg_hi, const float* __restrict__ R1,
-                        const float* __restrict__ R2, const double* __restrict__ d_scal,
-                        const int32_t* __restrict__ err, UpdateParams up, float4* __restrict__ G4,
-                        float* __restrict__ Gw, float* __restrict__ Gw0) {
+                        const float* __restrict__ R2, int n_blocks,
+                        const double* __restrict__ d_scal, const int32_t* __restrict__ err,
+                        UpdateParams up, float4* __restrict__ G4, float* __restrict__ Gw,
+                        float* __restrict__ Gw0) {
     constexpr int CHB = PullCfg<LPR>::CHB;
     constexpr int REC = PullCfg<LPR>::REC;
     if (FUSED && *err) return;  // a bad index was seen: leave the model untouched
@@ -671,26 +686,30 @@ fm_pull_finalize_kernel(float4* __restrict__ V4, float* __restrict__ W, float* _
         }
     }
     for (int64_t i = tid / LPR; i < n_slots; i += ngroups) {
-        const int s = __ldg(seg_lo + i), e = __ldg(seg_hi + i);
         float4 A = f4_zero();
         float D = 0.f, C = 0.f;
-        if (e > s) {
-            const float* r = R1 + i * REC;
-            A = __ldg(reinterpret_cast<const float4*>(r) + fq);
-            float4 dc = __ldg(reinterpret_cast<const float4*>(r) + LPR);
-            D = dc.x;
-            C = dc.y;
-            const int c1 = (e - 1) / CHB;
-            for (int c = s / CHB + 1; c <= c1; ++c) {
-                const float* r2 = R2 + (int64_t)c * REC;
-                const float4 a = __ldg(reinterpret_cast<const float4*>(r2) + fq);
-                dc = __ldg(reinterpret_cast<const float4*>(r2) + LPR);
-                A.x += a.x; A.y += a.y; A.z += a.z; A.w += a.w;
+        for (int blk = 0; blk < n_blocks; ++blk) {  // row blocks in order: fixed summation order
+            const int64_t slot = (int64_t)blk * n_slots + i;
+            const int s = __ldg(seg_lo + slot), e = __ldg(seg_hi + slot);
+            if (e > s) {
+                const float* r = R1 + slot * REC;
+                const float4 a0 = __ldg(reinterpret_cast<const float4*>(r) + fq);
+                float4 dc = __ldg(reinterpret_cast<const float4*>(r) + LPR);
+                A.x += a0.x; A.y += a0.y; A.z += a0.z; A.w += a0.w;
                 D += dc.x;
                 C += dc.y;
+                const int c1 = (e - 1) / CHB;
+                for (int c = s / CHB + 1; c <= c1; ++c) {
+                    const float* r2 = R2 + (int64_t)c * REC;
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(r2) + fq);
+                    dc = __ldg(reinterpret_cast<const float4*>(r2) + LPR);
+                    A.x += a.x; A.y += a.y; A.z += a.z; A.w += a.w;
+                    D += dc.x;
+                    C += dc.y;
+                }
             }
-            if (BINARY) D = C;
         }
+        if (BINARY) D = C;
         float4 v = V4[i * LPR + fq];
         float4 g;
         g.x = A.x - v.x * D;
@@ -721,34 +740,65 @@ static int64_t pull_chunks_for(int64_t nnz) {
     return (nnz + PullCfg<LPR>::CHB - 1) / PullCfg<LPR>::CHB;
 }
 
-size_t pull_scratch_bytes(const ModelView& m, int64_t nnz) {
+// Row blocking of the sort key: rows per block = the largest power of two whose
+// S rows fit in ~16 MB (so a block stays L2 resident while the reduce sweeps it); the number of
+// blocks is capped so that the per-(block, feature) records stay within ~2 GB.
+void pull_plan(const ModelView& m, int64_t n_rows, int* blk_shift, int* n_blocks) {
+    static int block_mb = -1;  // SFM_PULL_BLOCK_MB: S bytes per row block (0 = no blocking)
+    if (block_mb < 0) {
+        const char* e = getenv("SFM_PULL_BLOCK_MB");
+        block_mb = e ? atoi(e) : 16;
+    }
+    if (block_mb <= 0) {
+        *blk_shift = 30;
+        *n_blocks = 1;
+        return;
+    }
+    int shift = 10;
+    while (shift < 30 && ((int64_t)2 << shift) * m.kp * 4 <= ((int64_t)block_mb << 20)) ++shift;
+    int64_t nb = n_rows > 0 ? ((n_rows - 1) >> shift) + 1 : 1;
+    const int64_t rec_bytes = (int64_t)(m.kp + 4) * 4 + 8;
+    int64_t cap = ((int64_t)2 << 30) / (m.n_slots * rec_bytes);
+    if (cap > 64) cap = 64;
+    if (cap < 1) cap = 1;
+    while (nb > cap) {
+        ++shift;
+        nb = ((n_rows - 1) >> shift) + 1;
+    }
+    *blk_shift = shift;
+    *n_blocks = (int)nb;
+}
+
+size_t pull_scratch_bytes(const ModelView& m, int64_t nnz, int n_blocks) {
     const int threads = m.lpr >= 4 ? 256 : 64 * m.lpr;
     const int64_t chb = (threads / m.lpr) * PULL_SUB;
     const int64_t rec = m.kp + 4;
-    return sizeof(float) * (size_t)rec * (size_t)(m.n_slots + (nnz + chb - 1) / chb + 1);
+    return sizeof(float) * (size_t)rec * (size_t)(m.n_slots * n_blocks + (nnz + chb - 1) / chb + 1);
 }
 
 template <int LPR>
-static cudaError_t pull_dispatch(const ModelView& m, int32_t* seg, const uint32_t* keys,
-                                 const uint2* pay, int64_t nnz, bool binary, const float* S,
+static cudaError_t pull_dispatch(const ModelView& m, int32_t* seg, int key_bits, int n_blocks,
+                                 const uint32_t* keys, const uint2* pay, int64_t nnz, bool binary,
+                                 const float* S,
                                  const float* mult, float* scratch, const double* d_scal,
                                  const int32_t* d_err, UpdateParams up, bool fused, float* grad,
                                  int sm_count, cudaStream_t st) {
     using Cfg = PullCfg<LPR>;
     float* R1 = scratch;
-    float* R2 = scratch + (size_t)m.n_slots * Cfg::REC;
+    const size_t nslot = (size_t)m.n_slots * n_blocks;
+    float* R2 = scratch + nslot * Cfg::REC;
     int32_t* seg_lo = seg;
-    int32_t* seg_hi = seg + m.n_slots;
-    cudaError_t e = cudaMemsetAsync(seg, 0, sizeof(int32_t) * 2 * (size_t)m.n_slots, st);
+    int32_t* seg_hi = seg + nslot;
+    cudaError_t e = cudaMemsetAsync(seg, 0, sizeof(int32_t) * 2 * nslot, st);
     if (e != cudaSuccess) return e;
     const int64_t nchunks = pull_chunks_for<LPR>(nnz);
     if (nchunks > 0) {
         if (binary)
             fm_pull_chunks_kernel<LPR, true><<<(unsigned)nchunks, Cfg::THREADS, 0, st>>>(
-                keys, pay, (const float4*)S, mult, (int)nnz, R1, R2, seg_lo, seg_hi);
+                keys, pay, (const float4*)S, mult, (int)nnz, R1, R2, seg_lo, seg_hi, key_bits, m.n_slots);
         else
             fm_pull_chunks_kernel<LPR, false><<<(unsigned)nchunks, Cfg::THREADS, 0, st>>>(
-                keys, pay, (const float4*)S, mult, (int)nnz, R1, R2, seg_lo, seg_hi);
+                keys, pay, (const float4*)S, mult, (int)nnz, R1, R2, seg_lo, seg_hi, key_bits, m.n_slots);
     }
     const int64_t threads = m.n_slots * LPR;
     int64_t blocks = (threads + 255) / 256;
@@ -758,8 +808,8 @@ static cudaError_t pull_dispatch(const ModelView& m, int32_t* seg, const uint32_
     float* gw = grad ? grad + m.n_slots * m.kp : nullptr;
     float* gw0 = grad ? gw + m.n_slots : nullptr;
 #define FIN_ARGS                                                                              \
-    (float4*)m.v, m.w, m.w0, m.n_slots, m.k0, m.k1, seg_lo, seg_hi, R1, R2, d_scal, d_err,    \
-        up, (float4*)grad, gw, gw0
+    (float4*)m.v, m.w, m.w0, m.n_slots, m.k0, m.k1, seg_lo, seg_hi, R1, R2, n_blocks, d_scal, \
+        d_err, up, (float4*)grad, gw, gw0
     const dim3 gd((unsigned)blocks), bd(256);
     if (fused) {
         if (binary) fm_pull_finalize_kernel<LPR, true, true><<<gd, bd, 0, st>>>(FIN_ARGS);
@@ -772,13 +822,14 @@ static cudaError_t pull_dispatch(const ModelView& m, int32_t* seg, const uint32_
     return cudaGetLastError();
 }
 
-cudaError_t launch_pull(const ModelView& m, int32_t* seg, const uint32_t* keys,
-                        const uint2* pay, int64_t nnz, bool binary, const float* S,
+cudaError_t launch_pull(const ModelView& m, int32_t* seg, int key_bits, int n_blocks,
+                        const uint32_t* keys, const uint2* pay, int64_t nnz, bool binary,
+                        const float* S,
                         const float* mult, float* scratch, const double* d_scal,
                         const int32_t* d_err, UpdateParams up, bool fused, float* grad,
                         int sm_count, cudaStream_t st, int64_t* launches) {
     *launches += nnz > 0 ? 2 : 1;
-#define PD(L) pull_dispatch<L>(m, seg, keys, pay, nnz, binary, S, mult, scratch, d_scal, d_err, up, fused, grad, sm_count, st)
+#define PD(L) pull_dispatch<L>(m, seg, key_bits, n_blocks, keys, pay, nnz, binary, S, mult, scratch, d_scal, d_err, up, fused, grad, sm_count, st)
     switch (m.lpr) {
         case 1: return PD(1);
         case 2: return PD(2);
