@@ -284,7 +284,9 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
                    fused ? nullptr : (float*)h->b_grad.p, h->sm_count, h->stream, L));
     pt.lap(&h->stats.ms_reduce);
     if (multi) {
-        RC(nccl_allreduce_f32(h->nccl, h->comm, (float*)h->b_grad.p, grad_len(h), h->stream,
+        // [gV | gw] only: the trailing gw0 slot already holds the GLOBAL value (it comes from
+        // the all-reduced scalar block above)
+        RC(nccl_allreduce_f32(h->nccl, h->comm, (float*)h->b_grad.p, grad_len(h) - 1, h->stream,
                               &h->err));
         pt.lap(&h->stats.ms_allreduce);
     }
