@@ -244,8 +244,9 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     RC(ensure(h, h->b_pull, pull_scratch_bytes(m, nnz, n_blocks)));
     const int end_bit = key_bits + blk_bits;
     size_t sort_bytes = 0;
+    const bool binary = b.val == nullptr;  // all-ones data: 4-byte payload (the row)
     if (nnz > 0) {
-        sort_bytes = sort_pairs_temp_bytes(nnz, end_bit);
+        sort_bytes = binary ? sort_pairs32_temp_bytes(nnz, end_bit) : sort_pairs_temp_bytes(nnz, end_bit);
         RC(ensure(h, h->b_sort_tmp, sort_bytes));
     }
     const bool multi = h->world > 1;
@@ -274,12 +275,18 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     }
     const uint32_t* keys_sorted = (const uint32_t*)h->b_keys[1].p;
     const uint2* pay_sorted = (const uint2*)h->b_pay[1].p;
-    if (nnz > 0)
-        CU(sort_pairs(h->b_sort_tmp.p, sort_bytes, o.keys, (uint32_t*)h->b_keys[1].p, o.pay,
-                      (uint2*)h->b_pay[1].p, nnz, end_bit, h->stream, L));
+    if (nnz > 0) {
+        if (binary)
+            CU(sort_pairs32(h->b_sort_tmp.p, sort_bytes, o.keys, (uint32_t*)h->b_keys[1].p,
+                            (const uint32_t*)o.pay, (uint32_t*)h->b_pay[1].p, nnz, end_bit,
+                            h->stream, L));
+        else
+            CU(sort_pairs(h->b_sort_tmp.p, sort_bytes, o.keys, (uint32_t*)h->b_keys[1].p, o.pay,
+                          (uint2*)h->b_pay[1].p, nnz, end_bit, h->stream, L));
+    }
     pt.lap(&h->stats.ms_sort);
     const UpdateParams up = update_params(h, iter);
-    CU(launch_pull(m, (int32_t*)h->b_seg.p, key_bits, n_blocks, keys_sorted, pay_sorted, nnz, b.val == nullptr,
+    CU(launch_pull(m, (int32_t*)h->b_seg.p, key_bits, n_blocks, keys_sorted, pay_sorted, nnz, binary,
                    o.S, o.mult, (float*)h->b_pull.p, h->d_scal, h->d_err, up, fused,
                    fused ? nullptr : (float*)h->b_grad.p, h->sm_count, h->stream, L));
     pt.lap(&h->stats.ms_reduce);

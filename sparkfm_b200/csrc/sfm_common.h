@@ -148,6 +148,10 @@ size_t sort_pairs_temp_bytes(int64_t n, int end_bit);
 cudaError_t sort_pairs(void* tmp, size_t tmp_bytes, const uint32_t* keys_in, uint32_t* keys_out,
                        const uint2* pay_in, uint2* pay_out, int64_t n, int end_bit,
                        cudaStream_t st, int64_t* launches);
+size_t sort_pairs32_temp_bytes(int64_t n, int end_bit);
+cudaError_t sort_pairs32(void* tmp, size_t tmp_bytes, const uint32_t* keys_in, uint32_t* keys_out,
+                         const uint32_t* val_in, uint32_t* val_out, int64_t n, int end_bit,
+                         cudaStream_t st, int64_t* launches);
 size_t scan_temp_bytes(int64_t n);
 cudaError_t exclusive_scan_i64(void* tmp, size_t tmp_bytes, const int64_t* in, int64_t* out,
                                int64_t n, cudaStream_t st, int64_t* launches);

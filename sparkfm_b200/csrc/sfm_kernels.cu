@@ -190,7 +190,6 @@ fm_forward_kernel(const float4* __restrict__ V4, const float* __restrict__ W,
         float4 s = f4_zero(), p = f4_zero();
         float lin = 0.f;
         const int zrow = (int)n_slots;  // the appended all-zero row
-        int id0 = zrow, id1 = zrow;     // the first 64 entries stay in registers for the emission
         for (int64_t tile = beg; tile < end; tile += 64) {
             const int64_t j0 = tile + lane, j1 = j0 + 32;
             int ia = zrow, ib = zrow;
@@ -209,17 +208,20 @@ fm_forward_kernel(const float4* __restrict__ V4, const float* __restrict__ W,
                 if ((uint32_t)ia > (uint32_t)zrow) ia = zrow;
                 if ((uint32_t)ib > (uint32_t)zrow) ib = zrow;
             }
-            if (TRAIN && HAS_VAL) {  // entry list for the reduce-by-feature: {row, x}
+            if (TRAIN) {
+                // entry list for the reduce-by-feature: key = block | feature, payload = {row, x}
+                // (8 bytes) or, for all-ones data, just the row (4 bytes: less to sort)
                 if (j0 < end) {
                     keys[obase + (j0 - beg)] = kpre | (ia == zrow ? 0u : (uint32_t)ia);
-                    pay[obase + (j0 - beg)] = make_uint2((uint32_t)pos, ia == zrow ? 0u : __float_as_uint(xa));
+                    if (HAS_VAL) pay[obase + (j0 - beg)] = make_uint2((uint32_t)pos, ia == zrow ? 0u : __float_as_uint(xa));
+                    else reinterpret_cast<uint32_t*>(pay)[obase + (j0 - beg)] = (uint32_t)pos;
                 }
                 if (j1 < end) {
                     keys[obase + (j1 - beg)] = kpre | (ib == zrow ? 0u : (uint32_t)ib);
-                    pay[obase + (j1 - beg)] = make_uint2((uint32_t)pos, ib == zrow ? 0u : __float_as_uint(xb));
+                    if (HAS_VAL) pay[obase + (j1 - beg)] = make_uint2((uint32_t)pos, ib == zrow ? 0u : __float_as_uint(xb));
+                    else reinterpret_cast<uint32_t*>(pay)[obase + (j1 - beg)] = (uint32_t)pos;
                 }
             }
-            if (tile == beg) { id0 = ia; id1 = ib; }
             const int cnt = (int)min((int64_t)64, end - tile);
             forward_tile<LPR, HAS_VAL>(V4, W, ia, xa, min(cnt, 32), slot, fq, s, p, lin);
             if (cnt > 32) forward_tile<LPR, HAS_VAL>(V4, W, ib, xb, cnt - 32, slot, fq, s, p, lin);
@@ -282,25 +284,6 @@ fm_forward_kernel(const float4* __restrict__ V4, const float* __restrict__ W,
             if (lane == 0) {
                 loss_out[pos] = ls;
                 mult_out[pos] = mu;
-            }
-            if (!HAS_VAL) {
-                // all-ones data: the entry list carries {row, mult_r}, so the reduce needs one
-                // gather per entry
-                const int64_t n = end - beg;
-                if (lane < n) {
-                    keys[obase + lane] = kpre | (id0 == zrow ? 0u : (uint32_t)id0);
-                    pay[obase + lane] = make_uint2((uint32_t)pos, id0 == zrow ? 0u : __float_as_uint(mu));
-                }
-                if (lane + 32 < n) {
-                    keys[obase + lane + 32] = kpre | (id1 == zrow ? 0u : (uint32_t)id1);
-                    pay[obase + lane + 32] = make_uint2((uint32_t)pos, id1 == zrow ? 0u : __float_as_uint(mu));
-                }
-                for (int64_t j = beg + 64 + lane; j < end; j += 32) {  // rows longer than 64
-                    const int id = __ldg(idx + j);
-                    const bool ok = (uint32_t)id < (uint64_t)n_slots;
-                    keys[obase + (j - beg)] = kpre | (ok ? (uint32_t)id : 0u);
-                    pay[obase + (j - beg)] = make_uint2((uint32_t)pos, ok ? __float_as_uint(mu) : 0u);
-                }
             }
         } else {
             if (lane == 0) yhat_out[pos] = yhat;
@@ -480,8 +463,9 @@ cudaError_t launch_metrics(const float* yhat, const float* label, int64_t n, dou
 // bank-conflict free; the only gathers left are the S rows.  The kernel also records where every
 // feature's run starts and ends (seg_lo / seg_hi, zeroed per step) for the finalize pass.
 // Records are REC = kp + 4 floats: [A (kp) | D | C | 0 | 0].
-// BINARY (data set without a value array): payload = {row, mult_r}, x = 1, D = C, one gather
-// (the S row) per entry; otherwise payload = {row, x} and mult_r is gathered too.
+// BINARY (data set without a value array): the sorted payload is just the row (4 bytes), x = 1,
+// D = C, mult_r is fetched while staging; otherwise payload = {row, x} and mult_r is gathered in
+// the walk.
 // ------------------------------------------------------------------------------------------
 constexpr int PULL_SUB = 32;
 #ifndef PULL_U
@@ -534,29 +518,46 @@ fm_pull_chunks_kernel(const uint32_t* __restrict__ keys, const uint2* __restrict
     for (int q = tid; q < CHB / 4; q += Cfg::THREADS) {
         const int e0 = q * 4;
         const int p = cstart + e0;
-        uint32_t k4[4];
-        uint2 p4[4];
+        uint32_t k4[4], r4[4];
+        float v4[4];
         if (p + 3 < nnz) {
             const uint4 kk = __ldg(reinterpret_cast<const uint4*>(keys + p));
-            const uint4 pa = __ldg(reinterpret_cast<const uint4*>(pay + p));
-            const uint4 pb = __ldg(reinterpret_cast<const uint4*>(pay + p) + 1);
             k4[0] = kk.x; k4[1] = kk.y; k4[2] = kk.z; k4[3] = kk.w;
-            p4[0] = make_uint2(pa.x, pa.y); p4[1] = make_uint2(pa.z, pa.w);
-            p4[2] = make_uint2(pb.x, pb.y); p4[3] = make_uint2(pb.z, pb.w);
+            if (BINARY) {
+                const uint4 rr = __ldg(reinterpret_cast<const uint4*>(
+                    reinterpret_cast<const uint32_t*>(pay) + p));
+                r4[0] = rr.x; r4[1] = rr.y; r4[2] = rr.z; r4[3] = rr.w;
+            } else {
+                const uint4 pa = __ldg(reinterpret_cast<const uint4*>(pay + p));
+                const uint4 pb = __ldg(reinterpret_cast<const uint4*>(pay + p) + 1);
+                r4[0] = pa.x; r4[1] = pa.z; r4[2] = pb.x; r4[3] = pb.z;
+                v4[0] = __uint_as_float(pa.y); v4[1] = __uint_as_float(pa.w);
+                v4[2] = __uint_as_float(pb.y); v4[3] = __uint_as_float(pb.w);
+            }
         } else {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const bool ok = p + u < nnz;
                 k4[u] = ok ? __ldg(keys + p + u) : PULL_SENTINEL;
-                p4[u] = ok ? __ldg(pay + p + u) : make_uint2(0u, 0u);
+                if (BINARY) {
+                    r4[u] = ok ? __ldg(reinterpret_cast<const uint32_t*>(pay) + p + u) : 0u;
+                } else {
+                    const uint2 pl = ok ? __ldg(pay + p + u) : make_uint2(0u, 0u);
+                    r4[u] = pl.x;
+                    v4[u] = __uint_as_float(pl.y);
+                }
             }
+        }
+        if (BINARY) {  // the row's multiplier rides along (4 MB array, L2 resident)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v4[u] = __ldg(mult + r4[u]);
         }
         const int gg = e0 / SUB, ee = e0 % SUB;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             key_s[ee + u][gg] = k4[u];
-            row_s[ee + u][gg] = p4[u].x;
-            val_s[ee + u][gg] = __uint_as_float(p4[u].y);
+            row_s[ee + u][gg] = r4[u];
+            val_s[ee + u][gg] = v4[u];
         }
     }
     if (tid == 0) {
@@ -747,7 +748,7 @@ void pull_plan(const ModelView& m, int64_t n_rows, int* blk_shift, int* n_blocks
     static int block_mb = -1;  // SFM_PULL_BLOCK_MB: S bytes per row block (0 = no blocking)
     if (block_mb < 0) {
         const char* e = getenv("SFM_PULL_BLOCK_MB");
-        block_mb = e ? atoi(e) : 16;
+        block_mb = e ? atoi(e) : 0;  // measured on C3: blocking does not pay (profiles/)
     }
     if (block_mb <= 0) {
         *blk_shift = 30;

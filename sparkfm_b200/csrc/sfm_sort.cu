@@ -28,6 +28,21 @@ cudaError_t sort_pairs(void* tmp, size_t tmp_bytes, const uint32_t* keys_in, uin
                                            reinterpret_cast<pay_t*>(pay_out), n, 0, end_bit, st);
 }
 
+size_t sort_pairs32_temp_bytes(int64_t n, int end_bit) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, end_bit);
+    return bytes;
+}
+
+cudaError_t sort_pairs32(void* tmp, size_t tmp_bytes, const uint32_t* keys_in, uint32_t* keys_out,
+                         const uint32_t* val_in, uint32_t* val_out, int64_t n, int end_bit,
+                         cudaStream_t st, int64_t* launches) {
+    *launches += 2 + (end_bit + 7) / 8;
+    return cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, val_in, val_out, n, 0,
+                                           end_bit, st);
+}
+
 size_t scan_temp_bytes(int64_t n) {
     size_t bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int64_t*)nullptr, (int64_t*)nullptr, n);
