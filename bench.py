@@ -276,16 +276,21 @@ def main():
                 ptrs.append(p)
             bufs.append(ptrs)
         h2d = (e2e_rows + 1) * 8 + e2e_rows * N_FIELDS * 4 + e2e_rows * 4
-        for s in range(3):
-            p = bufs[s % nb]
-            hd.train_step_csr_raw(it, p[0], p[1], None, p[2], e2e_rows)
-            it += 1
+        def run_pipelined(n_steps, it0):
+            # stage batch s+1 (async H2D on the copy stream) while batch s trains
+            p = bufs[0]
+            hd.stage_csr_raw(0, p[0], p[1], None, p[2], e2e_rows)
+            for s in range(n_steps):
+                if s + 1 < n_steps:
+                    q = bufs[(s + 1) % nb]
+                    hd.stage_csr_raw((s + 1) & 1, q[0], q[1], None, q[2], e2e_rows)
+                hd.train_step_staged(s & 1, it0 + s)
+            return it0 + n_steps
+
+        it = run_pipelined(3, it)
         barrier()
         t0 = time.perf_counter()
-        for s in range(args.e2e_steps):
-            p = bufs[s % nb]
-            hd.train_step_csr_raw(it, p[0], p[1], None, p[2], e2e_rows)
-            it += 1
+        it = run_pipelined(args.e2e_steps, it)
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -293,10 +298,27 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": e2e_rows * world * args.e2e_steps / float(tt[0]), "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 36, "steps": args.e2e_steps,
-               "timing": "wall clock around the C-ABI calls (each returns after its D2H read)"}
+               "api": "sfm_stage_csr (pinned host CSR -> device, copy stream) + "
+                      "sfm_train_step_staged (returns the mean loss)",
+               "timing": "wall clock around the C-ABI calls, every H2D/D2H inside the timed region"}
         for ptrs in bufs:
             for p in ptrs:
                 L.sfm_host_free(p)
+
+    # ---- predict rows/s (FMModel.predict over resident rows; outputs copied back to the host)
+    n_pred = min(n_local, 4_000_000)
+    hd.predict_resident(0, n_pred)
+    barrier()
+    hd.timer_start()
+    for _ in range(3):
+        hd.predict_resident(0, n_pred)
+    pms = hd.timer_stop() / 3
+    pred_rows_s = n_pred / (pms * 1e-3)
+    predict = {"value": pred_rows_s * world, "unit": "rows/s", "rows_per_call": n_pred,
+               "ms_per_call": pms,
+               "roofline_frac": pred_rows_s * (4 * N_FIELDS * (K + 3) + 4) / 1e9 / peak,
+               "note": "sfm_predict_resident incl. the D2H copy of the predictions; algorithmic "
+                       "bytes 4m(k+3)+4 per row"}
 
     # ---- CPU baseline (rank 0, N = 1 only)
     cpu = None
@@ -317,7 +339,8 @@ def main():
                        "parallelism": f"dp{world}",
                        "l2": "inputs larger than L2: each step streams a fresh sampled batch "
                              "(>=156 MB of indices out of a 7 GB resident set)"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "predict": predict,
+            "gpu_launches": int(launches),
             "clocks": clk, "loss_first_last": [float(hist[0]), float(hist[-1])],
         }
         print(json.dumps(line), flush=True)

@@ -178,6 +178,16 @@ int32_t sfm_train_step(sfm_handle* h, const int64_t* row_ids, int64_t n_ids, int
 int32_t sfm_train_step_csr(sfm_handle* h, const int64_t* row_ptr, const int32_t* idx,
                            const float* val, const float* label, int64_t n_rows, int64_t iter,
                            double* mean_loss_out, int64_t* batch_out);
+/* Pipelined form of sfm_train_step_csr for streaming hosts: sfm_stage_csr queues the host->device
+ * copy of a mini-batch into staging slot 0 or 1 on the library's copy stream and returns at once
+ * (the host buffers must stay unchanged until the sfm_train_step_staged that consumes the slot
+ * returns; use sfm_host_alloc'd pinned memory for the copy to be asynchronous);
+ * sfm_train_step_staged runs the iteration on a staged slot.  Staging batch t+1 before training on
+ * batch t overlaps PCIe with compute. */
+int32_t sfm_stage_csr(sfm_handle* h, int32_t slot, const int64_t* row_ptr, const int32_t* idx,
+                      const float* val, const float* label, int64_t n_rows);
+int32_t sfm_train_step_staged(sfm_handle* h, int32_t slot, int64_t iter, double* mean_loss_out,
+                              int64_t* batch_out);
 /* The loop of FM.learnWith (fm/impl/FactorizationMachines.scala:42-46) with the built-in
  * sampler: iterations first_iter .. first_iter + n_iters - 1 on the resident data set, no host
  * round trip in between.  loss_history[n_iters] (may be NULL) gets each iteration's mean loss. */

@@ -161,54 +161,61 @@ static int download_v(sfm_handle* h, const float* dev_padded, float* v) {
     return SFM_OK;
 }
 
-// Copies a host CSR batch into the staging buffers and returns a view of it.
-static int stage_csr(sfm_handle* h, const int64_t* row_ptr, const int32_t* idx, const float* val,
-                     const float* label, int64_t n_rows, BatchView* out) {
+// Queues the copy of a host CSR batch into a staging slot on stream `st`.
+static int stage_csr(sfm_handle* h, Stage& sg, cudaStream_t st, const int64_t* row_ptr,
+                     const int32_t* idx, const float* val, const float* label, int64_t n_rows) {
+    sg.valid = false;
     if (n_rows < 0 || (n_rows > 0 && !row_ptr)) return set_err(h, SFM_ERR_ARG, "bad CSR arguments");
     const int64_t nnz = n_rows > 0 ? row_ptr[n_rows] - row_ptr[0] : 0;
     if (nnz < 0 || nnz >= 2147483647LL) return set_err(h, SFM_ERR_ARG, "batch nnz out of range [0, 2^31-1)");
     if (nnz > 0 && !idx) return set_err(h, SFM_ERR_ARG, "idx is NULL");
     if (n_rows > 0 && row_ptr[0] != 0) return set_err(h, SFM_ERR_INDEX, "row_ptr[0] must be 0");
-    RC(ensure(h, h->b_stage_rowptr, sizeof(int64_t) * (size_t)(n_rows + 1)));
-    RC(ensure(h, h->b_stage_idx, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1)));
-    if (val) RC(ensure(h, h->b_stage_val, sizeof(float) * (size_t)(nnz > 0 ? nnz : 1)));
-    if (label) RC(ensure(h, h->b_stage_label, sizeof(float) * (size_t)(n_rows > 0 ? n_rows : 1)));
+    RC(ensure(h, sg.rowptr, sizeof(int64_t) * (size_t)(n_rows + 1)));
+    RC(ensure(h, sg.idx, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1)));
+    if (val) RC(ensure(h, sg.val, sizeof(float) * (size_t)(nnz > 0 ? nnz : 1)));
+    if (label) RC(ensure(h, sg.label, sizeof(float) * (size_t)(n_rows > 0 ? n_rows : 1)));
     if (n_rows > 0) {
-        CU(cudaMemcpyAsync(h->b_stage_rowptr.p, row_ptr, sizeof(int64_t) * (size_t)(n_rows + 1),
-                           cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(sg.rowptr.p, row_ptr, sizeof(int64_t) * (size_t)(n_rows + 1),
+                           cudaMemcpyHostToDevice, st));
         h->stats.h2d_bytes += (int64_t)sizeof(int64_t) * (n_rows + 1);
         if (label) {
-            CU(cudaMemcpyAsync(h->b_stage_label.p, label, sizeof(float) * (size_t)n_rows,
-                               cudaMemcpyHostToDevice, h->stream));
+            CU(cudaMemcpyAsync(sg.label.p, label, sizeof(float) * (size_t)n_rows,
+                               cudaMemcpyHostToDevice, st));
             h->stats.h2d_bytes += (int64_t)sizeof(float) * n_rows;
         }
     } else {
-        CU(cudaMemsetAsync(h->b_stage_rowptr.p, 0, sizeof(int64_t), h->stream));
+        CU(cudaMemsetAsync(sg.rowptr.p, 0, sizeof(int64_t), st));
     }
     if (nnz > 0) {
-        CU(cudaMemcpyAsync(h->b_stage_idx.p, idx, sizeof(int32_t) * (size_t)nnz,
-                           cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(sg.idx.p, idx, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
         h->stats.h2d_bytes += (int64_t)sizeof(int32_t) * nnz;
         if (val) {
-            CU(cudaMemcpyAsync(h->b_stage_val.p, val, sizeof(float) * (size_t)nnz,
-                               cudaMemcpyHostToDevice, h->stream));
+            CU(cudaMemcpyAsync(sg.val.p, val, sizeof(float) * (size_t)nnz, cudaMemcpyHostToDevice, st));
             h->stats.h2d_bytes += (int64_t)sizeof(float) * nnz;
         }
     }
-    // row_ptr monotonicity is checked by the forward kernel (end < beg sets the error flag)
-    out->row_ptr = (const int64_t*)h->b_stage_rowptr.p;
-    out->idx = (const int32_t*)h->b_stage_idx.p;
-    out->val = val ? (const float*)h->b_stage_val.p : nullptr;
-    out->label = label ? (const float*)h->b_stage_label.p : nullptr;
+    // row_ptr monotonicity and bounds are checked by the forward kernel (error flag)
+    sg.n_rows = n_rows;
+    sg.nnz = nnz;
+    sg.has_val = val != nullptr;
+    sg.has_label = label != nullptr;
+    sg.valid = true;
+    return SFM_OK;
+}
+
+static void stage_view(const Stage& sg, BatchView* out) {
+    out->row_ptr = (const int64_t*)sg.rowptr.p;
+    out->idx = (const int32_t*)sg.idx.p;
+    out->val = sg.has_val ? (const float*)sg.val.p : nullptr;
+    out->label = sg.has_label ? (const float*)sg.label.p : nullptr;
     out->row_ids = nullptr;
     out->row_lo = 0;
-    out->n_rows = n_rows;
-    out->nnz = nnz;
-    out->idx_len = nnz;
-    out->out_ptr = (const int64_t*)h->b_stage_rowptr.p;
+    out->n_rows = sg.n_rows;
+    out->nnz = sg.nnz;
+    out->idx_len = sg.nnz;
+    out->out_ptr = (const int64_t*)sg.rowptr.p;
     out->out_base = 0;
     out->uniform_m = -1;
-    return SFM_OK;
 }
 
 static int read_err_flag(sfm_handle* h) {
@@ -501,6 +508,13 @@ int32_t sfm_create(const sfm_config* cfg, sfm_handle** out) {
     CK(cudaEventCreate(&h->ev_t0));
     CK(cudaEventCreate(&h->ev_t1));
     CK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+    for (Stage& sg : h->stage) CK(cudaEventCreateWithFlags(&sg.ready, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&h->ev_samp[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_used[i], cudaEventDisableTiming));
+    }
+    CK(cudaMalloc(&h->d_count2, sizeof(int32_t) * 2));
+    CK(cudaMallocHost(&h->h_count2, sizeof(int32_t) * 2));
     // one extra, always-zero row at index n_slots: the target of padded / rejected entries
     CK(cudaMalloc(&m.v, sizeof(float) * (size_t)(m.n_slots + 1) * m.kp));
     CK(cudaMalloc(&m.w, sizeof(float) * (size_t)(m.n_slots + 1)));
@@ -529,10 +543,25 @@ int32_t sfm_destroy(sfm_handle* h) {
     sfm_unload_dataset(h);
     Buf* bufs[] = {&h->b_row_ids, &h->b_out_ptr, &h->b_S, &h->b_mult, &h->b_loss, &h->b_yhat,
                    &h->b_keys[0], &h->b_keys[1], &h->b_pay[0], &h->b_pay[1], &h->b_seg,
-                   &h->b_sort_tmp, &h->b_grad, &h->b_partials, &h->b_stage_rowptr,
-                   &h->b_stage_idx, &h->b_stage_val, &h->b_stage_label, &h->b_sel_tmp, &h->b_lens,
+                   &h->b_sort_tmp, &h->b_grad, &h->b_partials, &h->b_sel_tmp, &h->b_lens,
                    &h->b_pull};
     for (Buf* b : bufs) free_buf(*b);
+    free_buf(h->b_ids2[0]);
+    free_buf(h->b_ids2[1]);
+    free_buf(h->b_samp_tmp);
+    if (h->d_count2) cudaFree(h->d_count2);
+    if (h->h_count2) cudaFreeHost(h->h_count2);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_samp[i]) cudaEventDestroy(h->ev_samp[i]);
+        if (h->ev_used[i]) cudaEventDestroy(h->ev_used[i]);
+    }
+    for (Stage& sg : h->stage) {
+        free_buf(sg.rowptr);
+        free_buf(sg.idx);
+        free_buf(sg.val);
+        free_buf(sg.label);
+        if (sg.ready) cudaEventDestroy(sg.ready);
+    }
     if (h->m.v) cudaFree(h->m.v);
     if (h->m.w) cudaFree(h->m.w);
     if (h->m.w0) cudaFree(h->m.w0);
@@ -756,7 +785,8 @@ int32_t sfm_predict(sfm_handle* h, const int64_t* row_ptr, const int32_t* idx, c
     if (n_rows > 0 && !out) return set_err(h, SFM_ERR_ARG, "out is NULL");
     CU(cudaSetDevice(h->device));
     BatchView b;
-    RC(stage_csr(h, row_ptr, idx, val, nullptr, n_rows, &b));
+    RC(stage_csr(h, h->stage[2], h->stream, row_ptr, idx, val, nullptr, n_rows));
+    stage_view(h->stage[2], &b);
     return predict_view(h, b, out);
 }
 
@@ -1045,9 +1075,56 @@ int32_t sfm_train_step_csr(sfm_handle* h, const int64_t* row_ptr, const int32_t*
     if (n_rows > 0 && !label) return set_err(h, SFM_ERR_ARG, "label is NULL");
     CU(cudaSetDevice(h->device));
     BatchView b;
-    RC(stage_csr(h, row_ptr, idx, val, label, n_rows, &b));
+    RC(stage_csr(h, h->stage[2], h->stream, row_ptr, idx, val, label, n_rows));
+    stage_view(h->stage[2], &b);
     RC(train_core(h, b, iter, false));
     return finish_step(h, mean_loss_out, batch_out);
+}
+
+int32_t sfm_stage_csr(sfm_handle* h, int32_t slot, const int64_t* row_ptr, const int32_t* idx,
+                      const float* val, const float* label, int64_t n_rows) {
+    if (!h) return SFM_ERR_ARG;
+    if (slot < 0 || slot > 1) return set_err(h, SFM_ERR_ARG, "slot must be 0 or 1");
+    if (n_rows > 0 && !label) return set_err(h, SFM_ERR_ARG, "label is NULL");
+    CU(cudaSetDevice(h->device));
+    Stage& sg = h->stage[slot];
+    RC(stage_csr(h, sg, h->copy_stream, row_ptr, idx, val, label, n_rows));
+    CU(cudaEventRecord(sg.ready, h->copy_stream));
+    return SFM_OK;
+}
+
+int32_t sfm_train_step_staged(sfm_handle* h, int32_t slot, int64_t iter, double* mean_loss_out,
+                              int64_t* batch_out) {
+    if (!h) return SFM_ERR_ARG;
+    if (slot < 0 || slot > 1) return set_err(h, SFM_ERR_ARG, "slot must be 0 or 1");
+    if (iter < 1) return set_err(h, SFM_ERR_ARG, "iter is 1-based");
+    Stage& sg = h->stage[slot];
+    if (!sg.valid) return set_err(h, SFM_ERR_STATE, "nothing staged in this slot");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamWaitEvent(h->stream, sg.ready, 0));
+    BatchView b;
+    stage_view(sg, &b);
+    RC(train_core(h, b, iter, false));
+    sg.valid = false;
+    return finish_step(h, mean_loss_out, batch_out);
+}
+
+// Queues the sampling of iteration `iter` into slot `slot` on the copy stream (it depends on the
+// seed only, so it runs while the previous iteration computes).
+static int sample_prefetch(sfm_handle* h, int64_t iter, int slot) {
+    const Dataset& ds = h->ds;
+    const double frac = (double)h->cfg.mini_batch_fraction;
+    const uint64_t thr = (uint64_t)floor(frac * 9007199254740992.0);
+    const uint64_t key = mix64(h->cfg.sampler_seed + (uint64_t)iter);
+    CU(cudaStreamWaitEvent(h->copy_stream, h->ev_used[slot], 0));  // slot's previous consumer
+    CU(sample_rows_device(h->b_samp_tmp.p, h->b_samp_tmp.cap, ds.n_rows, ds.global_offset, key, thr,
+                          (int32_t*)h->b_ids2[slot].p, h->d_count2 + slot, h->copy_stream,
+                          &h->stats.kernel_launches));
+    CU(cudaMemcpyAsync(h->h_count2 + slot, h->d_count2 + slot, sizeof(int32_t),
+                       cudaMemcpyDeviceToHost, h->copy_stream));
+    CU(cudaEventRecord(h->ev_samp[slot], h->copy_stream));
+    h->stats.d2h_bytes += 4;
+    return SFM_OK;
 }
 
 int32_t sfm_train(sfm_handle* h, int64_t first_iter, int64_t n_iters, double* loss_history) {
@@ -1055,17 +1132,43 @@ int32_t sfm_train(sfm_handle* h, int64_t first_iter, int64_t n_iters, double* lo
     if (!h->ds.loaded) return set_err(h, SFM_ERR_STATE, "no resident data set");
     if (first_iter < 1 || n_iters < 0) return set_err(h, SFM_ERR_ARG, "bad iteration range");
     CU(cudaSetDevice(h->device));
+    const Dataset& ds = h->ds;
+    const double frac = (double)h->cfg.mini_batch_fraction;
+    const bool sampled = frac < 1.0 && frac > 0.0 && ds.n_rows > 0;
+    if (sampled) {
+        for (int i = 0; i < 2; ++i) RC(ensure(h, h->b_ids2[i], sizeof(int32_t) * (size_t)ds.n_rows));
+        RC(ensure(h, h->b_samp_tmp, select_temp_bytes(ds.n_rows)));
+        CU(cudaEventRecord(h->ev_used[0], h->stream));
+        CU(cudaEventRecord(h->ev_used[1], h->stream));
+        if (n_iters > 0) RC(sample_prefetch(h, first_iter, 0));
+    }
     double* hist = nullptr;
     if (n_iters > 0) CU(cudaMallocHost(&hist, sizeof(double) * SC_N * (size_t)n_iters));
     int rc = SFM_OK;
     for (int64_t t = 0; t < n_iters && rc == SFM_OK; ++t) {
         const int32_t* ids_dev = nullptr;
         int64_t n = 0;
-        rc = sample_device(h, first_iter + t, &ids_dev, &n);
+        const int slot = (int)(t & 1);
+        if (sampled) {
+            if (cudaEventSynchronize(h->ev_samp[slot]) != cudaSuccess) {
+                rc = set_err(h, SFM_ERR_CUDA, "sampler prefetch failed");
+                break;
+            }
+            n = h->h_count2[slot];
+            ids_dev = (const int32_t*)h->b_ids2[slot].p;
+            if (cudaStreamWaitEvent(h->stream, h->ev_samp[slot], 0) != cudaSuccess)
+                rc = set_err(h, SFM_ERR_CUDA, "cudaStreamWaitEvent failed");
+            // next iteration's batch is drawn while this one computes
+            if (rc == SFM_OK && t + 1 < n_iters) rc = sample_prefetch(h, first_iter + t + 1, slot ^ 1);
+        } else {
+            rc = sample_device(h, first_iter + t, &ids_dev, &n);
+        }
         BatchView b;
         if (rc == SFM_OK) rc = resident_batch(h, ids_dev, n, &b);
         if (rc == SFM_OK && b.nnz >= 2147483647LL) rc = set_err(h, SFM_ERR_ARG, "batch nnz must be < 2^31-1");
         if (rc == SFM_OK) rc = train_core(h, b, first_iter + t, false);
+        if (rc == SFM_OK && sampled && cudaEventRecord(h->ev_used[slot], h->stream) != cudaSuccess)
+            rc = set_err(h, SFM_ERR_CUDA, "cudaEventRecord failed");
         if (rc == SFM_OK &&
             cudaMemcpyAsync(hist + SC_N * t, h->d_scal, sizeof(double) * SC_N,
                             cudaMemcpyDeviceToHost, h->stream) != cudaSuccess)
@@ -1073,6 +1176,7 @@ int32_t sfm_train(sfm_handle* h, int64_t first_iter, int64_t n_iters, double* lo
     }
     if (rc == SFM_OK) rc = read_err_flag(h);
     else cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->copy_stream);
     if (rc == SFM_OK && loss_history)
         for (int64_t t = 0; t < n_iters; ++t) {
             const double c = hist[SC_N * t + SC_COUNT];

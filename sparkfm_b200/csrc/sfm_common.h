@@ -30,6 +30,15 @@ struct Dataset {
     bool loaded = false;
 };
 
+// Device staging area of one host CSR mini-batch (slots 0/1: sfm_stage_csr, slot 2: the
+// synchronous entry points).
+struct Stage {
+    Buf rowptr, idx, val, label;
+    int64_t n_rows = 0, nnz = 0;
+    bool has_val = false, has_label = false, valid = false;
+    cudaEvent_t ready = nullptr;
+};
+
 // One mini-batch as the kernels see it.
 struct BatchView {
     const int64_t* row_ptr;  // CSR row pointers of the array the rows live in
@@ -70,8 +79,13 @@ struct sfm_handle {
     sfm::Dataset ds;
     // batch scratch (all growable)
     sfm::Buf b_row_ids, b_out_ptr, b_S, b_mult, b_loss, b_yhat, b_keys[2], b_pay[2], b_seg,
-        b_sort_tmp, b_grad, b_partials, b_stage_rowptr, b_stage_idx, b_stage_val, b_stage_label,
-        b_sel_tmp, b_lens, b_pull;
+        b_sort_tmp, b_grad, b_partials, b_sel_tmp, b_lens, b_pull;
+    sfm::Stage stage[3];
+    // sampler prefetch (sfm_train): ids / count of the NEXT iteration are produced on copy_stream
+    sfm::Buf b_ids2[2], b_samp_tmp;
+    int32_t* d_count2 = nullptr;   // [2] device
+    int32_t* h_count2 = nullptr;   // [2] pinned
+    cudaEvent_t ev_samp[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
     double* d_scal = nullptr;  // [SC_N] device
     int32_t* d_err = nullptr;  // device error flag
     int32_t* d_count = nullptr;  // device int (sampler count)

@@ -211,6 +211,30 @@ class Handle:
             C.byref(batch)))
         return float(loss.value), int(batch.value)
 
+    def stage_csr_raw(self, slot, row_ptr_p, idx_p, val_p, label_p, n_rows):
+        """Queue the H2D copy of a (pinned) host CSR batch into staging slot 0/1."""
+        self._ck(self._L.sfm_stage_csr(
+            self._h, int(slot), C.cast(row_ptr_p, C.POINTER(C.c_int64)),
+            C.cast(idx_p, C.POINTER(C.c_int32)),
+            C.cast(val_p, C.POINTER(C.c_float)) if val_p else None,
+            C.cast(label_p, C.POINTER(C.c_float)), int(n_rows)))
+
+    def stage_csr(self, slot, row_ptr, idx, val, label):
+        """numpy variant; the arrays must stay alive until the staged step has run."""
+        self._staged = getattr(self, "_staged", {})
+        arrs = (_arr(row_ptr, np.int64), _arr(idx, np.int32), _arr(val, np.float32),
+                _arr(label, np.float32))
+        self._staged[slot] = arrs
+        self._ck(self._L.sfm_stage_csr(self._h, int(slot), _p(arrs[0], C.c_int64),
+                                       _p(arrs[1], C.c_int32), _p(arrs[2], C.c_float),
+                                       _p(arrs[3], C.c_float), len(arrs[0]) - 1))
+
+    def train_step_staged(self, slot, it):
+        loss, batch = C.c_double(), C.c_int64()
+        self._ck(self._L.sfm_train_step_staged(self._h, int(slot), int(it), C.byref(loss),
+                                               C.byref(batch)))
+        return float(loss.value), int(batch.value)
+
     def train(self, first_iter, n_iters):
         hist = np.zeros(max(n_iters, 0), dtype=np.float64)
         self._ck(self._L.sfm_train(self._h, int(first_iter), int(n_iters), _p(hist, C.c_double)))
