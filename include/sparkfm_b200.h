@@ -45,6 +45,18 @@ typedef enum {
     SFM_ERR_STATE = -7   /* call not valid now (no dataset loaded, comm not initialised) */
 } sfm_status;
 
+/* Mini-batch samplers (neither exists in the reference).
+ * BERNOULLI: every iteration draws its own Bernoulli(mini_batch_fraction) sample (MLlib's
+ *   `sample(false, fraction, 42 + i)` semantics); the batch is transposed (sorted by feature)
+ *   inside every iteration.
+ * PARTITION: the rows are split ONCE into P = round(1 / mini_batch_fraction) disjoint random
+ *   mini-batches, iteration t uses batch (t - 1) mod P (epoch-wise sampling without
+ *   replacement).  The transposition of each batch is built at its first use and kept resident,
+ *   like the reference's cached `transposeInput` (DataSet.scala:48), so steady-state iterations
+ *   do no sorting.  mini_batch_fraction >= 1 is full-batch gradient descent either way. */
+#define SFM_SAMPLER_BERNOULLI 0
+#define SFM_SAMPLER_PARTITION 1
+
 #define SFM_TASK_REGRESSION 0     /* Task.Regression      (Task.scala:5) */
 #define SFM_TASK_CLASSIFICATION 1 /* Task.Classification  (Task.scala:5) */
 
@@ -64,8 +76,8 @@ typedef struct sfm_config {
     float regw;                /* L2 on w                               FMModel.scala:30    */
     float regv;                /* L2 on V                               FMModel.scala:31    */
     float step_size;           /* SGD step; eta_t = step_size / sqrt(t)                     */
-    float mini_batch_fraction; /* Bernoulli row-sampling rate per iteration, (0, 1]         */
-    int32_t reserved0;
+    float mini_batch_fraction; /* row-sampling rate per iteration, (0, 1]                   */
+    int32_t sampler_mode;      /* SFM_SAMPLER_*                                             */
     uint64_t sampler_seed;     /* iteration t samples with seed sampler_seed + t (MLlib: 42) */
 } sfm_config;
 
@@ -196,6 +208,10 @@ int32_t sfm_train(sfm_handle* h, int64_t first_iter, int64_t n_iters, double* lo
  * [row_lo, row_hi) selected in iteration iter.  out has capacity row_hi - row_lo. */
 int32_t sfm_sample_rows(uint64_t seed, int64_t iter, double fraction, int64_t row_lo,
                         int64_t row_hi, int64_t* out, int64_t* n_out);
+/* Host twin of the PARTITION sampler: global row ids of [row_lo, row_hi) that belong to
+ * mini-batch `part` of `n_parts` (row r is in part (mix64(mix64(seed) ^ mix64(r)) >> 11) % n_parts). */
+int32_t sfm_partition_rows(uint64_t seed, int64_t n_parts, int64_t part, int64_t row_lo,
+                           int64_t row_hi, int64_t* out, int64_t* n_out);
 /* Gradient of the current model on resident rows, no update: grad_v[n_slots][k], grad_w[n_slots],
  * grad_w0 (any may be NULL), loss_sum.  After sfm_comm_init the result is the sum over ranks.
  * For tests and for hosts that run their own updater. */

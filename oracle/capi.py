@@ -60,6 +60,8 @@ def lib():
                                         C.c_double, C.c_int64, dp, C.c_int]
         L.fmo_sample_rows.restype = C.c_int64
         L.fmo_sample_rows.argtypes = [C.c_uint64, C.c_int64, C.c_double, C.c_int64, C.c_int64, lp]
+        L.fmo_partition_rows.restype = C.c_int64
+        L.fmo_partition_rows.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, lp]
         L.fmo_init_v.restype = None
         L.fmo_init_v.argtypes = [dp, C.c_int64, C.c_double, C.c_double, C.c_uint64]
         L.fmo_max_threads.restype = C.c_int
@@ -151,6 +153,18 @@ def sample_rows(seed, it, fraction, row_lo, row_hi):
     out = np.empty(max(row_hi - row_lo, 0), dtype=np.int64)
     n = lib().fmo_sample_rows(seed, it, fraction, row_lo, row_hi, _l(out))
     return out[:n].copy()
+
+
+def partition_rows(seed, n_parts, part, row_lo, row_hi):
+    out = np.empty(max(row_hi - row_lo, 0), dtype=np.int64)
+    n = lib().fmo_partition_rows(seed, n_parts, part, row_lo, row_hi, _l(out))
+    return out[:n].copy()
+
+
+def n_parts_for(fraction):
+    """P = round(1 / fraction), at least 1 (fraction is the fp32 value that crosses the ABI)."""
+    f = float(np.float32(fraction))
+    return 1 if f >= 1.0 else max(1, int(np.floor(1.0 / f + 0.5)))
 
 
 def max_threads():

@@ -262,6 +262,16 @@ int64_t fmo_sample_rows(uint64_t seed, int64_t iter, double fraction, int64_t ro
     return n;
 }
 
+int64_t fmo_partition_rows(uint64_t seed, int64_t n_parts, int64_t part, int64_t row_lo,
+                           int64_t row_hi, int64_t* out) {
+    const uint64_t key = fmo_mix64(seed);
+    int64_t n = 0;
+    for (int64_t r = row_lo; r < row_hi; ++r)
+        if ((int64_t)((fmo_mix64(key ^ fmo_mix64((uint64_t)r)) >> 11) % (uint64_t)n_parts) == part)
+            out[n++] = r;
+    return n;
+}
+
 void fmo_init_v(double* v, int64_t count, double mean, double stdev, uint64_t seed) {
     const uint64_t s = fmo_mix64(seed);
     const double two_pi = 6.283185307179586476925286766559;

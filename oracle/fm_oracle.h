@@ -107,6 +107,11 @@ double fmo_train_step_mt(const fmo_params* p, double* w0, double* w, double* v,
 int64_t fmo_sample_rows(uint64_t seed, int64_t iter, double fraction, int64_t row_lo,
                         int64_t row_hi, int64_t* out);
 
+/* PARTITION sampler: row r belongs to mini-batch
+ * (mix64(mix64(seed) ^ mix64(r)) >> 11) % n_parts; iteration t uses mini-batch (t-1) % n_parts. */
+int64_t fmo_partition_rows(uint64_t seed, int64_t n_parts, int64_t part, int64_t row_lo,
+                           int64_t row_hi, int64_t* out);
+
 /* Seeded N(mean, stdev^2) initialisation of V (the reference's init at
  * FMModel.scala:19-22 ignores its seed, so this is a documented replacement): element e gets
  * Box-Muller of u1 = ((mix64(s+2e) >> 11) + 1) * 2^-53, u2 = (mix64(s+2e+1) >> 11) * 2^-53

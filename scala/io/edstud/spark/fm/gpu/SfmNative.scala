@@ -25,7 +25,7 @@ object SfmNative {
         JAVA_INT.withName("k0"), JAVA_INT.withName("k1"), JAVA_INT.withName("device"),
         JAVA_LONG.withName("n_slots"), JAVA_FLOAT.withName("reg0"), JAVA_FLOAT.withName("regw"),
         JAVA_FLOAT.withName("regv"), JAVA_FLOAT.withName("step_size"),
-        JAVA_FLOAT.withName("mini_batch_fraction"), JAVA_INT.withName("reserved0"),
+        JAVA_FLOAT.withName("mini_batch_fraction"), JAVA_INT.withName("sampler_mode"),
         JAVA_LONG.withName("sampler_seed"))
 
     val create       = fn("sfm_create", JAVA_INT, ADDRESS, ADDRESS)

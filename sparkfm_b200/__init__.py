@@ -4,8 +4,9 @@ this package is the ctypes binding plus a Python mirror of the reference's opera
 from . import _lib  # noqa: F401
 from .api import (DataSet, FM, FMLearn, FMModel, FMUtils, FMWithSGD, FactorizationMachines,  # noqa: F401
                   LabeledPoint, Model, SGD, SparseVector, Task)
-from .handle import Handle, device_count, format_libfm, parse_libfm, sample_rows  # noqa: F401
+from .handle import (Handle, device_count, format_libfm, parse_libfm, partition_rows,  # noqa: F401
+                     sample_rows)
 
 __all__ = ["DataSet", "FM", "FMLearn", "FMModel", "FMUtils", "FMWithSGD", "FactorizationMachines",
            "LabeledPoint", "Model", "SGD", "SparseVector", "Task", "Handle", "device_count",
-           "format_libfm", "parse_libfm", "sample_rows"]
+           "format_libfm", "parse_libfm", "partition_rows", "sample_rows"]

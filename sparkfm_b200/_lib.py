@@ -24,7 +24,7 @@ class SfmConfig(C.Structure):
         ("abi_version", C.c_int32), ("task", C.c_int32), ("k", C.c_int32), ("k0", C.c_int32),
         ("k1", C.c_int32), ("device", C.c_int32), ("n_slots", C.c_int64),
         ("reg0", C.c_float), ("regw", C.c_float), ("regv", C.c_float),
-        ("step_size", C.c_float), ("mini_batch_fraction", C.c_float), ("reserved0", C.c_int32),
+        ("step_size", C.c_float), ("mini_batch_fraction", C.c_float), ("sampler_mode", C.c_int32),
         ("sampler_seed", C.c_uint64),
     ]
 
@@ -82,6 +82,8 @@ SIGNATURES = {
     "sfm_train": (C.c_int32, [_H, C.c_int64, C.c_int64, _f64p]),
     "sfm_sample_rows": (C.c_int32, [C.c_uint64, C.c_int64, C.c_double, C.c_int64, C.c_int64,
                                     _i64p, _i64p]),
+    "sfm_partition_rows": (C.c_int32, [C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                       _i64p, _i64p]),
     "sfm_gradient": (C.c_int32, [_H, _i64p, C.c_int64, _f32p, _f32p, _f32p, _f64p, _i64p]),
     "sfm_comm_unique_id": (C.c_int32, [_u8p]),
     "sfm_comm_init": (C.c_int32, [_H, _u8p, C.c_int32, C.c_int32]),

@@ -229,19 +229,27 @@ static int read_err_flag(sfm_handle* h) {
 // The launch sequence of one SGD iteration on one rank.  Asynchronous: the caller
 // synchronises.  If grad_keep, the (all-reduced) dense gradient stays in h->b_grad and no update
 // is applied.
-static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad_keep) {
+static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad_keep,
+                      const PartCache* pc = nullptr) {
     ModelView& m = h->m;
     const int64_t n = b.n_rows, nnz = b.nnz;
     int64_t* L = &h->stats.kernel_launches;
     RC(ensure(h, h->b_S, sizeof(float) * (size_t)(n > 0 ? n : 1) * m.kp));
     RC(ensure(h, h->b_mult, sizeof(float) * (size_t)(n > 0 ? n : 1)));
     RC(ensure(h, h->b_loss, sizeof(float) * (size_t)(n > 0 ? n : 1)));
-    for (int i = 0; i < 2; ++i) {
-        RC(ensure(h, h->b_keys[i], sizeof(uint32_t) * (size_t)(nnz > 0 ? nnz : 1)));
-        RC(ensure(h, h->b_pay[i], sizeof(uint2) * (size_t)(nnz > 0 ? nnz : 1)));
-    }
+    const bool binary = b.val == nullptr;  // all-ones data: 4-byte payload (the row)
+    if (!pc)
+        for (int i = 0; i < 2; ++i) {
+            RC(ensure(h, h->b_keys[i], sizeof(uint32_t) * (size_t)(nnz > 0 ? nnz : 1)));
+            RC(ensure(h, h->b_pay[i], (binary ? sizeof(uint32_t) : sizeof(uint2)) * (size_t)(nnz > 0 ? nnz : 1)));
+        }
     int blk_shift = 30, n_blocks = 1;
-    pull_plan(m, n, &blk_shift, &n_blocks);
+    if (pc) {
+        blk_shift = pc->blk_shift;
+        n_blocks = pc->n_blocks;
+    } else {
+        pull_plan(m, n, &blk_shift, &n_blocks);
+    }
     const int key_bits = bits_for(m.n_slots);
     int blk_bits = 0;
     while (((int64_t)1 << blk_bits) < n_blocks) ++blk_bits;
@@ -251,8 +259,7 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     RC(ensure(h, h->b_pull, pull_scratch_bytes(m, nnz, n_blocks)));
     const int end_bit = key_bits + blk_bits;
     size_t sort_bytes = 0;
-    const bool binary = b.val == nullptr;  // all-ones data: 4-byte payload (the row)
-    if (nnz > 0) {
+    if (nnz > 0 && !pc) {
         sort_bytes = binary ? sort_pairs32_temp_bytes(nnz, end_bit) : sort_pairs_temp_bytes(nnz, end_bit);
         RC(ensure(h, h->b_sort_tmp, sort_bytes));
     }
@@ -269,8 +276,8 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     o.mult = (float*)h->b_mult.p;
     o.loss = (float*)h->b_loss.p;
     o.yhat = nullptr;
-    o.keys = (uint32_t*)h->b_keys[0].p;
-    o.pay = (uint2*)h->b_pay[0].p;
+    o.keys = pc ? nullptr : (uint32_t*)h->b_keys[0].p;   // cached transposition: nothing to emit
+    o.pay = pc ? nullptr : (uint2*)h->b_pay[0].p;
     o.key_bits = key_bits;
     o.blk_shift = blk_shift;
     CU(launch_forward(m, b, o, true, h->d_err, h->sm_count, h->stream, L));
@@ -280,9 +287,9 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
         RC(nccl_allreduce_f64(h->nccl, h->comm, h->d_scal, SC_N, h->stream, &h->err));
         pt.lap(&h->stats.ms_allreduce);
     }
-    const uint32_t* keys_sorted = (const uint32_t*)h->b_keys[1].p;
-    const uint2* pay_sorted = (const uint2*)h->b_pay[1].p;
-    if (nnz > 0) {
+    const uint32_t* keys_sorted = pc ? (const uint32_t*)pc->keys.p : (const uint32_t*)h->b_keys[1].p;
+    const uint2* pay_sorted = pc ? (const uint2*)pc->pay.p : (const uint2*)h->b_pay[1].p;
+    if (nnz > 0 && !pc) {
         if (binary)
             CU(sort_pairs32(h->b_sort_tmp.p, sort_bytes, o.keys, (uint32_t*)h->b_keys[1].p,
                             (const uint32_t*)o.pay, (uint32_t*)h->b_pay[1].p, nnz, end_bit,
@@ -391,6 +398,115 @@ static int sample_device(sfm_handle* h, int64_t iter, const int32_t** ids_dev, i
     return SFM_OK;
 }
 
+static void free_parts(sfm_handle* h) {
+    for (PartCache& pc : h->parts) {
+        free_buf(pc.row_ids);
+        free_buf(pc.keys);
+        free_buf(pc.pay);
+    }
+    h->parts.clear();
+}
+
+static int64_t n_parts_for(const sfm_handle* h) {
+    const double f = (double)h->cfg.mini_batch_fraction;
+    if (!(f < 1.0)) return 1;
+    const int64_t p = (int64_t)floor(1.0 / f + 0.5);
+    return p < 1 ? 1 : p;
+}
+
+// Fixed mini-batch of iteration `iter` under the PARTITION sampler (or the whole data set when
+// mini_batch_fraction >= 1): builds its resident transposition at first use (select rows, emit
+// the entry list, stable radix sort by feature) and returns the cached view.
+static int partition_batch(sfm_handle* h, int64_t iter, BatchView* b, const PartCache** out) {
+    const Dataset& ds = h->ds;
+    const int64_t P = n_parts_for(h);
+    if ((int64_t)h->parts.size() != P) {
+        CU(cudaStreamSynchronize(h->stream));
+        free_parts(h);
+        h->parts.resize((size_t)P);
+    }
+    const int64_t part = (iter - 1) % P;
+    PartCache& pc = h->parts[(size_t)part];
+    int64_t* L = &h->stats.kernel_launches;
+    if (!pc.built) {
+        const int32_t* ids_dev = nullptr;
+        int64_t n = ds.n_rows;
+        if (P > 1) {
+            RC(ensure(h, h->b_row_ids, sizeof(int32_t) * (size_t)(ds.n_rows > 0 ? ds.n_rows : 1)));
+            n = 0;
+            if (ds.n_rows > 0) {
+                const size_t sb = select_temp_bytes(ds.n_rows);
+                RC(ensure(h, h->b_sel_tmp, sb));
+                CU(partition_rows_device(h->b_sel_tmp.p, sb, ds.n_rows, ds.global_offset,
+                                         mix64(h->cfg.sampler_seed), P, part,
+                                         (int32_t*)h->b_row_ids.p, h->d_count, h->stream, L));
+                CU(cudaMemcpyAsync(h->h_flags + 1, h->d_count, sizeof(int32_t),
+                                   cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaStreamSynchronize(h->stream));
+                n = h->h_flags[1];
+            }
+            RC(ensure(h, pc.row_ids, sizeof(int32_t) * (size_t)(n > 0 ? n : 1)));
+            if (n > 0)
+                CU(cudaMemcpyAsync(pc.row_ids.p, h->b_row_ids.p, sizeof(int32_t) * (size_t)n,
+                                   cudaMemcpyDeviceToDevice, h->stream));
+            ids_dev = (const int32_t*)pc.row_ids.p;
+        }
+        BatchView v;
+        RC(resident_batch(h, ids_dev, n, &v));   // ragged rows: output offsets via scan
+        if (v.nnz >= 2147483647LL) return set_err(h, SFM_ERR_ARG, "batch nnz must be < 2^31-1");
+        pull_plan(h->m, n, &pc.blk_shift, &pc.n_blocks);
+        pc.key_bits = bits_for(h->m.n_slots);
+        int blk_bits = 0;
+        while (((int64_t)1 << blk_bits) < pc.n_blocks) ++blk_bits;
+        if (pc.key_bits + blk_bits > 32) return set_err(h, SFM_ERR_ARG, "sort key does not fit 32 bits");
+        const bool binary = v.val == nullptr;
+        const size_t pay_sz = binary ? sizeof(uint32_t) : sizeof(uint2);
+        const size_t cnt = (size_t)(v.nnz > 0 ? v.nnz : 1);
+        RC(ensure(h, h->b_keys[0], sizeof(uint32_t) * cnt));
+        RC(ensure(h, h->b_pay[0], pay_sz * cnt));
+        RC(ensure(h, pc.keys, sizeof(uint32_t) * cnt));
+        RC(ensure(h, pc.pay, pay_sz * cnt));
+        if (v.nnz > 0) {
+            CU(launch_emit(v, pc.key_bits, pc.blk_shift, h->m.n_slots, (uint32_t*)h->b_keys[0].p,
+                           (uint2*)h->b_pay[0].p, h->sm_count, h->stream, L));
+            const int end_bit = pc.key_bits + blk_bits;
+            const size_t sb = binary ? sort_pairs32_temp_bytes(v.nnz, end_bit)
+                                     : sort_pairs_temp_bytes(v.nnz, end_bit);
+            RC(ensure(h, h->b_sort_tmp, sb));
+            if (binary)
+                CU(sort_pairs32(h->b_sort_tmp.p, sb, (const uint32_t*)h->b_keys[0].p,
+                                (uint32_t*)pc.keys.p, (const uint32_t*)h->b_pay[0].p,
+                                (uint32_t*)pc.pay.p, v.nnz, end_bit, h->stream, L));
+            else
+                CU(sort_pairs(h->b_sort_tmp.p, sb, (const uint32_t*)h->b_keys[0].p,
+                              (uint32_t*)pc.keys.p, (const uint2*)h->b_pay[0].p, (uint2*)pc.pay.p,
+                              v.nnz, end_bit, h->stream, L));
+        }
+        pc.n_rows = n;
+        pc.nnz = v.nnz;
+        pc.built = true;
+    }
+    // steady state: no scan, no sort -- the forward only needs the row list
+    b->row_ptr = ds.row_ptr;
+    b->idx = ds.idx;
+    b->val = ds.val;
+    b->label = ds.label;
+    b->row_ids = P > 1 ? (const int32_t*)pc.row_ids.p : nullptr;
+    b->row_lo = 0;
+    b->n_rows = pc.n_rows;
+    b->nnz = pc.nnz;
+    b->idx_len = ds.nnz;
+    b->out_ptr = nullptr;
+    b->out_base = 0;
+    b->uniform_m = ds.uniform_m;
+    *out = &pc;
+    return SFM_OK;
+}
+
+static bool use_partitions(const sfm_handle* h) {
+    return h->cfg.sampler_mode == SFM_SAMPLER_PARTITION || !((double)h->cfg.mini_batch_fraction < 1.0);
+}
+
 static int finish_step(sfm_handle* h, double* mean_loss_out, int64_t* batch_out) {
     CU(cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(double) * SC_N, cudaMemcpyDeviceToHost,
                        h->stream));
@@ -472,6 +588,8 @@ int32_t sfm_create(const sfm_config* cfg, sfm_handle** out) {
     if ((cfg->n_slots + 1) * (int64_t)(kp_for(cfg->k) / 4) >= 4294967296LL)
         return SFM_ERR_ARG;  // V row offsets are 32-bit float4 indices in the kernels
     if (cfg->task != SFM_TASK_REGRESSION && cfg->task != SFM_TASK_CLASSIFICATION) return SFM_ERR_ARG;
+    if (cfg->sampler_mode != SFM_SAMPLER_BERNOULLI && cfg->sampler_mode != SFM_SAMPLER_PARTITION)
+        return SFM_ERR_ARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -713,6 +831,7 @@ int32_t sfm_save(sfm_handle* h, const char* path) {
     hd.reg0 = h->cfg.reg0; hd.regw = h->cfg.regw; hd.regv = h->cfg.regv;
     hd.step_size = h->cfg.step_size; hd.mini_batch_fraction = h->cfg.mini_batch_fraction;
     hd.sampler_seed = h->cfg.sampler_seed;
+    hd.pad = (uint32_t)h->cfg.sampler_mode;
     FILE* f = fopen(path, "wb");
     if (!f) return set_err(h, SFM_ERR_IO, std::string("cannot open for writing: ") + path);
     bool ok = fwrite(&hd, sizeof hd, 1, f) == 1 && fwrite(&w0, sizeof w0, 1, f) == 1 &&
@@ -747,6 +866,7 @@ int32_t sfm_load(const char* path, int32_t device, sfm_handle** out) {
     cfg.n_slots = hd.n_slots; cfg.reg0 = hd.reg0; cfg.regw = hd.regw; cfg.regv = hd.regv;
     cfg.step_size = hd.step_size; cfg.mini_batch_fraction = hd.mini_batch_fraction;
     cfg.sampler_seed = hd.sampler_seed;
+    cfg.sampler_mode = (int32_t)hd.pad;
     sfm_handle* h = nullptr;
     RC(sfm_create(&cfg, &h));
     const int rc = sfm_set_model(h, w0, wf.data(), vf.empty() ? nullptr : vf.data());
@@ -795,6 +915,7 @@ int32_t sfm_unload_dataset(sfm_handle* h) {
     if (!h) return SFM_ERR_ARG;
     Dataset& ds = h->ds;
     if (h->stream) cudaStreamSynchronize(h->stream);
+    free_parts(h);
     if (ds.row_ptr) cudaFree(ds.row_ptr);
     if (ds.idx) cudaFree(ds.idx);
     if (ds.val) cudaFree(ds.val);
@@ -1057,6 +1178,12 @@ int32_t sfm_train_step(sfm_handle* h, const int64_t* row_ids, int64_t n_ids, int
         if (n_ids < 0 || (n_ids > 0 && !row_ids)) return set_err(h, SFM_ERR_ARG, "bad row id list");
         RC(upload_row_ids(h, row_ids, n_ids, &ids_dev));
         n = n_ids;
+    } else if (use_partitions(h)) {
+        BatchView pb;
+        const PartCache* pc = nullptr;
+        RC(partition_batch(h, iter, &pb, &pc));
+        RC(train_core(h, pb, iter, false, pc));
+        return finish_step(h, mean_loss_out, batch_out);
     } else {
         RC(sample_device(h, iter, &ids_dev, &n));
     }
@@ -1134,7 +1261,8 @@ int32_t sfm_train(sfm_handle* h, int64_t first_iter, int64_t n_iters, double* lo
     CU(cudaSetDevice(h->device));
     const Dataset& ds = h->ds;
     const double frac = (double)h->cfg.mini_batch_fraction;
-    const bool sampled = frac < 1.0 && frac > 0.0 && ds.n_rows > 0;
+    const bool parts = use_partitions(h);
+    const bool sampled = !parts && frac < 1.0 && frac > 0.0 && ds.n_rows > 0;
     if (sampled) {
         for (int i = 0; i < 2; ++i) RC(ensure(h, h->b_ids2[i], sizeof(int32_t) * (size_t)ds.n_rows));
         RC(ensure(h, h->b_samp_tmp, select_temp_bytes(ds.n_rows)));
@@ -1160,13 +1288,18 @@ int32_t sfm_train(sfm_handle* h, int64_t first_iter, int64_t n_iters, double* lo
                 rc = set_err(h, SFM_ERR_CUDA, "cudaStreamWaitEvent failed");
             // next iteration's batch is drawn while this one computes
             if (rc == SFM_OK && t + 1 < n_iters) rc = sample_prefetch(h, first_iter + t + 1, slot ^ 1);
-        } else {
+        } else if (!parts) {
             rc = sample_device(h, first_iter + t, &ids_dev, &n);
         }
         BatchView b;
-        if (rc == SFM_OK) rc = resident_batch(h, ids_dev, n, &b);
-        if (rc == SFM_OK && b.nnz >= 2147483647LL) rc = set_err(h, SFM_ERR_ARG, "batch nnz must be < 2^31-1");
-        if (rc == SFM_OK) rc = train_core(h, b, first_iter + t, false);
+        const PartCache* pc = nullptr;
+        if (parts) {
+            rc = partition_batch(h, first_iter + t, &b, &pc);
+        } else {
+            if (rc == SFM_OK) rc = resident_batch(h, ids_dev, n, &b);
+            if (rc == SFM_OK && b.nnz >= 2147483647LL) rc = set_err(h, SFM_ERR_ARG, "batch nnz must be < 2^31-1");
+        }
+        if (rc == SFM_OK) rc = train_core(h, b, first_iter + t, false, pc);
         if (rc == SFM_OK && sampled && cudaEventRecord(h->ev_used[slot], h->stream) != cudaSuccess)
             rc = set_err(h, SFM_ERR_CUDA, "cudaEventRecord failed");
         if (rc == SFM_OK &&

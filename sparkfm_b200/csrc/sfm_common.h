@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/sparkfm_b200.h"
 
@@ -37,6 +38,16 @@ struct Stage {
     int64_t n_rows = 0, nnz = 0;
     bool has_val = false, has_label = false, valid = false;
     cudaEvent_t ready = nullptr;
+};
+
+// Resident transposition of one fixed mini-batch (PARTITION sampler / full batch): the batch's
+// entries sorted by (feature, batch position), built at first use -- the analogue of the
+// reference's cached `transposeInput` (DataSet.scala:48).
+struct PartCache {
+    bool built = false;
+    int64_t n_rows = 0, nnz = 0;
+    int key_bits = 0, blk_shift = 30, n_blocks = 1;
+    Buf row_ids, keys, pay;
 };
 
 // One mini-batch as the kernels see it.
@@ -81,6 +92,7 @@ struct sfm_handle {
     sfm::Buf b_row_ids, b_out_ptr, b_S, b_mult, b_loss, b_yhat, b_keys[2], b_pay[2], b_seg,
         b_sort_tmp, b_grad, b_partials, b_sel_tmp, b_lens, b_pull;
     sfm::Stage stage[3];
+    std::vector<sfm::PartCache> parts;  // PARTITION sampler caches (size P)
     // sampler prefetch (sfm_train): ids / count of the NEXT iteration are produced on copy_stream
     sfm::Buf b_ids2[2], b_samp_tmp;
     int32_t* d_count2 = nullptr;   // [2] device
@@ -144,6 +156,10 @@ cudaError_t launch_update(const ModelView& m, const float* grad, const double* d
 // per-row evaluation sums {sum (y-yhat)^2, sum (y-yhat), #sign agree, sum logloss} -> out[4]
 cudaError_t launch_metrics(const float* yhat, const float* label, int64_t n, double* partials,
                            double* out4, cudaStream_t st, int64_t* launches);
+// writes the (key, payload) entry list of a batch without running the model (partition caches)
+cudaError_t launch_emit(const BatchView& b, int key_bits, int blk_shift, int64_t n_slots,
+                        uint32_t* keys, uint2* pay, int sm_count, cudaStream_t st,
+                        int64_t* launches);
 cudaError_t launch_row_lens(const int64_t* row_ptr, const int32_t* row_ids, int64_t n,
                             int64_t* lens, cudaStream_t st, int64_t* launches);
 cudaError_t launch_idx_range(const int32_t* idx, int64_t nnz, int32_t* d_minmax, cudaStream_t st,
@@ -170,6 +186,9 @@ size_t scan_temp_bytes(int64_t n);
 cudaError_t exclusive_scan_i64(void* tmp, size_t tmp_bytes, const int64_t* in, int64_t* out,
                                int64_t n, cudaStream_t st, int64_t* launches);
 size_t select_temp_bytes(int64_t n);
+cudaError_t partition_rows_device(void* tmp, size_t tmp_bytes, int64_t n, int64_t global_off,
+                                  uint64_t key, int64_t n_parts, int64_t part, int32_t* out_rows,
+                                  int32_t* d_count, cudaStream_t st, int64_t* launches);
 // Bernoulli row sampler of DESIGN.md section 2.5 over local rows [0, n): global id = off + r
 cudaError_t sample_rows_device(void* tmp, size_t tmp_bytes, int64_t n, int64_t global_off,
                                uint64_t key, uint64_t thr, int32_t* out_rows, int32_t* d_count,

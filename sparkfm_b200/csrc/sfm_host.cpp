@@ -262,3 +262,15 @@ extern "C" int32_t sfm_sample_rows(uint64_t seed, int64_t iter, double fraction,
     *n_out = n;
     return SFM_OK;
 }
+
+extern "C" int32_t sfm_partition_rows(uint64_t seed, int64_t n_parts, int64_t part, int64_t row_lo,
+                                      int64_t row_hi, int64_t* out, int64_t* n_out) {
+    if (!n_out || (row_hi > row_lo && !out) || n_parts < 1 || part < 0 || part >= n_parts)
+        return SFM_ERR_ARG;
+    const uint64_t key = mix64(seed);
+    int64_t n = 0;
+    for (int64_t r = row_lo; r < row_hi; ++r)
+        if ((int64_t)((mix64(key ^ mix64((uint64_t)r)) >> 11) % (uint64_t)n_parts) == part) out[n++] = r;
+    *n_out = n;
+    return SFM_OK;
+}

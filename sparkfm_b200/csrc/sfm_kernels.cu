@@ -208,7 +208,7 @@ fm_forward_kernel(const float4* __restrict__ V4, const float* __restrict__ W,
                 if ((uint32_t)ia > (uint32_t)zrow) ia = zrow;
                 if ((uint32_t)ib > (uint32_t)zrow) ib = zrow;
             }
-            if (TRAIN) {
+            if (TRAIN && keys != nullptr) {  // (nullptr: the transposition is cached)
                 // entry list for the reduce-by-feature: key = block | feature, payload = {row, x}
                 // (8 bytes) or, for all-ones data, just the row (4 bytes: less to sort)
                 if (j0 < end) {
@@ -890,6 +890,63 @@ cudaError_t launch_update(const ModelView& m, const float* grad, const double* d
     fm_update_kernel<<<(unsigned)blocks, 256, 0, st>>>((float4*)m.v, m.w, m.w0, nv4, m.n_slots,
                                                        m.k0, m.k1, (const float4*)grad, gw,
                                                        gw + m.n_slots, d_scal, d_err, up);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Entry list of a batch without the model: key = (row block << key_bits) | feature,
+// payload = row (all-ones data) or {row, x}.  Used once per fixed mini-batch (PARTITION sampler).
+// ------------------------------------------------------------------------------------------
+template <bool HAS_VAL>
+__global__ void __launch_bounds__(256)
+emit_entries_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ idx,
+                    const float* __restrict__ val, const int32_t* __restrict__ row_ids,
+                    int64_t row_lo, int64_t n_rows, const int64_t* __restrict__ out_ptr,
+                    int64_t out_base, int uniform_m, int key_bits, int blk_shift, int64_t n_slots,
+                    uint32_t* __restrict__ keys, uint2* __restrict__ pay) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t pos = warp0; pos < n_rows; pos += nwarps) {
+        const int64_t r = row_ids ? (int64_t)__ldg(row_ids + pos) : row_lo + pos;
+        int64_t beg, end;
+        if (uniform_m >= 0) {
+            beg = r * uniform_m;
+            end = beg + uniform_m;
+        } else {
+            beg = __ldg(row_ptr + r);
+            end = __ldg(row_ptr + r + 1);
+        }
+        const int64_t obase = out_ptr ? __ldg(out_ptr + pos) - out_base : pos * (int64_t)uniform_m;
+        const uint32_t kpre = (uint32_t)(pos >> blk_shift) << key_bits;
+        for (int64_t j = beg + lane; j < end; j += 32) {
+            const int id = __ldg(idx + j);
+            const bool ok = (uint32_t)id < (uint64_t)n_slots;  // validated at load; belt and braces
+            keys[obase + (j - beg)] = kpre | (ok ? (uint32_t)id : 0u);
+            if (HAS_VAL)
+                pay[obase + (j - beg)] = make_uint2((uint32_t)pos, ok ? __float_as_uint(__ldg(val + j)) : 0u);
+            else
+                reinterpret_cast<uint32_t*>(pay)[obase + (j - beg)] = (uint32_t)pos;
+        }
+    }
+}
+
+cudaError_t launch_emit(const BatchView& b, int key_bits, int blk_shift, int64_t n_slots,
+                        uint32_t* keys, uint2* pay, int sm_count, cudaStream_t st,
+                        int64_t* launches) {
+    if (b.n_rows <= 0) return cudaSuccess;
+    ++*launches;
+    int64_t blocks = (b.n_rows + 7) / 8;
+    const int64_t cap = (int64_t)sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (b.val)
+        emit_entries_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(
+            b.row_ptr, b.idx, b.val, b.row_ids, b.row_lo, b.n_rows, b.out_ptr, b.out_base,
+            b.uniform_m, key_bits, blk_shift, n_slots, keys, pay);
+    else
+        emit_entries_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(
+            b.row_ptr, b.idx, b.val, b.row_ids, b.row_lo, b.n_rows, b.out_ptr, b.out_base,
+            b.uniform_m, key_bits, blk_shift, n_slots, keys, pay);
     return cudaGetLastError();
 }
 

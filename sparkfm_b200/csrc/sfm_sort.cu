@@ -71,6 +71,24 @@ struct InBatch {
     }
 };
 
+// PARTITION sampler: row r (global) belongs to part (mix64(key ^ mix64(r)) >> 11) % n_parts.
+struct InPart {
+    uint64_t key, n_parts, part;
+    int64_t off;
+    __host__ __device__ bool operator()(const int32_t& r) const {
+        return ((mix64_s(key ^ mix64_s((uint64_t)(off + r))) >> 11) % n_parts) == part;
+    }
+};
+
+cudaError_t partition_rows_device(void* tmp, size_t tmp_bytes, int64_t n, int64_t global_off,
+                                  uint64_t key, int64_t n_parts, int64_t part, int32_t* out_rows,
+                                  int32_t* d_count, cudaStream_t st, int64_t* launches) {
+    *launches += 2;
+    cub::CountingInputIterator<int32_t> it(0);
+    return cub::DeviceSelect::If(tmp, tmp_bytes, it, out_rows, d_count, (int)n,
+                                 InPart{key, (uint64_t)n_parts, (uint64_t)part, global_off}, st);
+}
+
 size_t select_temp_bytes(int64_t n) {
     size_t bytes = 0;
     cub::CountingInputIterator<int32_t> it(0);

@@ -25,11 +25,13 @@ def _arr(a, dt):
 
 class Handle:
     def __init__(self, n_slots, k, task=REGRESSION, k0=True, k1=True, reg=(0.0, 0.0, 0.0),
-                 step_size=0.1, mini_batch_fraction=1.0, sampler_seed=42, device=0):
+                 step_size=0.1, mini_batch_fraction=1.0, sampler_seed=42, device=0,
+                 sampler_mode=0):
         self._L = _lib.load()
         cfg = SfmConfig(_lib.SFM_ABI_VERSION, int(task), int(k), int(bool(k0)), int(bool(k1)),
                         int(device), int(n_slots), float(reg[0]), float(reg[1]), float(reg[2]),
-                        float(step_size), float(mini_batch_fraction), 0, int(sampler_seed))
+                        float(step_size), float(mini_batch_fraction), int(sampler_mode),
+                        int(sampler_seed))
         self._h = C.c_void_p()
         check(self._L.sfm_create(C.byref(cfg), C.byref(self._h)))
         self.n_slots, self.k = int(n_slots), int(k)
@@ -296,6 +298,16 @@ def sample_rows(seed, it, fraction, row_lo, row_hi):
     n = C.c_int64()
     check(L.sfm_sample_rows(int(seed), int(it), float(fraction), int(row_lo), int(row_hi),
                             _p(out, C.c_int64), C.byref(n)))
+    return out[:n.value].copy()
+
+
+def partition_rows(seed, n_parts, part, row_lo, row_hi):
+    """Host twin of the PARTITION sampler through the C ABI."""
+    L = _lib.load()
+    out = np.empty(max(row_hi - row_lo, 0), dtype=np.int64)
+    n = C.c_int64()
+    check(L.sfm_partition_rows(int(seed), int(n_parts), int(part), int(row_lo), int(row_hi),
+                               _p(out, C.c_int64), C.byref(n)))
     return out[:n.value].copy()
 
 

@@ -390,3 +390,64 @@ def test_criteo_shaped_small_slice_trains_like_oracle():
         lg, batch = hd.train_step(it)
         assert batch == len(ids) and abs(lg - lo) <= LOSS_RTOL * lo, (it, lg, lo)
     hd.close()
+
+
+# ------------------------------------------------------------------------------ PARTITION sampler
+def test_partition_sampler_matches_oracle_and_explicit_rows():
+    """SFM_SAMPLER_PARTITION: rows split once into P = round(1/fraction) disjoint mini-batches,
+    iteration t uses batch (t-1) mod P, transposition cached at first use.  Same loss curve as the
+    oracle fed the same row lists, and bitwise the same model as passing those rows explicitly
+    (which sorts inside every iteration) -- over more than one epoch, so cached batches are reused."""
+    rng = np.random.default_rng(71)
+    n_slots, k, n_rows, frac = 1500, 16, 5000, 0.26        # P = round(3.85) = 4
+    row_ptr, idx, val = synth.ragged_rows(n_rows, n_slots, 18, seed=71, values="normal")
+    label = np.where(rng.random(n_rows) < 0.4, 1.0, -1.0).astype(np.float32)
+    w0, w, v = make_model(rng, n_slots, k, 0.05, 0.05)
+    P = ocapi.n_parts_for(frac)
+    assert P == 4
+    parts = [ocapi.partition_rows(42, P, p, 0, n_rows) for p in range(P)]
+    assert sorted(np.concatenate(parts).tolist()) == list(range(n_rows))      # a partition
+    from sparkfm_b200 import partition_rows
+    assert all(np.array_equal(partition_rows(42, P, p, 0, n_rows), parts[p]) for p in range(P))
+    kw = dict(task=1, reg=(0.0, 1e-4, 1e-3), step_size=0.4, mini_batch_fraction=frac, sampler_seed=42)
+    a = Handle(n_slots, k, sampler_mode=1, **kw)
+    b = Handle(n_slots, k, sampler_mode=0, **kw)
+    orc = OracleFM(n_slots, k, task=1, reg=(0.0, float(np.float32(1e-4)), float(np.float32(1e-3))))
+    orc.set_model(w0, w, v)
+    for h in (a, b):
+        h.set_model(w0, w, v)
+        h.load_dataset(row_ptr, idx, val, label)
+    hist = a.train(1, 6)                                    # device loop, first epoch builds caches
+    for it in range(1, 11):
+        ids = parts[(it - 1) % P]
+        la = hist[it - 1] if it <= 6 else a.train_step(it)[0]
+        lb, nb = b.train_step(it, ids)                      # explicit rows: per-iteration sort
+        lo = orc.train_step(row_ptr, idx, val.astype(np.float64), label, ids, it,
+                            float(np.float32(0.4))) / len(ids)
+        assert nb == len(ids) and la == lb
+        assert abs(la - lo) <= LOSS_RTOL * abs(lo), (it, la, lo)
+    ma, mb = a.get_model(), b.get_model()
+    assert ma[0] == mb[0] and np.array_equal(ma[1], mb[1]) and np.array_equal(ma[2], mb[2])
+    a.close()
+    b.close()
+
+
+def test_partition_sampler_uniform_all_ones_rows():
+    """The Criteo-shaped layout (uniform one-hot rows, no value array) through the cached path."""
+    n_slots, k, n_rows = 8000, 16, 20_000
+    rp, idx, _, label = synth.ctr_csr(0, n_rows, 39, n_slots, 9)
+    kw = dict(task=1, reg=(0, 0, 1e-4), step_size=0.2, mini_batch_fraction=0.2, sampler_seed=5)
+    a = Handle(n_slots, k, sampler_mode=1, **kw)
+    b = Handle(n_slots, k, sampler_mode=0, **kw)
+    for h in (a, b):
+        h.init_model(0.0, 0.01, 3)
+        h.load_dataset(rp, idx, None, label)
+    P = ocapi.n_parts_for(0.2)
+    la = a.train(1, 12)
+    for it in range(1, 13):
+        lb, _ = b.train_step(it, ocapi.partition_rows(5, P, (it - 1) % P, 0, n_rows))
+        assert la[it - 1] == lb
+    ma, mb = a.get_model(), b.get_model()
+    assert np.array_equal(ma[2], mb[2]) and np.array_equal(ma[1], mb[1])
+    a.close()
+    b.close()
