@@ -69,18 +69,22 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md).  The poller is started before the
+    warm-up (nvidia-smi needs ~0.2 s to come up); only samples whose timestamp falls inside the
+    timed region are kept -- if the region is shorter than one poll, the samples taken under load
+    since the warm-up are used and `window` says so."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -89,23 +93,37 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=3)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        ok = [(t, r) for t, r in self.rows if len(r) >= 10 and r[2].replace(".", "").isdigit()]
+        inside = [r for t, r in ok if self.t0 is not None and self.t0 <= t <= self.t1 + 0.05]
+        window = "timed region"
+        if not inside:
+            inside = [r for t, r in ok if self.t0 is None or t <= self.t1 + 0.05][-8:]
+            window = "warm-up + timed region (timed region shorter than one poll)"
+        sm = [float(r[2]) for r in inside]
+        mx = [float(r[3]) for r in inside if r[3].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for j, n in enumerate(names)
-                   if any(len(r) >= 9 and r[5 + j].lower().startswith("active") for r in self.rows)]
+                   if any(r[6 + j].lower().startswith("active") for r in inside)]
         return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm),
+                "window": window}
 
 
 def cpu_oracle_throughput(batch_rows, steps, threads, rows_total=1_500_000):
@@ -136,7 +154,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     per_step = 1_000_000
-    val, threads, sample = cpu_oracle_throughput(per_step, max(args.steps, 1), None)
+    val, threads, sample = cpu_oracle_throughput(per_step, min(max(args.steps, 1), 120), None)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step / val * 1e3,
@@ -151,18 +169,40 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """stdout must carry exactly one JSON line: library chatter (NCCL prints its version banner to
+    stdout) is diverted to stderr at the file-descriptor level; emit() writes to the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=45_000_000, help="data set rows (whole job)")
     ap.add_argument("--batch", type=int, default=1_000_000, help="mini-batch rows per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-partition", action="store_true")
@@ -207,16 +247,18 @@ def main():
 
     # ---- resident arm: warm-up, then exactly K steps, device-timed
     it = 1
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     hd.train(it, args.warmup)
     it += args.warmup
     hd.stats_reset()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     barrier()
+    clocks.mark_begin()
     hd.timer_start()
     hist = hd.train(it, args.steps)
     ms = hd.timer_stop()
     barrier()
+    clocks.mark_end()
     clk = clocks.stop()
     it += args.steps
     st = hd.stats()
@@ -370,7 +412,7 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, threads, sample = cpu_oracle_throughput(args.batch, 4, None)
+        v, threads, sample = cpu_oracle_throughput(args.batch, 60, None)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": sample + "; CPU restatement (OpenMP), not Spark local[N]"}
 
@@ -391,7 +433,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk, "loss_first_last": [float(hist[0]), float(hist[-1])],
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     hd.close()
     if world > 1:
         dist.destroy_process_group()
