@@ -216,6 +216,7 @@ static void stage_view(const Stage& sg, BatchView* out) {
     out->out_ptr = (const int64_t*)sg.rowptr.p;
     out->out_base = 0;
     out->uniform_m = -1;
+    out->validated = false;
 }
 
 static int read_err_flag(sfm_handle* h) {
@@ -332,6 +333,7 @@ static int resident_batch(sfm_handle* h, const int32_t* ids_dev, int64_t n_ids, 
     b->row_lo = 0;
     b->idx_len = ds.nnz;
     b->uniform_m = ds.uniform_m;
+    b->validated = true;   // sfm_load_dataset / sfm_synth_ctr_dataset checked the index range
     b->out_base = 0;
     if (!ids_dev) {
         b->n_rows = ds.n_rows;
@@ -499,6 +501,7 @@ static int partition_batch(sfm_handle* h, int64_t iter, BatchView* b, const Part
     b->out_ptr = nullptr;
     b->out_base = 0;
     b->uniform_m = ds.uniform_m;
+    b->validated = true;
     *out = &pc;
     return SFM_OK;
 }

@@ -64,6 +64,7 @@ struct BatchView {
     const int64_t* out_ptr;  // batch position -> first output slot (+out_base), nullptr = pos*m
     int64_t out_base;
     int32_t uniform_m;
+    bool validated = false;  // idx already checked against n_slots (resident data set)
 };
 
 struct ModelView {
