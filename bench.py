@@ -293,8 +293,22 @@ def main():
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     step_bytes = (rows_all / args.steps) * b_train(N_FIELDS, K) + world * b_step(N_SLOTS, K)
     step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            tj = json.load(fh)
+        key = {"fm_forward_kernel": "fm_forward_onehot16_kernel",
+               "fm_pull_kernel": "fm_pull_chunks_kernel"}[dom]
+        traffic = tj[key]["dram_bytes_per_launch"]
+        if dom == "fm_pull_kernel":
+            traffic += tj["fm_pull_finalize_kernel"]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "ncu --set full capture of the same kernel(s), dram__bytes_read.sum"
+                                  " + dram__bytes_write.sum per launch (profiles/ncu_traffic.json)",
+                "algorithmic_bytes_per_launch": dom_bytes, "peak_source": peak_src,
                 "step": {"achieved": step_gbs, "frac": step_gbs / (peak * world),
                          "note": "whole step incl. sort/scan overhead, algorithmic bytes "
                                  "8m(k+2)+4 per sample + 12(1+n_slots(k+1)) per step"},
