@@ -1,0 +1,164 @@
+#!/usr/bin/env python
+"""Runs BASELINE.json configs 1, 2 and 4 at FULL size on one B200 through the public API, checks
+the per-iteration loss against the fp64 CPU oracle where the oracle finishes in seconds (C1, C2)
+and size-independent properties elsewhere, and writes gpurun_out/configs_r1.json.
+(Config 3 is bench.py; config 5 is bench.py under torchrun at N = 1, 2, 4, 8.)"""
+import json
+import os
+import sys
+import time
+
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")  # the oracle's OpenMP team must not spin
+import numpy as np  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import capi as ocapi  # noqa: E402
+from oracle.capi import OracleFM  # noqa: E402
+from sparkfm_b200 import FMUtils, Handle, synth  # noqa: E402
+
+OUT = {}
+
+
+def timed_steps(hd, it0, n):
+    """Device-timed (CUDA events on the library's stream); best of two runs of n iterations."""
+    best = None
+    for rep in range(2):
+        hd.synchronize()
+        hd.timer_start()
+        hist = hd.train(it0 + rep * n, n)
+        ms = hd.timer_stop()
+        best = ms if best is None else min(best, ms)
+    return hist, best / n
+
+
+def config1():
+    """100k x 10k LIBSVM-format binary classification, ~20 nnz/row, k=8, logistic, full batch."""
+    row_ptr, idx, val, label = synth.classification_c1()
+    t0 = time.perf_counter()
+    text = synth.to_libfm_text(row_ptr, idx, val, label).encode()
+    t_text = time.perf_counter() - t0
+    path = "/tmp/c1.libfm"
+    open(path, "wb").write(text)
+    t0 = time.perf_counter()
+    ds = FMUtils.loadLibFMFile(path)
+    t_parse = time.perf_counter() - t0
+    assert np.array_equal(ds.idx, idx) and np.array_equal(ds.row_ptr, row_ptr)      # bit-exact packing
+    assert np.array_equal(ds.val, val.astype(np.float64)) and ds.dimension == int(idx.max())
+    n_slots, k = ds.dimension + 1, 8
+    reg, step = (0.0, 1e-4, 1e-4), 1.0
+    hd = Handle(n_slots, k, task=1, reg=reg, step_size=step, mini_batch_fraction=1.0)
+    hd.init_model(0.0, 0.01, 1)
+    w0, w, v = hd.get_model()
+    hd.load_dataset(ds.row_ptr, ds.idx, ds.val, ds.labels)
+    orc = OracleFM(n_slots, k, task=1, reg=tuple(float(np.float32(r)) for r in reg))
+    orc.set_model(w0, w, v)
+    ids = np.arange(ds.size, dtype=np.int64)
+    worst = 0.0
+    losses = []
+    for it in range(1, 9):
+        lo = orc.train_step(ds.row_ptr, ds.idx, ds.val, ds.labels, ids, it, step, threads=8) / ds.size
+        lg, batch = hd.train_step(it)
+        assert batch == ds.size
+        worst = max(worst, abs(lg - lo) / lo)
+        losses.append(lg)
+    assert worst < 1e-4, worst
+    hist, ms = timed_steps(hd, 9, 50)
+    pred = hd.predict_resident(0, ds.size)
+    want = orc.predict(ds.row_ptr, ds.idx, ds.val, fast=True, threads=8)
+    # models have drifted apart by fp32 rounding over 8+ steps; compare predictions of the SAME model
+    o2 = OracleFM(n_slots, k, task=1)
+    o2.set_model(*hd.get_model())
+    want = o2.predict(ds.row_ptr, ds.idx, ds.val, fast=True, threads=8)
+    perr = float(np.max(np.abs(pred - want) / np.maximum(np.abs(want), np.mean(np.abs(want)))))
+    assert perr < 1e-5, perr
+    OUT["C1"] = {"rows": ds.size, "n_slots": n_slots, "k": k, "nnz": int(ds.row_ptr[-1]),
+                 "text_bytes": len(text), "parse_s": t_parse, "parse_MBps": len(text) / t_parse / 1e6,
+                 "loss_rel_err_max_8_iters": worst, "loss_first_last": [losses[0], float(hist[-1])],
+                 "ms_per_full_batch_step": ms, "samples_per_s": ds.size / (ms * 1e-3),
+                 "predict_rel_err_max": perr, "accuracy": hd.evaluate()["accuracy"]}
+    hd.close()
+
+
+def config2():
+    """1M x 100k regression, ~50 nnz/row, values N(0,1), k=16, squared loss, miniBatchFraction 0.1."""
+    row_ptr, idx, val, y = synth.regression_c2()
+    n_rows, n_slots, k = len(y), 100_000, 16
+    reg, step, frac = (0.0, 1e-4, 1e-3), 0.02, 0.1
+    hd = Handle(n_slots, k, task=0, reg=reg, step_size=step, mini_batch_fraction=frac, sampler_seed=42)
+    hd.init_model(0.0, 0.01, 1)
+    w0, w, v = hd.get_model()
+    hd.load_dataset(row_ptr, idx, val, y)
+    orc = OracleFM(n_slots, k, task=0, reg=tuple(float(np.float32(r)) for r in reg))
+    orc.set_model(w0, w, v)
+    v64 = val.astype(np.float64)
+    worst = 0.0
+    f32 = float(np.float32(frac))
+    s32 = float(np.float32(step))
+    losses = []
+    for it in range(1, 11):
+        ids = ocapi.sample_rows(42, it, f32, 0, n_rows)
+        lo = orc.train_step(row_ptr, idx, v64, y, ids, it, s32, threads=8) / len(ids)
+        lg, batch = hd.train_step(it)
+        assert batch == len(ids)
+        worst = max(worst, abs(lg - lo) / lo)
+        losses.append(lg)
+    assert worst < 1e-4, worst
+    hist, ms = timed_steps(hd, 11, 100)
+    rows = hd.stats()["train_rows"]
+    ev = hd.evaluate()
+    OUT["C2"] = {"rows": n_rows, "n_slots": n_slots, "k": k, "nnz": int(row_ptr[-1]),
+                 "loss_rel_err_max_10_iters": worst, "loss_first_last": [losses[0], float(hist[-1])],
+                 "ms_per_step": ms, "batch_rows": int(round(n_rows * frac)),
+                 "samples_per_s": n_rows * frac / (ms * 1e-3), "rmse_after": ev["rmse"],
+                 "train_rows_total": rows}
+    hd.close()
+
+
+def config4():
+    """Avazu-shaped: 24 one-hot fields, 10M hashed features, k=64, logistic -- model REPLICATED on
+    one GPU here (row-sharded V is not implemented in round 1)."""
+    n_fields, n_slots, k, n_rows, batch = 24, 10_000_000, 64, 8_000_000, 500_000
+    card = synth.ctr_field_log2_cards(n_fields)
+    cdf, off = synth.zipf_tables(card)
+    res = {}
+    for mode, name in ((0, "bernoulli"), (1, "partition")):
+        hd = Handle(n_slots, k, task=1, reg=(0.0, 0.0, 1e-5), step_size=0.1,
+                    mini_batch_fraction=batch / n_rows, sampler_seed=42, sampler_mode=mode)
+        hd.init_model(0.0, 0.01, 1)
+        hd.synth_ctr_dataset(n_rows, 0, card, cdf, off, 20260104)
+        n_parts = round(n_rows / batch)
+        warm = n_parts if mode == 1 else 3
+        h0 = hd.train(1, warm)
+        hist, ms = timed_steps(hd, warm + 1, 20)
+        res[name] = {"ms_per_step": ms, "samples_per_s": batch / (ms * 1e-3),
+                     "loss_first_last": [float(h0[0]), float(hist[-1])]}
+        assert hist[-1] < h0[0]
+        if mode == 0:
+            # determinism at full size: rerun from the same state gives the same bits
+            a = Handle(n_slots, k, task=1, reg=(0.0, 0.0, 1e-5), step_size=0.1,
+                       mini_batch_fraction=batch / n_rows, sampler_seed=42)
+            a.init_model(0.0, 0.01, 1)
+            a.synth_ctr_dataset(n_rows, 0, card, cdf, off, 20260104)
+            ha = a.train(1, warm)
+            assert np.array_equal(ha, h0)
+            a.close()
+            res["bitwise_rerun"] = True
+        hd.close()
+    m = n_fields
+    res.update({"rows": n_rows, "n_slots": n_slots, "k": k, "batch": batch,
+                "algorithmic_bytes_per_sample": 8 * m * (k + 2) + 4,
+                "roofline_samples_per_s": 6554.2e9 / (8 * m * (k + 2) + 4)})
+    OUT["C4_replicated_1gpu"] = res
+
+
+if __name__ == "__main__":
+    for fn in (config1, config2, config4):
+        t0 = time.perf_counter()
+        fn()
+        print(fn.__name__, "ok", f"{time.perf_counter() - t0:.1f}s", flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "configs_r1.json"), "w") as fh:
+        json.dump(OUT, fh, indent=1)
+    print(json.dumps(OUT, indent=1))
