@@ -56,6 +56,12 @@ typedef enum {
  *   do no sorting.  mini_batch_fraction >= 1 is full-batch gradient descent either way. */
 #define SFM_SAMPLER_BERNOULLI 0
 #define SFM_SAMPLER_PARTITION 1
+/* OR-ed into sfm_config.sampler_mode: row-shard V and w over the ranks of the communicator
+ * (BASELINE config 4: "V row-sharded across GPUs with all-to-all row gather").  Rank g owns the
+ * features [g*ceil(n_slots/G), ...); the parameters are allocated by sfm_comm_init, so the model
+ * calls (init / set / get / save) and every predict / train call come after it and are
+ * COLLECTIVE: every rank makes them, each with its own rows.  sfm_gradient is not available. */
+#define SFM_FLAG_SHARD_V 0x100
 
 #define SFM_TASK_REGRESSION 0     /* Task.Regression      (Task.scala:5) */
 #define SFM_TASK_CLASSIFICATION 1 /* Task.Classification  (Task.scala:5) */

@@ -126,24 +126,28 @@ static size_t grad_len(const sfm_handle* h) {
 }
 
 // Upload an unpadded [n_slots][k] fp32 host matrix into the padded device V.
-static int upload_v(sfm_handle* h, const float* v) {
+// Uploads `rows` rows of an unpadded [rows][k] fp32 host matrix into a padded device matrix.
+static int upload_v_rows(sfm_handle* h, float* dst, const float* v, int64_t rows) {
     const ModelView& m = h->m;
+    if (rows <= 0) return SFM_OK;
     if (m.k == 0 || !v) {
-        CU(cudaMemsetAsync(m.v, 0, sizeof(float) * (size_t)m.n_slots * m.kp, h->stream));
+        CU(cudaMemsetAsync(dst, 0, sizeof(float) * (size_t)rows * m.kp, h->stream));
         return SFM_OK;
     }
-    const size_t bytes = sizeof(float) * (size_t)m.n_slots * m.k;
+    const size_t bytes = sizeof(float) * (size_t)rows * m.k;
     if (m.k == m.kp) {
-        CU(cudaMemcpyAsync(m.v, v, bytes, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(dst, v, bytes, cudaMemcpyHostToDevice, h->stream));
     } else {
         RC(ensure(h, h->b_grad, bytes));
         CU(cudaMemcpyAsync(h->b_grad.p, v, bytes, cudaMemcpyHostToDevice, h->stream));
-        CU(launch_pad_v((const float*)h->b_grad.p, m.v, m.n_slots, m.k, m.kp, false, h->stream,
+        CU(launch_pad_v((const float*)h->b_grad.p, dst, rows, m.k, m.kp, false, h->stream,
                         &h->stats.kernel_launches));
     }
     h->stats.h2d_bytes += (int64_t)bytes;
     return SFM_OK;
 }
+
+static int upload_v(sfm_handle* h, const float* v) { return upload_v_rows(h, h->m.v, v, h->m.n_slots); }
 
 static int download_v(sfm_handle* h, const float* dev_padded, float* v) {
     const ModelView& m = h->m;
@@ -160,6 +164,14 @@ static int download_v(sfm_handle* h, const float* dev_padded, float* v) {
     h->stats.d2h_bytes += (int64_t)bytes;
     return SFM_OK;
 }
+
+static bool is_sharded(const sfm_handle* h) { return h->shard != nullptr; }
+
+#define NEED_MODEL(h)                                                                          \
+    do {                                                                                       \
+        if ((h)->shard_requested && !(h)->shard)                                               \
+            return set_err((h), SFM_ERR_STATE, "SFM_FLAG_SHARD_V: call sfm_comm_init first");  \
+    } while (0)
 
 // Queues the copy of a host CSR batch into a staging slot on stream `st`.
 static int stage_csr(sfm_handle* h, Stage& sg, cudaStream_t st, const int64_t* row_ptr,
@@ -227,11 +239,34 @@ static int read_err_flag(sfm_handle* h) {
     return SFM_OK;
 }
 
+// Row-sharded models index a lookup table with the raw feature ids, so host-supplied batches are
+// range-checked first (resident data sets were checked when they were loaded).
+static int validate_view(sfm_handle* h, const BatchView& b) {
+    if (b.validated || b.nnz <= 0) return SFM_OK;
+    int32_t* mm = h->d_count + 1;
+    const int32_t init[2] = {INT32_MAX, INT32_MIN};
+    RC(ensure_pinned(h, 64));
+    memcpy(h->h_pinned, init, sizeof init);
+    CU(cudaMemcpyAsync(mm, h->h_pinned, sizeof init, cudaMemcpyHostToDevice, h->stream));
+    CU(launch_idx_range(b.idx, b.nnz, mm, h->stream, &h->stats.kernel_launches));
+    CU(cudaMemcpyAsync(h->h_flags + 4, mm, sizeof init, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->h_flags[4] < 0 || (int64_t)h->h_flags[5] >= h->m.n_slots)
+        return set_err(h, SFM_ERR_INDEX, "feature index outside [0, n_slots) in the batch");
+    return SFM_OK;
+}
+
 // The launch sequence of one SGD iteration on one rank.  Asynchronous: the caller
 // synchronises.  If grad_keep, the (all-reduced) dense gradient stays in h->b_grad and no update
 // is applied.
 static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad_keep,
                       const PartCache* pc = nullptr) {
+    NEED_MODEL(h);
+    if (is_sharded(h)) {
+        if (grad_keep) return set_err(h, SFM_ERR_STATE, "sfm_gradient is not available with SFM_FLAG_SHARD_V");
+        RC(validate_view(h, b));
+        return shard_train(h, b, iter);
+    }
     ModelView& m = h->m;
     const int64_t n = b.n_rows, nnz = b.nnz;
     int64_t* L = &h->stats.kernel_launches;
@@ -506,6 +541,28 @@ static int partition_batch(sfm_handle* h, int64_t iter, BatchView* b, const Part
     return SFM_OK;
 }
 
+// View of the resident rows [lo, hi) whose output offsets start at 0 (needed when the entry list
+// of a sub-range is materialised: row-sharded predict / evaluate).
+static int subrange_view(sfm_handle* h, int64_t lo, int64_t hi, BatchView* b) {
+    const Dataset& ds = h->ds;
+    b->row_lo = lo;
+    b->n_rows = hi - lo;
+    if (ds.uniform_m >= 0) {
+        b->nnz = (hi - lo) * ds.uniform_m;
+        b->out_ptr = nullptr;
+        b->out_base = 0;
+        return SFM_OK;
+    }
+    int64_t* ends = (int64_t*)(h->h_flags + 8);  // 2 x int64
+    CU(cudaMemcpyAsync(ends, ds.row_ptr + lo, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(ends + 1, ds.row_ptr + hi, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    b->nnz = ends[1] - ends[0];
+    b->out_ptr = ds.row_ptr + lo;
+    b->out_base = ends[0];
+    return SFM_OK;
+}
+
 static bool use_partitions(const sfm_handle* h) {
     return h->cfg.sampler_mode == SFM_SAMPLER_PARTITION || !((double)h->cfg.mini_batch_fraction < 1.0);
 }
@@ -591,7 +648,9 @@ int32_t sfm_create(const sfm_config* cfg, sfm_handle** out) {
     if ((cfg->n_slots + 1) * (int64_t)(kp_for(cfg->k) / 4) >= 4294967296LL)
         return SFM_ERR_ARG;  // V row offsets are 32-bit float4 indices in the kernels
     if (cfg->task != SFM_TASK_REGRESSION && cfg->task != SFM_TASK_CLASSIFICATION) return SFM_ERR_ARG;
-    if (cfg->sampler_mode != SFM_SAMPLER_BERNOULLI && cfg->sampler_mode != SFM_SAMPLER_PARTITION)
+    const int32_t sampler = cfg->sampler_mode & 0xFF;
+    if ((sampler != SFM_SAMPLER_BERNOULLI && sampler != SFM_SAMPLER_PARTITION) ||
+        (cfg->sampler_mode & ~(0xFF | SFM_FLAG_SHARD_V)))
         return SFM_ERR_ARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -602,6 +661,8 @@ int32_t sfm_create(const sfm_config* cfg, sfm_handle** out) {
     sfm_handle* h = new (std::nothrow) sfm_handle;
     if (!h) return SFM_ERR_OOM;
     h->cfg = *cfg;
+    h->cfg.sampler_mode = sampler;
+    h->shard_requested = (cfg->sampler_mode & SFM_FLAG_SHARD_V) != 0;
     h->device = cfg->device;
     ModelView& m = h->m;
     m.n_slots = cfg->n_slots;
@@ -637,16 +698,19 @@ int32_t sfm_create(const sfm_config* cfg, sfm_handle** out) {
     CK(cudaMalloc(&h->d_count2, sizeof(int32_t) * 2));
     CK(cudaMallocHost(&h->h_count2, sizeof(int32_t) * 2));
     // one extra, always-zero row at index n_slots: the target of padded / rejected entries
-    CK(cudaMalloc(&m.v, sizeof(float) * (size_t)(m.n_slots + 1) * m.kp));
-    CK(cudaMalloc(&m.w, sizeof(float) * (size_t)(m.n_slots + 1)));
+    // (row-sharded models allocate their shard in sfm_comm_init instead)
+    if (!h->shard_requested) {
+        CK(cudaMalloc(&m.v, sizeof(float) * (size_t)(m.n_slots + 1) * m.kp));
+        CK(cudaMalloc(&m.w, sizeof(float) * (size_t)(m.n_slots + 1)));
+    }
     CK(cudaMalloc(&m.w0, sizeof(float) * 4));
     CK(cudaMalloc(&h->d_scal, sizeof(double) * 8));
     CK(cudaMalloc(&h->d_err, sizeof(int32_t) * 4));
     CK(cudaMalloc(&h->d_count, sizeof(int32_t) * 4));
     CK(cudaMallocHost(&h->h_scal, sizeof(double) * 8));
-    CK(cudaMallocHost(&h->h_flags, sizeof(int32_t) * 8));
-    CK(cudaMemsetAsync(m.v, 0, sizeof(float) * (size_t)(m.n_slots + 1) * m.kp, h->stream));
-    CK(cudaMemsetAsync(m.w, 0, sizeof(float) * (size_t)(m.n_slots + 1), h->stream));
+    CK(cudaMallocHost(&h->h_flags, sizeof(int32_t) * 16));
+    if (m.v) CK(cudaMemsetAsync(m.v, 0, sizeof(float) * (size_t)(m.n_slots + 1) * m.kp, h->stream));
+    if (m.w) CK(cudaMemsetAsync(m.w, 0, sizeof(float) * (size_t)(m.n_slots + 1), h->stream));
     CK(cudaMemsetAsync(m.w0, 0, sizeof(float) * 4, h->stream));
     CK(cudaMemsetAsync(h->d_scal, 0, sizeof(double) * 8, h->stream));
     CK(cudaMemsetAsync(h->d_err, 0, sizeof(int32_t) * 4, h->stream));
@@ -667,6 +731,17 @@ int32_t sfm_destroy(sfm_handle* h) {
                    &h->b_sort_tmp, &h->b_grad, &h->b_partials, &h->b_sel_tmp, &h->b_lens,
                    &h->b_pull};
     for (Buf* b : bufs) free_buf(*b);
+    if (h->shard) {
+        ShardState& ss = *h->shard;
+        Buf* sb[] = {&ss.flags, &ss.crank, &ss.uniq, &ss.small, &ss.lut, &ss.req, &ss.out_v, &ss.out_w,
+                     &ss.t_v, &ss.t_w, &ss.bidx, &ss.bval, &ss.blabel, &ss.gr_v, &ss.gr_w, &ss.acc};
+        for (Buf* b : sb) free_buf(*b);
+        if (ss.v) cudaFree(ss.v);
+        if (ss.w) cudaFree(ss.w);
+        if (ss.h_small) cudaFreeHost(ss.h_small);
+        delete h->shard;
+        h->shard = nullptr;
+    }
     free_buf(h->b_ids2[0]);
     free_buf(h->b_ids2[1]);
     free_buf(h->b_samp_tmp);
@@ -706,6 +781,7 @@ const char* sfm_last_error(const sfm_handle* h) { return h ? h->err.c_str() : "n
 int32_t sfm_get_config(const sfm_handle* h, sfm_config* out) {
     if (!h || !out) return SFM_ERR_ARG;
     *out = h->cfg;
+    if (h->shard_requested) out->sampler_mode |= SFM_FLAG_SHARD_V;
     return SFM_OK;
 }
 
@@ -723,6 +799,7 @@ int32_t sfm_set_hyper(sfm_handle* h, float reg0, float regw, float regv, float s
 // ------------------------------------------------------------------------------ model ----
 int32_t sfm_set_model(sfm_handle* h, float w0, const float* w, const float* v) {
     if (!h) return SFM_ERR_ARG;
+    NEED_MODEL(h);
     CU(cudaSetDevice(h->device));
     ModelView& m = h->m;
     if (m.k > 0 && !v) return set_err(h, SFM_ERR_ARG, "v is NULL");
@@ -730,6 +807,19 @@ int32_t sfm_set_model(sfm_handle* h, float w0, const float* w, const float* v) {
     float* st = (float*)h->h_pinned;
     st[0] = w0;
     CU(cudaMemcpyAsync(m.w0, st, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    if (is_sharded(h)) {  // every rank is handed the full arrays and keeps its own rows
+        ShardState& ss = *h->shard;
+        if (ss.n_own > 0) {
+            if (w)
+                CU(cudaMemcpyAsync(ss.w, w + ss.own_lo, sizeof(float) * (size_t)ss.n_own,
+                                   cudaMemcpyHostToDevice, h->stream));
+            else
+                CU(cudaMemsetAsync(ss.w, 0, sizeof(float) * (size_t)ss.n_own, h->stream));
+            RC(upload_v_rows(h, ss.v, v ? v + (size_t)ss.own_lo * m.k : nullptr, ss.n_own));
+        }
+        CU(cudaStreamSynchronize(h->stream));
+        return SFM_OK;
+    }
     if (w) {
         CU(cudaMemcpyAsync(m.w, w, sizeof(float) * (size_t)m.n_slots, cudaMemcpyHostToDevice,
                            h->stream));
@@ -744,11 +834,28 @@ int32_t sfm_set_model(sfm_handle* h, float w0, const float* w, const float* v) {
 
 int32_t sfm_get_model(sfm_handle* h, float* w0, float* w, float* v) {
     if (!h) return SFM_ERR_ARG;
+    NEED_MODEL(h);
     CU(cudaSetDevice(h->device));
     ModelView& m = h->m;
     RC(ensure_pinned(h, 64));
     float* st = (float*)h->h_pinned;
     CU(cudaMemcpyAsync(st, m.w0, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (is_sharded(h)) {  // collective: all-gather the shards, then copy out like a replica
+        ShardState& ss = *h->shard;
+        const size_t rows = (size_t)ss.n_per * h->world;
+        RC(ensure(h, h->b_pull, sizeof(float) * rows * (m.kp + 1)));
+        float* gv = (float*)h->b_pull.p;
+        float* gw = gv + rows * m.kp;
+        RC(nccl_allgather_f32(h->nccl, h->comm, ss.v, gv, (size_t)ss.n_per * m.kp, h->stream, &h->err));
+        RC(nccl_allgather_f32(h->nccl, h->comm, ss.w, gw, (size_t)ss.n_per, h->stream, &h->err));
+        if (w)
+            CU(cudaMemcpyAsync(w, gw, sizeof(float) * (size_t)m.n_slots, cudaMemcpyDeviceToHost,
+                               h->stream));
+        RC(download_v(h, gv, v));
+        CU(cudaStreamSynchronize(h->stream));
+        if (w0) *w0 = st[0];
+        return SFM_OK;
+    }
     if (w) {
         CU(cudaMemcpyAsync(w, m.w, sizeof(float) * (size_t)m.n_slots, cudaMemcpyDeviceToHost,
                            h->stream));
@@ -799,14 +906,34 @@ int32_t sfm_get_model_f64(sfm_handle* h, double* w0, double* w, double* v) {
 
 int32_t sfm_init_model(sfm_handle* h, double mean, double stdev, uint64_t seed) {
     if (!h) return SFM_ERR_ARG;
+    NEED_MODEL(h);
     const ModelView& m = h->m;
+    if (is_sharded(h)) {  // each rank draws only the elements of its own rows (same stream of numbers)
+        ShardState& ss = *h->shard;
+        CU(cudaSetDevice(h->device));
+        std::vector<float> vf;
+        try {
+            vf.resize((size_t)ss.n_own * (size_t)m.k);
+        } catch (const std::bad_alloc&) {
+            return set_err(h, SFM_ERR_OOM, "host allocation failed");
+        }
+        if (!vf.empty())
+            init_gaussian_f32(vf.data(), ss.own_lo * m.k, (int64_t)vf.size(), mean, stdev, seed);
+        CU(cudaMemsetAsync(m.w0, 0, sizeof(float), h->stream));
+        if (ss.n_own > 0) {
+            CU(cudaMemsetAsync(ss.w, 0, sizeof(float) * (size_t)ss.n_own, h->stream));
+            RC(upload_v_rows(h, ss.v, vf.empty() ? nullptr : vf.data(), ss.n_own));
+        }
+        CU(cudaStreamSynchronize(h->stream));
+        return SFM_OK;
+    }
     std::vector<float> vf;
     try {
         vf.resize((size_t)m.n_slots * (size_t)m.k);
     } catch (const std::bad_alloc&) {
         return set_err(h, SFM_ERR_OOM, "host allocation failed");
     }
-    if (!vf.empty()) init_gaussian_f32(vf.data(), (int64_t)vf.size(), mean, stdev, seed);
+    if (!vf.empty()) init_gaussian_f32(vf.data(), 0, (int64_t)vf.size(), mean, stdev, seed);
     return sfm_set_model(h, 0.f, nullptr, vf.empty() ? nullptr : vf.data());
 }
 
@@ -883,14 +1010,20 @@ int32_t sfm_load(const char* path, int32_t device, sfm_handle** out) {
 
 // ------------------------------------------------------------------------------ scorer ---
 static int predict_view(sfm_handle* h, const BatchView& b, float* out_host) {
+    NEED_MODEL(h);
     RC(ensure(h, h->b_yhat, sizeof(float) * (size_t)(b.n_rows > 0 ? b.n_rows : 1)));
     PhaseTimer pt(h);
     CU(cudaMemsetAsync(h->d_err, 0, sizeof(int32_t), h->stream));
     FwdOut o;
     memset(&o, 0, sizeof o);
     o.yhat = (float*)h->b_yhat.p;
-    CU(launch_forward(h->m, b, o, false, h->d_err, h->sm_count, h->stream,
-                      &h->stats.kernel_launches));
+    if (is_sharded(h)) {
+        RC(validate_view(h, b));
+        RC(shard_forward(h, b));
+    } else {
+        CU(launch_forward(h->m, b, o, false, h->d_err, h->sm_count, h->stream,
+                          &h->stats.kernel_launches));
+    }
     pt.lap(&h->stats.ms_predict);
     if (b.n_rows > 0 && out_host) {
         CU(cudaMemcpyAsync(out_host, o.yhat, sizeof(float) * (size_t)b.n_rows,
@@ -1110,11 +1243,13 @@ int32_t sfm_predict_resident(sfm_handle* h, int64_t row_lo, int64_t row_hi, floa
     b.row_lo = row_lo;
     b.n_rows = row_hi - row_lo;
     b.nnz = 0;  // statistics only; not read back for a sub-range
+    if (is_sharded(h)) RC(subrange_view(h, row_lo, row_hi, &b));
     return predict_view(h, b, out);
 }
 
 int32_t sfm_evaluate(sfm_handle* h, double metrics[5]) {
     if (!h || !metrics) return SFM_ERR_ARG;
+    NEED_MODEL(h);
     const Dataset& ds = h->ds;
     if (!ds.loaded) return set_err(h, SFM_ERR_STATE, "no resident data set");
     CU(cudaSetDevice(h->device));
@@ -1132,8 +1267,13 @@ int32_t sfm_evaluate(sfm_handle* h, double metrics[5]) {
         FwdOut o;
         memset(&o, 0, sizeof o);
         o.yhat = (float*)h->b_yhat.p;
-        CU(launch_forward(h->m, b, o, false, h->d_err, h->sm_count, h->stream,
-                          &h->stats.kernel_launches));
+        if (is_sharded(h)) {
+            RC(subrange_view(h, lo, lo + b.n_rows, &b));
+            RC(shard_forward(h, b));
+        } else {
+            CU(launch_forward(h->m, b, o, false, h->d_err, h->sm_count, h->stream,
+                              &h->stats.kernel_launches));
+        }
         CU(launch_metrics(o.yhat, ds.label + lo, b.n_rows, (double*)h->b_partials.p, acc,
                           h->stream, &h->stats.kernel_launches));
         h->stats.predict_rows += b.n_rows;
@@ -1376,6 +1516,28 @@ int32_t sfm_comm_init(sfm_handle* h, const uint8_t id[SFM_UNIQUE_ID_BYTES], int3
     RC(nccl_init(h->nccl, &h->comm, id, rank, world_size, &h->err));
     h->rank = rank;
     h->world = world_size;
+    if (h->shard_requested) {
+        ShardState* ss = new (std::nothrow) ShardState;
+        if (!ss) return set_err(h, SFM_ERR_OOM, "host allocation failed");
+        const ModelView& m = h->m;
+        ss->n_per = (m.n_slots + world_size - 1) / world_size;
+        ss->own_lo = (int64_t)rank * ss->n_per;
+        ss->n_own = m.n_slots - ss->own_lo;
+        if (ss->n_own > ss->n_per) ss->n_own = ss->n_per;
+        if (ss->n_own < 0) ss->n_own = 0;
+        const size_t rows = (size_t)(ss->n_per > 0 ? ss->n_per : 1);
+        if (cudaMalloc(&ss->v, sizeof(float) * rows * m.kp) != cudaSuccess ||
+            cudaMalloc(&ss->w, sizeof(float) * rows) != cudaSuccess) {
+            cudaGetLastError();
+            if (ss->v) cudaFree(ss->v);
+            delete ss;
+            return set_err(h, SFM_ERR_OOM, "cannot allocate the model shard");
+        }
+        cudaMemsetAsync(ss->v, 0, sizeof(float) * rows * m.kp, h->stream);
+        cudaMemsetAsync(ss->w, 0, sizeof(float) * rows, h->stream);
+        CU(cudaStreamSynchronize(h->stream));
+        h->shard = ss;
+    }
     return SFM_OK;
 }
 
@@ -1388,7 +1550,8 @@ int32_t sfm_comm_info(const sfm_handle* h, int32_t* rank, int32_t* world_size) {
 
 int32_t sfm_comm_broadcast_model(sfm_handle* h) {
     if (!h) return SFM_ERR_ARG;
-    if (h->world <= 1) return SFM_OK;
+    if (h->world <= 1 || is_sharded(h)) return SFM_OK;   // shards are disjoint: nothing to copy
+    NEED_MODEL(h);
     CU(cudaSetDevice(h->device));
     const ModelView& m = h->m;
     RC(nccl_bcast_f32(h->nccl, h->comm, m.v, (size_t)m.n_slots * m.kp, 0, h->stream, &h->err));

@@ -50,6 +50,17 @@ struct PartCache {
     Buf row_ids, keys, pay;
 };
 
+// Row-sharded model (sfm_shard.cu): this rank owns features [own_lo, own_lo + n_own).
+struct ShardState {
+    int64_t n_per = 0, own_lo = 0, n_own = 0;
+    float* v = nullptr;   // [n_per][kp]
+    float* w = nullptr;   // [n_per]
+    Buf flags, crank, uniq, small, lut, req, out_v, out_w, t_v, t_w, bidx, bval, blabel, gr_v, gr_w,
+        acc;
+    int32_t* h_small = nullptr;
+    size_t h_small_cap = 0;
+};
+
 // One mini-batch as the kernels see it.
 struct BatchView {
     const int64_t* row_ptr;  // CSR row pointers of the array the rows live in
@@ -94,6 +105,8 @@ struct sfm_handle {
         b_sort_tmp, b_grad, b_partials, b_sel_tmp, b_lens, b_pull;
     sfm::Stage stage[3];
     std::vector<sfm::PartCache> parts;  // PARTITION sampler caches (size P)
+    bool shard_requested = false;       // SFM_FLAG_SHARD_V at create; active once comm is up
+    sfm::ShardState* shard = nullptr;
     // sampler prefetch (sfm_train): ids / count of the NEXT iteration are produced on copy_stream
     sfm::Buf b_ids2[2], b_samp_tmp;
     int32_t* d_count2 = nullptr;   // [2] device
@@ -103,7 +116,7 @@ struct sfm_handle {
     int32_t* d_err = nullptr;  // device error flag
     int32_t* d_count = nullptr;  // device int (sampler count)
     double* h_scal = nullptr;  // pinned [SC_N]
-    int32_t* h_flags = nullptr;  // pinned [4]: err, count
+    int32_t* h_flags = nullptr;  // pinned [16]: err, count, int64 total, min/max, 2 x int64
     void* h_pinned = nullptr;  // pinned staging for small host copies
     size_t h_pinned_cap = 0;
     // comm
@@ -195,9 +208,15 @@ cudaError_t sample_rows_device(void* tmp, size_t tmp_bytes, int64_t n, int64_t g
                                uint64_t key, uint64_t thr, int32_t* out_rows, int32_t* d_count,
                                cudaStream_t st, int64_t* launches);
 
+// ---- row-sharded model (sfm_shard.cu)
+int shard_forward(sfm_handle* h, const BatchView& b);                 // yhat -> h->b_yhat
+int shard_train(sfm_handle* h, const BatchView& b, int64_t iter);
+
 // ---- host side (sfm_host.cpp)
 uint64_t mix64(uint64_t x);
-void init_gaussian_f32(float* v, int64_t count, double mean, double stdev, uint64_t seed);
+// elements [first, first + count) of the seeded Gaussian stream
+void init_gaussian_f32(float* v, int64_t first, int64_t count, double mean, double stdev,
+                       uint64_t seed);
 
 // ---- NCCL via dlopen (sfm_nccl.cpp)
 Nccl* nccl_load(std::string* err);
@@ -210,6 +229,14 @@ int nccl_allreduce_f64(Nccl* n, void* comm, double* buf, size_t count, cudaStrea
                        std::string* err);
 int nccl_bcast_f32(Nccl* n, void* comm, float* buf, size_t count, int root, cudaStream_t st,
                    std::string* err);
+int nccl_allgather_i32(Nccl* n, void* comm, const int32_t* send, int32_t* recv, size_t count,
+                       cudaStream_t st, std::string* err);
+int nccl_allgather_f32(Nccl* n, void* comm, const float* send, float* recv, size_t count,
+                       cudaStream_t st, std::string* err);
+int nccl_alltoallv_4b(Nccl* n, void* comm, int rank, int world, const void* send,
+                      const int64_t* send_off, const int64_t* send_cnt, void* recv,
+                      const int64_t* recv_off, const int64_t* recv_cnt, int64_t width,
+                      cudaStream_t st, std::string* err);
 int nccl_group_start(Nccl* n);
 int nccl_group_end(Nccl* n);
 

@@ -22,7 +22,8 @@ uint64_t mix64(uint64_t x) {
 }
 
 // DESIGN.md 2.1.  Box-Muller in fp64 with glibc's log/cos, rounded once to fp32.
-void init_gaussian_f32(float* v, int64_t count, double mean, double stdev, uint64_t seed) {
+void init_gaussian_f32(float* v, int64_t first, int64_t count, double mean, double stdev,
+                       uint64_t seed) {
     const uint64_t s = mix64(seed);
     const double two_pi = 6.283185307179586476925286766559;
     unsigned nt = std::thread::hardware_concurrency();
@@ -33,12 +34,12 @@ void init_gaussian_f32(float* v, int64_t count, double mean, double stdev, uint6
     for (unsigned t = 0; t < nt; ++t) {
         const int64_t lo = count * t / nt, hi = count * (t + 1) / nt;
         th.emplace_back([=] {
-            for (int64_t e = lo; e < hi; ++e) {
-                const double u1 =
-                    (double)((mix64(s + 2ULL * (uint64_t)e) >> 11) + 1ULL) * 0x1.0p-53;
-                const double u2 = (double)(mix64(s + 2ULL * (uint64_t)e + 1ULL) >> 11) * 0x1.0p-53;
+            for (int64_t i = lo; i < hi; ++i) {
+                const uint64_t e = (uint64_t)(first + i);
+                const double u1 = (double)((mix64(s + 2ULL * e) >> 11) + 1ULL) * 0x1.0p-53;
+                const double u2 = (double)(mix64(s + 2ULL * e + 1ULL) >> 11) * 0x1.0p-53;
                 const double z = sqrt(-2.0 * log(u1)) * cos(two_pi * u2);
-                v[e] = (float)(mean + stdev * z);
+                v[i] = (float)(mean + stdev * z);
             }
         });
     }

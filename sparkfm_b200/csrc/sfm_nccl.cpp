@@ -15,7 +15,7 @@ namespace sfm {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess = 0 };
-enum { ncclFloat32 = 7, ncclFloat64 = 8 };  // ncclDataType_t
+enum { ncclInt32 = 2, ncclFloat32 = 7, ncclFloat64 = 8 };  // ncclDataType_t
 enum { ncclSum = 0 };                      // ncclRedOp_t
 
 struct Nccl {
@@ -25,6 +25,9 @@ struct Nccl {
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -64,6 +67,9 @@ Nccl* nccl_load(std::string* err) {
     SYM(CommDestroy, "ncclCommDestroy")
     SYM(AllReduce, "ncclAllReduce")
     SYM(Broadcast, "ncclBroadcast")
+    SYM(AllGather, "ncclAllGather")
+    SYM(Send, "ncclSend")
+    SYM(Recv, "ncclRecv")
     SYM(GroupStart, "ncclGroupStart")
     SYM(GroupEnd, "ncclGroupEnd")
     SYM(GetErrorString, "ncclGetErrorString")
@@ -126,6 +132,66 @@ int nccl_bcast_f32(Nccl* n, void* comm, float* buf, size_t count, int root, cuda
     const int rc = n->Broadcast(buf, buf, count, ncclFloat32, root, (ncclComm_t)comm, st);
     if (rc != ncclSuccess) {
         if (err) *err = nerr(n, "ncclBroadcast", rc);
+        return SFM_ERR_NCCL;
+    }
+    return SFM_OK;
+}
+
+int nccl_allgather_i32(Nccl* n, void* comm, const int32_t* send, int32_t* recv, size_t count,
+                       cudaStream_t st, std::string* err) {
+    const int rc = n->AllGather(send, recv, count, ncclInt32, (ncclComm_t)comm, st);
+    if (rc != ncclSuccess) {
+        if (err) *err = nerr(n, "ncclAllGather(i32)", rc);
+        return SFM_ERR_NCCL;
+    }
+    return SFM_OK;
+}
+
+int nccl_allgather_f32(Nccl* n, void* comm, const float* send, float* recv, size_t count,
+                       cudaStream_t st, std::string* err) {
+    const int rc = n->AllGather(send, recv, count, ncclFloat32, (ncclComm_t)comm, st);
+    if (rc != ncclSuccess) {
+        if (err) *err = nerr(n, "ncclAllGather(f32)", rc);
+        return SFM_ERR_NCCL;
+    }
+    return SFM_OK;
+}
+
+// Variable all-to-all of 4-byte elements: rank r sends send_cnt[p] * width elements starting at
+// send_off[p] * width to peer p and receives recv_cnt[p] * width at recv_off[p] * width.  The self
+// part is a device copy; zero-sized parts are skipped on both sides (both know the counts).
+int nccl_alltoallv_4b(Nccl* n, void* comm, int rank, int world, const void* send,
+                      const int64_t* send_off, const int64_t* send_cnt, void* recv,
+                      const int64_t* recv_off, const int64_t* recv_cnt, int64_t width,
+                      cudaStream_t st, std::string* err) {
+    const char* sb = (const char*)send;
+    char* rb = (char*)recv;
+    if (send_cnt[rank] > 0) {
+        if (send_cnt[rank] != recv_cnt[rank]) {
+            if (err) *err = "alltoallv: self counts differ";
+            return SFM_ERR_NCCL;
+        }
+        if (cudaMemcpyAsync(rb + recv_off[rank] * width * 4, sb + send_off[rank] * width * 4,
+                            (size_t)(send_cnt[rank] * width * 4), cudaMemcpyDeviceToDevice, st) !=
+            cudaSuccess) {
+            if (err) *err = "alltoallv: self copy failed";
+            return SFM_ERR_CUDA;
+        }
+    }
+    int rc = n->GroupStart();
+    for (int p = 0; p < world && rc == ncclSuccess; ++p) {
+        if (p == rank) continue;
+        if (send_cnt[p] > 0)
+            rc = n->Send(sb + send_off[p] * width * 4, (size_t)(send_cnt[p] * width), ncclFloat32, p,
+                         (ncclComm_t)comm, st);
+        if (rc == ncclSuccess && recv_cnt[p] > 0)
+            rc = n->Recv(rb + recv_off[p] * width * 4, (size_t)(recv_cnt[p] * width), ncclFloat32, p,
+                         (ncclComm_t)comm, st);
+    }
+    const int rc2 = n->GroupEnd();
+    if (rc == ncclSuccess) rc = rc2;
+    if (rc != ncclSuccess) {
+        if (err) *err = nerr(n, "ncclSend/ncclRecv", rc);
         return SFM_ERR_NCCL;
     }
     return SFM_OK;

@@ -26,11 +26,12 @@ def _arr(a, dt):
 class Handle:
     def __init__(self, n_slots, k, task=REGRESSION, k0=True, k1=True, reg=(0.0, 0.0, 0.0),
                  step_size=0.1, mini_batch_fraction=1.0, sampler_seed=42, device=0,
-                 sampler_mode=0):
+                 sampler_mode=0, shard_v=False):
         self._L = _lib.load()
         cfg = SfmConfig(_lib.SFM_ABI_VERSION, int(task), int(k), int(bool(k0)), int(bool(k1)),
                         int(device), int(n_slots), float(reg[0]), float(reg[1]), float(reg[2]),
-                        float(step_size), float(mini_batch_fraction), int(sampler_mode),
+                        float(step_size), float(mini_batch_fraction),
+                        int(sampler_mode) | (0x100 if shard_v else 0),
                         int(sampler_seed))
         self._h = C.c_void_p()
         check(self._L.sfm_create(C.byref(cfg), C.byref(self._h)))

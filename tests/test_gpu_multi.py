@@ -89,3 +89,92 @@ def test_two_gpus_match_one_gpu(tmp_path):
     assert np.max(np.abs(m1[2] - a["v"])) <= 1e-4 * np.abs(m1[2]).max()
     assert abs(hd.evaluate()["rmse"] - float(a["rmse"])) < 1e-5
     hd.close()
+
+
+# ------------------------------------------------------------------------------ row-sharded V
+def _shard_data(kind):
+    from sparkfm_b200 import synth
+    rng = np.random.default_rng(17)
+    if kind == "onehot":          # uniform all-ones rows, k = 16: forward fast path on the compact model
+        n_slots, k, n_rows = 20_001, 16, 24_000
+        rp, idx, _, label = synth.ctr_csr(0, n_rows, 13, n_slots, 5)
+        val = None
+    else:                          # ragged valued rows, k = 5 (padded): generic kernels
+        n_slots, k, n_rows = 3_001, 5, 9_000
+        rp, idx, val = synth.ragged_rows(n_rows, n_slots, 11, seed=3, values="normal")
+        label = np.where(rng.random(n_rows) < 0.4, 1.0, -1.0).astype(np.float32)
+    model = (0.01, rng.normal(0, 0.05, n_slots).astype(np.float32),
+             rng.normal(0, 0.05, (n_slots, k)).astype(np.float32))
+    return n_slots, k, n_rows, rp, idx, val, label, model
+
+
+def _shard_worker(rank, world, port, out_dir, kind):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from sparkfm_b200 import Handle
+        from sparkfm_b200._lib import SfmError
+        from sparkfm_b200.dist import init_comm, shard_range
+        n_slots, k, n_rows, rp, idx, val, label, (w0, w, v) = _shard_data(kind)
+        lo, hi = shard_range(n_rows, rank, world)
+        hd = Handle(n_slots, k, device=rank, shard_v=True, **KW)
+        try:
+            hd.set_model(w0, w, v)
+            raise AssertionError("model calls must fail before sfm_comm_init")
+        except SfmError:
+            pass
+        init_comm(hd, device="cpu")
+        hd.set_model(w0, w, v)                       # every rank keeps its own rows
+        g = hd.get_model()                           # collective all-gather
+        assert g[0] == np.float32(w0) and np.array_equal(g[1], w) and np.array_equal(g[2], v)
+        sub_val = None if val is None else val[rp[lo]:rp[hi]]
+        hd.load_dataset(rp[lo:hi + 1] - rp[lo], idx[rp[lo]:rp[hi]], sub_val, label[lo:hi],
+                        global_row_offset=lo)
+        pred0 = hd.predict_resident(0, hi - lo)
+        losses = [hd.train_step(it) for it in range(1, ITERS + 1)]
+        m = hd.get_model()
+        ev = hd.evaluate()
+        np.savez(os.path.join(out_dir, f"s{rank}.npz"), loss=np.array([l for l, _ in losses]),
+                 batch=np.array([b for _, b in losses]), w0=m[0], w=m[1], v=m[2], rmse=ev["rmse"],
+                 pred0=pred0, lo=lo, hi=hi)
+        hd.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("kind", ["onehot", "ragged"])
+def test_row_sharded_model_matches_replicated(tmp_path, kind):
+    """SFM_FLAG_SHARD_V on 2 GPUs (each owns half of V / w, touched rows travel by all-to-all)
+    against ONE GPU holding the whole model and every row: same predictions, same per-iteration
+    loss (1e-4), same final model; reruns are bitwise identical."""
+    import torch.multiprocessing as mp
+    from sparkfm_b200 import Handle
+    runs = []
+    for rep in range(2):
+        d = tmp_path / f"rep{rep}"
+        d.mkdir()
+        mp.spawn(_shard_worker, args=(2, _free_port(), str(d), kind), nprocs=2, join=True)
+        runs.append([np.load(d / f"s{r}.npz") for r in range(2)])
+    a, b = runs[0]
+    for key in ("loss", "batch", "w0", "w", "v"):
+        assert np.array_equal(a[key], b[key]), key              # get_model is the same on both ranks
+        assert np.array_equal(a[key], runs[1][0][key]), key      # and reproducible
+    n_slots, k, n_rows, rp, idx, val, label, (w0, w, v) = _shard_data(kind)
+    hd = Handle(n_slots, k, device=0, **KW)
+    hd.set_model(w0, w, v)
+    hd.load_dataset(rp, idx, val, label)
+    p1 = hd.predict_resident(0, n_rows)
+    p2 = np.concatenate([a["pred0"], b["pred0"]])
+    assert np.max(np.abs(p1 - p2)) <= 1e-6 * max(np.abs(p1).max(), 1e-3)
+    one = [hd.train_step(it) for it in range(1, ITERS + 1)]
+    assert [bt for _, bt in one] == a["batch"].tolist()
+    for (l1, _), l2 in zip(one, a["loss"]):
+        assert abs(l1 - l2) <= 1e-4 * abs(l1)
+    m1 = hd.get_model()
+    assert np.max(np.abs(m1[2] - a["v"])) <= 1e-4 * np.abs(m1[2]).max()
+    assert np.max(np.abs(m1[1] - a["w"])) <= 1e-4 * max(np.abs(m1[1]).max(), 1e-3)
+    assert abs(hd.evaluate()["rmse"] - float(a["rmse"])) < 1e-5
+    hd.close()
