@@ -108,6 +108,7 @@ struct PhaseTimer {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
         *acc += ms;
+        if (acc != &h->stats.ms_predict) h->stats.ms_total_train += ms;
         cudaEventRecord(h->ev_a, h->stream);
     }
 };

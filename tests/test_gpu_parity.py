@@ -451,3 +451,35 @@ def test_partition_sampler_uniform_all_ones_rows():
     assert np.array_equal(ma[2], mb[2]) and np.array_equal(ma[1], mb[1])
     a.close()
     b.close()
+
+
+def test_pipelined_staging_matches_synchronous_csr_path():
+    """sfm_stage_csr + sfm_train_step_staged (H2D of batch t+1 overlapped with the step on batch t)
+    must give the same bits as sfm_train_step_csr on the same batches."""
+    rng = np.random.default_rng(81)
+    n_slots, k = 2500, 16
+    w0, w, v = make_model(rng, n_slots, k)
+    batches = []
+    for s in range(5):
+        rp, idx, val = synth.ragged_rows(1500 + 100 * s, n_slots, 14, seed=90 + s, values="normal")
+        lab = rng.normal(0, 1, len(rp) - 1).astype(np.float32)
+        batches.append((rp, idx, val if s % 2 == 0 else None, lab))
+    kw = dict(task=0, reg=(0.0, 1e-3, 1e-3), step_size=0.05)
+    a, b = Handle(n_slots, k, **kw), Handle(n_slots, k, **kw)
+    for h in (a, b):
+        h.set_model(w0, w, v)
+    la = [a.train_step_csr(s + 1, *batches[s])[0] for s in range(5)]
+    lb = []
+    b.stage_csr(0, *batches[0])
+    for s in range(5):
+        if s + 1 < 5:
+            b.stage_csr((s + 1) & 1, *batches[s + 1])
+        lb.append(b.train_step_staged(s & 1, s + 1)[0])
+    assert la == lb
+    ma, mb = a.get_model(), b.get_model()
+    assert ma[0] == mb[0] and np.array_equal(ma[1], mb[1]) and np.array_equal(ma[2], mb[2])
+    with pytest.raises(SfmError) as ei:
+        b.train_step_staged(0, 6)           # slot already consumed
+    assert ei.value.status == SFM_ERR_STATE
+    a.close()
+    b.close()
