@@ -320,9 +320,32 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     CU(launch_forward(m, b, o, true, h->d_err, h->sm_count, h->stream, L));
     CU(launch_scalar_reduce(o.loss, o.mult, n, (double*)h->b_partials.p, h->d_scal, h->stream, L));
     pt.lap(&h->stats.ms_forward);
+    // Multi-GPU, reduce / all-reduce overlap: the feature range is cut into Q
+    // slices; slice q's gradient is all-reduced and applied on the comm stream while the reduce of
+    // slice q+1 runs on the compute stream.
+    int n_slices = 1;
+    if (multi && !grad_keep && n_blocks == 1 && nnz > 0 && !h->phase_timing) {
+        static int q_env = -1;
+        if (q_env < 0) {
+            const char* e = getenv("SFM_AR_SLICES");
+            q_env = e ? atoi(e) : 4;
+            if (q_env < 1) q_env = 1;
+            if (q_env > 8) q_env = 8;
+        }
+        n_slices = q_env;
+        if (m.n_slots < 64 * n_slices) n_slices = 1;
+    }
+    const bool sliced = n_slices > 1;
     if (multi) {
-        RC(nccl_allreduce_f64(h->nccl, h->comm, h->d_scal, SC_N, h->stream, &h->err));
-        pt.lap(&h->stats.ms_allreduce);
+        if (sliced) {
+            CU(cudaEventRecord(h->ev_pool[0], h->stream));
+            CU(cudaStreamWaitEvent(h->comm_stream, h->ev_pool[0], 0));
+            RC(nccl_allreduce_f64(h->nccl, h->comm, h->d_scal, SC_N, h->comm_stream, &h->err));
+            CU(cudaEventRecord(h->ev_pool[1], h->comm_stream));
+        } else {
+            RC(nccl_allreduce_f64(h->nccl, h->comm, h->d_scal, SC_N, h->stream, &h->err));
+            pt.lap(&h->stats.ms_allreduce);
+        }
     }
     const uint32_t* keys_sorted = pc ? (const uint32_t*)pc->keys.p : (const uint32_t*)h->b_keys[1].p;
     const uint2* pay_sorted = pc ? (const uint2*)pc->pay.p : (const uint2*)h->b_pay[1].p;
@@ -337,6 +360,56 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     }
     pt.lap(&h->stats.ms_sort);
     const UpdateParams up = update_params(h, iter);
+    if (sliced) {
+        // where each feature slice starts in the sorted entry list (cached with the transposition)
+        int32_t pos[17];
+        pos[0] = 0;
+        pos[n_slices] = (int32_t)nnz;
+        PartCache* pcm = const_cast<PartCache*>(pc);
+        if (pcm && pcm->n_slices == n_slices) {
+            for (int q = 1; q < n_slices; ++q) pos[q] = pcm->slice_pos[q];
+        } else {
+            CU(launch_slice_bounds(keys_sorted, nnz, n_slices, m.n_slots, h->d_slice, h->stream, L));
+            CU(cudaMemcpyAsync(h->h_slice, h->d_slice, sizeof(int32_t) * 16, cudaMemcpyDeviceToHost,
+                               h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            for (int q = 1; q < n_slices; ++q) pos[q] = h->h_slice[q];
+            if (pcm) {
+                pcm->n_slices = n_slices;
+                for (int q = 1; q < n_slices; ++q) pcm->slice_pos[q] = pos[q];
+            }
+        }
+        const int64_t chb = pull_chunk_entries(m);
+        const int64_t nchunks = (nnz + chb - 1) / chb;
+        float* grad = (float*)h->b_grad.p;
+        float* gw = grad + m.n_slots * m.kp;
+        CU(cudaStreamWaitEvent(h->stream, h->ev_pool[1], 0));   // all-reduced scalars
+        for (int q = 0; q < n_slices; ++q) {
+            PullSlice sl;
+            sl.feat_lo = (int64_t)q * m.n_slots / n_slices;
+            sl.feat_hi = (int64_t)(q + 1) * m.n_slots / n_slices;
+            sl.chunk_lo = q == 0 ? 0 : (pos[q] + chb - 1) / chb;
+            sl.chunk_hi = q == n_slices - 1 ? nchunks : (pos[q + 1] + chb - 1) / chb;
+            sl.first = q == 0;
+            CU(launch_pull_slice(m, (int32_t*)h->b_seg.p, key_bits, n_blocks, keys_sorted, pay_sorted,
+                                 nnz, binary, o.S, o.mult, (float*)h->b_pull.p, h->d_scal, h->d_err,
+                                 up, false, grad, h->sm_count, h->stream, sl, L));
+            CU(cudaEventRecord(h->ev_pool[2 + q], h->stream));
+            CU(cudaStreamWaitEvent(h->comm_stream, h->ev_pool[2 + q], 0));
+            const size_t nf = (size_t)(sl.feat_hi - sl.feat_lo);
+            RC(nccl_allreduce_f32(h->nccl, h->comm, grad + (size_t)sl.feat_lo * m.kp, nf * m.kp,
+                                  h->comm_stream, &h->err));
+            RC(nccl_allreduce_f32(h->nccl, h->comm, gw + sl.feat_lo, nf, h->comm_stream, &h->err));
+            CU(launch_update_range(m, grad, h->d_scal, h->d_err, up, sl.feat_lo, sl.feat_hi,
+                                   h->comm_stream, L));
+        }
+        CU(cudaEventRecord(h->ev_pool[2 + n_slices], h->comm_stream));
+        CU(cudaStreamWaitEvent(h->stream, h->ev_pool[2 + n_slices], 0));
+        h->stats.train_steps += 1;
+        h->stats.train_rows += n;
+        h->stats.train_nnz += nnz;
+        return SFM_OK;
+    }
     CU(launch_pull(m, (int32_t*)h->b_seg.p, key_bits, n_blocks, keys_sorted, pay_sorted, nnz, binary,
                    o.S, o.mult, (float*)h->b_pull.p, h->d_scal, h->d_err, up, fused,
                    fused ? nullptr : (float*)h->b_grad.p, h->sm_count, h->stream, L));
@@ -696,6 +769,10 @@ int32_t sfm_create(const sfm_config* cfg, sfm_handle** out) {
         CK(cudaEventCreateWithFlags(&h->ev_samp[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_used[i], cudaEventDisableTiming));
     }
+    CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : h->ev_pool) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CK(cudaMalloc(&h->d_slice, sizeof(int32_t) * 16));
+    CK(cudaMallocHost(&h->h_slice, sizeof(int32_t) * 16));
     CK(cudaMalloc(&h->d_count2, sizeof(int32_t) * 2));
     CK(cudaMallocHost(&h->h_count2, sizeof(int32_t) * 2));
     // one extra, always-zero row at index n_slots: the target of padded / rejected entries
@@ -746,6 +823,14 @@ int32_t sfm_destroy(sfm_handle* h) {
     free_buf(h->b_ids2[0]);
     free_buf(h->b_ids2[1]);
     free_buf(h->b_samp_tmp);
+    if (h->comm_stream) {
+        cudaStreamSynchronize(h->comm_stream);
+        cudaStreamDestroy(h->comm_stream);
+    }
+    for (cudaEvent_t e : h->ev_pool)
+        if (e) cudaEventDestroy(e);
+    if (h->d_slice) cudaFree(h->d_slice);
+    if (h->h_slice) cudaFreeHost(h->h_slice);
     if (h->d_count2) cudaFree(h->d_count2);
     if (h->h_count2) cudaFreeHost(h->h_count2);
     for (int i = 0; i < 2; ++i) {

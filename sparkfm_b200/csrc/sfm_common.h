@@ -48,6 +48,8 @@ struct PartCache {
     int64_t n_rows = 0, nnz = 0;
     int key_bits = 0, blk_shift = 30, n_blocks = 1;
     Buf row_ids, keys, pay;
+    int n_slices = 0;           // multi-GPU overlap: sorted position where each feature slice starts
+    int32_t slice_pos[16] = {0};
 };
 
 // Row-sharded model (sfm_shard.cu): this rank owns features [own_lo, own_lo + n_own).
@@ -112,6 +114,10 @@ struct sfm_handle {
     int32_t* d_count2 = nullptr;   // [2] device
     int32_t* h_count2 = nullptr;   // [2] pinned
     cudaEvent_t ev_samp[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
+    cudaEvent_t ev_pool[20] = {nullptr};   // reduce / all-reduce overlap (multi-GPU)
+    cudaStream_t comm_stream = nullptr;
+    int32_t* d_slice = nullptr;            // [16] device
+    int32_t* h_slice = nullptr;            // [16] pinned
     double* d_scal = nullptr;  // [SC_N] device
     int32_t* d_err = nullptr;  // device error flag
     int32_t* d_count = nullptr;  // device int (sampler count)
@@ -161,6 +167,23 @@ cudaError_t launch_pull(const ModelView& m, int32_t* seg, int key_bits, int n_bl
                         const float* mult, float* scratch, const double* d_scal,
                         const int32_t* d_err, UpdateParams up, bool fused, float* grad,
                         int sm_count, cudaStream_t st, int64_t* launches);
+// a slice of the reduce: chunk range of the sorted entries + feature range of the finalize
+struct PullSlice {
+    int64_t chunk_lo = -1, chunk_hi = -1, feat_lo = -1, feat_hi = -1;   // -1 = everything
+    bool first = true;                                                   // zero the run bounds
+};
+cudaError_t launch_pull_slice(const ModelView& m, int32_t* seg, int key_bits, int n_blocks,
+                              const uint32_t* keys, const uint2* pay, int64_t nnz, bool binary,
+                              const float* S, const float* mult, float* scratch,
+                              const double* d_scal, const int32_t* d_err, UpdateParams up,
+                              bool fused, float* grad, int sm_count, cudaStream_t st,
+                              const PullSlice& sl, int64_t* launches);
+int64_t pull_chunk_entries(const ModelView& m);
+cudaError_t launch_slice_bounds(const uint32_t* keys, int64_t nnz, int n_slices, int64_t n_slots,
+                                int32_t* d_pos, cudaStream_t st, int64_t* launches);
+cudaError_t launch_update_range(const ModelView& m, const float* grad, const double* d_scal,
+                                const int32_t* d_err, UpdateParams up, int64_t feat_lo,
+                                int64_t feat_hi, cudaStream_t st, int64_t* launches);
 size_t pull_scratch_bytes(const ModelView& m, int64_t nnz, int n_blocks);
 void pull_plan(const ModelView& m, int64_t n_rows, int* blk_shift, int* n_blocks);
 // dense update from an (all-reduced) gradient buffer

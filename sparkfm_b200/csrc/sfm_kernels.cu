@@ -633,8 +633,9 @@ fm_pull_chunks_kernel(const uint32_t* __restrict__ keys, const uint2* __restrict
                       const float4* __restrict__ S4, const float* __restrict__ mult, int nnz,
                       float* __restrict__ R1, float* __restrict__ R2,
                       int32_t* __restrict__ seg_lo, int32_t* __restrict__ seg_hi, int key_bits,
-                      int64_t n_slots) {
+                      int64_t n_slots, int chunk_base) {
     using Cfg = PullCfg<LPR>;
+    const int chunk = blockIdx.x + chunk_base;   // slices of the chunk grid can be launched apart
     const uint32_t kmask = (1u << key_bits) - 1u;
     // key = (row block << key_bits) | feature  ->  slot block * n_slots + feature
     auto slot_of = [=](uint32_t key) -> int64_t {
@@ -651,7 +652,7 @@ fm_pull_chunks_kernel(const uint32_t* __restrict__ keys, const uint2* __restrict
     const int tid = threadIdx.x;
     const int g = tid / LPR;
     const int fq = tid % LPR;
-    const int cstart = blockIdx.x * CHB;
+    const int cstart = chunk * CHB;
 
     // ---- stage the tile: thread -> 4 consecutive entries (one 16-byte + two 16-byte loads)
     for (int q = tid; q < CHB / 4; q += Cfg::THREADS) {
@@ -738,7 +739,7 @@ fm_pull_chunks_kernel(const uint32_t* __restrict__ keys, const uint2* __restrict
                 // the run of `cur` ended at position p0 + base + u
                 if (cur != PULL_SENTINEL) {
                     if (cur_is_head) {
-                        if (g == 0) store_rec<LPR>(R2 + (int64_t)blockIdx.x * REC, fq, A, D, C);
+                        if (g == 0) store_rec<LPR>(R2 + (int64_t)chunk * REC, fq, A, D, C);
                         else { headA[g][fq] = A; if (fq == 0) headDC[g] = make_float2(D, C); }
                     } else {
                         store_rec<LPR>(R1 + slot_of(cur) * REC, fq, A, D, C);
@@ -788,7 +789,7 @@ fm_pull_chunks_kernel(const uint32_t* __restrict__ keys, const uint2* __restrict
                 if (key_s[SUB - 1][g2] != cur) break;   // the run ended inside g2
             }
         }
-        float* dst = cur_is_head ? R2 + (int64_t)blockIdx.x * REC : R1 + slot_of(cur) * REC;
+        float* dst = cur_is_head ? R2 + (int64_t)chunk * REC : R1 + slot_of(cur) * REC;
         store_rec<LPR>(dst, fq, A, D, C);
     }
 }
@@ -803,7 +804,7 @@ fm_pull_finalize_kernel(float4* __restrict__ V4, float* __restrict__ W, float* _
                         const float* __restrict__ R2, int n_blocks,
                         const double* __restrict__ d_scal, const int32_t* __restrict__ err,
                         UpdateParams up, float4* __restrict__ G4, float* __restrict__ Gw,
-                        float* __restrict__ Gw0) {
+                        float* __restrict__ Gw0, int64_t feat_lo, int64_t feat_hi) {
     constexpr int CHB = PullCfg<LPR>::CHB;
     constexpr int REC = PullCfg<LPR>::REC;
     if (FUSED && *err) return;  // a bad index was seen: leave the model untouched
@@ -814,7 +815,7 @@ fm_pull_finalize_kernel(float4* __restrict__ V4, float* __restrict__ W, float* _
     const float inv = count > 0.0 ? (float)(1.0 / count) : 0.f;
     const bool active = count > 0.0;
 
-    if (tid == 0) {
+    if (tid == 0 && feat_lo == 0) {
         const float g0 = (float)d_scal[SC_GW0];
         if (FUSED) {
             if (k0 && active) {
@@ -825,7 +826,7 @@ fm_pull_finalize_kernel(float4* __restrict__ V4, float* __restrict__ W, float* _
             *Gw0 = k0 ? g0 : 0.f;
         }
     }
-    for (int64_t i = tid / LPR; i < n_slots; i += ngroups) {
+    for (int64_t i = feat_lo + tid / LPR; i < feat_hi; i += ngroups) {
         float4 A = f4_zero();
         float D = 0.f, C = 0.f;
         for (int blk = 0; blk < n_blocks; ++blk) {  // row blocks in order: fixed summation order
@@ -916,31 +917,43 @@ size_t pull_scratch_bytes(const ModelView& m, int64_t nnz, int n_blocks) {
     return sizeof(float) * (size_t)rec * (size_t)(m.n_slots * n_blocks + (nnz + chb - 1) / chb + 1);
 }
 
+// One slice of the reduce: chunks [chunk_lo, chunk_hi) of the sorted entries (level 0/1), then the
+// finalize of features [feat_lo, feat_hi) (level 2 + gradient / update).  The whole reduce is the
+// slice {0, nchunks, 0, n_slots} with `first` set (zeroes the run bounds).
 template <int LPR>
 static cudaError_t pull_dispatch(const ModelView& m, int32_t* seg, int key_bits, int n_blocks,
                                  const uint32_t* keys, const uint2* pay, int64_t nnz, bool binary,
-                                 const float* S,
-                                 const float* mult, float* scratch, const double* d_scal,
-                                 const int32_t* d_err, UpdateParams up, bool fused, float* grad,
-                                 int sm_count, cudaStream_t st) {
+                                 const float* S, const float* mult, float* scratch,
+                                 const double* d_scal, const int32_t* d_err, UpdateParams up,
+                                 bool fused, float* grad, int sm_count, cudaStream_t st,
+                                 const PullSlice& sl) {
     using Cfg = PullCfg<LPR>;
     float* R1 = scratch;
     const size_t nslot = (size_t)m.n_slots * n_blocks;
     float* R2 = scratch + nslot * Cfg::REC;
     int32_t* seg_lo = seg;
     int32_t* seg_hi = seg + nslot;
-    cudaError_t e = cudaMemsetAsync(seg, 0, sizeof(int32_t) * 2 * nslot, st);
-    if (e != cudaSuccess) return e;
-    const int64_t nchunks = pull_chunks_for<LPR>(nnz);
-    if (nchunks > 0) {
-        if (binary)
-            fm_pull_chunks_kernel<LPR, true><<<(unsigned)nchunks, Cfg::THREADS, 0, st>>>(
-                keys, pay, (const float4*)S, mult, (int)nnz, R1, R2, seg_lo, seg_hi, key_bits, m.n_slots);
-        else
-            fm_pull_chunks_kernel<LPR, false><<<(unsigned)nchunks, Cfg::THREADS, 0, st>>>(
-                keys, pay, (const float4*)S, mult, (int)nnz, R1, R2, seg_lo, seg_hi, key_bits, m.n_slots);
+    if (sl.first) {
+        cudaError_t e = cudaMemsetAsync(seg, 0, sizeof(int32_t) * 2 * nslot, st);
+        if (e != cudaSuccess) return e;
     }
-    const int64_t threads = m.n_slots * LPR;
+    const int64_t nchunks_all = pull_chunks_for<LPR>(nnz);
+    const int64_t c_lo = sl.chunk_lo < 0 ? 0 : sl.chunk_lo;
+    const int64_t c_hi = sl.chunk_hi < 0 || sl.chunk_hi > nchunks_all ? nchunks_all : sl.chunk_hi;
+    if (c_hi > c_lo) {
+        if (binary)
+            fm_pull_chunks_kernel<LPR, true><<<(unsigned)(c_hi - c_lo), Cfg::THREADS, 0, st>>>(
+                keys, pay, (const float4*)S, mult, (int)nnz, R1, R2, seg_lo, seg_hi, key_bits,
+                m.n_slots, (int)c_lo);
+        else
+            fm_pull_chunks_kernel<LPR, false><<<(unsigned)(c_hi - c_lo), Cfg::THREADS, 0, st>>>(
+                keys, pay, (const float4*)S, mult, (int)nnz, R1, R2, seg_lo, seg_hi, key_bits,
+                m.n_slots, (int)c_lo);
+    }
+    const int64_t f_lo = sl.feat_lo < 0 ? 0 : sl.feat_lo;
+    const int64_t f_hi = sl.feat_hi < 0 || sl.feat_hi > m.n_slots ? m.n_slots : sl.feat_hi;
+    if (f_hi <= f_lo) return cudaGetLastError();
+    const int64_t threads = (f_hi - f_lo) * LPR;
     int64_t blocks = (threads + 255) / 256;
     const int64_t cap = (int64_t)sm_count * 32;
     if (blocks > cap) blocks = cap;
@@ -949,7 +962,7 @@ static cudaError_t pull_dispatch(const ModelView& m, int32_t* seg, int key_bits,
     float* gw0 = grad ? gw + m.n_slots : nullptr;
 #define FIN_ARGS                                                                              \
     (float4*)m.v, m.w, m.w0, m.n_slots, m.k0, m.k1, seg_lo, seg_hi, R1, R2, n_blocks, d_scal, \
-        d_err, up, (float4*)grad, gw, gw0
+        d_err, up, (float4*)grad, gw, gw0, f_lo, f_hi
     const dim3 gd((unsigned)blocks), bd(256);
     if (fused) {
         if (binary) fm_pull_finalize_kernel<LPR, true, true><<<gd, bd, 0, st>>>(FIN_ARGS);
@@ -962,14 +975,14 @@ static cudaError_t pull_dispatch(const ModelView& m, int32_t* seg, int key_bits,
     return cudaGetLastError();
 }
 
-cudaError_t launch_pull(const ModelView& m, int32_t* seg, int key_bits, int n_blocks,
-                        const uint32_t* keys, const uint2* pay, int64_t nnz, bool binary,
-                        const float* S,
-                        const float* mult, float* scratch, const double* d_scal,
-                        const int32_t* d_err, UpdateParams up, bool fused, float* grad,
-                        int sm_count, cudaStream_t st, int64_t* launches) {
-    *launches += nnz > 0 ? 2 : 1;
-#define PD(L) pull_dispatch<L>(m, seg, key_bits, n_blocks, keys, pay, nnz, binary, S, mult, scratch, d_scal, d_err, up, fused, grad, sm_count, st)
+cudaError_t launch_pull_slice(const ModelView& m, int32_t* seg, int key_bits, int n_blocks,
+                              const uint32_t* keys, const uint2* pay, int64_t nnz, bool binary,
+                              const float* S, const float* mult, float* scratch,
+                              const double* d_scal, const int32_t* d_err, UpdateParams up,
+                              bool fused, float* grad, int sm_count, cudaStream_t st,
+                              const PullSlice& sl, int64_t* launches) {
+    *launches += 2;
+#define PD(L) pull_dispatch<L>(m, seg, key_bits, n_blocks, keys, pay, nnz, binary, S, mult, scratch, d_scal, d_err, up, fused, grad, sm_count, st, sl)
     switch (m.lpr) {
         case 1: return PD(1);
         case 2: return PD(2);
@@ -982,22 +995,58 @@ cudaError_t launch_pull(const ModelView& m, int32_t* seg, int key_bits, int n_bl
     return cudaErrorInvalidValue;
 }
 
+cudaError_t launch_pull(const ModelView& m, int32_t* seg, int key_bits, int n_blocks,
+                        const uint32_t* keys, const uint2* pay, int64_t nnz, bool binary,
+                        const float* S, const float* mult, float* scratch, const double* d_scal,
+                        const int32_t* d_err, UpdateParams up, bool fused, float* grad,
+                        int sm_count, cudaStream_t st, int64_t* launches) {
+    PullSlice all;
+    return launch_pull_slice(m, seg, key_bits, n_blocks, keys, pay, nnz, binary, S, mult, scratch,
+                             d_scal, d_err, up, fused, grad, sm_count, st, all, launches);
+}
+
+int64_t pull_chunk_entries(const ModelView& m) {
+    const int threads = m.lpr >= 4 ? 256 : 64 * m.lpr;
+    return (int64_t)(threads / m.lpr) * PULL_SUB;
+}
+
+// pos[q] = first sorted position whose key >= q * n_slots / n_slices   (q = 1 .. n_slices-1)
+__global__ void slice_bounds_kernel(const uint32_t* __restrict__ keys, int nnz, int n_slices,
+                                    int64_t n_slots, int32_t* __restrict__ pos) {
+    const int q = threadIdx.x + 1;
+    if (q >= n_slices) return;
+    const uint32_t target = (uint32_t)((int64_t)q * n_slots / n_slices);
+    int lo = 0, hi = nnz;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (keys[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    pos[q] = lo;
+}
+
+cudaError_t launch_slice_bounds(const uint32_t* keys, int64_t nnz, int n_slices, int64_t n_slots,
+                                int32_t* d_pos, cudaStream_t st, int64_t* launches) {
+    ++*launches;
+    slice_bounds_kernel<<<1, 64, 0, st>>>(keys, (int)nnz, n_slices, n_slots, d_pos);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // Dense update from the all-reduced gradient [gV | gw | gw0]  (DESIGN.md 2.3).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 fm_update_kernel(float4* __restrict__ V4, float* __restrict__ W, float* __restrict__ W0,
-                 int64_t nv4, int64_t n_slots, int k0, int k1, const float4* __restrict__ G4,
-                 const float* __restrict__ Gw, const float* __restrict__ Gw0,
-                 const double* __restrict__ d_scal, const int32_t* __restrict__ err,
-                 UpdateParams up) {
+                 int lpr, int64_t feat_lo, int64_t feat_hi, int k0, int k1,
+                 const float4* __restrict__ G4, const float* __restrict__ Gw,
+                 const float* __restrict__ Gw0, const double* __restrict__ d_scal,
+                 const int32_t* __restrict__ err, UpdateParams up) {
     if (*err) return;
     const double count = d_scal[SC_COUNT];
     if (!(count > 0.0)) return;
     const float inv = (float)(1.0 / count);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (int64_t i = tid; i < nv4; i += stride) {
+    for (int64_t i = feat_lo * lpr + tid; i < feat_hi * lpr; i += stride) {
         float4 v = V4[i];
         const float4 g = __ldg(G4 + i);
         v.x -= up.eta * (g.x * inv + up.regv * v.x);
@@ -1007,29 +1056,35 @@ fm_update_kernel(float4* __restrict__ V4, float* __restrict__ W, float* __restri
         V4[i] = v;
     }
     if (k1)
-        for (int64_t i = tid; i < n_slots; i += stride) {
+        for (int64_t i = feat_lo + tid; i < feat_hi; i += stride) {
             const float w = W[i];
             W[i] = w - up.eta * (__ldg(Gw + i) * inv + up.regw * w);
         }
-    if (k0 && tid == 0) {
+    if (k0 && tid == 0 && feat_lo == 0) {
         const float w0 = *W0;
         *W0 = w0 - up.eta * (*Gw0 * inv + up.reg0 * w0);
     }
 }
 
-cudaError_t launch_update(const ModelView& m, const float* grad, const double* d_scal,
-                          const int32_t* d_err, UpdateParams up, cudaStream_t st,
-                          int64_t* launches) {
+cudaError_t launch_update_range(const ModelView& m, const float* grad, const double* d_scal,
+                                const int32_t* d_err, UpdateParams up, int64_t feat_lo,
+                                int64_t feat_hi, cudaStream_t st, int64_t* launches) {
     ++*launches;
-    const int64_t nv4 = m.n_slots * m.lpr;
+    const int64_t nv4 = (feat_hi - feat_lo) * m.lpr;
     int64_t blocks = (nv4 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
     const float* gw = grad + m.n_slots * m.kp;
-    fm_update_kernel<<<(unsigned)blocks, 256, 0, st>>>((float4*)m.v, m.w, m.w0, nv4, m.n_slots,
-                                                       m.k0, m.k1, (const float4*)grad, gw,
+    fm_update_kernel<<<(unsigned)blocks, 256, 0, st>>>((float4*)m.v, m.w, m.w0, m.lpr, feat_lo,
+                                                       feat_hi, m.k0, m.k1, (const float4*)grad, gw,
                                                        gw + m.n_slots, d_scal, d_err, up);
     return cudaGetLastError();
+}
+
+cudaError_t launch_update(const ModelView& m, const float* grad, const double* d_scal,
+                          const int32_t* d_err, UpdateParams up, cudaStream_t st,
+                          int64_t* launches) {
+    return launch_update_range(m, grad, d_scal, d_err, up, 0, m.n_slots, st, launches);
 }
 
 // ------------------------------------------------------------------------------------------
