@@ -328,7 +328,7 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
         static int q_env = -1;
         if (q_env < 0) {
             const char* e = getenv("SFM_AR_SLICES");
-            q_env = e ? atoi(e) : 4;
+            q_env = e ? atoi(e) : 1;   // off by default: pays only when the all-reduce is long
             if (q_env < 1) q_env = 1;
             if (q_env > 8) q_env = 8;
         }
@@ -381,8 +381,10 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
         }
         const int64_t chb = pull_chunk_entries(m);
         const int64_t nchunks = (nnz + chb - 1) / chb;
+        // slice-major gradient buffer: slice q = [gV rows of the slice | gw of the slice], so one
+        // all-reduce per slice; gw0 sits at the very end
         float* grad = (float*)h->b_grad.p;
-        float* gw = grad + m.n_slots * m.kp;
+        float* gw0 = grad + (size_t)m.n_slots * (m.kp + 1);
         CU(cudaStreamWaitEvent(h->stream, h->ev_pool[1], 0));   // all-reduced scalars
         for (int q = 0; q < n_slices; ++q) {
             PullSlice sl;
@@ -391,17 +393,19 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
             sl.chunk_lo = q == 0 ? 0 : (pos[q] + chb - 1) / chb;
             sl.chunk_hi = q == n_slices - 1 ? nchunks : (pos[q + 1] + chb - 1) / chb;
             sl.first = q == 0;
+            const size_t nf = (size_t)(sl.feat_hi - sl.feat_lo);
+            float* base = grad + (size_t)sl.feat_lo * (m.kp + 1);
+            sl.gv = base - (size_t)sl.feat_lo * m.kp;          // kernels index with global feature ids
+            sl.gw = base + nf * m.kp - sl.feat_lo;
+            sl.gw0 = gw0;
             CU(launch_pull_slice(m, (int32_t*)h->b_seg.p, key_bits, n_blocks, keys_sorted, pay_sorted,
                                  nnz, binary, o.S, o.mult, (float*)h->b_pull.p, h->d_scal, h->d_err,
                                  up, false, grad, h->sm_count, h->stream, sl, L));
             CU(cudaEventRecord(h->ev_pool[2 + q], h->stream));
             CU(cudaStreamWaitEvent(h->comm_stream, h->ev_pool[2 + q], 0));
-            const size_t nf = (size_t)(sl.feat_hi - sl.feat_lo);
-            RC(nccl_allreduce_f32(h->nccl, h->comm, grad + (size_t)sl.feat_lo * m.kp, nf * m.kp,
-                                  h->comm_stream, &h->err));
-            RC(nccl_allreduce_f32(h->nccl, h->comm, gw + sl.feat_lo, nf, h->comm_stream, &h->err));
-            CU(launch_update_range(m, grad, h->d_scal, h->d_err, up, sl.feat_lo, sl.feat_hi,
-                                   h->comm_stream, L));
+            RC(nccl_allreduce_f32(h->nccl, h->comm, base, nf * (m.kp + 1), h->comm_stream, &h->err));
+            CU(launch_update_ptrs(m, sl.gv, sl.gw, sl.gw0, h->d_scal, h->d_err, up, sl.feat_lo,
+                                  sl.feat_hi, h->comm_stream, L));
         }
         CU(cudaEventRecord(h->ev_pool[2 + n_slices], h->comm_stream));
         CU(cudaStreamWaitEvent(h->stream, h->ev_pool[2 + n_slices], 0));

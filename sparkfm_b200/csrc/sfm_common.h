@@ -171,7 +171,12 @@ cudaError_t launch_pull(const ModelView& m, int32_t* seg, int key_bits, int n_bl
 struct PullSlice {
     int64_t chunk_lo = -1, chunk_hi = -1, feat_lo = -1, feat_hi = -1;   // -1 = everything
     bool first = true;                                                   // zero the run bounds
+    float *gv = nullptr, *gw = nullptr, *gw0 = nullptr;   // optional pre-biased gradient pointers
 };
+cudaError_t launch_update_ptrs(const ModelView& m, const float* gv, const float* gw,
+                               const float* gw0, const double* d_scal, const int32_t* d_err,
+                               UpdateParams up, int64_t feat_lo, int64_t feat_hi, cudaStream_t st,
+                               int64_t* launches);
 cudaError_t launch_pull_slice(const ModelView& m, int32_t* seg, int key_bits, int n_blocks,
                               const uint32_t* keys, const uint2* pay, int64_t nnz, bool binary,
                               const float* S, const float* mult, float* scratch,

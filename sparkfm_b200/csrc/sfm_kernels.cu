@@ -827,6 +827,8 @@ fm_pull_finalize_kernel(float4* __restrict__ V4, float* __restrict__ W, float* _
         }
     }
     for (int64_t i = feat_lo + tid / LPR; i < feat_hi; i += ngroups) {
+        float4 v = V4[i * LPR + fq];   // issued before the dependent record loads
+        const float wi = (fq == 0 && k1) ? W[i] : 0.f;
         float4 A = f4_zero();
         float D = 0.f, C = 0.f;
         for (int blk = 0; blk < n_blocks; ++blk) {  // row blocks in order: fixed summation order
@@ -851,7 +853,6 @@ fm_pull_finalize_kernel(float4* __restrict__ V4, float* __restrict__ W, float* _
             }
         }
         if (BINARY) D = C;
-        float4 v = V4[i * LPR + fq];
         float4 g;
         g.x = A.x - v.x * D;
         g.y = A.y - v.y * D;
@@ -864,10 +865,7 @@ fm_pull_finalize_kernel(float4* __restrict__ V4, float* __restrict__ W, float* _
                 v.z -= up.eta * (g.z * inv + up.regv * v.z);
                 v.w -= up.eta * (g.w * inv + up.regv * v.w);
                 V4[i * LPR + fq] = v;
-                if (fq == 0 && k1) {
-                    const float w = W[i];
-                    W[i] = w - up.eta * (C * inv + up.regw * w);
-                }
+                if (fq == 0 && k1) W[i] = wi - up.eta * (C * inv + up.regw * wi);
             }
         } else {
             G4[i * LPR + fq] = g;
@@ -955,14 +953,20 @@ static cudaError_t pull_dispatch(const ModelView& m, int32_t* seg, int key_bits,
     if (f_hi <= f_lo) return cudaGetLastError();
     const int64_t threads = (f_hi - f_lo) * LPR;
     int64_t blocks = (threads + 255) / 256;
-    const int64_t cap = (int64_t)sm_count * 32;
+    const int64_t cap = (int64_t)sm_count * 128;   // short dependent chains: favour parallelism
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
+    float* gv = grad;
     float* gw = grad ? grad + m.n_slots * m.kp : nullptr;
     float* gw0 = grad ? gw + m.n_slots : nullptr;
+    if (sl.gv) {  // slice-major gradient layout: pointers pre-biased so that global indices work
+        gv = sl.gv;
+        gw = sl.gw;
+        gw0 = sl.gw0;
+    }
 #define FIN_ARGS                                                                              \
     (float4*)m.v, m.w, m.w0, m.n_slots, m.k0, m.k1, seg_lo, seg_hi, R1, R2, n_blocks, d_scal, \
-        d_err, up, (float4*)grad, gw, gw0, f_lo, f_hi
+        d_err, up, (float4*)gv, gw, gw0, f_lo, f_hi
     const dim3 gd((unsigned)blocks), bd(256);
     if (fused) {
         if (binary) fm_pull_finalize_kernel<LPR, true, true><<<gd, bd, 0, st>>>(FIN_ARGS);
@@ -1066,19 +1070,27 @@ fm_update_kernel(float4* __restrict__ V4, float* __restrict__ W, float* __restri
     }
 }
 
-cudaError_t launch_update_range(const ModelView& m, const float* grad, const double* d_scal,
-                                const int32_t* d_err, UpdateParams up, int64_t feat_lo,
-                                int64_t feat_hi, cudaStream_t st, int64_t* launches) {
+cudaError_t launch_update_ptrs(const ModelView& m, const float* gv, const float* gw,
+                               const float* gw0, const double* d_scal, const int32_t* d_err,
+                               UpdateParams up, int64_t feat_lo, int64_t feat_hi, cudaStream_t st,
+                               int64_t* launches) {
     ++*launches;
     const int64_t nv4 = (feat_hi - feat_lo) * m.lpr;
     int64_t blocks = (nv4 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    const float* gw = grad + m.n_slots * m.kp;
     fm_update_kernel<<<(unsigned)blocks, 256, 0, st>>>((float4*)m.v, m.w, m.w0, m.lpr, feat_lo,
-                                                       feat_hi, m.k0, m.k1, (const float4*)grad, gw,
-                                                       gw + m.n_slots, d_scal, d_err, up);
+                                                       feat_hi, m.k0, m.k1, (const float4*)gv, gw,
+                                                       gw0, d_scal, d_err, up);
     return cudaGetLastError();
+}
+
+cudaError_t launch_update_range(const ModelView& m, const float* grad, const double* d_scal,
+                                const int32_t* d_err, UpdateParams up, int64_t feat_lo,
+                                int64_t feat_hi, cudaStream_t st, int64_t* launches) {
+    const float* gw = grad + m.n_slots * m.kp;
+    return launch_update_ptrs(m, grad, gw, gw + m.n_slots, d_scal, d_err, up, feat_lo, feat_hi, st,
+                              launches);
 }
 
 cudaError_t launch_update(const ModelView& m, const float* grad, const double* d_scal,
