@@ -6,7 +6,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <charconv>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -77,13 +79,58 @@ static bool java_double(const char* b, const char* e, double* out) {
     const char* num_end = q;
     if (q < e && (*q == 'f' || *q == 'F' || *q == 'd' || *q == 'D')) ++q;
     if (q != e) return false;
-    char buf[64];
-    std::string big;
-    const size_t n = (size_t)(num_end - b);
-    const char* src;
-    if (n < sizeof(buf)) { memcpy(buf, b, n); buf[n] = 0; src = buf; }
-    else { big.assign(b, n); src = big.c_str(); }
-    *out = strtod(src, nullptr);
+    {
+        // Clinger's fast path: <= 15 significant digits and |10-exponent| <= 22 -> the mantissa
+        // and the power of ten are exact doubles, one correctly rounded multiply / divide gives the
+        // same bits as strtod
+        static const double P10[] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,
+                                     1e8,  1e9,  1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
+                                     1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+        uint64_t mant = 0;
+        int nd = 0, frac = 0, ex = 0;
+        bool seen_dot = false, exneg = false, ok = true;
+        const char* z = p;
+        for (; z < num_end; ++z) {
+            const char c = *z;
+            if (c >= '0' && c <= '9') {
+                if (nd > 0 || c != '0') {
+                    if (++nd > 15) { ok = false; break; }
+                    mant = mant * 10 + (uint64_t)(c - '0');
+                }
+                if (seen_dot) ++frac;
+            } else if (c == '.') {
+                seen_dot = true;
+            } else {  // exponent part
+                ++z;
+                if (z < num_end && (*z == '+' || *z == '-')) { exneg = *z == '-'; ++z; }
+                for (; z < num_end; ++z) {
+                    ex = ex * 10 + (*z - '0');
+                    if (ex > 400) { ok = false; break; }
+                }
+                break;
+            }
+        }
+        if (ok) {
+            const int e10 = (exneg ? -ex : ex) - frac;
+            if (e10 >= -22 && e10 <= 22) {
+                double v = (double)mant;
+                v = e10 < 0 ? v / P10[-e10] : v * P10[e10];
+                *out = neg ? -v : v;
+                return true;
+            }
+        }
+    }
+    // general case: std::from_chars is correctly rounded (same bits as strtod) and locale-free
+    double v = 0.0;
+    const std::from_chars_result r = std::from_chars(p, num_end, v, std::chars_format::general);
+    if (r.ec == std::errc::result_out_of_range) {
+        // overflow -> +-Infinity, underflow -> +-0 like Double.parseDouble; let strtod decide
+        std::string tmp(p, num_end);
+        v = strtod(tmp.c_str(), nullptr);
+    } else if (r.ec != std::errc() || r.ptr != num_end) {
+        return false;
+    }
+    *out = neg ? -v : v;
     return true;
 }
 
@@ -109,19 +156,22 @@ static bool java_int(const char* b, const char* e, int32_t* out) {
 
 using namespace sfm;
 
-extern "C" int32_t sfm_parse_libfm(const char* text, uint64_t len, int32_t num_features,
-                                   int64_t* n_rows, int64_t* nnz, int32_t* dimension_out,
-                                   double* label, int64_t* row_ptr, int32_t* idx, double* val,
-                                   int64_t* err_line) {
-    if (!text && len) return SFM_ERR_ARG;
-    if (!n_rows || !nnz) return SFM_ERR_ARG;
-    const bool fill = idx != nullptr || label != nullptr || row_ptr != nullptr || val != nullptr;
+namespace {
+
+struct ChunkStat {
+    int64_t rows = 0, ents = 0, lines = 0, err_line = -1;   // err_line: 1-based inside the chunk
+    int32_t max_index = INT32_MIN;
+    bool empty_row = false;
+};
+
+// Parses the physical lines of [p, end) (a chunk that starts at a line start and ends after a
+// line terminator or at the end of the text).  Counting pass: out arrays null.  Filling pass:
+// rows / entries are written starting at row0 / ent0.
+static void parse_chunk(const char* p, const char* end, ChunkStat* st, double* label,
+                        int64_t* row_ptr, int32_t* idx, double* val, int64_t row0, int64_t ent0) {
     int64_t rows = 0, ents = 0, line_no = 0;
     int32_t max_index = INT32_MIN;
     bool empty_row = false;
-    const char* p = text;
-    const char* end = text + len;
-    if (fill && row_ptr) row_ptr[0] = 0;
     while (p < end) {
         // one physical line: terminated by \n, \r\n or \r (Hadoop LineReader, used by sc.textFile)
         const char* le = p;
@@ -141,10 +191,10 @@ extern "C" int32_t sfm_parse_libfm(const char* text, uint64_t len, int32_t num_f
         while (te < e && *te != ' ') ++te;
         double lab;
         if (!java_double(t, te, &lab)) {                      // items.head.toDouble         :29
-            if (err_line) *err_line = line_no;
-            return SFM_ERR_IO;
+            st->err_line = line_no;
+            return;
         }
-        if (fill && label) label[rows] = lab;
+        if (label) label[row0 + rows] = lab;
         int64_t row_ents = 0;
         t = te;
         while (t < e) {
@@ -156,8 +206,8 @@ extern "C" int32_t sfm_parse_libfm(const char* text, uint64_t len, int32_t num_f
             const char* c0 = t;
             while (c0 < te && *c0 != ':') ++c0;
             if (c0 == te) {                                   // no ':' -> indexAndValue(1) throws
-                if (err_line) *err_line = line_no;
-                return SFM_ERR_IO;
+                st->err_line = line_no;
+                return;
             }
             const char* v0 = c0 + 1;
             const char* v1 = v0;
@@ -168,13 +218,11 @@ extern "C" int32_t sfm_parse_libfm(const char* text, uint64_t len, int32_t num_f
             bool rest_empty = true;
             for (const char* z = v0; z < te; ++z) if (*z != ':') { rest_empty = false; break; }
             if (rest_empty || !java_int(t, c0, &id) || !java_double(v0, v1, &x)) {
-                if (err_line) *err_line = line_no;
-                return SFM_ERR_IO;
+                st->err_line = line_no;
+                return;
             }
-            if (fill) {
-                if (idx) idx[ents] = id;
-                if (val) val[ents] = x;
-            }
+            if (idx) idx[ent0 + ents] = id;
+            if (val) val[ent0 + ents] = x;
             if (id > max_index) max_index = id;
             ++ents;
             ++row_ents;
@@ -182,7 +230,79 @@ extern "C" int32_t sfm_parse_libfm(const char* text, uint64_t len, int32_t num_f
         }
         if (row_ents == 0) empty_row = true;
         ++rows;
-        if (fill && row_ptr) row_ptr[rows] = ents;
+        if (row_ptr) row_ptr[row0 + rows] = ent0 + ents;
+    }
+    st->rows = rows;
+    st->ents = ents;
+    st->lines = line_no;
+    st->max_index = max_index;
+    st->empty_row = empty_row;
+}
+
+}  // namespace
+
+// Multi-threaded: the text is cut at line boundaries into one chunk per thread; a counting pass
+// gives every chunk its first row / entry, a filling pass writes the arrays.  The result is
+// identical to a sequential parse (text ingest at speed).
+extern "C" int32_t sfm_parse_libfm(const char* text, uint64_t len, int32_t num_features,
+                                   int64_t* n_rows, int64_t* nnz, int32_t* dimension_out,
+                                   double* label, int64_t* row_ptr, int32_t* idx, double* val,
+                                   int64_t* err_line) {
+    if (!text && len) return SFM_ERR_ARG;
+    if (!n_rows || !nnz) return SFM_ERR_ARG;
+    const bool fill = idx != nullptr || label != nullptr || row_ptr != nullptr || val != nullptr;
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > 64) nt = 64;
+    const uint64_t min_chunk = 1u << 20;
+    if (len / min_chunk < nt) nt = (unsigned)(len / min_chunk);
+    if (nt < 1) nt = 1;
+    // chunk boundaries: advance to just after the next line terminator
+    std::vector<const char*> cut(nt + 1);
+    const char* end = text + len;
+    cut[0] = text;
+    cut[nt] = end;
+    for (unsigned t = 1; t < nt; ++t) {
+        const char* p = text + len * t / nt;
+        if (p < cut[t - 1]) p = cut[t - 1];
+        while (p < end && *p != '\n' && *p != '\r') ++p;
+        if (p < end) p += (*p == '\r' && p + 1 < end && p[1] == '\n') ? 2 : 1;
+        cut[t] = p;
+    }
+    std::vector<ChunkStat> st(nt);
+    auto run = [&](bool filling, const std::vector<int64_t>* row0, const std::vector<int64_t>* ent0) {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t)
+            th.emplace_back([&, t] {
+                if (filling)
+                    parse_chunk(cut[t], cut[t + 1], &st[t], label, row_ptr, idx, val, (*row0)[t],
+                                (*ent0)[t]);
+                else
+                    parse_chunk(cut[t], cut[t + 1], &st[t], nullptr, nullptr, nullptr, nullptr, 0, 0);
+            });
+        for (auto& x : th) x.join();
+    };
+    run(false, nullptr, nullptr);
+    int64_t rows = 0, ents = 0, lines_before = 0;
+    int32_t max_index = INT32_MIN;
+    bool empty_row = false;
+    std::vector<int64_t> row0(nt), ent0(nt);
+    for (unsigned t = 0; t < nt; ++t) {
+        if (st[t].err_line >= 0) {  // the first failing chunk holds the first failing line
+            if (err_line) *err_line = lines_before + st[t].err_line;
+            return SFM_ERR_IO;
+        }
+        row0[t] = rows;
+        ent0[t] = ents;
+        rows += st[t].rows;
+        ents += st[t].ents;
+        lines_before += st[t].lines;
+        if (st[t].max_index > max_index) max_index = st[t].max_index;
+        empty_row = empty_row || st[t].empty_row;
+    }
+    if (fill) {
+        if (row_ptr) row_ptr[0] = 0;
+        run(true, &row0, &ent0);
     }
     *n_rows = rows;
     *nnz = ents;
