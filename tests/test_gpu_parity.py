@@ -483,3 +483,44 @@ def test_pipelined_staging_matches_synchronous_csr_path():
     assert ei.value.status == SFM_ERR_STATE
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("k,task", [(32, 0), (64, 1), (128, 0)])
+def test_train_wide_factor_counts(k, task):
+    """kp = 32 / 64 / 128 (8 / 16 / 32 lanes per V row): every lane mapping of the forward and of the
+    reduce-by-feature against the oracle."""
+    _train_case(task=task, k=k, n_slots=900, n_rows=2500, mean_nnz=14, values="uniform",
+                reg=(0.0, 1e-4, 1e-3), step=0.05, frac=0.4, iters=5, seed=100 + k)
+
+
+def test_empty_and_tiny_batches():
+    """A sampling rate so small that iterations draw 0 or 1 rows: an empty batch leaves the model
+    untouched and reports loss 0; single-row batches still match the oracle."""
+    rng = np.random.default_rng(91)
+    n_slots, k, n_rows = 300, 8, 400
+    row_ptr, idx, val = synth.ragged_rows(n_rows, n_slots, 6, seed=91, values="normal")
+    label = rng.normal(0, 1, n_rows).astype(np.float32)
+    w0, w, v = make_model(rng, n_slots, k)
+    frac = 0.002
+    hd = Handle(n_slots, k, task=0, reg=(0.0, 1e-3, 1e-3), step_size=0.1, mini_batch_fraction=frac,
+                sampler_seed=3)
+    hd.set_model(w0, w, v)
+    hd.load_dataset(row_ptr, idx, val, label)
+    orc = OracleFM(n_slots, k, task=0, reg=(0.0, float(np.float32(1e-3)), float(np.float32(1e-3))))
+    orc.set_model(w0, w, v)
+    sizes = []
+    for it in range(1, 13):
+        ids = ocapi.sample_rows(3, it, float(np.float32(frac)), 0, n_rows)
+        sizes.append(len(ids))
+        before = hd.get_model()
+        lg, batch = hd.train_step(it)
+        assert batch == len(ids)
+        if len(ids) == 0:
+            after = hd.get_model()
+            assert lg == 0.0 and before[0] == after[0] and np.array_equal(before[2], after[2])
+        else:
+            lo = orc.train_step(row_ptr, idx, val.astype(np.float64), label, ids, it,
+                                float(np.float32(0.1))) / len(ids)
+            assert abs(lg - lo) <= LOSS_RTOL * max(abs(lo), 1e-6)
+    assert 0 in sizes and max(sizes) >= 1, sizes
+    hd.close()
