@@ -41,7 +41,7 @@ sys.path.insert(0, ROOT)
 N_FIELDS, N_SLOTS, K, ZIPF_S = 39, 1_000_000, 16, 1.1
 DATA_SEED, INIT_SEED, SAMPLER_SEED = 20260103, 1, 42
 STEP_SIZE, REG = 0.1, (0.0, 0.0, 1e-5)
-METRIC, UNIT = "fm_sgd_train_samples_per_sec", "samples/s"
+METRIC, UNIT = "FM SGD train samples/sec", "samples/s"   # BASELINE.json "metric"
 
 
 def b_train(m, k):   # algorithmic bytes per sample
