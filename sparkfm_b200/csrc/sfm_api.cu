@@ -266,7 +266,8 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     if (is_sharded(h)) {
         if (grad_keep) return set_err(h, SFM_ERR_STATE, "sfm_gradient is not available with SFM_FLAG_SHARD_V");
         RC(validate_view(h, b));
-        return shard_train(h, b, iter);
+        const int slot = pc ? (int)(pc - h->parts.data()) : -1;
+        return shard_train(h, b, iter, slot);
     }
     ModelView& m = h->m;
     const int64_t n = b.n_rows, nnz = b.nnz;
@@ -514,6 +515,7 @@ static int sample_device(sfm_handle* h, int64_t iter, const int32_t** ids_dev, i
 }
 
 static void free_parts(sfm_handle* h) {
+    shard_clear_cache(h);
     for (PartCache& pc : h->parts) {
         free_buf(pc.row_ids);
         free_buf(pc.keys);
@@ -579,9 +581,11 @@ static int partition_batch(sfm_handle* h, int64_t iter, BatchView* b, const Part
         const size_t cnt = (size_t)(v.nnz > 0 ? v.nnz : 1);
         RC(ensure(h, h->b_keys[0], sizeof(uint32_t) * cnt));
         RC(ensure(h, h->b_pay[0], pay_sz * cnt));
-        RC(ensure(h, pc.keys, sizeof(uint32_t) * cnt));
-        RC(ensure(h, pc.pay, pay_sz * cnt));
-        if (v.nnz > 0) {
+        if (!is_sharded(h)) {
+            RC(ensure(h, pc.keys, sizeof(uint32_t) * cnt));
+            RC(ensure(h, pc.pay, pay_sz * cnt));
+        }
+        if (v.nnz > 0 && !is_sharded(h)) {   // row-sharded models cache their own plan (sfm_shard.cu)
             CU(launch_emit(v, pc.key_bits, pc.blk_shift, h->m.n_slots, (uint32_t*)h->b_keys[0].p,
                            (uint2*)h->b_pay[0].p, h->sm_count, h->stream, L));
             const int end_bit = pc.key_bits + blk_bits;
@@ -611,7 +615,7 @@ static int partition_batch(sfm_handle* h, int64_t iter, BatchView* b, const Part
     b->n_rows = pc.n_rows;
     b->nnz = pc.nnz;
     b->idx_len = ds.nnz;
-    b->out_ptr = nullptr;
+    b->out_ptr = (P > 1 || ds.uniform_m >= 0) ? nullptr : ds.row_ptr;   // identity batch, ragged rows
     b->out_base = 0;
     b->uniform_m = ds.uniform_m;
     b->validated = true;
@@ -815,8 +819,11 @@ int32_t sfm_destroy(sfm_handle* h) {
     for (Buf* b : bufs) free_buf(*b);
     if (h->shard) {
         ShardState& ss = *h->shard;
-        Buf* sb[] = {&ss.flags, &ss.crank, &ss.uniq, &ss.small, &ss.lut, &ss.req, &ss.out_v, &ss.out_w,
-                     &ss.t_v, &ss.t_w, &ss.bidx, &ss.bval, &ss.blabel, &ss.gr_v, &ss.gr_w, &ss.acc};
+        shard_clear_cache(h);
+        Buf* sb[] = {&ss.flags, &ss.keys_tmp, &ss.small, &ss.lut, &ss.out_v, &ss.out_w, &ss.t_v, &ss.t_w,
+                     &ss.gr_v, &ss.gr_w, &ss.acc, &ss.scratch.crank, &ss.scratch.pay, &ss.scratch.uniq,
+                     &ss.scratch.req, &ss.scratch.bidx, &ss.scratch.bval, &ss.scratch.blabel,
+                     &ss.scratch.optr};
         for (Buf* b : sb) free_buf(*b);
         if (ss.v) cudaFree(ss.v);
         if (ss.w) cudaFree(ss.w);

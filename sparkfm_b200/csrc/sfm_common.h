@@ -52,13 +52,25 @@ struct PartCache {
     int32_t slice_pos[16] = {0};
 };
 
-// Row-sharded model (sfm_shard.cu): this rank owns features [own_lo, own_lo + n_own).
+// Row-sharded model (sfm_shard.cu).  ShardBatch = everything about a batch that depends on its
+// ROW SET only (not on the model): sorted entries with compact feature ids, the unique features,
+// the request lists exchanged with the owners, the compact copy of the batch.  Built per step for
+// sampled batches; built once and kept for the fixed batches of the PARTITION sampler.
+struct ShardBatch {
+    bool built = false;
+    int64_t U = 0, R = 0;   // unique features of this batch; rows requested from this rank
+    std::vector<int64_t> send_off, send_cnt, recv_off, recv_cnt;
+    Buf crank, pay, uniq, req, bidx, bval, blabel, optr;
+};
+
+// this rank owns features [own_lo, own_lo + n_own)
 struct ShardState {
     int64_t n_per = 0, own_lo = 0, n_own = 0;
     float* v = nullptr;   // [n_per][kp]
     float* w = nullptr;   // [n_per]
-    Buf flags, crank, uniq, small, lut, req, out_v, out_w, t_v, t_w, bidx, bval, blabel, gr_v, gr_w,
-        acc;
+    Buf flags, keys_tmp, small, lut, out_v, out_w, t_v, t_w, gr_v, gr_w, acc;
+    ShardBatch scratch;
+    std::vector<ShardBatch> cached;   // one per PARTITION mini-batch
     int32_t* h_small = nullptr;
     size_t h_small_cap = 0;
 };
@@ -238,7 +250,8 @@ cudaError_t sample_rows_device(void* tmp, size_t tmp_bytes, int64_t n, int64_t g
 
 // ---- row-sharded model (sfm_shard.cu)
 int shard_forward(sfm_handle* h, const BatchView& b);                 // yhat -> h->b_yhat
-int shard_train(sfm_handle* h, const BatchView& b, int64_t iter);
+int shard_train(sfm_handle* h, const BatchView& b, int64_t iter, int cache_slot);  // -1: no cache
+void shard_clear_cache(sfm_handle* h);
 
 // ---- host side (sfm_host.cpp)
 uint64_t mix64(uint64_t x);

@@ -172,19 +172,34 @@ static int bits_for64(int64_t n) {
     return b;
 }
 
-// ------------------------------------------------------------------------------------------
-// Steps 1-4a: builds the compact model (T_v, T_w) and the compact batch for `b`.
-// ------------------------------------------------------------------------------------------
+static void free_b(Buf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+static void free_shard_batch(ShardBatch& sb) {
+    Buf* bs[] = {&sb.crank, &sb.pay, &sb.uniq, &sb.req, &sb.bidx, &sb.bval, &sb.blabel, &sb.optr};
+    for (Buf* b : bs) free_b(*b);
+    sb.built = false;
+}
+
+void shard_clear_cache(sfm_handle* h) {
+    if (!h->shard) return;
+    for (ShardBatch& sb : h->shard->cached) free_shard_batch(sb);
+    h->shard->cached.clear();
+}
+
+// what the compute kernels need for one iteration
 struct ShardPlan {
-    int64_t U = 0, R = 0;                 // unique features here; rows requested from me
-    std::vector<int64_t> send_off, send_cnt, recv_off, recv_cnt;
-    ModelView mc;                          // compact model view
+    ModelView mc;                          // compact model view (T_v, T_w)
     BatchView bc;                          // compact batch view
-    const uint32_t* ckeys = nullptr;       // sorted compact keys
-    const uint2* pay = nullptr;            // sorted payload
 };
 
-static int shard_prepare(sfm_handle* h, const BatchView& b, bool need_label, ShardPlan* sp) {
+// ------------------------------------------------------------------------------------------
+// Steps 1, 2, 3a, 4a: everything that depends on the batch's rows only.
+// ------------------------------------------------------------------------------------------
+static int shard_build(sfm_handle* h, const BatchView& b, bool need_label, ShardBatch& sb) {
     ShardState& s = *h->shard;
     const ModelView& m = h->m;
     int64_t* L = &h->stats.kernel_launches;
@@ -193,13 +208,13 @@ static int shard_prepare(sfm_handle* h, const BatchView& b, bool need_label, Sha
     const bool binary = b.val == nullptr;
     const size_t pay_sz = binary ? sizeof(uint32_t) : sizeof(uint2);
     const size_t cntE = (size_t)(E > 0 ? E : 1);
-    for (int i = 0; i < 2; ++i) {
-        RC(ensure(h, h->b_keys[i], sizeof(uint32_t) * cntE));
-        RC(ensure(h, h->b_pay[i], pay_sz * cntE));
-    }
+    RC(ensure(h, h->b_keys[0], sizeof(uint32_t) * cntE));
+    RC(ensure(h, h->b_pay[0], pay_sz * cntE));
+    RC(ensure(h, s.keys_tmp, sizeof(uint32_t) * cntE));
     RC(ensure(h, s.flags, sizeof(uint32_t) * cntE));
-    RC(ensure(h, s.crank, sizeof(uint32_t) * cntE));
-    RC(ensure(h, s.uniq, sizeof(int32_t) * cntE));
+    RC(ensure(h, sb.pay, pay_sz * cntE));
+    RC(ensure(h, sb.crank, sizeof(uint32_t) * cntE));
+    RC(ensure(h, sb.uniq, sizeof(int32_t) * cntE));
     RC(ensure(h, s.small, sizeof(int32_t) * (size_t)(4 + 2 * (G + 1) + G * G)));
     RC(ensure(h, s.lut, sizeof(int32_t) * (size_t)m.n_slots));
     int32_t* d_nu = (int32_t*)s.small.p;           // [0]   n_uniq
@@ -208,38 +223,52 @@ static int shard_prepare(sfm_handle* h, const BatchView& b, bool need_label, Sha
     int32_t* d_all = d_cnt + (G + 1);              // [G*G]
     const int key_bits = bits_for64(m.n_slots);
 
+    // entry offsets of the batch rows
+    BatchView bb = b;
+    if (b.uniform_m < 0 && b.row_ids) {   // ragged sampled rows: own copy of the offsets
+        RC(ensure(h, sb.optr, sizeof(int64_t) * (size_t)(n + 1)));
+        RC(ensure(h, h->b_lens, sizeof(int64_t) * (size_t)(n + 1)));
+        CU(cudaMemsetAsync((int64_t*)h->b_lens.p + n, 0, sizeof(int64_t), h->stream));
+        CU(launch_row_lens(b.row_ptr, b.row_ids, n, (int64_t*)h->b_lens.p, h->stream, L));
+        const size_t tb = scan_temp_bytes(n + 1);
+        RC(ensure(h, h->b_sel_tmp, tb));
+        CU(exclusive_scan_i64(h->b_sel_tmp.p, tb, (const int64_t*)h->b_lens.p, (int64_t*)sb.optr.p,
+                              n + 1, h->stream, L));
+        bb.out_ptr = (const int64_t*)sb.optr.p;
+        bb.out_base = 0;
+    }
     // 1. entries sorted by feature
     CU(cudaMemsetAsync(d_nu, 0, sizeof(int32_t) * 4, h->stream));
     if (E > 0) {
-        CU(launch_emit(b, key_bits, 30, m.n_slots, (uint32_t*)h->b_keys[0].p, (uint2*)h->b_pay[0].p,
+        CU(launch_emit(bb, key_bits, 30, m.n_slots, (uint32_t*)h->b_keys[0].p, (uint2*)h->b_pay[0].p,
                        h->sm_count, h->stream, L));
-        const size_t sb = binary ? sort_pairs32_temp_bytes(E, key_bits) : sort_pairs_temp_bytes(E, key_bits);
-        RC(ensure(h, h->b_sort_tmp, sb));
+        const size_t tb = binary ? sort_pairs32_temp_bytes(E, key_bits) : sort_pairs_temp_bytes(E, key_bits);
+        RC(ensure(h, h->b_sort_tmp, tb));
         if (binary)
-            CU(sort_pairs32(h->b_sort_tmp.p, sb, (const uint32_t*)h->b_keys[0].p,
-                            (uint32_t*)h->b_keys[1].p, (const uint32_t*)h->b_pay[0].p,
-                            (uint32_t*)h->b_pay[1].p, E, key_bits, h->stream, L));
+            CU(sort_pairs32(h->b_sort_tmp.p, tb, (const uint32_t*)h->b_keys[0].p,
+                            (uint32_t*)s.keys_tmp.p, (const uint32_t*)h->b_pay[0].p,
+                            (uint32_t*)sb.pay.p, E, key_bits, h->stream, L));
         else
-            CU(sort_pairs(h->b_sort_tmp.p, sb, (const uint32_t*)h->b_keys[0].p,
-                          (uint32_t*)h->b_keys[1].p, (const uint2*)h->b_pay[0].p,
-                          (uint2*)h->b_pay[1].p, E, key_bits, h->stream, L));
+            CU(sort_pairs(h->b_sort_tmp.p, tb, (const uint32_t*)h->b_keys[0].p,
+                          (uint32_t*)s.keys_tmp.p, (const uint2*)h->b_pay[0].p, (uint2*)sb.pay.p, E,
+                          key_bits, h->stream, L));
         // 2. unique features + compact ids
-        const uint32_t* keys1 = (const uint32_t*)h->b_keys[1].p;
+        const uint32_t* keys1 = (const uint32_t*)s.keys_tmp.p;
         run_flags_kernel<<<(unsigned)grid_for(E), 256, 0, h->stream>>>(keys1, E, (uint32_t*)s.flags.p);
-        size_t tb = 0;
-        cub::DeviceScan::InclusiveSum(nullptr, tb, (const uint32_t*)nullptr, (uint32_t*)nullptr, E);
-        RC(ensure(h, h->b_sel_tmp, tb));
-        CU(cub::DeviceScan::InclusiveSum(h->b_sel_tmp.p, tb, (const uint32_t*)s.flags.p,
-                                         (uint32_t*)s.crank.p, E, h->stream));
+        size_t tb2 = 0;
+        cub::DeviceScan::InclusiveSum(nullptr, tb2, (const uint32_t*)nullptr, (uint32_t*)nullptr, E);
+        RC(ensure(h, h->b_sel_tmp, tb2));
+        CU(cub::DeviceScan::InclusiveSum(h->b_sel_tmp.p, tb2, (const uint32_t*)s.flags.p,
+                                         (uint32_t*)sb.crank.p, E, h->stream));
         uniq_scatter_kernel<<<(unsigned)grid_for(E), 256, 0, h->stream>>>(
-            keys1, (const uint32_t*)s.flags.p, (uint32_t*)s.crank.p, E, (int32_t*)s.uniq.p, d_nu);
+            keys1, (const uint32_t*)s.flags.p, (uint32_t*)sb.crank.p, E, (int32_t*)sb.uniq.p, d_nu);
         *L += 4;
     }
-    owner_bounds_kernel<<<1, 256, 0, h->stream>>>((const int32_t*)s.uniq.p, d_nu, s.n_per, G,
+    owner_bounds_kernel<<<1, 256, 0, h->stream>>>((const int32_t*)sb.uniq.p, d_nu, s.n_per, G,
                                                   d_bounds, d_cnt);
     ++*L;
     CU(cudaGetLastError());
-    // 3a. everybody learns everybody's request counts
+    // 3a. everybody learns everybody's request counts (the one host sync of a build)
     RC(nccl_allgather_i32(h->nccl, h->comm, d_cnt, d_all, (size_t)G, h->stream, &h->err));
     const size_t hs = sizeof(int32_t) * (size_t)(4 + 2 * (G + 1) + G * G);
     if (s.h_small_cap < hs) {
@@ -252,48 +281,29 @@ static int shard_prepare(sfm_handle* h, const BatchView& b, bool need_label, Sha
     const int32_t* hv = s.h_small;
     const int32_t* h_bounds = hv + 4;
     const int32_t* h_all = hv + 4 + 2 * (G + 1);
-    sp->U = hv[0];
-    sp->send_off.assign(G, 0); sp->send_cnt.assign(G, 0);
-    sp->recv_off.assign(G, 0); sp->recv_cnt.assign(G, 0);
+    sb.U = hv[0];
+    sb.send_off.assign(G, 0); sb.send_cnt.assign(G, 0);
+    sb.recv_off.assign(G, 0); sb.recv_cnt.assign(G, 0);
     int64_t R = 0;
     for (int p = 0; p < G; ++p) {
-        sp->send_off[p] = h_bounds[p];
-        sp->send_cnt[p] = h_bounds[p + 1] - h_bounds[p];
-        sp->recv_off[p] = R;
-        sp->recv_cnt[p] = h_all[p * G + h->rank];
-        R += sp->recv_cnt[p];
+        sb.send_off[p] = h_bounds[p];
+        sb.send_cnt[p] = h_bounds[p + 1] - h_bounds[p];
+        sb.recv_off[p] = R;
+        sb.recv_cnt[p] = h_all[p * G + h->rank];
+        R += sb.recv_cnt[p];
     }
-    sp->R = R;
-    const int64_t U = sp->U;
-    // 3b. ids to the owners, rows back
-    RC(ensure(h, s.req, sizeof(int32_t) * (size_t)(R > 0 ? R : 1)));
-    RC(ensure(h, s.out_v, sizeof(float) * (size_t)(R > 0 ? R : 1) * m.kp));
-    RC(ensure(h, s.out_w, sizeof(float) * (size_t)(R > 0 ? R : 1)));
-    RC(ensure(h, s.t_v, sizeof(float) * (size_t)(U + 1) * m.kp));
-    RC(ensure(h, s.t_w, sizeof(float) * (size_t)(U + 1)));
-    RC(nccl_alltoallv_4b(h->nccl, h->comm, h->rank, G, s.uniq.p, sp->send_off.data(),
-                         sp->send_cnt.data(), s.req.p, sp->recv_off.data(), sp->recv_cnt.data(), 1,
+    sb.R = R;
+    const int64_t U = sb.U;
+    RC(ensure(h, sb.req, sizeof(int32_t) * (size_t)(R > 0 ? R : 1)));
+    RC(nccl_alltoallv_4b(h->nccl, h->comm, h->rank, G, sb.uniq.p, sb.send_off.data(),
+                         sb.send_cnt.data(), sb.req.p, sb.recv_off.data(), sb.recv_cnt.data(), 1,
                          h->stream, &h->err));
-    if (R > 0) {
-        gather_rows_kernel<<<(unsigned)grid_for(R * m.lpr), 256, 0, h->stream>>>(
-            (const float4*)s.v, s.w, (const int32_t*)s.req.p, R, s.own_lo, m.lpr, (float4*)s.out_v.p,
-            (float*)s.out_w.p);
-        ++*L;
-    }
-    RC(nccl_alltoallv_4b(h->nccl, h->comm, h->rank, G, s.out_v.p, sp->recv_off.data(),
-                         sp->recv_cnt.data(), s.t_v.p, sp->send_off.data(), sp->send_cnt.data(),
-                         m.kp, h->stream, &h->err));
-    RC(nccl_alltoallv_4b(h->nccl, h->comm, h->rank, G, s.out_w.p, sp->recv_off.data(),
-                         sp->recv_cnt.data(), s.t_w.p, sp->send_off.data(), sp->send_cnt.data(), 1,
-                         h->stream, &h->err));
-    CU(cudaMemsetAsync((float*)s.t_v.p + (size_t)U * m.kp, 0, sizeof(float) * m.kp, h->stream));
-    CU(cudaMemsetAsync((float*)s.t_w.p + U, 0, sizeof(float), h->stream));
-    // 4a. compact batch
-    RC(ensure(h, s.bidx, sizeof(int32_t) * cntE));
-    if (!binary) RC(ensure(h, s.bval, sizeof(float) * cntE));
-    RC(ensure(h, s.blabel, sizeof(float) * (size_t)(n > 0 ? n : 1)));
+    // 4a. compact copy of the batch
+    RC(ensure(h, sb.bidx, sizeof(int32_t) * cntE));
+    if (!binary) RC(ensure(h, sb.bval, sizeof(float) * cntE));
+    RC(ensure(h, sb.blabel, sizeof(float) * (size_t)(n > 0 ? n : 1)));
     if (U > 0) {
-        lut_scatter_kernel<<<(unsigned)grid_for(U), 256, 0, h->stream>>>((const int32_t*)s.uniq.p, U,
+        lut_scatter_kernel<<<(unsigned)grid_for(U), 256, 0, h->stream>>>((const int32_t*)sb.uniq.p, U,
                                                                          (int32_t*)s.lut.p);
         ++*L;
     }
@@ -301,47 +311,83 @@ static int shard_prepare(sfm_handle* h, const BatchView& b, bool need_label, Sha
         int64_t blocks = (n + 7) / 8;
         if (blocks > (int64_t)h->sm_count * 16) blocks = (int64_t)h->sm_count * 16;
         remap_batch_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(
-            b.row_ptr, b.idx, b.val, need_label ? b.label : nullptr, b.row_ids, b.row_lo, n,
-            b.out_ptr, b.out_base, b.uniform_m, (const int32_t*)s.lut.p, (int32_t*)s.bidx.p,
-            binary ? nullptr : (float*)s.bval.p, need_label ? (float*)s.blabel.p : nullptr);
+            bb.row_ptr, bb.idx, bb.val, need_label ? bb.label : nullptr, bb.row_ids, bb.row_lo, n,
+            bb.out_ptr, bb.out_base, bb.uniform_m, (const int32_t*)s.lut.p, (int32_t*)sb.bidx.p,
+            binary ? nullptr : (float*)sb.bval.p, need_label ? (float*)sb.blabel.p : nullptr);
         ++*L;
     }
     CU(cudaGetLastError());
+    sb.built = true;
+    return SFM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Step 3b: owners gather the requested rows, all-to-all -> compact tables; fills the plan.
+// ------------------------------------------------------------------------------------------
+static int shard_fetch(sfm_handle* h, const BatchView& b, const ShardBatch& sb, ShardPlan* sp) {
+    ShardState& s = *h->shard;
+    const ModelView& m = h->m;
+    int64_t* L = &h->stats.kernel_launches;
+    const int G = h->world;
+    const int64_t U = sb.U, R = sb.R, E = b.nnz;
+    const bool binary = b.val == nullptr;
+    RC(ensure(h, s.out_v, sizeof(float) * (size_t)(R > 0 ? R : 1) * m.kp));
+    RC(ensure(h, s.out_w, sizeof(float) * (size_t)(R > 0 ? R : 1)));
+    RC(ensure(h, s.t_v, sizeof(float) * (size_t)(U + 1) * m.kp));
+    RC(ensure(h, s.t_w, sizeof(float) * (size_t)(U + 1)));
+    if (R > 0) {
+        gather_rows_kernel<<<(unsigned)grid_for(R * m.lpr), 256, 0, h->stream>>>(
+            (const float4*)s.v, s.w, (const int32_t*)sb.req.p, R, s.own_lo, m.lpr, (float4*)s.out_v.p,
+            (float*)s.out_w.p);
+        ++*L;
+    }
+    RC(nccl_alltoallv_4b(h->nccl, h->comm, h->rank, G, s.out_v.p, sb.recv_off.data(),
+                         sb.recv_cnt.data(), s.t_v.p, sb.send_off.data(), sb.send_cnt.data(), m.kp,
+                         h->stream, &h->err));
+    RC(nccl_alltoallv_4b(h->nccl, h->comm, h->rank, G, s.out_w.p, sb.recv_off.data(),
+                         sb.recv_cnt.data(), s.t_w.p, sb.send_off.data(), sb.send_cnt.data(), 1,
+                         h->stream, &h->err));
+    CU(cudaMemsetAsync((float*)s.t_v.p + (size_t)U * m.kp, 0, sizeof(float) * m.kp, h->stream));
+    CU(cudaMemsetAsync((float*)s.t_w.p + U, 0, sizeof(float), h->stream));
     sp->mc = m;
     sp->mc.v = (float*)s.t_v.p;
     sp->mc.w = (float*)s.t_w.p;
     sp->mc.n_slots = U;
     BatchView& bc = sp->bc;
     bc = b;
-    bc.idx = (const int32_t*)s.bidx.p;
-    bc.val = binary ? nullptr : (const float*)s.bval.p;
-    bc.label = (const float*)s.blabel.p;
+    bc.idx = (const int32_t*)sb.bidx.p;
+    bc.val = binary ? nullptr : (const float*)sb.bval.p;
+    bc.label = (const float*)sb.blabel.p;
     bc.row_ids = nullptr;
     bc.row_lo = 0;
     bc.idx_len = E;
+    bc.out_base = 0;
     bc.validated = true;
     if (b.uniform_m >= 0) {
         bc.row_ptr = nullptr;      // rows are pos*m .. pos*m+m in the compact copy
         bc.out_ptr = nullptr;
+    } else if (b.row_ids) {
+        bc.row_ptr = (const int64_t*)sb.optr.p;   // offsets computed by shard_build
+        bc.out_ptr = bc.row_ptr;
     } else {
-        // the batch offsets double as the compact CSR row pointers; they may carry a base offset
-        // (sub-range of the resident set), so the compact arrays are addressed relative to it
+        // contiguous rows: the data set's own row pointers double as the compact CSR pointers;
+        // they carry a base offset, so the compact arrays are addressed relative to it
         bc.row_ptr = b.out_ptr;
         bc.out_ptr = b.out_ptr;
         bc.out_base = b.out_base;
-        bc.idx = (const int32_t*)s.bidx.p - b.out_base;
-        if (!binary) bc.val = (const float*)s.bval.p - b.out_base;
+        bc.idx = (const int32_t*)sb.bidx.p - b.out_base;
+        if (!binary) bc.val = (const float*)sb.bval.p - b.out_base;
         bc.idx_len = E + b.out_base;
     }
-    sp->ckeys = (const uint32_t*)s.crank.p;
-    sp->pay = (const uint2*)h->b_pay[1].p;
     return SFM_OK;
 }
 
 // Forward only (predict / evaluate) on a sharded model: yhat -> h->b_yhat.
 int shard_forward(sfm_handle* h, const BatchView& b) {
+    ShardBatch& sb = h->shard->scratch;
     ShardPlan sp;
-    RC(shard_prepare(h, b, false, &sp));
+    RC(shard_build(h, b, false, sb));
+    RC(shard_fetch(h, b, sb, &sp));
     RC(ensure(h, h->b_yhat, sizeof(float) * (size_t)(b.n_rows > 0 ? b.n_rows : 1)));
     FwdOut o;
     memset(&o, 0, sizeof o);
@@ -352,7 +398,7 @@ int shard_forward(sfm_handle* h, const BatchView& b) {
 }
 
 // One SGD iteration on a sharded model (asynchronous after its internal count sync).
-int shard_train(sfm_handle* h, const BatchView& b, int64_t iter) {
+int shard_train(sfm_handle* h, const BatchView& b, int64_t iter, int cache_slot) {
     ShardState& s = *h->shard;
     const ModelView& m = h->m;
     int64_t* L = &h->stats.kernel_launches;
@@ -361,9 +407,17 @@ int shard_train(sfm_handle* h, const BatchView& b, int64_t iter) {
     if ((n + 1) * (int64_t)m.lpr >= 4294967296LL)
         return set_err(h, SFM_ERR_ARG, "batch too large: rows * kp/4 must stay below 2^32");
     CU(cudaMemsetAsync(h->d_err, 0, sizeof(int32_t), h->stream));
+    // fixed mini-batches (PARTITION sampler) keep their row-dependent plan; sampled ones rebuild it
+    ShardBatch* sbp = &s.scratch;
+    if (cache_slot >= 0) {
+        if ((size_t)cache_slot >= s.cached.size()) s.cached.resize((size_t)cache_slot + 1);
+        sbp = &s.cached[(size_t)cache_slot];
+    }
+    ShardBatch& sb = *sbp;
+    if (cache_slot < 0 || !sb.built) RC(shard_build(h, b, true, sb));
     ShardPlan sp;
-    RC(shard_prepare(h, b, true, &sp));
-    const int64_t U = sp.U, R = sp.R;
+    RC(shard_fetch(h, b, sb, &sp));
+    const int64_t U = sb.U, R = sb.R;
     const bool binary = b.val == nullptr;
     RC(ensure(h, h->b_S, sizeof(float) * (size_t)(n > 0 ? n : 1) * m.kp));
     RC(ensure(h, h->b_mult, sizeof(float) * (size_t)(n > 0 ? n : 1)));
@@ -390,7 +444,8 @@ int shard_train(sfm_handle* h, const BatchView& b, int64_t iter) {
     up.reg0 = h->cfg.reg0;
     up.regw = h->cfg.regw;
     up.regv = h->cfg.regv;
-    CU(launch_pull(mc, (int32_t*)h->b_seg.p, 31, 1, sp.ckeys, sp.pay, E, binary, o.S, o.mult,
+    CU(launch_pull(mc, (int32_t*)h->b_seg.p, 31, 1, (const uint32_t*)sb.crank.p,
+                   (const uint2*)sb.pay.p, E, binary, o.S, o.mult,
                    (float*)h->b_pull.p, h->d_scal, h->d_err, up, false, (float*)h->b_grad.p,
                    h->sm_count, h->stream, L));
     // 5. gradient rows back to their owners, summed in rank order, dense update of the own shard
@@ -400,19 +455,19 @@ int shard_train(sfm_handle* h, const BatchView& b, int64_t iter) {
     RC(ensure(h, s.acc, sizeof(float) * acc_len));
     float* gcv = (float*)h->b_grad.p;
     float* gcw = gcv + (size_t)Uc * m.kp;
-    RC(nccl_alltoallv_4b(h->nccl, h->comm, h->rank, G, gcv, sp.send_off.data(), sp.send_cnt.data(),
-                         s.gr_v.p, sp.recv_off.data(), sp.recv_cnt.data(), m.kp, h->stream, &h->err));
-    RC(nccl_alltoallv_4b(h->nccl, h->comm, h->rank, G, gcw, sp.send_off.data(), sp.send_cnt.data(),
-                         s.gr_w.p, sp.recv_off.data(), sp.recv_cnt.data(), 1, h->stream, &h->err));
+    RC(nccl_alltoallv_4b(h->nccl, h->comm, h->rank, G, gcv, sb.send_off.data(), sb.send_cnt.data(),
+                         s.gr_v.p, sb.recv_off.data(), sb.recv_cnt.data(), m.kp, h->stream, &h->err));
+    RC(nccl_alltoallv_4b(h->nccl, h->comm, h->rank, G, gcw, sb.send_off.data(), sb.send_cnt.data(),
+                         s.gr_w.p, sb.recv_off.data(), sb.recv_cnt.data(), 1, h->stream, &h->err));
     CU(cudaMemsetAsync(s.acc.p, 0, sizeof(float) * acc_len, h->stream));
     float* acc_v = (float*)s.acc.p;
     float* acc_w = acc_v + (size_t)s.n_own * m.kp;
     for (int src = 0; src < G; ++src) {   // rank order: the summation order is fixed
-        const int64_t c = sp.recv_cnt[src];
+        const int64_t c = sb.recv_cnt[src];
         if (c <= 0) continue;
         scatter_add_rows_kernel<<<(unsigned)grid_for(c * m.lpr), 256, 0, h->stream>>>(
-            (const float4*)s.gr_v.p + sp.recv_off[src] * m.lpr, (const float*)s.gr_w.p + sp.recv_off[src],
-            (const int32_t*)s.req.p + sp.recv_off[src], c, s.own_lo, m.lpr, (float4*)acc_v, acc_w);
+            (const float4*)s.gr_v.p + sb.recv_off[src] * m.lpr, (const float*)s.gr_w.p + sb.recv_off[src],
+            (const int32_t*)sb.req.p + sb.recv_off[src], c, s.own_lo, m.lpr, (float4*)acc_v, acc_w);
         ++*L;
     }
     set_tail_kernel<<<1, 1, 0, h->stream>>>(acc_w + s.n_own, h->d_scal, m.k0);

@@ -108,7 +108,7 @@ def _shard_data(kind):
     return n_slots, k, n_rows, rp, idx, val, label, model
 
 
-def _shard_worker(rank, world, port, out_dir, kind):
+def _shard_worker(rank, world, port, out_dir, kind, mode=0):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -119,7 +119,7 @@ def _shard_worker(rank, world, port, out_dir, kind):
         from sparkfm_b200.dist import init_comm, shard_range
         n_slots, k, n_rows, rp, idx, val, label, (w0, w, v) = _shard_data(kind)
         lo, hi = shard_range(n_rows, rank, world)
-        hd = Handle(n_slots, k, device=rank, shard_v=True, **KW)
+        hd = Handle(n_slots, k, device=rank, shard_v=True, sampler_mode=mode, **KW)
         try:
             hd.set_model(w0, w, v)
             raise AssertionError("model calls must fail before sfm_comm_init")
@@ -145,25 +145,26 @@ def _shard_worker(rank, world, port, out_dir, kind):
 
 
 @pytest.mark.skipif(device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("kind", ["onehot", "ragged"])
-def test_row_sharded_model_matches_replicated(tmp_path, kind):
+@pytest.mark.parametrize("kind,mode", [("onehot", 0), ("ragged", 0), ("onehot", 1), ("ragged", 1)])
+def test_row_sharded_model_matches_replicated(tmp_path, kind, mode):
     """SFM_FLAG_SHARD_V on 2 GPUs (each owns half of V / w, touched rows travel by all-to-all)
     against ONE GPU holding the whole model and every row: same predictions, same per-iteration
-    loss (1e-4), same final model; reruns are bitwise identical."""
+    loss (1e-4), same final model; reruns are bitwise identical.  mode 1 = PARTITION sampler: the
+    row-dependent exchange plan of each fixed mini-batch is cached (ITERS > P, so it is reused)."""
     import torch.multiprocessing as mp
     from sparkfm_b200 import Handle
     runs = []
     for rep in range(2):
         d = tmp_path / f"rep{rep}"
         d.mkdir()
-        mp.spawn(_shard_worker, args=(2, _free_port(), str(d), kind), nprocs=2, join=True)
+        mp.spawn(_shard_worker, args=(2, _free_port(), str(d), kind, mode), nprocs=2, join=True)
         runs.append([np.load(d / f"s{r}.npz") for r in range(2)])
     a, b = runs[0]
     for key in ("loss", "batch", "w0", "w", "v"):
         assert np.array_equal(a[key], b[key]), key              # get_model is the same on both ranks
         assert np.array_equal(a[key], runs[1][0][key]), key      # and reproducible
     n_slots, k, n_rows, rp, idx, val, label, (w0, w, v) = _shard_data(kind)
-    hd = Handle(n_slots, k, device=0, **KW)
+    hd = Handle(n_slots, k, device=0, sampler_mode=mode, **KW)
     hd.set_model(w0, w, v)
     hd.load_dataset(rp, idx, val, label)
     p1 = hd.predict_resident(0, n_rows)
