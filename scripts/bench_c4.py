@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--rows", type=int, default=8_000_000, help="rows per GPU")
     ap.add_argument("--batch", type=int, default=500_000, help="mini-batch rows per GPU")
-    ap.add_argument("--modes", default="sharded,replicated")
+    ap.add_argument("--modes", default="sharded,sharded_partition,replicated")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -47,24 +47,27 @@ def main():
     b_train = 8 * m * (K + 2) + 4
     b_step = 12 * (1 + N_SLOTS * (K + 1))
     for mode in args.modes.split(","):
-        if mode == "sharded" and world == 1:
+        sharded = mode.startswith("sharded")
+        if sharded and world == 1:
             continue
+        part = mode.endswith("partition")
         hd = Handle(N_SLOTS, K, task=1, reg=(0.0, 0.0, 1e-5), step_size=0.1,
                     mini_batch_fraction=args.batch / args.rows, sampler_seed=42, device=local,
-                    shard_v=(mode == "sharded"))
+                    shard_v=sharded, sampler_mode=1 if part else 0)
         if world > 1:
             init_comm(hd, device=f"cuda:{local}")
         hd.init_model(0.0, 0.01, 1)
-        if world > 1 and mode != "sharded":
+        if world > 1 and not sharded:
             hd.comm_broadcast_model()
         hd.synth_ctr_dataset(args.rows, rank * args.rows, card, cdf, off, 20260104)
-        h0 = hd.train(1, args.warmup)
+        warm = max(args.warmup, round(args.rows / args.batch)) if part else args.warmup
+        h0 = hd.train(1, warm)    # PARTITION: the first epoch builds every batch's plan
         hd.stats_reset()
         hd.synchronize()
         if world > 1:
             dist.barrier()
         hd.timer_start()
-        hist = hd.train(args.warmup + 1, args.steps)
+        hist = hd.train(warm + 1, args.steps)
         ms = hd.timer_stop()
         rows = hd.stats()["train_rows"]
         t = torch.tensor([ms, float(rows)], dtype=torch.float64, device="cuda")
@@ -75,7 +78,7 @@ def main():
             dist.all_reduce(ts, op=dist.ReduceOp.SUM)
             ms, rows = float(tm[0]), float(ts[1])
         # sharded: the dense step bytes are spread over the ranks (each updates 1/N of the model)
-        step_bytes = b_step * (1 if mode == "sharded" else world)
+        step_bytes = b_step * (1 if sharded else world)
         gbs = (rows * b_train + args.steps * step_bytes) / (ms * 1e-3) / 1e9
         out[mode] = {"ms_per_step": ms / args.steps, "samples_per_s": rows / (ms * 1e-3),
                      "roofline_step_frac": gbs / (6554.2 * world),
