@@ -831,6 +831,14 @@ int32_t sfm_destroy(sfm_handle* h) {
         delete h->shard;
         h->shard = nullptr;
     }
+    for (PartCache& pc : h->pre) {
+        free_buf(pc.row_ids);
+        free_buf(pc.keys);
+        free_buf(pc.pay);
+    }
+    free_buf(h->b_pre_keys0);
+    free_buf(h->b_pre_pay0);
+    free_buf(h->b_sort_tmp2);
     free_buf(h->b_ids2[0]);
     free_buf(h->b_ids2[1]);
     free_buf(h->b_samp_tmp);
@@ -1501,6 +1509,87 @@ static int sample_prefetch(sfm_handle* h, int64_t iter, int slot) {
     return SFM_OK;
 }
 
+// Grows a buffer that the copy stream works on (ensure() only drains the compute stream).
+static int ensure_side(sfm_handle* h, Buf& b, size_t bytes) {
+    if (bytes <= b.cap) return SFM_OK;
+    CU(cudaStreamSynchronize(h->copy_stream));
+    return ensure(h, b, bytes);
+}
+
+// Bernoulli sampler, uniform rows: sample the batch of iteration `iter`, emit its entry list and
+// radix-sort it by feature -- all on the copy stream, one iteration ahead, so that the sort
+// (DRAM-bandwidth bound) runs concurrently with the previous iteration's forward (L1 bound) and
+// reduce (latency bound) instead of after them.  The host only waits for the
+// 4-byte batch size.
+static int transpose_prefetch(sfm_handle* h, int64_t iter, int slot) {
+    const Dataset& ds = h->ds;
+    const ModelView& m = h->m;
+    int64_t* L = &h->stats.kernel_launches;
+    const double frac = (double)h->cfg.mini_batch_fraction;
+    const uint64_t thr = (uint64_t)floor(frac * 9007199254740992.0);
+    const uint64_t key = mix64(h->cfg.sampler_seed + (uint64_t)iter);
+    PartCache& pc = h->pre[slot];
+    cudaStream_t cs = h->copy_stream;
+    CU(cudaStreamWaitEvent(cs, h->ev_used[slot], 0));   // the slot's previous consumer is done
+    CU(sample_rows_device(h->b_samp_tmp.p, h->b_samp_tmp.cap, ds.n_rows, ds.global_offset, key, thr,
+                          (int32_t*)h->b_ids2[slot].p, h->d_count2 + slot, cs, L));
+    CU(cudaMemcpyAsync(h->h_count2 + slot, h->d_count2 + slot, sizeof(int32_t),
+                       cudaMemcpyDeviceToHost, cs));
+    CU(cudaEventRecord(h->ev_pool[18], cs));
+    CU(cudaEventSynchronize(h->ev_pool[18]));
+    h->stats.d2h_bytes += 4;
+    const int64_t n = h->h_count2[slot];
+    const int64_t nnz = n * ds.uniform_m;
+    if (nnz >= 2147483647LL) return set_err(h, SFM_ERR_ARG, "batch nnz must be < 2^31-1");
+    pc.n_rows = n;
+    pc.nnz = nnz;
+    pc.n_slices = 0;
+    pc.key_bits = bits_for(m.n_slots);
+    pull_plan(m, n, &pc.blk_shift, &pc.n_blocks);
+    int blk_bits = 0;
+    while (((int64_t)1 << blk_bits) < pc.n_blocks) ++blk_bits;
+    if (pc.key_bits + blk_bits > 32) return set_err(h, SFM_ERR_ARG, "sort key does not fit 32 bits");
+    const bool binary = ds.val == nullptr;
+    const size_t pay_sz = binary ? sizeof(uint32_t) : sizeof(uint2);
+    const size_t cnt = (size_t)(nnz > 0 ? nnz : 1);
+    RC(ensure_side(h, h->b_pre_keys0, sizeof(uint32_t) * cnt));
+    RC(ensure_side(h, h->b_pre_pay0, pay_sz * cnt));
+    RC(ensure_side(h, pc.keys, sizeof(uint32_t) * cnt));
+    RC(ensure_side(h, pc.pay, pay_sz * cnt));
+    if (nnz > 0) {
+        BatchView v;
+        v.row_ptr = ds.row_ptr;
+        v.idx = ds.idx;
+        v.val = ds.val;
+        v.label = ds.label;
+        v.row_ids = (const int32_t*)h->b_ids2[slot].p;
+        v.row_lo = 0;
+        v.n_rows = n;
+        v.nnz = nnz;
+        v.idx_len = ds.nnz;
+        v.out_ptr = nullptr;
+        v.out_base = 0;
+        v.uniform_m = ds.uniform_m;
+        v.validated = true;
+        CU(launch_emit(v, pc.key_bits, pc.blk_shift, m.n_slots, (uint32_t*)h->b_pre_keys0.p,
+                       (uint2*)h->b_pre_pay0.p, h->sm_count, cs, L));
+        const int end_bit = pc.key_bits + blk_bits;
+        const size_t sb = binary ? sort_pairs32_temp_bytes(nnz, end_bit) : sort_pairs_temp_bytes(nnz, end_bit);
+        RC(ensure_side(h, h->b_sort_tmp2, sb));
+        if (binary)
+            CU(sort_pairs32(h->b_sort_tmp2.p, sb, (const uint32_t*)h->b_pre_keys0.p,
+                            (uint32_t*)pc.keys.p, (const uint32_t*)h->b_pre_pay0.p,
+                            (uint32_t*)pc.pay.p, nnz, end_bit, cs, L));
+        else
+            CU(sort_pairs(h->b_sort_tmp2.p, sb, (const uint32_t*)h->b_pre_keys0.p,
+                          (uint32_t*)pc.keys.p, (const uint2*)h->b_pre_pay0.p, (uint2*)pc.pay.p, nnz,
+                          end_bit, cs, L));
+    }
+    pc.built = true;
+    CU(cudaEventRecord(h->ev_samp[slot], cs));
+    return SFM_OK;
+}
+
 int32_t sfm_train(sfm_handle* h, int64_t first_iter, int64_t n_iters, double* loss_history) {
     if (!h) return SFM_ERR_ARG;
     if (!h->ds.loaded) return set_err(h, SFM_ERR_STATE, "no resident data set");
@@ -1510,12 +1599,20 @@ int32_t sfm_train(sfm_handle* h, int64_t first_iter, int64_t n_iters, double* lo
     const double frac = (double)h->cfg.mini_batch_fraction;
     const bool parts = use_partitions(h);
     const bool sampled = !parts && frac < 1.0 && frac > 0.0 && ds.n_rows > 0;
+    // uniform rows: the whole transposition of the next batch is built ahead on the copy stream
+    static int ahead_env = -1;
+    if (ahead_env < 0) {
+        const char* e = getenv("SFM_SORT_AHEAD");
+        ahead_env = e ? atoi(e) : 0;   // measured: co-scheduling the sort with the gather kernels does not pay
+    }
+    const bool ahead = sampled && ds.uniform_m >= 0 && !is_sharded(h) && !h->phase_timing &&
+                       ahead_env != 0;
     if (sampled) {
         for (int i = 0; i < 2; ++i) RC(ensure(h, h->b_ids2[i], sizeof(int32_t) * (size_t)ds.n_rows));
         RC(ensure(h, h->b_samp_tmp, select_temp_bytes(ds.n_rows)));
         CU(cudaEventRecord(h->ev_used[0], h->stream));
         CU(cudaEventRecord(h->ev_used[1], h->stream));
-        if (n_iters > 0) RC(sample_prefetch(h, first_iter, 0));
+        if (n_iters > 0) RC(ahead ? transpose_prefetch(h, first_iter, 0) : sample_prefetch(h, first_iter, 0));
     }
     double* hist = nullptr;
     if (n_iters > 0) CU(cudaMallocHost(&hist, sizeof(double) * SC_N * (size_t)n_iters));
@@ -1524,6 +1621,35 @@ int32_t sfm_train(sfm_handle* h, int64_t first_iter, int64_t n_iters, double* lo
         const int32_t* ids_dev = nullptr;
         int64_t n = 0;
         const int slot = (int)(t & 1);
+        if (ahead) {
+            // the batch (rows + sorted entries) was prepared on the copy stream; only the device waits
+            const PartCache& pre = h->pre[slot];
+            BatchView b;
+            b.row_ptr = ds.row_ptr;
+            b.idx = ds.idx;
+            b.val = ds.val;
+            b.label = ds.label;
+            b.row_ids = (const int32_t*)h->b_ids2[slot].p;
+            b.row_lo = 0;
+            b.n_rows = pre.n_rows;
+            b.nnz = pre.nnz;
+            b.idx_len = ds.nnz;
+            b.out_ptr = nullptr;
+            b.out_base = 0;
+            b.uniform_m = ds.uniform_m;
+            b.validated = true;
+            if (cudaStreamWaitEvent(h->stream, h->ev_samp[slot], 0) != cudaSuccess)
+                rc = set_err(h, SFM_ERR_CUDA, "cudaStreamWaitEvent failed");
+            if (rc == SFM_OK) rc = train_core(h, b, first_iter + t, false, &pre);
+            if (rc == SFM_OK && cudaEventRecord(h->ev_used[slot], h->stream) != cudaSuccess)
+                rc = set_err(h, SFM_ERR_CUDA, "cudaEventRecord failed");
+            if (rc == SFM_OK &&
+                cudaMemcpyAsync(hist + SC_N * t, h->d_scal, sizeof(double) * SC_N,
+                                cudaMemcpyDeviceToHost, h->stream) != cudaSuccess)
+                rc = set_err(h, SFM_ERR_CUDA, "loss history copy failed");
+            if (rc == SFM_OK && t + 1 < n_iters) rc = transpose_prefetch(h, first_iter + t + 1, slot ^ 1);
+            continue;
+        }
         if (sampled) {
             if (cudaEventSynchronize(h->ev_samp[slot]) != cudaSuccess) {
                 rc = set_err(h, SFM_ERR_CUDA, "sampler prefetch failed");

@@ -119,6 +119,8 @@ struct sfm_handle {
         b_sort_tmp, b_grad, b_partials, b_sel_tmp, b_lens, b_pull;
     sfm::Stage stage[3];
     std::vector<sfm::PartCache> parts;  // PARTITION sampler caches (size P)
+    sfm::PartCache pre[2];              // Bernoulli sampler: transposition built one step ahead
+    sfm::Buf b_pre_keys0, b_pre_pay0, b_sort_tmp2;
     bool shard_requested = false;       // SFM_FLAG_SHARD_V at create; active once comm is up
     sfm::ShardState* shard = nullptr;
     // sampler prefetch (sfm_train): ids / count of the NEXT iteration are produced on copy_stream
