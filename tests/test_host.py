@@ -170,3 +170,37 @@ def test_dataset_size_dimension_and_packing():
     assert empty.isEmpty and empty.size == 0 and empty.dimension == 0
     with pytest.raises(ValueError):
         DataSet([1.0], [0, 0], [], []).dimension   # `_.index.max` on an empty row throws
+
+
+def test_parser_multithreaded_chunks_are_seamless():
+    """A text above the 1 MB-per-chunk threshold is cut at line boundaries and parsed by several
+    threads (count pass + fill pass): same arrays as the pure-Python parser, CRLF / CR / comment /
+    blank lines at arbitrary places, and the reported error line counts physical lines across
+    chunks."""
+    rng = np.random.default_rng(4)
+    lines = []
+    for r in range(60_000):
+        if r % 997 == 0:
+            lines.append("# comment %d" % r)
+        if r % 1301 == 0:
+            lines.append("   ")
+        m = int(rng.integers(1, 12))
+        toks = ["%d:%s" % (int(rng.integers(0, 5000)), repr(float(np.float32(rng.normal()))))
+                for _ in range(m)]
+        lines.append(("%d " % (r % 3 - 1)) + " ".join(toks) + ("  " if r % 5 == 0 else ""))
+    seps = ["\n", "\r\n", "\r"]
+    text = "".join(l + seps[i % 3] for i, l in enumerate(lines)).encode()
+    assert len(text) > 3 * (1 << 20)
+    lab, rp, idx, val, d = parse_libfm(text)
+    py = "".join(l + "\n" for l in lines)
+    olab, orp, oidx, oval, od = fn.parse_libfm_lines(py.split("\n"))
+    assert d == od and np.array_equal(rp, orp) and np.array_equal(idx, oidx)
+    assert val.tobytes() == oval.tobytes() and lab.tobytes() == olab.tobytes()
+    # an error deep inside a later chunk: line number = physical line (1-based)
+    bad_at = len(lines) * 3 // 4
+    broken = list(lines)
+    broken[bad_at] = "1 7:oops"
+    text2 = "".join(l + "\n" for l in broken).encode()
+    with pytest.raises(ValueError) as ei:
+        parse_libfm(text2)
+    assert f"line {bad_at + 1}" in str(ei.value)
