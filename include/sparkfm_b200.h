@@ -178,6 +178,12 @@ int32_t sfm_predict_resident(sfm_handle* h, int64_t row_lo, int64_t row_hi, floa
  * sign(y) == sign(yhat), >= 0 counted positive (:29, without its integer division),
  * [3] = mean logistic loss, [4] = N. */
 int32_t sfm_evaluate(sfm_handle* h, double metrics[5]);
+/* Area under the ROC curve of the model on THIS rank's resident rows (label > 0 = positive): the
+ * predictions are radix-sorted on the device and the rank-sum (Mann-Whitney) statistic is taken
+ * with average ranks for tied scores.  out[0] = AUC (NaN if one class is empty), out[1] = number
+ * of positives, out[2] = number of negatives.  (The reference has no AUC; listed under "next" in
+ * SURVEY.md section 8f.)  Not collective: with several ranks each one reports its own shard. */
+int32_t sfm_evaluate_auc(sfm_handle* h, double out[3]);
 
 /* ---------------------------------------------------------------- learner -------------- */
 /* One call of the learner plugin, `FMLearn.learn(fm, dataset)` (fm/FMLearn.scala:12), for an

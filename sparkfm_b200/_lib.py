@@ -74,6 +74,7 @@ SIGNATURES = {
     "sfm_dataset_info": (C.c_int32, [_H, _i64p, _i64p, _i32p]),
     "sfm_predict_resident": (C.c_int32, [_H, C.c_int64, C.c_int64, _f32p]),
     "sfm_evaluate": (C.c_int32, [_H, _f64p]),
+    "sfm_evaluate_auc": (C.c_int32, [_H, _f64p]),
     "sfm_train_step": (C.c_int32, [_H, _i64p, C.c_int64, C.c_int64, _f64p, _i64p]),
     "sfm_train_step_csr": (C.c_int32, [_H, _i64p, _i32p, _f32p, _f32p, C.c_int64, C.c_int64,
                                        _f64p, _i64p]),

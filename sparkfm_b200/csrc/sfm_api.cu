@@ -1420,6 +1420,62 @@ int32_t sfm_evaluate(sfm_handle* h, double metrics[5]) {
     return SFM_OK;
 }
 
+int32_t sfm_evaluate_auc(sfm_handle* h, double out[3]) {
+    if (!h || !out) return SFM_ERR_ARG;
+    NEED_MODEL(h);
+    const Dataset& ds = h->ds;
+    if (!ds.loaded) return set_err(h, SFM_ERR_STATE, "no resident data set");
+    CU(cudaSetDevice(h->device));
+    const int64_t n = ds.n_rows;
+    out[0] = NAN;
+    out[1] = out[2] = 0.0;
+    if (n == 0) return SFM_OK;
+    // scores of every resident row, tile by tile, into one buffer
+    Buf& sc = h->b_S;      // reused as scratch: [scores | sorted scores | rows | sorted rows]
+    RC(ensure(h, sc, sizeof(float) * 4 * (size_t)n));
+    float* score = (float*)sc.p;
+    float* score_s = score + n;
+    uint32_t* rows = (uint32_t*)(score_s + n);
+    uint32_t* rows_s = rows + n;
+    RC(ensure(h, h->b_partials, sizeof(double) * 4 * 512));
+    CU(cudaMemsetAsync(h->d_err, 0, sizeof(int32_t), h->stream));
+    const int64_t tile = 1 << 22;
+    for (int64_t lo = 0; lo < n; lo += tile) {
+        BatchView b;
+        RC(resident_batch(h, nullptr, 0, &b));
+        b.row_lo = lo;
+        b.n_rows = (n - lo) < tile ? (n - lo) : tile;
+        if (is_sharded(h)) {
+            RC(subrange_view(h, lo, lo + b.n_rows, &b));
+            RC(shard_forward(h, b));
+            CU(cudaMemcpyAsync(score + lo, h->b_yhat.p, sizeof(float) * (size_t)b.n_rows,
+                               cudaMemcpyDeviceToDevice, h->stream));
+        } else {
+            FwdOut o;
+            memset(&o, 0, sizeof o);
+            o.yhat = score + lo;
+            CU(launch_forward(h->m, b, o, false, h->d_err, h->sm_count, h->stream,
+                              &h->stats.kernel_launches));
+        }
+        h->stats.predict_rows += b.n_rows;
+    }
+    CU(launch_iota_u32(rows, n, h->stream, &h->stats.kernel_launches));
+    const size_t tb = sort_f32_u32_temp_bytes(n);
+    RC(ensure(h, h->b_sort_tmp, tb));
+    CU(sort_f32_u32(h->b_sort_tmp.p, tb, score, score_s, rows, rows_s, n, h->stream,
+                    &h->stats.kernel_launches));
+    double* d2 = h->d_scal + 4;
+    CU(launch_auc_ranks(score_s, rows_s, ds.label, n, (double*)h->b_partials.p, d2, h->stream,
+                        &h->stats.kernel_launches));
+    CU(cudaMemcpyAsync(h->h_scal + 4, d2, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->stream));
+    RC(read_err_flag(h));
+    const double rank_sum = h->h_scal[4], n_pos = h->h_scal[5], n_neg = (double)n - n_pos;
+    out[1] = n_pos;
+    out[2] = n_neg;
+    if (n_pos > 0 && n_neg > 0) out[0] = (rank_sum - n_pos * (n_pos + 1.0) / 2.0) / (n_pos * n_neg);
+    return SFM_OK;
+}
+
 // ------------------------------------------------------------------------------ learner ---
 int32_t sfm_train_step(sfm_handle* h, const int64_t* row_ids, int64_t n_ids, int64_t iter,
                        double* mean_loss_out, int64_t* batch_out) {

@@ -238,6 +238,15 @@ size_t sort_pairs32_temp_bytes(int64_t n, int end_bit);
 cudaError_t sort_pairs32(void* tmp, size_t tmp_bytes, const uint32_t* keys_in, uint32_t* keys_out,
                          const uint32_t* val_in, uint32_t* val_out, int64_t n, int end_bit,
                          cudaStream_t st, int64_t* launches);
+size_t sort_f32_u32_temp_bytes(int64_t n);
+cudaError_t sort_f32_u32(void* tmp, size_t tmp_bytes, const float* keys_in, float* keys_out,
+                         const uint32_t* val_in, uint32_t* val_out, int64_t n, cudaStream_t st,
+                         int64_t* launches);
+// sum of (tie-averaged, 1-based) ranks of the positive rows and their count -> out2[0..1]
+cudaError_t launch_auc_ranks(const float* sorted_scores, const uint32_t* sorted_rows,
+                             const float* label, int64_t n, double* partials, double* out2,
+                             cudaStream_t st, int64_t* launches);
+cudaError_t launch_iota_u32(uint32_t* p, int64_t n, cudaStream_t st, int64_t* launches);
 size_t scan_temp_bytes(int64_t n);
 cudaError_t exclusive_scan_i64(void* tmp, size_t tmp_bytes, const int64_t* in, int64_t* out,
                                int64_t n, cudaStream_t st, int64_t* launches);

@@ -574,6 +574,77 @@ metrics2_kernel(const double* __restrict__ partials, int nblocks, double* __rest
         for (int v = 0; v < 4; ++v) out4[v] += acc[v];  // accumulates over tiles of rows
 }
 
+// AUC: rank-sum of the positives over the ascending-sorted scores, ties get their average rank
+__global__ void __launch_bounds__(RED_THREADS)
+auc_ranks1_kernel(const float* __restrict__ score, const uint32_t* __restrict__ row,
+                  const float* __restrict__ label, int64_t n, double* __restrict__ partials) {
+    __shared__ double sm[2 * RED_THREADS];
+    const int64_t span = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * span;
+    const int64_t hi = min(n, lo + span);
+    double acc[2] = {0.0, 0.0};
+    for (int64_t i = lo + threadIdx.x; i < hi; i += RED_THREADS) {
+        if (!(label[row[i]] > 0.f)) continue;
+        const float sc = score[i];
+        int64_t first = i, last = i;
+        if (i > 0 && score[i - 1] == sc) {           // tie group: find its ends by binary search
+            int64_t a = 0, b = i;
+            while (a < b) { const int64_t mid = (a + b) >> 1; if (score[mid] < sc) a = mid + 1; else b = mid; }
+            first = a;
+        }
+        if (i + 1 < n && score[i + 1] == sc) {
+            int64_t a = i + 1, b = n;
+            while (a < b) { const int64_t mid = (a + b) >> 1; if (score[mid] <= sc) a = mid + 1; else b = mid; }
+            last = a - 1;
+        }
+        acc[0] += 0.5 * (double)(first + last) + 1.0;
+        acc[1] += 1.0;
+    }
+    block_tree<2>(acc, sm);
+    if (threadIdx.x == 0) {
+        partials[2 * blockIdx.x] = acc[0];
+        partials[2 * blockIdx.x + 1] = acc[1];
+    }
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+auc_ranks2_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ out2) {
+    __shared__ double sm[2 * RED_THREADS];
+    double acc[2] = {0.0, 0.0};
+    for (int i = threadIdx.x; i < nblocks; i += RED_THREADS) {
+        acc[0] += partials[2 * i];
+        acc[1] += partials[2 * i + 1];
+    }
+    block_tree<2>(acc, sm);
+    if (threadIdx.x == 0) {
+        out2[0] = acc[0];
+        out2[1] = acc[1];
+    }
+}
+
+cudaError_t launch_auc_ranks(const float* sorted_scores, const uint32_t* sorted_rows,
+                             const float* label, int64_t n, double* partials, double* out2,
+                             cudaStream_t st, int64_t* launches) {
+    *launches += 2;
+    auc_ranks1_kernel<<<RED_BLOCKS, RED_THREADS, 0, st>>>(sorted_scores, sorted_rows, label, n, partials);
+    auc_ranks2_kernel<<<1, RED_THREADS, 0, st>>>(partials, RED_BLOCKS, out2);
+    return cudaGetLastError();
+}
+
+__global__ void iota_u32_kernel(uint32_t* __restrict__ p, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = (uint32_t)i;
+}
+
+cudaError_t launch_iota_u32(uint32_t* p, int64_t n, cudaStream_t st, int64_t* launches) {
+    if (n <= 0) return cudaSuccess;
+    ++*launches;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    iota_u32_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_metrics(const float* yhat, const float* label, int64_t n, double* partials,
                            double* out4, cudaStream_t st, int64_t* launches) {
     *launches += 2;

@@ -43,6 +43,22 @@ cudaError_t sort_pairs32(void* tmp, size_t tmp_bytes, const uint32_t* keys_in, u
                                            end_bit, st);
 }
 
+size_t sort_f32_u32_temp_bytes(int64_t n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const float*)nullptr, (float*)nullptr,
+                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, n);
+    return bytes;
+}
+
+// ascending sort of float scores with their row numbers (AUC)
+cudaError_t sort_f32_u32(void* tmp, size_t tmp_bytes, const float* keys_in, float* keys_out,
+                         const uint32_t* val_in, uint32_t* val_out, int64_t n, cudaStream_t st,
+                         int64_t* launches) {
+    *launches += 6;
+    return cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, val_in, val_out, n, 0,
+                                           32, st);
+}
+
 size_t scan_temp_bytes(int64_t n) {
     size_t bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int64_t*)nullptr, (int64_t*)nullptr, n);

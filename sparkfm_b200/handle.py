@@ -178,6 +178,11 @@ class Handle:
         self._ck(self._L.sfm_evaluate(self._h, _p(m, C.c_double)))
         return {"rmse": m[0], "mean_error": m[1], "accuracy": m[2], "logloss": m[3], "n": int(m[4])}
 
+    def evaluate_auc(self):
+        m = np.zeros(3, dtype=np.float64)
+        self._ck(self._L.sfm_evaluate_auc(self._h, _p(m, C.c_double)))
+        return {"auc": m[0], "n_pos": int(m[1]), "n_neg": int(m[2])}
+
     # ------------------------------------------------------------------ learner
     def train_step(self, it, row_ids=None):
         """One SGD iteration on resident rows; row_ids None -> built-in sampler.

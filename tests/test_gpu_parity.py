@@ -551,3 +551,36 @@ def test_long_run_loss_curve_stays_on_the_oracle():
     gm = hd.get_model()
     assert np.max(np.abs(gm[2] - orc.v)) <= 1e-4 * np.abs(orc.v).max()
     hd.close()
+
+
+def test_device_auc_matches_rank_statistic_with_ties():
+    """sfm_evaluate_auc = Mann-Whitney AUC with average ranks for ties, on the device.  Checked
+    against scipy's rankdata on the SAME fp32 scores (duplicated rows and empty rows create ties)."""
+    from scipy.stats import rankdata
+    rng = np.random.default_rng(101)
+    n_slots, k, n_base = 400, 8, 3000
+    rp0, idx0, val0 = synth.ragged_rows(n_base, n_slots, 5, seed=101, values="ones")
+    # duplicate every third row and add 50 empty rows -> many exact ties
+    rows = [(idx0[rp0[r]:rp0[r + 1]]) for r in range(n_base)]
+    rows += [rows[r] for r in range(0, n_base, 3)] + [np.zeros(0, np.int32)] * 50
+    rp = np.cumsum([0] + [len(r) for r in rows]).astype(np.int64)
+    idx = np.concatenate(rows).astype(np.int32)
+    n_rows = len(rows)
+    label = np.where(rng.random(n_rows) < 0.3, 1.0, 0.0).astype(np.float32)
+    w0, w, v = make_model(rng, n_slots, k)
+    hd = Handle(n_slots, k, task=1)
+    hd.set_model(w0, w, v)
+    hd.load_dataset(rp, idx, None, label)
+    got = hd.evaluate_auc()
+    score = hd.predict_resident(0, n_rows)
+    pos = label > 0
+    n_pos, n_neg = int(pos.sum()), int((~pos).sum())
+    ranks = rankdata(score.astype(np.float64), method="average")
+    want = (ranks[pos].sum() - n_pos * (n_pos + 1) / 2) / (n_pos * n_neg)
+    assert len(np.unique(score)) < n_rows - 500        # the ties are really there
+    assert got["n_pos"] == n_pos and got["n_neg"] == n_neg
+    assert abs(got["auc"] - want) < 1e-12
+    # degenerate: one class only -> NaN
+    hd.load_dataset(rp, idx, None, np.ones(n_rows, np.float32))
+    assert np.isnan(hd.evaluate_auc()["auc"])
+    hd.close()
