@@ -232,6 +232,11 @@ class FMModel(Model):
         self._cache(dataset)
         return self._hd.evaluate()["accuracy"]
 
+    def computeAUC(self, dataset: DataSet) -> float:
+        """Area under the ROC curve (not in the reference; SURVEY.md 8f 'next')."""
+        self._cache(dataset)
+        return self._hd.evaluate_auc()["auc"]
+
     # ---- persistence (north_star; absent from the reference)
     def save(self, path):
         self._hd.save(path)
