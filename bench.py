@@ -439,11 +439,11 @@ def main():
                                    "Zipf 1.1, k=16, logistic loss, 45M rows resident in HBM",
                        "rows": args.rows, "batch_per_gpu": args.batch,
                        "global_batch": int(rows_all / args.steps), "n_slots": N_SLOTS, "k": K,
-                       "parallelism": f"dp{world}",
+                       "parallelism": f"dp{world}", "gradient_exchange": hd.comm_mode(),
                        "l2": "inputs larger than L2: each step streams a fresh sampled batch "
                              "(>=156 MB of indices out of a 7 GB resident set)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "predict": predict,
-            "partition_sampler": part,
+            "partition_sampler": part, "comm_mode": hd.comm_mode(),
             "gpu_launches": int(launches),
             "clocks": clk, "loss_first_last": [float(hist[0]), float(hist[-1])],
         }

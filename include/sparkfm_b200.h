@@ -240,6 +240,15 @@ int32_t sfm_comm_unique_id(uint8_t id[SFM_UNIQUE_ID_BYTES]);
 int32_t sfm_comm_init(sfm_handle* h, const uint8_t id[SFM_UNIQUE_ID_BYTES], int32_t rank,
                       int32_t world_size);
 int32_t sfm_comm_info(const sfm_handle* h, int32_t* rank, int32_t* world_size);
+/* How gradients are combined after sfm_comm_init: SFM_COMM_NONE (one GPU), SFM_COMM_NCCL (dense
+ * ncclAllReduce + update kernel), SFM_COMM_PEER (ONE kernel that sums the ranks' gradients over
+ * NVLink peer memory, updates and writes every replica; chosen when every rank can map the
+ * others' buffers, SFM_P2P=0 in the environment forces NCCL), SFM_COMM_SHARDED (SFM_FLAG_SHARD_V). */
+#define SFM_COMM_NONE 0
+#define SFM_COMM_NCCL 1
+#define SFM_COMM_PEER 2
+#define SFM_COMM_SHARDED 3
+int32_t sfm_comm_mode(const sfm_handle* h, int32_t* mode);
 /* Copies rank 0's model to every rank. */
 int32_t sfm_comm_broadcast_model(sfm_handle* h);
 

@@ -234,7 +234,13 @@ static void stage_view(const Stage& sg, BatchView* out) {
 
 static int read_err_flag(sfm_handle* h) {
     CU(cudaMemcpyAsync(h->h_flags, h->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    h->h_flags[1] = 0;
+    if (h->p2p)
+        CU(cudaMemcpyAsync(h->h_flags + 1, p2p_timeout_flag(h), sizeof(int32_t),
+                           cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    if (h->h_flags[1])
+        return set_err(h, SFM_ERR_NCCL, "peer-memory gradient exchange timed out waiting for a rank");
     if (h->h_flags[0])
         return set_err(h, SFM_ERR_INDEX, "feature index outside [0, n_slots) in the batch");
     return SFM_OK;
@@ -303,7 +309,8 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     }
     const bool multi = h->world > 1;
     const bool fused = !multi && !grad_keep;
-    if (!fused) RC(ensure(h, h->b_grad, sizeof(float) * grad_len(h)));
+    const bool p2p = multi && h->p2p && !grad_keep;   // sum + update in one kernel over NVLink
+    if (!fused && !p2p) RC(ensure(h, h->b_grad, sizeof(float) * grad_len(h)));
 
     if ((n + 1) * (int64_t)m.lpr >= 4294967296LL)
         return set_err(h, SFM_ERR_ARG, "batch too large: rows * kp/4 must stay below 2^32");
@@ -325,7 +332,7 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     // slices; slice q's gradient is all-reduced and applied on the comm stream while the reduce of
     // slice q+1 runs on the compute stream.
     int n_slices = 1;
-    if (multi && !grad_keep && n_blocks == 1 && nnz > 0 && !h->phase_timing) {
+    if (multi && !p2p && !grad_keep && n_blocks == 1 && nnz > 0 && !h->phase_timing) {
         static int q_env = -1;
         if (q_env < 0) {
             const char* e = getenv("SFM_AR_SLICES");
@@ -417,8 +424,17 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     }
     CU(launch_pull(m, (int32_t*)h->b_seg.p, key_bits, n_blocks, keys_sorted, pay_sorted, nnz, binary,
                    o.S, o.mult, (float*)h->b_pull.p, h->d_scal, h->d_err, up, fused,
-                   fused ? nullptr : (float*)h->b_grad.p, h->sm_count, h->stream, L));
+                   fused ? nullptr : (p2p ? p2p_grad_buffer(h) : (float*)h->b_grad.p), h->sm_count,
+                   h->stream, L));
     pt.lap(&h->stats.ms_reduce);
+    if (p2p) {
+        RC(p2p_reduce_update(h, up));
+        pt.lap(&h->stats.ms_allreduce);
+        h->stats.train_steps += 1;
+        h->stats.train_rows += n;
+        h->stats.train_nnz += nnz;
+        return SFM_OK;
+    }
     if (multi) {
         // [gV | gw] only: the trailing gw0 slot already holds the GLOBAL value (it comes from
         // the all-reduced scalar block above)
@@ -810,6 +826,7 @@ int32_t sfm_destroy(sfm_handle* h) {
     if (!h) return SFM_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    p2p_teardown(h);
     if (h->comm) nccl_destroy(h->nccl, h->comm);
     sfm_unload_dataset(h);
     Buf* bufs[] = {&h->b_row_ids, &h->b_out_ptr, &h->b_S, &h->b_mult, &h->b_loss, &h->b_yhat,
@@ -1823,6 +1840,8 @@ int32_t sfm_comm_init(sfm_handle* h, const uint8_t id[SFM_UNIQUE_ID_BYTES], int3
         cudaMemsetAsync(ss->w, 0, sizeof(float) * rows, h->stream);
         CU(cudaStreamSynchronize(h->stream));
         h->shard = ss;
+    } else {
+        RC(p2p_setup(h));
     }
     return SFM_OK;
 }
@@ -1831,6 +1850,15 @@ int32_t sfm_comm_info(const sfm_handle* h, int32_t* rank, int32_t* world_size) {
     if (!h) return SFM_ERR_ARG;
     if (rank) *rank = h->rank;
     if (world_size) *world_size = h->world;
+    return SFM_OK;
+}
+
+int32_t sfm_comm_mode(const sfm_handle* h, int32_t* mode) {
+    if (!h || !mode) return SFM_ERR_ARG;
+    *mode = h->world <= 1 ? SFM_COMM_NONE
+            : h->shard    ? SFM_COMM_SHARDED
+            : h->p2p      ? SFM_COMM_PEER
+                          : SFM_COMM_NCCL;
     return SFM_OK;
 }
 

@@ -101,7 +101,8 @@ struct ModelView {
     int32_t k0, k1, task;
 };
 
-struct Nccl;  // sfm_nccl.cpp
+struct Nccl;      // sfm_nccl.cpp
+struct P2PState;  // sfm_p2p.cu
 
 }  // namespace sfm
 
@@ -123,6 +124,7 @@ struct sfm_handle {
     sfm::Buf b_pre_keys0, b_pre_pay0, b_sort_tmp2;
     bool shard_requested = false;       // SFM_FLAG_SHARD_V at create; active once comm is up
     sfm::ShardState* shard = nullptr;
+    sfm::P2PState* p2p = nullptr;       // NVLink peer-memory reduce+update (replicated multi-GPU)
     // sampler prefetch (sfm_train): ids / count of the NEXT iteration are produced on copy_stream
     sfm::Buf b_ids2[2], b_samp_tmp;
     int32_t* d_count2 = nullptr;   // [2] device
@@ -173,6 +175,13 @@ cudaError_t launch_scalar_reduce(const float* loss, const float* mult, int64_t n
 struct UpdateParams {
     float eta, reg0, regw, regv;
 };
+#ifdef __CUDACC__
+// theta - eta * (g / B + lambda * theta)   with the roundings pinned, so every kernel
+// that applies the update (fused finalize, dense update, peer-memory update) gives the same bits.
+__device__ __forceinline__ float sgd_step(float theta, float g, float inv, float eta, float reg) {
+    return __fmaf_rn(-eta, __fmaf_rn(g, inv, __fmul_rn(reg, theta)), theta);
+}
+#endif
 // reduce-by-feature over the sorted entries.  fused: apply the SGD update in place (one GPU);
 // else write the dense gradient grad = [gV n_slots*kp | gw n_slots | gw0].
 cudaError_t launch_pull(const ModelView& m, int32_t* seg, int key_bits, int n_blocks,
@@ -263,6 +272,13 @@ cudaError_t sample_rows_device(void* tmp, size_t tmp_bytes, int64_t n, int64_t g
 int shard_forward(sfm_handle* h, const BatchView& b);                 // yhat -> h->b_yhat
 int shard_train(sfm_handle* h, const BatchView& b, int64_t iter, int cache_slot);  // -1: no cache
 void shard_clear_cache(sfm_handle* h);
+
+// ---- gradient sum + update over NVLink peer memory (sfm_p2p.cu)
+int p2p_setup(sfm_handle* h);      // collective; leaves h->p2p null when any rank cannot take part
+void p2p_teardown(sfm_handle* h);
+float* p2p_grad_buffer(sfm_handle* h);
+const int32_t* p2p_timeout_flag(sfm_handle* h);
+int p2p_reduce_update(sfm_handle* h, UpdateParams up);
 
 // ---- host side (sfm_host.cpp)
 uint64_t mix64(uint64_t x);

@@ -891,7 +891,7 @@ fm_pull_finalize_kernel(float4* __restrict__ V4, float* __restrict__ W, float* _
         if (FUSED) {
             if (k0 && active) {
                 const float w0 = *W0;
-                *W0 = w0 - up.eta * (g0 * inv + up.reg0 * w0);
+                *W0 = sgd_step(w0, g0, inv, up.eta, up.reg0);
             }
         } else {
             *Gw0 = k0 ? g0 : 0.f;
@@ -925,18 +925,18 @@ fm_pull_finalize_kernel(float4* __restrict__ V4, float* __restrict__ W, float* _
         }
         if (BINARY) D = C;
         float4 g;
-        g.x = A.x - v.x * D;
-        g.y = A.y - v.y * D;
-        g.z = A.z - v.z * D;
-        g.w = A.w - v.w * D;
+        g.x = __fmaf_rn(-v.x, D, A.x);
+        g.y = __fmaf_rn(-v.y, D, A.y);
+        g.z = __fmaf_rn(-v.z, D, A.z);
+        g.w = __fmaf_rn(-v.w, D, A.w);
         if (FUSED) {
             if (active) {
-                v.x -= up.eta * (g.x * inv + up.regv * v.x);
-                v.y -= up.eta * (g.y * inv + up.regv * v.y);
-                v.z -= up.eta * (g.z * inv + up.regv * v.z);
-                v.w -= up.eta * (g.w * inv + up.regv * v.w);
+                v.x = sgd_step(v.x, g.x, inv, up.eta, up.regv);
+                v.y = sgd_step(v.y, g.y, inv, up.eta, up.regv);
+                v.z = sgd_step(v.z, g.z, inv, up.eta, up.regv);
+                v.w = sgd_step(v.w, g.w, inv, up.eta, up.regv);
                 V4[i * LPR + fq] = v;
-                if (fq == 0 && k1) W[i] = wi - up.eta * (C * inv + up.regw * wi);
+                if (fq == 0 && k1) W[i] = sgd_step(wi, C, inv, up.eta, up.regw);
             }
         } else {
             G4[i * LPR + fq] = g;
@@ -1124,20 +1124,20 @@ fm_update_kernel(float4* __restrict__ V4, float* __restrict__ W, float* __restri
     for (int64_t i = feat_lo * lpr + tid; i < feat_hi * lpr; i += stride) {
         float4 v = V4[i];
         const float4 g = __ldg(G4 + i);
-        v.x -= up.eta * (g.x * inv + up.regv * v.x);
-        v.y -= up.eta * (g.y * inv + up.regv * v.y);
-        v.z -= up.eta * (g.z * inv + up.regv * v.z);
-        v.w -= up.eta * (g.w * inv + up.regv * v.w);
+        v.x = sgd_step(v.x, g.x, inv, up.eta, up.regv);
+        v.y = sgd_step(v.y, g.y, inv, up.eta, up.regv);
+        v.z = sgd_step(v.z, g.z, inv, up.eta, up.regv);
+        v.w = sgd_step(v.w, g.w, inv, up.eta, up.regv);
         V4[i] = v;
     }
     if (k1)
         for (int64_t i = feat_lo + tid; i < feat_hi; i += stride) {
             const float w = W[i];
-            W[i] = w - up.eta * (__ldg(Gw + i) * inv + up.regw * w);
+            W[i] = sgd_step(w, __ldg(Gw + i), inv, up.eta, up.regw);
         }
     if (k0 && tid == 0 && feat_lo == 0) {
         const float w0 = *W0;
-        *W0 = w0 - up.eta * (*Gw0 * inv + up.reg0 * w0);
+        *W0 = sgd_step(w0, *Gw0, inv, up.eta, up.reg0);
     }
 }
 

@@ -1,0 +1,354 @@
+// sfm_p2p.cu -- gradient sum + SGD update fused into ONE kernel over NVLink peer memory
+// (replicated data-parallel mode; replaces ncclAllReduce(68 MB) + fm_update_kernel).
+//
+// Every rank keeps its dense gradient [gV | gw] in a buffer the other ranks can read
+// (CUDA IPC, peer access over NVLink / NVSwitch) and its model replica in a buffer the others can
+// write.  Rank r owns the feature slice [r*n/G, (r+1)*n/G).  One iteration:
+//
+//   1. finalize writes the local gradient, then a signal kernel stores the step number into every
+//      peer's "ready" word (release, system scope);
+//   2. p2p_reduce_update_kernel waits until all G ready words carry this step, then for its OWN
+//      slice: loads the G partial gradients with peer loads (no local caching), adds them IN RANK
+//      ORDER (bitwise reproducible and identical on every rank), applies
+//      theta <- theta - eta*(g/B + lambda*theta) and stores the new parameters into ALL G replicas
+//      (peer stores).  The last CTA to finish stores the step number into every peer's "done" word;
+//   3. a one-thread kernel waits for the G done words before the next forward may read the model.
+//
+// Per rank and step (G-1)/G of the gradient slice comes in and (G-1)/G of the parameter slice
+// goes out over NVLink, overlapped inside one kernel -- the reduce-scatter, the update and the
+// all-gather of a ring all-reduce, without intermediate buffers.  All waits have a time-out that
+// raises the handle's error flag instead of hanging.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "sfm_common.h"
+
+namespace sfm {
+
+#define CU(call)                                                                        \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess)                                                          \
+            return set_err(h, e_ == cudaErrorMemoryAllocation ? SFM_ERR_OOM : SFM_ERR_CUDA, \
+                           std::string(#call) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+#define RC(call)                       \
+    do {                               \
+        int rc_ = (call);              \
+        if (rc_ != SFM_OK) return rc_; \
+    } while (0)
+
+constexpr int P2P_MAXG = 16;
+// done_ctr words: [0] CTA completion counter, [1] sticky "a peer wait timed out" flag
+
+struct DevPeers {
+    float4* v[P2P_MAXG];
+    float* w[P2P_MAXG];
+    const float4* g4[P2P_MAXG];
+    const float* gw[P2P_MAXG];
+    uint32_t* sig[P2P_MAXG];   // [2][P2P_MAXG]: ready words, done words
+};
+
+struct P2PState {
+    float* grad = nullptr;
+    uint32_t* sig = nullptr;
+    uint32_t* done_ctr = nullptr;
+    void* opened[P2P_MAXG][4];
+    DevPeers peers;
+    uint32_t epoch = 0;
+    unsigned long long timeout_ns = 0;
+};
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// one thread: wait until sig[base + p] has reached `epoch` for every rank p
+__device__ bool p2p_wait(const uint32_t* sig, int base, int world, uint32_t epoch,
+                         unsigned long long timeout_ns, uint32_t* timed_out) {
+    if (ld_volatile_u32(timed_out)) return false;   // sticky: never wait again after a time-out
+    const unsigned long long t0 = global_ns();
+    for (int p = 0; p < world; ++p) {
+        while ((int32_t)(ld_volatile_u32(sig + base + p) - epoch) < 0) {
+            if (global_ns() - t0 > timeout_ns) {
+                st_volatile_u32(timed_out, 1u);
+                return false;
+            }
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
+    return true;
+}
+
+__global__ void p2p_signal_kernel(DevPeers P, int world, int rank, int phase, uint32_t epoch) {
+    const int p = threadIdx.x;
+    if (p < world) {
+        __threadfence_system();
+        st_volatile_u32(P.sig[p] + phase * P2P_MAXG + rank, epoch);
+    }
+}
+
+__global__ void p2p_wait_kernel(const uint32_t* sig, int phase, int world, uint32_t epoch,
+                                unsigned long long timeout_ns, uint32_t* timed_out) {
+    if (threadIdx.x == 0) p2p_wait(sig, phase * P2P_MAXG, world, epoch, timeout_ns, timed_out);
+}
+
+__device__ __forceinline__ float4 ld_peer4(const float4* p) {   // no caching of peer data
+    float4 r;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ float ld_peer1(const float* p) {
+    float r;
+    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
+template <int W>   // W = number of ranks rounded up to 2 / 4 / 8 / 16 (loads are issued together)
+__global__ void __launch_bounds__(256)
+p2p_reduce_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_t v4_lo,
+                         int64_t v4_hi, int64_t w_lo, int64_t w_hi, int k0, int k1,
+                         float* __restrict__ W0, const float* __restrict__ Gw0,
+                         const uint32_t* sig, const double* __restrict__ d_scal,
+                         const int32_t* __restrict__ err, UpdateParams up,
+                         unsigned long long timeout_ns, uint32_t* done_ctr) {
+    __shared__ int ok;
+    if (threadIdx.x == 0) ok = p2p_wait(sig, 0, world, epoch, timeout_ns, done_ctr + 1) ? 1 : 0;
+    __syncthreads();
+    const double count = d_scal[SC_COUNT];
+    const bool active = ok && count > 0.0 && *err == 0;
+    if (active) {
+        const float inv = (float)(1.0 / count);
+        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+        const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (int64_t e = v4_lo + tid; e < v4_hi; e += stride) {
+            float4 x[W];
+#pragma unroll
+            for (int p = 0; p < W; ++p)
+                x[p] = p < world ? ld_peer4(P.g4[p] + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 g = x[0];
+#pragma unroll
+            for (int p = 1; p < W; ++p) {   // rank order: fixed summation order
+                g.x += x[p].x; g.y += x[p].y; g.z += x[p].z; g.w += x[p].w;
+            }
+            float4 v = P.v[rank][e];
+            v.x = sgd_step(v.x, g.x, inv, up.eta, up.regv);
+            v.y = sgd_step(v.y, g.y, inv, up.eta, up.regv);
+            v.z = sgd_step(v.z, g.z, inv, up.eta, up.regv);
+            v.w = sgd_step(v.w, g.w, inv, up.eta, up.regv);
+#pragma unroll
+            for (int p = 0; p < W; ++p)
+                if (p < world) P.v[p][e] = v;
+        }
+        if (k1)
+            for (int64_t i = w_lo + tid; i < w_hi; i += stride) {
+                float g = 0.f;
+#pragma unroll
+                for (int p = 0; p < W; ++p) g += p < world ? ld_peer1(P.gw[p] + i) : 0.f;
+                const float w = P.w[rank][i];
+                const float wn = sgd_step(w, g, inv, up.eta, up.regw);
+#pragma unroll
+                for (int p = 0; p < W; ++p)
+                    if (p < world) P.w[p][i] = wn;
+            }
+        if (k0 && tid == 0) {   // w0 is replicated: every rank applies the same global scalar
+            const float w0 = *W0;
+            *W0 = sgd_step(w0, *Gw0, inv, up.eta, up.reg0);
+        }
+    }
+    // completion: the last CTA tells every peer that this slice has been written everywhere
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned ticket = atomicAdd(done_ctr, 1u);
+        if (ticket == gridDim.x - 1) {
+            *done_ctr = 0;
+            __threadfence_system();
+            for (int p = 0; p < world; ++p) st_volatile_u32(P.sig[p] + P2P_MAXG + rank, epoch);
+        }
+    }
+}
+
+void p2p_teardown(sfm_handle* h) {
+    P2PState* s = h->p2p;
+    if (!s) return;
+    for (int p = 0; p < h->world && p < P2P_MAXG; ++p)
+        for (int j = 0; j < 4; ++j)
+            if (s->opened[p][j]) cudaIpcCloseMemHandle(s->opened[p][j]);
+    if (s->grad) cudaFree(s->grad);
+    if (s->sig) cudaFree(s->sig);
+    if (s->done_ctr) cudaFree(s->done_ctr);
+    delete s;
+    h->p2p = nullptr;
+}
+
+// Collective.  Enables the P2P path if EVERY rank could export its buffers and open all peers'.
+int p2p_setup(sfm_handle* h) {
+    const char* env = getenv("SFM_P2P");
+    const int want = env ? atoi(env) : 1;
+    const int G = h->world;
+    if (G < 2 || G > P2P_MAXG || h->shard_requested) return SFM_OK;
+    const ModelView& m = h->m;
+    P2PState* s = new (std::nothrow) P2PState;
+    if (!s) return SFM_OK;
+    memset(s->opened, 0, sizeof s->opened);
+    memset(&s->peers, 0, sizeof s->peers);
+    const size_t glen = (size_t)m.n_slots * (m.kp + 1) + 1;
+    bool ok = want != 0;
+    cudaIpcMemHandle_t mine[4];
+    memset(mine, 0, sizeof mine);
+    if (ok) ok = cudaMalloc(&s->grad, sizeof(float) * glen) == cudaSuccess;
+    if (ok) ok = cudaMalloc(&s->sig, sizeof(uint32_t) * 2 * P2P_MAXG) == cudaSuccess;
+    if (ok) ok = cudaMalloc(&s->done_ctr, sizeof(uint32_t) * 4) == cudaSuccess;
+    if (ok) {
+        cudaMemsetAsync(s->sig, 0, sizeof(uint32_t) * 2 * P2P_MAXG, h->stream);
+        cudaMemsetAsync(s->done_ctr, 0, sizeof(uint32_t) * 4, h->stream);
+        ok = cudaIpcGetMemHandle(&mine[0], m.v) == cudaSuccess &&
+             cudaIpcGetMemHandle(&mine[1], m.w) == cudaSuccess &&
+             cudaIpcGetMemHandle(&mine[2], s->grad) == cudaSuccess &&
+             cudaIpcGetMemHandle(&mine[3], s->sig) == cudaSuccess;
+    }
+    cudaGetLastError();
+    // exchange {ok, 4 handles} with everybody: 4 * 64 bytes + 1 word per rank
+    constexpr int HW = 4 * (int)(sizeof(cudaIpcMemHandle_t) / 4);
+    constexpr int WORDS = 1 + HW + 4;   // ok | 4 handles | device uuid
+    std::vector<int32_t> send(WORDS), recv((size_t)WORDS * G);
+    send[0] = ok ? 1 : 0;
+    memcpy(send.data() + 1, mine, sizeof mine);
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, h->device) == cudaSuccess)
+            memcpy(send.data() + 1 + HW, &prop.uuid, 16);
+        else
+            send[0] = 0;
+        cudaGetLastError();
+    }
+    const char* tenv = getenv("SFM_P2P_TIMEOUT_S");
+    const double tsec = tenv ? atof(tenv) : 120.0;
+    s->timeout_ns = (unsigned long long)((tsec > 0.001 ? tsec : 0.001) * 1e9);
+    Buf dsend, drecv;
+    int rc = ensure(h, dsend, sizeof(int32_t) * WORDS);
+    if (rc == SFM_OK) rc = ensure(h, drecv, sizeof(int32_t) * WORDS * G);
+    if (rc == SFM_OK &&
+        cudaMemcpyAsync(dsend.p, send.data(), sizeof(int32_t) * WORDS, cudaMemcpyHostToDevice,
+                        h->stream) != cudaSuccess)
+        rc = SFM_ERR_CUDA;
+    if (rc == SFM_OK)
+        rc = nccl_allgather_i32(h->nccl, h->comm, (const int32_t*)dsend.p, (int32_t*)drecv.p, WORDS,
+                                h->stream, &h->err);
+    if (rc == SFM_OK &&
+        (cudaMemcpyAsync(recv.data(), drecv.p, sizeof(int32_t) * WORDS * G, cudaMemcpyDeviceToHost,
+                         h->stream) != cudaSuccess ||
+         cudaStreamSynchronize(h->stream) != cudaSuccess))
+        rc = SFM_ERR_CUDA;
+    if (dsend.p) cudaFree(dsend.p);
+    if (drecv.p) cudaFree(drecv.p);
+    if (rc != SFM_OK) {   // the all-gather itself failed: nothing more can be agreed on
+        h->p2p = s;
+        p2p_teardown(h);
+        return rc;
+    }
+    bool all_ok = true;
+    for (int p = 0; p < G; ++p) all_ok = all_ok && recv[(size_t)p * WORDS] == 1;
+    // two ranks on one GPU could starve each other's wait loops: NCCL path for those
+    for (int p = 0; p < G && all_ok; ++p)
+        for (int q = 0; q < p; ++q)
+            if (!memcmp(&recv[(size_t)p * WORDS + 1 + HW], &recv[(size_t)q * WORDS + 1 + HW], 16))
+                all_ok = false;
+    bool opened_ok = all_ok;
+    if (all_ok) {
+        for (int p = 0; p < G && opened_ok; ++p) {
+            void* ptr[4];
+            if (p == h->rank) {
+                ptr[0] = m.v; ptr[1] = m.w; ptr[2] = s->grad; ptr[3] = s->sig;
+            } else {
+                cudaIpcMemHandle_t hd[4];
+                memcpy(hd, recv.data() + (size_t)p * WORDS + 1, sizeof hd);
+                for (int j = 0; j < 4 && opened_ok; ++j) {
+                    if (cudaIpcOpenMemHandle(&ptr[j], hd[j], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                        cudaGetLastError();
+                        opened_ok = false;
+                    } else {
+                        s->opened[p][j] = ptr[j];
+                    }
+                }
+            }
+            if (!opened_ok) break;
+            s->peers.v[p] = (float4*)ptr[0];
+            s->peers.w[p] = (float*)ptr[1];
+            s->peers.g4[p] = (const float4*)ptr[2];
+            s->peers.gw[p] = (const float*)ptr[2] + (size_t)m.n_slots * m.kp;
+            s->peers.sig[p] = (uint32_t*)ptr[3];
+        }
+    }
+    // second agreement: did everybody manage to open everything?
+    double flag = opened_ok ? 0.0 : 1.0;
+    double* dflag = h->d_scal + 6;
+    int rc2 = SFM_OK;
+    if (cudaMemcpyAsync(dflag, &flag, sizeof(double), cudaMemcpyHostToDevice, h->stream) != cudaSuccess)
+        rc2 = SFM_ERR_CUDA;
+    if (rc2 == SFM_OK) rc2 = nccl_allreduce_f64(h->nccl, h->comm, dflag, 1, h->stream, &h->err);
+    if (rc2 == SFM_OK &&
+        (cudaMemcpyAsync(&flag, dflag, sizeof(double), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+         cudaStreamSynchronize(h->stream) != cudaSuccess))
+        rc2 = SFM_ERR_CUDA;
+    h->p2p = s;
+    if (rc2 != SFM_OK || flag != 0.0) {
+        p2p_teardown(h);   // fall back to the NCCL all-reduce path on every rank
+        return rc2;
+    }
+    return SFM_OK;
+}
+
+float* p2p_grad_buffer(sfm_handle* h) { return h->p2p ? h->p2p->grad : nullptr; }
+const int32_t* p2p_timeout_flag(sfm_handle* h) {
+    return h->p2p ? (const int32_t*)(h->p2p->done_ctr + 1) : nullptr;
+}
+
+// Steps 1-3 above, queued on the compute stream after the finalize kernel wrote p2p grad.
+int p2p_reduce_update(sfm_handle* h, UpdateParams up) {
+    P2PState* s = h->p2p;
+    const ModelView& m = h->m;
+    const int G = h->world, r = h->rank;
+    int64_t* L = &h->stats.kernel_launches;
+    const uint32_t epoch = ++s->epoch;
+    const int64_t f_lo = (int64_t)r * m.n_slots / G, f_hi = (int64_t)(r + 1) * m.n_slots / G;
+    p2p_signal_kernel<<<1, 32, 0, h->stream>>>(s->peers, G, r, 0, epoch);
+    int64_t blocks = ((f_hi - f_lo) * m.lpr + 255) / 256;
+    const int64_t cap = (int64_t)h->sm_count * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+#define RU_ARGS                                                                                \
+    s->peers, G, r, epoch, f_lo * m.lpr, f_hi * m.lpr, f_lo, f_hi, m.k0, m.k1, m.w0,          \
+        s->grad + (size_t)m.n_slots * (m.kp + 1), s->sig, h->d_scal, h->d_err, up,            \
+        s->timeout_ns, s->done_ctr
+    if (G <= 2)      p2p_reduce_update_kernel<2><<<(unsigned)blocks, 256, 0, h->stream>>>(RU_ARGS);
+    else if (G <= 4) p2p_reduce_update_kernel<4><<<(unsigned)blocks, 256, 0, h->stream>>>(RU_ARGS);
+    else if (G <= 8) p2p_reduce_update_kernel<8><<<(unsigned)blocks, 256, 0, h->stream>>>(RU_ARGS);
+    else             p2p_reduce_update_kernel<16><<<(unsigned)blocks, 256, 0, h->stream>>>(RU_ARGS);
+#undef RU_ARGS
+    p2p_wait_kernel<<<1, 32, 0, h->stream>>>(s->sig, 1, G, epoch, s->timeout_ns, s->done_ctr + 1);
+    *L += 3;
+    CU(cudaGetLastError());
+    return SFM_OK;
+}
+
+}  // namespace sfm

@@ -270,6 +270,12 @@ class Handle:
         buf = (C.c_uint8 * _lib.SFM_UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
         self._ck(self._L.sfm_comm_init(self._h, buf, int(rank), int(world_size)))
 
+    def comm_mode(self) -> str:
+        """'none' | 'nccl' | 'peer' (fused sum + update over NVLink peer memory) | 'sharded'."""
+        m = C.c_int32()
+        self._ck(self._L.sfm_comm_mode(self._h, C.byref(m)))
+        return ("none", "nccl", "peer", "sharded")[m.value]
+
     def comm_broadcast_model(self):
         self._ck(self._L.sfm_comm_broadcast_model(self._h))
 

@@ -32,8 +32,10 @@ def _data():
                             rng.normal(0, 0.05, (N_SLOTS, K)).astype(np.float32))
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, p2p="1"):
     import torch.distributed as dist
+    os.environ["SFM_P2P"] = p2p
+    os.environ["SFM_P2P_TIMEOUT_S"] = "20"
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)  # rendezvous only
@@ -47,6 +49,8 @@ def _worker(rank, world, port, out_dir):
             hd.set_model(w0, w, v)
         init_comm(hd, device="cpu")
         hd.comm_broadcast_model()
+        mode = hd.comm_mode()
+        assert mode == ("nccl" if p2p == "0" else mode)      # SFM_P2P=0 must force NCCL
         sub = idx[rp[lo]:rp[hi]]
         hd.load_dataset(rp[lo:hi + 1] - rp[lo], sub, None, label[lo:hi], global_row_offset=lo)
         losses = [hd.train_step(it) for it in range(1, ITERS + 1)]
@@ -54,7 +58,7 @@ def _worker(rank, world, port, out_dir):
         ev = hd.evaluate()
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), loss=np.array([l for l, _ in losses]),
                  batch=np.array([b for _, b in losses]), w0=m[0], w=m[1], v=m[2], rmse=ev["rmse"],
-                 n=ev["n"])
+                 n=ev["n"], mode=mode)
         hd.close()
     finally:
         dist.destroy_process_group()
@@ -62,15 +66,23 @@ def _worker(rank, world, port, out_dir):
 
 @pytest.mark.skipif(device_count() < 2, reason="needs 2 GPUs")
 def test_two_gpus_match_one_gpu(tmp_path):
+    """Run 0 and 1: default gradient exchange (the fused sum + update kernel over NVLink peer
+    memory when the GPUs can map each other, see `mode`); run 2: SFM_P2P=0, the NCCL all-reduce
+    path.  With two ranks both sum a + b, so all three runs must agree bit for bit."""
     import torch.multiprocessing as mp
     from sparkfm_b200 import Handle
     runs = []
-    for rep in range(2):
+    for rep in range(3):
         d = tmp_path / f"rep{rep}"
         d.mkdir()
-        mp.spawn(_worker, args=(2, _free_port(), str(d)), nprocs=2, join=True)
+        mp.spawn(_worker, args=(2, _free_port(), str(d), "0" if rep == 2 else "1"), nprocs=2,
+                 join=True)
         runs.append([np.load(d / f"r{r}.npz") for r in range(2)])
     a, b = runs[0]
+    print("gradient exchange mode:", str(a["mode"]))
+    assert str(runs[2][0]["mode"]) == "nccl"
+    for key in ("loss", "batch", "w0", "w", "v"):
+        assert np.array_equal(a[key], runs[2][0][key]), key   # peer-memory path == NCCL path
     # replicas identical across ranks, and reproducible across reruns
     for key in ("loss", "batch", "w0", "w", "v"):
         assert np.array_equal(a[key], b[key]), key
