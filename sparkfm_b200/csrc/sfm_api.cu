@@ -350,7 +350,7 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
             CU(cudaStreamWaitEvent(h->comm_stream, h->ev_pool[0], 0));
             RC(nccl_allreduce_f64(h->nccl, h->comm, h->d_scal, SC_N, h->comm_stream, &h->err));
             CU(cudaEventRecord(h->ev_pool[1], h->comm_stream));
-        } else {
+        } else if (!p2p) {   // peer-memory path: the scalars travel with the gradient
             RC(nccl_allreduce_f64(h->nccl, h->comm, h->d_scal, SC_N, h->stream, &h->err));
             pt.lap(&h->stats.ms_allreduce);
         }

@@ -5,8 +5,9 @@
 // (CUDA IPC, peer access over NVLink / NVSwitch) and its model replica in a buffer the others can
 // write.  Rank r owns the feature slice [r*n/G, (r+1)*n/G).  One iteration:
 //
-//   1. finalize writes the local gradient, then a signal kernel stores the step number into every
-//      peer's "ready" word (release, system scope);
+//   1. finalize writes the local gradient, then a signal kernel copies the rank's loss / count /
+//      gw0 sums next to it and stores the step number into every peer's "ready" word (release,
+//      system scope) -- the scalar all-reduce of the NCCL path is folded into the same exchange;
 //   2. p2p_reduce_update_kernel waits until all G ready words carry this step, then for its OWN
 //      slice: loads the G partial gradients with peer loads (no local caching), adds them IN RANK
 //      ORDER (bitwise reproducible and identical on every rank), applies
@@ -48,6 +49,7 @@ struct DevPeers {
     float* w[P2P_MAXG];
     const float4* g4[P2P_MAXG];
     const float* gw[P2P_MAXG];
+    const double* scal[P2P_MAXG];   // [SC_N] per-rank loss / count / gw0 sums of this step
     uint32_t* sig[P2P_MAXG];   // [2][P2P_MAXG]: ready words, done words
 };
 
@@ -95,8 +97,11 @@ __device__ bool p2p_wait(const uint32_t* sig, int base, int world, uint32_t epoc
     return true;
 }
 
-__global__ void p2p_signal_kernel(DevPeers P, int world, int rank, int phase, uint32_t epoch) {
+__global__ void p2p_signal_kernel(DevPeers P, int world, int rank, int phase, uint32_t epoch,
+                                  const double* __restrict__ d_scal) {
     const int p = threadIdx.x;
+    if (p < SC_N) const_cast<double*>(P.scal[rank])[p] = d_scal[p];
+    __syncthreads();
     if (p < world) {
         __threadfence_system();
         st_volatile_u32(P.sig[p] + phase * P2P_MAXG + rank, epoch);
@@ -126,15 +131,31 @@ template <int W>   // W = number of ranks rounded up to 2 / 4 / 8 / 16 (loads ar
 __global__ void __launch_bounds__(256)
 p2p_reduce_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_t v4_lo,
                          int64_t v4_hi, int64_t w_lo, int64_t w_hi, int k0, int k1,
-                         float* __restrict__ W0, const float* __restrict__ Gw0,
-                         const uint32_t* sig, const double* __restrict__ d_scal,
+                         float* __restrict__ W0, const uint32_t* sig, double* __restrict__ d_scal,
                          const int32_t* __restrict__ err, UpdateParams up,
                          unsigned long long timeout_ns, uint32_t* done_ctr) {
     __shared__ int ok;
-    if (threadIdx.x == 0) ok = p2p_wait(sig, 0, world, epoch, timeout_ns, done_ctr + 1) ? 1 : 0;
+    __shared__ double tot[SC_N];
+    if (threadIdx.x == 0) {
+        ok = p2p_wait(sig, 0, world, epoch, timeout_ns, done_ctr + 1) ? 1 : 0;
+        if (ok) {   // global loss / count / gw0: rank-order fp64 sums, the same on every rank
+            for (int j = 0; j < SC_N; ++j) {
+                double a = 0.0;
+                for (int p = 0; p < world; ++p) {
+                    double x;
+                    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(x) : "l"(P.scal[p] + j));
+                    a += x;
+                }
+                tot[j] = a;
+            }
+        } else {
+            for (int j = 0; j < SC_N; ++j) tot[j] = 0.0;
+        }
+    }
     __syncthreads();
-    const double count = d_scal[SC_COUNT];
+    const double count = tot[SC_COUNT];
     const bool active = ok && count > 0.0 && *err == 0;
+    if (ok && blockIdx.x == 0 && threadIdx.x < SC_N) d_scal[threadIdx.x] = tot[threadIdx.x];
     if (active) {
         const float inv = (float)(1.0 / count);
         const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -171,7 +192,7 @@ p2p_reduce_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_
             }
         if (k0 && tid == 0) {   // w0 is replicated: every rank applies the same global scalar
             const float w0 = *W0;
-            *W0 = sgd_step(w0, *Gw0, inv, up.eta, up.reg0);
+            *W0 = sgd_step(w0, (float)tot[SC_GW0], inv, up.eta, up.reg0);
         }
     }
     // completion: the last CTA tells every peer that this slice has been written everywhere
@@ -212,10 +233,11 @@ int p2p_setup(sfm_handle* h) {
     memset(s->opened, 0, sizeof s->opened);
     memset(&s->peers, 0, sizeof s->peers);
     const size_t glen = (size_t)m.n_slots * (m.kp + 1) + 1;
+    const size_t scal_off = (glen + 3) / 4 * 4;   // floats; the [SC_N] doubles sit 16-byte aligned
     bool ok = want != 0;
     cudaIpcMemHandle_t mine[4];
     memset(mine, 0, sizeof mine);
-    if (ok) ok = cudaMalloc(&s->grad, sizeof(float) * glen) == cudaSuccess;
+    if (ok) ok = cudaMalloc(&s->grad, sizeof(float) * scal_off + sizeof(double) * SC_N) == cudaSuccess;
     if (ok) ok = cudaMalloc(&s->sig, sizeof(uint32_t) * 2 * P2P_MAXG) == cudaSuccess;
     if (ok) ok = cudaMalloc(&s->done_ctr, sizeof(uint32_t) * 4) == cudaSuccess;
     if (ok) {
@@ -296,6 +318,7 @@ int p2p_setup(sfm_handle* h) {
             s->peers.w[p] = (float*)ptr[1];
             s->peers.g4[p] = (const float4*)ptr[2];
             s->peers.gw[p] = (const float*)ptr[2] + (size_t)m.n_slots * m.kp;
+            s->peers.scal[p] = (const double*)((const float*)ptr[2] + scal_off);
             s->peers.sig[p] = (uint32_t*)ptr[3];
         }
     }
@@ -331,15 +354,14 @@ int p2p_reduce_update(sfm_handle* h, UpdateParams up) {
     int64_t* L = &h->stats.kernel_launches;
     const uint32_t epoch = ++s->epoch;
     const int64_t f_lo = (int64_t)r * m.n_slots / G, f_hi = (int64_t)(r + 1) * m.n_slots / G;
-    p2p_signal_kernel<<<1, 32, 0, h->stream>>>(s->peers, G, r, 0, epoch);
+    p2p_signal_kernel<<<1, 32, 0, h->stream>>>(s->peers, G, r, 0, epoch, h->d_scal);
     int64_t blocks = ((f_hi - f_lo) * m.lpr + 255) / 256;
-    const int64_t cap = (int64_t)h->sm_count * 4;
+    const int64_t cap = (int64_t)h->sm_count * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
 #define RU_ARGS                                                                                \
     s->peers, G, r, epoch, f_lo * m.lpr, f_hi * m.lpr, f_lo, f_hi, m.k0, m.k1, m.w0,          \
-        s->grad + (size_t)m.n_slots * (m.kp + 1), s->sig, h->d_scal, h->d_err, up,            \
-        s->timeout_ns, s->done_ctr
+        s->sig, h->d_scal, h->d_err, up, s->timeout_ns, s->done_ctr
     if (G <= 2)      p2p_reduce_update_kernel<2><<<(unsigned)blocks, 256, 0, h->stream>>>(RU_ARGS);
     else if (G <= 4) p2p_reduce_update_kernel<4><<<(unsigned)blocks, 256, 0, h->stream>>>(RU_ARGS);
     else if (G <= 8) p2p_reduce_update_kernel<8><<<(unsigned)blocks, 256, 0, h->stream>>>(RU_ARGS);
