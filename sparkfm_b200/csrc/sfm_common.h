@@ -247,6 +247,18 @@ size_t sort_pairs32_temp_bytes(int64_t n, int end_bit);
 cudaError_t sort_pairs32(void* tmp, size_t tmp_bytes, const uint32_t* keys_in, uint32_t* keys_out,
                          const uint32_t* val_in, uint32_t* val_out, int64_t n, int end_bit,
                          cudaStream_t st, int64_t* launches);
+// wide-digit radix sort written for this path (sfm_radix.cu); same contract as sort_pairs*
+bool radix_usable(int64_t n, int end_bit);   // false: SFM_SORT=cub or outside its limits
+size_t radix_temp_bytes(int64_t n, int end_bit, int pay_bytes);
+cudaError_t radix_sort_pairs32(void* tmp, size_t tmp_bytes, const uint32_t* keys_in,
+                               uint32_t* keys_out, const uint32_t* pay_in, uint32_t* pay_out,
+                               int64_t n, int end_bit, cudaStream_t st, int64_t* launches);
+cudaError_t radix_sort_pairs64(void* tmp, size_t tmp_bytes, const uint32_t* keys_in,
+                               uint32_t* keys_out, const uint2* pay_in, uint2* pay_out, int64_t n,
+                               int end_bit, cudaStream_t st, int64_t* launches);
+size_t scan_u32_temp_bytes(int64_t n);
+cudaError_t exclusive_scan_u32(void* tmp, size_t tmp_bytes, const uint32_t* in, uint32_t* out,
+                               int64_t n, cudaStream_t st, int64_t* launches);
 size_t sort_f32_u32_temp_bytes(int64_t n);
 cudaError_t sort_f32_u32(void* tmp, size_t tmp_bytes, const float* keys_in, float* keys_out,
                          const uint32_t* val_in, uint32_t* val_out, int64_t n, cudaStream_t st,
