@@ -323,6 +323,12 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     o.yhat = nullptr;
     o.keys = pc ? nullptr : (uint32_t*)h->b_keys[0].p;   // cached transposition: nothing to emit
     o.pay = pc ? nullptr : (uint2*)h->b_pay[0].p;
+    // all-ones rows of m entries in row order: entry i belongs to batch row i / m, so the forward
+    // kernel writes no payload and the first sort pass derives it (saves 8 bytes per entry)
+    const int implicit_div = (!pc && binary && b.uniform_m > 0 && b.uniform_m < 512 && !b.out_ptr &&
+                              b.out_base == 0 && nnz > 0 && radix_usable(nnz, end_bit))
+                                 ? b.uniform_m : 0;
+    if (implicit_div) o.pay = nullptr;
     o.key_bits = key_bits;
     o.blk_shift = blk_shift;
     CU(launch_forward(m, b, o, true, h->d_err, h->sm_count, h->stream, L));
@@ -361,7 +367,7 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
         if (binary)
             CU(sort_pairs32(h->b_sort_tmp.p, sort_bytes, o.keys, (uint32_t*)h->b_keys[1].p,
                             (const uint32_t*)o.pay, (uint32_t*)h->b_pay[1].p, nnz, end_bit,
-                            h->stream, L));
+                            h->stream, L, implicit_div));
         else
             CU(sort_pairs(h->b_sort_tmp.p, sort_bytes, o.keys, (uint32_t*)h->b_keys[1].p, o.pay,
                           (uint2*)h->b_pay[1].p, nnz, end_bit, h->stream, L));

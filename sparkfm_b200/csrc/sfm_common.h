@@ -244,15 +244,18 @@ cudaError_t sort_pairs(void* tmp, size_t tmp_bytes, const uint32_t* keys_in, uin
                        const uint2* pay_in, uint2* pay_out, int64_t n, int end_bit,
                        cudaStream_t st, int64_t* launches);
 size_t sort_pairs32_temp_bytes(int64_t n, int end_bit);
+// implicit_div = m > 0 (only when radix_usable): val_in may be null, value of position i is i / m
 cudaError_t sort_pairs32(void* tmp, size_t tmp_bytes, const uint32_t* keys_in, uint32_t* keys_out,
                          const uint32_t* val_in, uint32_t* val_out, int64_t n, int end_bit,
-                         cudaStream_t st, int64_t* launches);
+                         cudaStream_t st, int64_t* launches, int implicit_div = 0);
 // wide-digit radix sort written for this path (sfm_radix.cu); same contract as sort_pairs*
 bool radix_usable(int64_t n, int end_bit);   // false: SFM_SORT=cub or outside its limits
 size_t radix_temp_bytes(int64_t n, int end_bit, int pay_bytes);
+// implicit_div = m > 0: pay_in is not read, the payload of input position i is i / m (m < 512)
 cudaError_t radix_sort_pairs32(void* tmp, size_t tmp_bytes, const uint32_t* keys_in,
                                uint32_t* keys_out, const uint32_t* pay_in, uint32_t* pay_out,
-                               int64_t n, int end_bit, cudaStream_t st, int64_t* launches);
+                               int64_t n, int end_bit, int implicit_div, cudaStream_t st,
+                               int64_t* launches);
 cudaError_t radix_sort_pairs64(void* tmp, size_t tmp_bytes, const uint32_t* keys_in,
                                uint32_t* keys_out, const uint2* pay_in, uint2* pay_out, int64_t n,
                                int end_bit, cudaStream_t st, int64_t* launches);

@@ -214,12 +214,12 @@ fm_forward_kernel(const float4* __restrict__ V4, const float* __restrict__ W,
                 if (j0 < end) {
                     keys[obase + (j0 - beg)] = kpre | (ia == zrow ? 0u : (uint32_t)ia);
                     if (HAS_VAL) pay[obase + (j0 - beg)] = make_uint2((uint32_t)pos, ia == zrow ? 0u : __float_as_uint(xa));
-                    else reinterpret_cast<uint32_t*>(pay)[obase + (j0 - beg)] = (uint32_t)pos;
+                    else if (pay) reinterpret_cast<uint32_t*>(pay)[obase + (j0 - beg)] = (uint32_t)pos;
                 }
                 if (j1 < end) {
                     keys[obase + (j1 - beg)] = kpre | (ib == zrow ? 0u : (uint32_t)ib);
                     if (HAS_VAL) pay[obase + (j1 - beg)] = make_uint2((uint32_t)pos, ib == zrow ? 0u : __float_as_uint(xb));
-                    else reinterpret_cast<uint32_t*>(pay)[obase + (j1 - beg)] = (uint32_t)pos;
+                    else if (pay) reinterpret_cast<uint32_t*>(pay)[obase + (j1 - beg)] = (uint32_t)pos;
                 }
             }
             const int cnt = (int)min((int64_t)64, end - tile);
@@ -342,8 +342,9 @@ fm_forward_onehot16_kernel(const float4* __restrict__ V4, const float* __restric
         if (TRAIN && keys != nullptr) {
             const uint32_t kpre = (uint32_t)(pos >> blk_shift) << key_bits;
             const uint32_t o = (uint32_t)pos * (uint32_t)m + lane;
-            if (has_a) { keys[o] = kpre | (uint32_t)ia; pay[o] = (uint32_t)pos; }
-            if (has_b) { keys[o + 32] = kpre | (uint32_t)ib; pay[o + 32] = (uint32_t)pos; }
+            // pay == nullptr: the sort derives the row from the entry position (o / m)
+            if (has_a) { keys[o] = kpre | (uint32_t)ia; if (pay) pay[o] = (uint32_t)pos; }
+            if (has_b) { keys[o + 32] = kpre | (uint32_t)ib; if (pay) pay[o + 32] = (uint32_t)pos; }
         }
         // ---- gathers: tile A (4 passes; lanes past m point at the zero row), then tile B
         float4 s = f4_zero(), p = f4_zero();

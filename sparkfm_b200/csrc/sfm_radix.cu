@@ -21,19 +21,22 @@
 
 namespace sfm {
 
-constexpr int RX_THREADS = 512;
+#ifndef SFM_RX_THREADS
+#define SFM_RX_THREADS 512
+#endif
+constexpr int RX_THREADS = SFM_RX_THREADS;   // 512: two CTAs per SM at 10-bit digits
 constexpr int RX_WARPS = RX_THREADS / 32;
 constexpr int RX_MAX_BITS = 10;
 
 // bytes of shared-memory region A: max(re-order buffers, per-warp peer masks at the widest digit)
 __host__ __device__ constexpr size_t rx_region_a(size_t pay_bytes) {
-    return (pay_bytes == 4 ? 512 * 16 : 512 * 8) * (4 + pay_bytes) >
-                   (size_t)4 * (512 / 32) * (1 << 10)
-               ? (pay_bytes == 4 ? 512 * 16 : 512 * 8) * (4 + pay_bytes)
-               : (size_t)4 * (512 / 32) * (1 << 10);
+    return (size_t)RX_THREADS * (pay_bytes == 4 ? 16 : 8) * (4 + pay_bytes) >
+                   (size_t)4 * RX_WARPS * (1 << RX_MAX_BITS)
+               ? (size_t)RX_THREADS * (pay_bytes == 4 ? 16 : 8) * (4 + pay_bytes)
+               : (size_t)4 * RX_WARPS * (1 << RX_MAX_BITS);
 }
 
-static_assert(RX_THREADS == 512 && RX_MAX_BITS == 10, "rx_region_a spells these out");
+static_assert(RX_THREADS % 32 == 0 && (1 << RX_MAX_BITS) / 2 <= 2 * RX_THREADS, "prefix phase: <= 2 words per thread");
 
 template <typename PayT>
 struct RxCfg {
@@ -80,11 +83,15 @@ radix_count_kernel(const uint32_t* __restrict__ keys, int n, int shift, int bits
         counts[(size_t)b * n_tiles + blockIdx.x] = rx_hist[b];
 }
 
-template <typename PayT>
-__global__ void __launch_bounds__(RX_THREADS, 2)
+// IMPLICIT: the payload of input position i is i / m (all-ones rows of m entries each, in row
+// order: the forward kernel then writes no payload at all); magic = ceil(2^40 / m), exact for
+// i < 2^31 and m < 512.
+template <typename PayT, bool IMPLICIT>
+__global__ void __launch_bounds__(RX_THREADS, 1024 / RX_THREADS)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const PayT* __restrict__ pay_in,
                      uint32_t* __restrict__ keys_out, PayT* __restrict__ pay_out, int n, int shift,
-                     int bits, const uint32_t* __restrict__ offsets, int n_tiles) {
+                     int bits, const uint32_t* __restrict__ offsets, int n_tiles,
+                     unsigned long long magic) {
     constexpr int IPT = RxCfg<PayT>::IPT;
     constexpr int TILE = RxCfg<PayT>::TILE;
     extern __shared__ __align__(16) unsigned char rx_smem[];
@@ -210,7 +217,12 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const PayT* __restric
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int p = strip + (r0 + u) * 32 + lane;
-            if (p < n_valid) pv[u] = pay_in[tile_base + p];
+            if (p < n_valid) {
+                if (IMPLICIT)
+                    pv[u] = (PayT)(((unsigned long long)(uint32_t)(tile_base + p) * magic) >> 40);
+                else
+                    pv[u] = pay_in[tile_base + p];
+            }
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -277,7 +289,7 @@ size_t radix_temp_bytes(int64_t n, int end_bit, int pay_bytes) {
 template <typename PayT>
 static cudaError_t radix_sort_t(void* tmp, size_t tmp_bytes, const uint32_t* keys_in,
                                 uint32_t* keys_out, const PayT* pay_in, PayT* pay_out, int64_t n64,
-                                int end_bit, cudaStream_t st, int64_t* launches) {
+                                int end_bit, int implicit_div, cudaStream_t st, int64_t* launches) {
     constexpr int TILE = RxCfg<PayT>::TILE;
     int P, bits[4];
     rx_plan(end_bit, &P, bits);
@@ -300,9 +312,12 @@ static cudaError_t radix_sort_t(void* tmp, size_t tmp_bytes, const uint32_t* key
     {   // per device and cheap: set on every call
         const size_t smem_max = rx_region_a(sizeof(PayT)) +
                                 ((size_t)6 + 2 * RX_WARPS) * ((size_t)1 << RX_MAX_BITS);
-        cudaError_t e = cudaFuncSetAttribute(radix_scatter_kernel<PayT>,
+        cudaError_t e = cudaFuncSetAttribute(radix_scatter_kernel<PayT, false>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem_max);
+        if (e == cudaSuccess && implicit_div)
+            e = cudaFuncSetAttribute(radix_scatter_kernel<PayT, true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         if (e != cudaSuccess) return e;
     }
     const uint32_t* src_k = keys_in;
@@ -319,8 +334,15 @@ static cudaError_t radix_sort_t(void* tmp, size_t tmp_bytes, const uint32_t* key
                                            (int64_t)tiles * nb, st, launches);
         if (e != cudaSuccess) return e;
         const size_t smem = rx_region_a(sizeof(PayT)) + ((size_t)6 + 2 * RX_WARPS) * nb;
-        radix_scatter_kernel<PayT><<<tiles, RX_THREADS, smem, st>>>(
-            src_k, src_p, dst_k, dst_p, n, shift, bits[j], counts, tiles);
+        if (j == 0 && implicit_div) {
+            const unsigned long long magic =
+                ((1ULL << 40) + (unsigned long long)implicit_div - 1) / (unsigned long long)implicit_div;
+            radix_scatter_kernel<PayT, true><<<tiles, RX_THREADS, smem, st>>>(
+                src_k, src_p, dst_k, dst_p, n, shift, bits[j], counts, tiles, magic);
+        } else {
+            radix_scatter_kernel<PayT, false><<<tiles, RX_THREADS, smem, st>>>(
+                src_k, src_p, dst_k, dst_p, n, shift, bits[j], counts, tiles, 0ULL);
+        }
         *launches += 2;
         src_k = dst_k;
         src_p = dst_p;
@@ -331,9 +353,12 @@ static cudaError_t radix_sort_t(void* tmp, size_t tmp_bytes, const uint32_t* key
 
 cudaError_t radix_sort_pairs32(void* tmp, size_t tmp_bytes, const uint32_t* keys_in,
                                uint32_t* keys_out, const uint32_t* pay_in, uint32_t* pay_out,
-                               int64_t n, int end_bit, cudaStream_t st, int64_t* launches) {
-    return radix_sort_t<uint32_t>(tmp, tmp_bytes, keys_in, keys_out, pay_in, pay_out, n, end_bit, st,
-                                  launches);
+                               int64_t n, int end_bit, int implicit_div, cudaStream_t st,
+                               int64_t* launches) {
+    if (implicit_div < 0 || implicit_div >= 512 || (!implicit_div && !pay_in))
+        return cudaErrorInvalidValue;
+    return radix_sort_t<uint32_t>(tmp, tmp_bytes, keys_in, keys_out, pay_in, pay_out, n, end_bit,
+                                  implicit_div, st, launches);
 }
 
 cudaError_t radix_sort_pairs64(void* tmp, size_t tmp_bytes, const uint32_t* keys_in,
@@ -341,7 +366,7 @@ cudaError_t radix_sort_pairs64(void* tmp, size_t tmp_bytes, const uint32_t* keys
                                int end_bit, cudaStream_t st, int64_t* launches) {
     return radix_sort_t<unsigned long long>(
         tmp, tmp_bytes, keys_in, keys_out, reinterpret_cast<const unsigned long long*>(pay_in),
-        reinterpret_cast<unsigned long long*>(pay_out), n, end_bit, st, launches);
+        reinterpret_cast<unsigned long long*>(pay_out), n, end_bit, 0, st, launches);
 }
 
 }  // namespace sfm

@@ -43,10 +43,11 @@ size_t sort_pairs32_temp_bytes(int64_t n, int end_bit) {
 
 cudaError_t sort_pairs32(void* tmp, size_t tmp_bytes, const uint32_t* keys_in, uint32_t* keys_out,
                          const uint32_t* val_in, uint32_t* val_out, int64_t n, int end_bit,
-                         cudaStream_t st, int64_t* launches) {
+                         cudaStream_t st, int64_t* launches, int implicit_div) {
     if (radix_usable(n, end_bit))
-        return radix_sort_pairs32(tmp, tmp_bytes, keys_in, keys_out, val_in, val_out, n, end_bit, st,
-                                  launches);
+        return radix_sort_pairs32(tmp, tmp_bytes, keys_in, keys_out, val_in, val_out, n, end_bit,
+                                  implicit_div, st, launches);
+    if (implicit_div || !val_in) return cudaErrorInvalidValue;   // the library sort needs real values
     *launches += 2 + (end_bit + 7) / 8;
     return cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, val_in, val_out, n, 0,
                                            end_bit, st);
