@@ -313,6 +313,18 @@ def main():
                          "note": "whole step incl. sort/scan overhead, algorithmic bytes "
                                  "8m(k+2)+4 per sample + 12(1+n_slots(k+1)) per step"},
                 "phase_ms": phases}
+    # the transposition sort (sfm_radix.cu) is overhead on top of the algorithmic bytes; its own
+    # traffic: per 10-bit pass the keys are read twice (count + scatter) and key + row written once
+    nnz_ph = ph["train_nnz"] / n_phase
+    key_bits = max(1, int(N_SLOTS - 1).bit_length())
+    passes = -(-key_bits // 10)
+    sort_bytes = nnz_ph * (passes * (4 + 8 + 8) - 4)      # first pass derives the row: no payload read
+    if phases["ms_sort"] > 0:
+        sort_gbs = sort_bytes / (phases["ms_sort"] * 1e-3) / 1e9
+        roofline["sort"] = {"kernels": "radix_count_kernel + radix_scatter_kernel (x%d passes)" % passes,
+                            "bytes_per_step": sort_bytes, "achieved": sort_gbs,
+                            "frac": sort_gbs / peak,
+                            "note": "own stable LSD radix sort, not part of the algorithmic bytes"}
 
     # ---- e2e arm: host CSR mini-batches through sfm_train_step_csr
     e2e = None
