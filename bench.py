@@ -80,8 +80,50 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.gpu, self.rows, self.proc = gpu_index, [], None
         self.t0 = self.t1 = None
+        self.nvml = None          # (module, handle) when NVML can be polled in-process
+        self.samples = []         # (time, sm MHz, max MHz, reasons bitmask)
+        self._stop = False
+
+    def _nvml_open(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        try:
+            import torch
+            u = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + u if not u.startswith("GPU-") else u).encode())
+        except Exception:
+            h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+        pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)   # probe
+        return pynvml, h
+
+    def _poll(self):
+        nv, h = self.nvml
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = None
+        while not self._stop:
+            try:
+                if mx is None:
+                    mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                self.samples.append((time.time(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                     float(mx), int(get_reasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        # in-process NVML polling (every 5 ms; the bench thread sits in a ctypes call, GIL released);
+        # nvidia-smi -lms as the fallback: its start-up can outlast a short timed region
+        try:
+            self.nvml = self._nvml_open()
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
@@ -101,7 +143,25 @@ class ClockSampler:
     def mark_end(self):
         self.t1 = time.time()
 
+    def _stop_nvml(self):
+        self._stop = True
+        self.t.join(timeout=1)
+        inside = [x for x in self.samples if self.t0 is not None and self.t0 <= x[0] <= self.t1]
+        window = "timed region"
+        if not inside:
+            inside = self.samples[-8:]
+            window = "warm-up + timed region (timed region shorter than one poll)"
+        bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20,
+                "hw_thermal_slowdown": 0x40}
+        reasons = [n for n, b in bits.items() if any(x[3] & b for x in inside)]
+        sm = [x[1] for x in inside]
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(x[2] for x in inside) if inside else None, "reasons": reasons,
+                "samples": len(sm), "window": window, "source": "NVML polled in-process every 5 ms"}
+
     def stop(self):
+        if self.nvml:
+            return self._stop_nvml()
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.06)
