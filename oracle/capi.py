@@ -64,6 +64,8 @@ def lib():
         L.fmo_partition_rows.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, lp]
         L.fmo_init_v.restype = None
         L.fmo_init_v.argtypes = [dp, C.c_int64, C.c_double, C.c_double, C.c_uint64]
+        L.fmo_als_sweep.restype = C.c_double
+        L.fmo_als_sweep.argtypes = [pp, dp, dp, dp, lp, ip, dp, dp, C.c_int64, C.c_int32, dp]
         L.fmo_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -147,6 +149,21 @@ class OracleFM:
                                        _l(row_ptr), _i(idx), _d(val), _d(label), _l(row_ids),
                                        len(row_ids), it, step_size, batch_count,
                                        _d(self._scratch), threads)
+
+
+    def als_sweep(self, row_ptr, idx, val, label, ref_quirks=False, store_f32=False):
+        """ALS.learn (fm/lib/ALS.scala:15-75): one sweep over w0, w, V in place.  Returns
+        (rmse of the residuals after the sweep, residuals e = yhat - y)."""
+        row_ptr, idx, val = _c(row_ptr, np.int64), _c(idx, np.int32), _c(val, np.float64)
+        label = _c(label, np.float64)
+        n = len(row_ptr) - 1
+        e = np.empty(max(n, 1), dtype=np.float64)
+        flags = (1 if ref_quirks else 0) | (2 if store_f32 else 0)
+        rmse = lib().fmo_als_sweep(C.byref(self.p), C.byref(self.w0), _d(self.w), _d(self.v),
+                                   _l(row_ptr), _i(idx), _d(val), _d(label), n, flags, _d(e))
+        if rmse < 0:
+            raise ValueError("fmo_als_sweep: a row stores the same feature twice (or out of memory)")
+        return rmse, e[:n]
 
 
 def sample_rows(seed, it, fraction, row_lo, row_hi):

@@ -162,6 +162,84 @@ def update(w0, w, v, gv, gw, gw0, it, step_size, batch_count, reg0, regw, regv,
     return w0, w, v
 
 
+def als_sweep(w0, w, v, row_ptr, idx, val, label, k0=True, k1=True, reg=(0.0, 0.0, 0.0),
+              ref_quirks=False, store_f32=False):
+    """ALS.learn, fm/lib/ALS.scala:15-75, transliterated with the Scala's own data structures
+    (`e` and `q` as maps keyed by row, `features` as a map id -> column) -- independent of the C
+    oracle's arrays.  Pure Python: small cases only.  Returns (w0, w, v, e list)."""
+    w = np.array(w, dtype=np.float64)
+    v = np.array(v, dtype=np.float64)
+    n_slots, k = v.shape
+    n = len(row_ptr) - 1
+    r0, rw, rv = (float(x) for x in reg)
+
+    def rnd(x):
+        return float(np.float32(x)) if store_f32 else x
+
+    def updatable(nv, old):                                   # :178-180
+        return not math.isnan(nv) and not math.isinf(nv) and nv != old
+
+    def compute_theta(theta, lam, sum_e_h, sum_h_sqr):         # :167-176
+        den = lam + sum_h_sqr
+        num = -(sum_e_h - theta * sum_h_sqr)
+        if den == 0.0:
+            nv = math.nan if num == 0.0 or math.isnan(num) else math.copysign(math.inf, num)
+        else:
+            nv = num / den
+        return nv if updatable(nv, theta) else theta
+
+    e = {}
+    for r in range(n):                                        # precomputeTermE :142-144
+        a, b = int(row_ptr[r]), int(row_ptr[r + 1])
+        e[r] = predict_row(w0, w, v, idx[a:b], val[a:b], k0, k1) - float(label[r])
+    if k0:                                                    # :19-28
+        total = 0.0
+        for r in range(n):
+            total = e[r] if r == 0 else total + e[r]
+        nw0 = rnd(compute_theta(w0, r0, total, float(n)))
+        if updatable(nw0, w0) and not ref_quirks:             # quirk (ii): lazily evaluated to + 0
+            for r in range(n):
+                e[r] = e[r] + (nw0 - w0)
+        w0 = nw0
+    features = {}                                             # transposeInput, DataSet.scala:31-38
+    for r in range(n):
+        for j in range(int(row_ptr[r]), int(row_ptr[r + 1])):
+            features.setdefault(int(idx[j]), []).append((r, float(val[j])))
+    id_end = n_slots - 1 if ref_quirks else n_slots           # quirk (i): `0 until num_attribute`
+
+    def draw_theta(theta, lam, h):                            # :156-165, h = [(row, value)]
+        sum_h_sqr = sum_e_h = 0.0
+        for j, (r, x) in enumerate(h):                        # :183-190 left folds
+            sum_h_sqr = x * x if j == 0 else sum_h_sqr + x * x
+            sum_e_h = e[r] * x if j == 0 else sum_e_h + e[r] * x
+        nt = rnd(compute_theta(theta, lam, sum_e_h, sum_h_sqr))
+        if updatable(nt, theta):
+            for r, x in h:                                    # updateError :194-198
+                e[r] += x * (nt - theta)
+        return nt
+
+    if k1:                                                    # :36-43
+        for i in range(id_end):
+            if i in features:
+                w[i] = draw_theta(w[i], rw, features[i])
+    for f in range(k):                                        # :45-70
+        q = {}
+        for r in range(n):                                    # precomputeTermQ :146-150
+            s = 0.0
+            for j in range(int(row_ptr[r]), int(row_ptr[r + 1])):
+                s += v[int(idx[j]), f] * float(val[j])
+            q[r] = s
+        for i in range(id_end):
+            if i in features:
+                old = float(v[i, f])
+                h = [(r, x * q[r] - x * x * old) for r, x in features[i]]
+                new = draw_theta(old, rv, h)
+                for r, x in features[i]:
+                    q[r] += x * (new - old)
+                v[i, f] = new
+    return w0, w, v, [e[r] for r in range(n)]
+
+
 def sample_rows(seed: int, it: int, fraction: float, row_lo: int, row_hi: int) -> np.ndarray:
     """DESIGN.md section 2.5 (vectorised)."""
     rows = np.arange(row_lo, row_hi, dtype=np.int64)

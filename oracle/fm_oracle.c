@@ -283,3 +283,121 @@ void fmo_init_v(double* v, int64_t count, double mean, double stdev, uint64_t se
         v[e] = (double)(float)(mean + stdev * z);
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * ALS.learn, fm/lib/ALS.scala:15-75 (see fm_oracle.h).
+ * ---------------------------------------------------------------------------------------- */
+static int als_updatable(double nv, double v) { /* :178-180 */
+    return !isnan(nv) && !isinf(nv) && nv != v;
+}
+
+/* computeTheta (:167-176): returns the accepted value (theta itself when rejected). */
+static double als_theta(double theta, double reg, double sum_e_h, double sum_h_sqr) {
+    const double nv = -(sum_e_h - theta * sum_h_sqr) / (reg + sum_h_sqr);
+    return als_updatable(nv, theta) ? nv : theta;
+}
+
+double fmo_als_sweep(const fmo_params* p, double* w0, double* w, double* v,
+                     const int64_t* row_ptr, const int32_t* idx, const double* val,
+                     const double* label, int64_t n_rows, int32_t flags, double* e_out) {
+    const int32_t k = p->k;
+    const int64_t n_slots = p->n_slots;
+    const int64_t nnz = n_rows > 0 ? row_ptr[n_rows] : 0;
+    const int quirks = (flags & FMO_ALS_REF_QUIRKS) != 0, f32 = (flags & FMO_ALS_STORE_F32) != 0;
+    const int64_t id_end = quirks ? n_slots - 1 : n_slots;       /* `0 until num_attribute` */
+    double* e = (double*)malloc(sizeof(double) * (size_t)(n_rows > 0 ? n_rows : 1));
+    double* q = (double*)malloc(sizeof(double) * (size_t)(n_rows > 0 ? n_rows : 1));
+    int64_t* colptr = (int64_t*)calloc((size_t)n_slots + 1, sizeof(int64_t));
+    int64_t* crow = (int64_t*)malloc(sizeof(int64_t) * (size_t)(nnz > 0 ? nnz : 1));
+    double* cval = (double*)malloc(sizeof(double) * (size_t)(nnz > 0 ? nnz : 1));
+    int64_t* fill = (int64_t*)malloc(sizeof(int64_t) * ((size_t)n_slots + 1));
+    double rmse = -1.0;
+    if (!e || !q || !colptr || !crow || !cval || !fill) goto done;
+
+    /* transposeInput (DataSet.scala:31-38): column id -> (row, value), rows ascending */
+    for (int64_t j = 0; j < nnz; ++j) colptr[idx[j] + 1]++;
+    for (int64_t i = 0; i < n_slots; ++i) colptr[i + 1] += colptr[i];
+    memcpy(fill, colptr, sizeof(int64_t) * ((size_t)n_slots + 1));
+    for (int64_t r = 0; r < n_rows; ++r)
+        for (int64_t j = row_ptr[r]; j < row_ptr[r + 1]; ++j) {
+            const int64_t at = fill[idx[j]]++;
+            if (at > colptr[idx[j]] && crow[at - 1] == r) goto done;   /* duplicate (row, id) */
+            crow[at] = r;
+            cval[at] = val[j];
+        }
+
+    /* e = predict - y (:142-144) */
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int64_t b = row_ptr[r];
+        e[r] = fmo_predict_row(p, *w0, w, v, idx + b, val + b, row_ptr[r + 1] - b) - label[r];
+    }
+
+    if (p->k0) { /* :19-28 */
+        double sum = 0.0;
+        if (n_rows > 0) {
+            sum = e[0];
+            for (int64_t r = 1; r < n_rows; ++r) sum = sum + e[r];   /* error.reduce(_+_) */
+        }
+        double nw0 = als_theta(*w0, p->reg0, sum, (double)n_rows);   /* drawGlobalBias :152-154 */
+        if (f32) nw0 = (double)(float)nw0;
+        if (als_updatable(nw0, *w0) && !quirks)                      /* quirk (ii): no correction */
+            for (int64_t r = 0; r < n_rows; ++r) e[r] = e[r] + (nw0 - *w0);
+        *w0 = nw0;
+    }
+
+    if (p->k1) { /* :36-43 */
+        for (int64_t id = 0; id < id_end; ++id) {
+            const int64_t a = colptr[id], b = colptr[id + 1];
+            if (b == a) continue;                                    /* features.contains(id) */
+            double sum_h_sqr = cval[a] * cval[a], sum_e_h = e[crow[a]] * cval[a]; /* :183-190 */
+            for (int64_t j = a + 1; j < b; ++j) {
+                sum_h_sqr = sum_h_sqr + cval[j] * cval[j];
+                sum_e_h = sum_e_h + e[crow[j]] * cval[j];
+            }
+            double nt = als_theta(w[id], p->regw, sum_e_h, sum_h_sqr);
+            if (f32) nt = (double)(float)nt;
+            if (als_updatable(nt, w[id]))                            /* drawTheta :156-165 */
+                for (int64_t j = a; j < b; ++j) e[crow[j]] += cval[j] * (nt - w[id]); /* :194-198 */
+            w[id] = nt;
+        }
+    }
+
+    for (int32_t f = 0; f < k; ++f) { /* :45-70 */
+        for (int64_t r = 0; r < n_rows; ++r) {                       /* precomputeTermQ :146-150 */
+            double s = 0.0;
+            for (int64_t j = row_ptr[r]; j < row_ptr[r + 1]; ++j)
+                s += v[(int64_t)idx[j] * k + f] * val[j];
+            q[r] = s;
+        }
+        for (int64_t id = 0; id < id_end; ++id) {
+            const int64_t a = colptr[id], b = colptr[id + 1];
+            if (b == a) continue;
+            const double vo = v[id * k + f];
+            double sum_h_sqr = 0.0, sum_e_h = 0.0;
+            for (int64_t j = a; j < b; ++j) {                        /* h = x q - x^2 v  (:56-58) */
+                const double h = cval[j] * q[crow[j]] - cval[j] * cval[j] * vo;
+                if (j == a) { sum_h_sqr = h * h; sum_e_h = e[crow[j]] * h; }
+                else { sum_h_sqr = sum_h_sqr + h * h; sum_e_h = sum_e_h + e[crow[j]] * h; }
+            }
+            double nv = als_theta(vo, p->regv, sum_e_h, sum_h_sqr);
+            if (f32) nv = (double)(float)nv;
+            if (als_updatable(nv, vo))
+                for (int64_t j = a; j < b; ++j) {
+                    const double h = cval[j] * q[crow[j]] - cval[j] * cval[j] * vo;
+                    e[crow[j]] += h * (nv - vo);
+                }
+            for (int64_t j = a; j < b; ++j) q[crow[j]] += cval[j] * (nv - vo);   /* :60-62 */
+            v[id * k + f] = nv;                                      /* :64 */
+        }
+    }
+
+    {
+        double ss = 0.0;
+        for (int64_t r = 0; r < n_rows; ++r) ss += e[r] * e[r];
+        rmse = n_rows > 0 ? sqrt(ss / (double)n_rows) : 0.0;
+        if (e_out) memcpy(e_out, e, sizeof(double) * (size_t)n_rows);
+    }
+done:
+    free(e); free(q); free(colptr); free(crow); free(cval); free(fill);
+    return rmse;
+}

@@ -118,6 +118,34 @@ int64_t fmo_partition_rows(uint64_t seed, int64_t n_parts, int64_t part, int64_t
  * with s = mix64(seed); rounded to fp32 then widened, so host fp32 copies are identical. */
 void fmo_init_v(double* v, int64_t count, double mean, double stdev, uint64_t seed);
 
+/* ALS.learn (fm/lib/ALS.scala:15-75), one call = one sweep over w0, w and every factor of V --
+ * the only trainer the reference ships.  Pinned by the reference SOURCE (no reference test or
+ * output exists).  Restated literally, fp64, driver-serial like the original:
+ *   e_r = predict(x_r) - y_r                                        (:17, :142-144)
+ *   w0*  = -(sum e - w0*N) / (reg0 + N); e += w0* - w0              (:19-28, :152-154, :167-176)
+ *   for id ascending, column h = {x_ri}:  theta* = -(sum e*h - theta*sum h^2)/(reg + sum h^2);
+ *       accepted iff finite and != theta (:178-180); then e_r += h_r (theta* - theta)   (:36-43)
+ *   for f, q_r = sum_i v_if x_ri (:146-150); for id ascending: h_r = x_ri q_r - x_ri^2 v_if,
+ *       same theta*, e update, then q_r += x_ri (v* - v)                                (:45-70)
+ * Columns are the transposed input (DataSet.scala:31-38): rows ascending; a column without
+ * stored entries is skipped (`features.contains(id)`).  A row must not store the same feature
+ * twice (the transposition would carry a duplicate index; the CUDA path rejects it).
+ * flags: FMO_ALS_REF_QUIRKS reproduces two behaviours of the reference that are bugs:
+ *   (i)  `for (id <- 0 until fm.num_attribute)` (:38, :52) never trains the last slot
+ *        id = n_slots - 1;
+ *   (ii) the residual correction after the w0 step (:24) is a lazy RDD closure over the mutable
+ *        model and evaluates to e + (w0* - w0*) = e: e is NOT corrected.
+ *   FMO_ALS_STORE_F32: every accepted parameter is rounded to fp32 before it is stored and
+ *   before the residual update uses it (what the fp32 device model does), so the CUDA path can
+ *   be compared tightly.
+ * e_out (n_rows doubles, may be NULL) receives the residuals after the sweep.
+ * Returns sqrt(mean e^2) after the sweep, or -1 on allocation failure / duplicate entries. */
+#define FMO_ALS_REF_QUIRKS 1
+#define FMO_ALS_STORE_F32 2
+double fmo_als_sweep(const fmo_params* p, double* w0, double* w, double* v,
+                     const int64_t* row_ptr, const int32_t* idx, const double* val,
+                     const double* label, int64_t n_rows, int32_t flags, double* e_out);
+
 int fmo_max_threads(void);
 
 #ifdef __cplusplus

@@ -174,3 +174,75 @@ def test_init_v_statistics_and_determinism():
     assert np.array_equal(a, a.astype(np.float32).astype(np.float64))  # fp32-representable
     o.init_v(0.0, 0.01, 6)
     assert not np.array_equal(a, o.v)
+
+
+# ------------------------------------------------------------------------------ ALS (the reference's trainer)
+def _als_problem(seed, n_rows=60, n_slots=23, k=3, mean_nnz=5, noise=0.05):
+    rng = np.random.default_rng(seed)
+    rp, idx, val = synth.ragged_rows(n_rows, n_slots, mean_nnz, seed=seed, values="normal")
+    val = val.astype(np.float64)
+    tw0, tw, tv = 0.3, rng.normal(0, 0.5, n_slots), rng.normal(0, 0.4, (n_slots, k))
+    y = fn.predict(tw0, tw, tv, rp, idx, val) + rng.normal(0, noise, n_rows)
+    model = (0.0, np.zeros(n_slots),
+             rng.normal(0, 0.1, (n_slots, k)).astype(np.float32).astype(np.float64))
+    return rp, idx, val, y, model
+
+
+@pytest.mark.parametrize("quirks,f32", [(False, False), (True, False), (False, True), (True, True)])
+def test_als_c_oracle_matches_scala_transliteration(quirks, f32):
+    """fmo_als_sweep (arrays, CSC) against the dict-based transliteration of fm/lib/ALS.scala:15-75:
+    same folds in the same order, so two sweeps agree to the last bit."""
+    rp, idx, val, y, (w0, w, v) = _als_problem(11)
+    n_slots, k = v.shape
+    reg = (0.0, 0.01, 0.02)
+    orc = OracleFM(n_slots, k, task=0, reg=reg)
+    orc.set_model(w0, w, v)
+    pw0, pw, pv = w0, w.copy(), v.copy()
+    for _ in range(2):
+        rmse, e = orc.als_sweep(rp, idx, val, y, ref_quirks=quirks, store_f32=f32)
+        pw0, pw, pv, pe = fn.als_sweep(pw0, pw, pv, rp, idx, val, y, reg=reg, ref_quirks=quirks,
+                                       store_f32=f32)
+        assert orc.w0.value == pw0
+        assert np.array_equal(orc.w, pw) and np.array_equal(orc.v, pv)
+        assert np.array_equal(e, np.array(pe))
+        assert abs(rmse - math.sqrt(np.mean(np.square(pe)))) < 1e-15
+    if f32:   # every stored parameter is exactly representable in fp32
+        assert np.array_equal(orc.v, orc.v.astype(np.float32).astype(np.float64))
+
+
+def test_als_sweeps_fit_a_planted_model_and_keep_residuals_consistent():
+    rp, idx, val, y, (w0, w, v) = _als_problem(5, n_rows=400, n_slots=40, k=4, mean_nnz=6)
+    orc = OracleFM(40, 4, task=0, reg=(0.0, 1e-3, 1e-3))
+    orc.set_model(w0, w, v)
+    hist = []
+    for _ in range(12):
+        rmse, e = orc.als_sweep(rp, idx, val, y)
+        hist.append(rmse)
+        # the cached residuals ARE yhat - y of the updated model (what makes ALS O(nnz) per sweep)
+        assert np.allclose(e, orc.predict(rp, idx, val) - y, rtol=0, atol=1e-9)
+    assert hist[-1] < 0.5 * hist[0] and all(b <= a + 1e-9 for a, b in zip(hist, hist[1:]))
+
+
+def test_als_reference_quirks_are_reproduced_on_request():
+    rp, idx, val, y, (w0, w, v) = _als_problem(7)
+    n_slots, k = v.shape
+    last = n_slots - 1
+    assert last in set(idx.tolist())
+    a = OracleFM(n_slots, k, task=0, reg=(0.0, 0.01, 0.01))
+    b = OracleFM(n_slots, k, task=0, reg=(0.0, 0.01, 0.01))
+    a.set_model(w0, w, v)
+    b.set_model(w0, w, v)
+    _, ea = a.als_sweep(rp, idx, val, y)
+    _, eb = b.als_sweep(rp, idx, val, y, ref_quirks=True)
+    # (i) `0 until num_attribute` never trains the last slot (ALS.scala:38,52)
+    assert b.w[last] == w[last] and np.array_equal(b.v[last], v[last])
+    assert a.w[last] != w[last]
+    # (ii) residuals are not corrected for the w0 step (ALS.scala:24): they drift from yhat - y
+    assert np.allclose(ea, a.predict(rp, idx, val) - y, atol=1e-9)
+    assert not np.allclose(eb, b.predict(rp, idx, val) - y, atol=1e-6)
+
+
+def test_als_rejects_a_repeated_feature_in_a_row():
+    orc = OracleFM(5, 2, task=0)
+    with pytest.raises(ValueError):
+        orc.als_sweep([0, 2], np.array([3, 3], np.int32), [1.0, 2.0], [0.5])
