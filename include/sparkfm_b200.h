@@ -230,6 +230,23 @@ int32_t sfm_partition_rows(uint64_t seed, int64_t n_parts, int64_t part, int64_t
 int32_t sfm_gradient(sfm_handle* h, const int64_t* row_ids, int64_t n_ids, float* grad_v,
                      float* grad_w, float* grad_w0, double* loss_sum, int64_t* batch_out);
 
+/* ---------------------------------------------------------------- ALS ------------------ */
+/* ALS.learn(fm, dataset) (fm/lib/ALS.scala:15-75), the trainer the reference ships: ONE sweep of the
+ * closed-form coordinate updates over w0, every w_i and every v_if (squared loss on the labels
+ * as stored, reg0/regw/regv of the handle) on the resident data set, in the reference's
+ * coordinate order, residual cache e and per-factor cache q in fp64 on the device.  The
+ * transposed input and the level schedule that makes the sequential sweep parallel are built at
+ * the first call and kept (the reference's cached `transposeInput`, DataSet.scala:48).
+ * flags: SFM_ALS_REF_QUIRKS reproduces two reference bugs (the last slot is never trained,
+ * ALS.scala:38,52; the residuals are not corrected after the w0 step, :24); 0 = the algorithm as
+ * written down.  rmse_out: sqrt(mean e^2) of the residuals after the sweep (the per-iteration
+ * train RMSE FactorizationMachines.scala:43 computes with an extra pass).  One GPU, replicated
+ * model; rows must not store a feature index twice (SFM_ERR_ARG). */
+#define SFM_ALS_REF_QUIRKS 1
+int32_t sfm_als_sweep(sfm_handle* h, int32_t flags, double* rmse_out);
+/* Residuals e_r = yhat_r - y_r after the last sweep, n = resident rows. */
+int32_t sfm_als_residuals(sfm_handle* h, double* out, int64_t n);
+
 /* ---------------------------------------------------------------- multi-GPU ------------ */
 /* Replaces Spark's driver-side combination of partition results (`.sum()` Model.scala:14,
  * `.reduce(_+_)` fm/lib/ALS.scala:153; MLlib treeAggregate in north_star) by an NCCL all-reduce

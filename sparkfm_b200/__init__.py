@@ -2,11 +2,11 @@
 learner-plugin interface.  The product is libsparkfm_b200.so (C ABI: include/sparkfm_b200.h);
 this package is the ctypes binding plus a Python mirror of the reference's operator API."""
 from . import _lib  # noqa: F401
-from .api import (DataSet, FM, FMLearn, FMModel, FMUtils, FMWithSGD, FactorizationMachines,  # noqa: F401
+from .api import (ALS, DataSet, FM, FMLearn, FMModel, FMUtils, FMWithSGD, FactorizationMachines,  # noqa: F401
                   LabeledPoint, Model, SGD, SparseVector, Task)
 from .handle import (Handle, device_count, format_libfm, parse_libfm, partition_rows,  # noqa: F401
                      sample_rows)
 
-__all__ = ["DataSet", "FM", "FMLearn", "FMModel", "FMUtils", "FMWithSGD", "FactorizationMachines",
+__all__ = ["ALS", "DataSet", "FM", "FMLearn", "FMModel", "FMUtils", "FMWithSGD", "FactorizationMachines",
            "LabeledPoint", "Model", "SGD", "SparseVector", "Task", "Handle", "device_count",
            "format_libfm", "parse_libfm", "partition_rows", "sample_rows"]

@@ -90,6 +90,8 @@ SIGNATURES = {
     "sfm_comm_init": (C.c_int32, [_H, _u8p, C.c_int32, C.c_int32]),
     "sfm_comm_info": (C.c_int32, [_H, _i32p, _i32p]),
     "sfm_comm_mode": (C.c_int32, [_H, _i32p]),
+    "sfm_als_sweep": (C.c_int32, [_H, C.c_int32, _f64p]),
+    "sfm_als_residuals": (C.c_int32, [_H, _f64p, C.c_int64]),
     "sfm_comm_broadcast_model": (C.c_int32, [_H]),
     "sfm_parse_libfm": (C.c_int32, [C.c_char_p, C.c_uint64, C.c_int32, _i64p, _i64p, _i32p,
                                     _f64p, _i64p, _i32p, _f64p, _i64p]),

@@ -293,6 +293,29 @@ class SGD(FMLearn):
         return fm
 
 
+class ALS(FMLearn):
+    """fm/lib/ALS.scala:11-200 -- the learner the reference ships: one `learn` call is one sweep of
+    closed-form coordinate updates over w0, w and V for squared loss, using the model's own
+    reg0 / regw / regv (FMModel.scala:29-31).  `refQuirks=True` reproduces the two reference bugs
+    described at `sfm_als_sweep` in include/sparkfm_b200.h."""
+
+    def __init__(self, refQuirks=False):
+        self.refQuirks = bool(refQuirks)
+        self.rmseHistory = []
+
+    @staticmethod
+    def run(refQuirks=False):
+        """ALS.run() (fm/lib/ALS.scala:202-208)."""
+        return ALS(refQuirks)
+
+    def learn(self, fm: FMModel, dataset: DataSet) -> FMModel:
+        fm._cache(dataset)
+        cfg = fm._hd.config()
+        fm._hd.set_hyper(fm.reg0, fm.regw, fm.regv, cfg.step_size, cfg.mini_batch_fraction)
+        self.rmseHistory.append(fm._hd.als_sweep(self.refQuirks))
+        return fm
+
+
 class FM:
     """fm/FM.scala:15-33."""
 

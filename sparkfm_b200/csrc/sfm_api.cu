@@ -1180,6 +1180,7 @@ int32_t sfm_unload_dataset(sfm_handle* h) {
     Dataset& ds = h->ds;
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_parts(h);
+    als_free(h);
     if (ds.row_ptr) cudaFree(ds.row_ptr);
     if (ds.idx) cudaFree(ds.idx);
     if (ds.val) cudaFree(ds.val);
@@ -1770,6 +1771,30 @@ int32_t sfm_train(sfm_handle* h, int64_t first_iter, int64_t n_iters, double* lo
     h->stats.d2h_bytes += (int64_t)sizeof(double) * SC_N * n_iters;
     if (hist) cudaFreeHost(hist);
     return rc;
+}
+
+// ------------------------------------------------------------------------------ ALS -------
+int32_t sfm_als_sweep(sfm_handle* h, int32_t flags, double* rmse_out) {
+    if (!h) return SFM_ERR_ARG;
+    NEED_MODEL(h);
+    if (h->world > 1 || is_sharded(h))
+        return set_err(h, SFM_ERR_STATE, "ALS runs on one GPU with a replicated model");
+    const Dataset& ds = h->ds;
+    if (!ds.loaded) return set_err(h, SFM_ERR_STATE, "no resident data set");
+    CU(cudaSetDevice(h->device));
+    BatchView b;
+    RC(resident_batch(h, nullptr, ds.n_rows, &b));
+    RC(als_sweep(h, b, flags, rmse_out));
+    h->stats.train_steps += 1;
+    h->stats.train_rows += ds.n_rows;
+    h->stats.train_nnz += ds.nnz * (int64_t)(h->m.k + 1);
+    return SFM_OK;
+}
+
+int32_t sfm_als_residuals(sfm_handle* h, double* out, int64_t n) {
+    if (!h || !out || n < 0) return SFM_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    return als_residuals(h, out, n);
 }
 
 int32_t sfm_gradient(sfm_handle* h, const int64_t* row_ids, int64_t n_ids, float* grad_v,

@@ -103,6 +103,7 @@ struct ModelView {
 
 struct Nccl;      // sfm_nccl.cpp
 struct P2PState;  // sfm_p2p.cu
+struct AlsState;  // sfm_als.cu
 
 }  // namespace sfm
 
@@ -125,6 +126,7 @@ struct sfm_handle {
     bool shard_requested = false;       // SFM_FLAG_SHARD_V at create; active once comm is up
     sfm::ShardState* shard = nullptr;
     sfm::P2PState* p2p = nullptr;       // NVLink peer-memory reduce+update (replicated multi-GPU)
+    sfm::AlsState* als = nullptr;       // ALS: resident transposed input, level schedule, e / q caches
     // sampler prefetch (sfm_train): ids / count of the NEXT iteration are produced on copy_stream
     sfm::Buf b_ids2[2], b_samp_tmp;
     int32_t* d_count2 = nullptr;   // [2] device
@@ -294,6 +296,11 @@ void p2p_teardown(sfm_handle* h);
 float* p2p_grad_buffer(sfm_handle* h);
 const int32_t* p2p_timeout_flag(sfm_handle* h);
 int p2p_reduce_update(sfm_handle* h, UpdateParams up);
+
+// ---- ALS sweep of the reference's own trainer (sfm_als.cu)
+int als_sweep(sfm_handle* h, const BatchView& all_rows, int32_t flags, double* rmse_out);
+int als_residuals(sfm_handle* h, double* out, int64_t n);
+void als_free(sfm_handle* h);
 
 // ---- host side (sfm_host.cpp)
 uint64_t mix64(uint64_t x);

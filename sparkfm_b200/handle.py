@@ -259,6 +259,19 @@ class Handle:
                                       C.byref(batch)))
         return gv, gw, float(gw0.value), float(loss.value), int(batch.value)
 
+    # ------------------------------------------------------------------ ALS
+    def als_sweep(self, ref_quirks: bool = False) -> float:
+        """ALS.learn (fm/lib/ALS.scala:15-75): one sweep over w0, w, V on the resident data set.
+        Returns the RMSE of the residuals after the sweep."""
+        out = C.c_double()
+        self._ck(self._L.sfm_als_sweep(self._h, 1 if ref_quirks else 0, C.byref(out)))
+        return out.value
+
+    def als_residuals(self, n_rows: int) -> np.ndarray:
+        e = np.empty(int(n_rows), dtype=np.float64)
+        self._ck(self._L.sfm_als_residuals(self._h, e.ctypes.data_as(C.POINTER(C.c_double)), len(e)))
+        return e
+
     # ------------------------------------------------------------------ multi-GPU
     @staticmethod
     def comm_unique_id() -> bytes:
