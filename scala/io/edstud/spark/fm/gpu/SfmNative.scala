@@ -49,6 +49,7 @@ object SfmNative {
     val train        = fn("sfm_train", JAVA_INT, ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS)
     val commUniqueId = fn("sfm_comm_unique_id", JAVA_INT, ADDRESS)
     val commInit     = fn("sfm_comm_init", JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT)
+    val alsSweep     = fn("sfm_als_sweep", JAVA_INT, ADDRESS, JAVA_INT, ADDRESS)       // ALS.learn, one sweep
     val commMode     = fn("sfm_comm_mode", JAVA_INT, ADDRESS, ADDRESS)   // 0 none, 1 NCCL, 2 NVLink peer kernel, 3 row-sharded
     val hostAlloc    = fn("sfm_host_alloc", JAVA_INT, ADDRESS, JAVA_LONG)
     val hostFree     = fn("sfm_host_free", JAVA_INT, ADDRESS)
