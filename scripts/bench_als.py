@@ -12,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def run(name, n_rows, n_slots, k, mean_nnz, values, sweeps=4):
+def run(name, n_rows, n_slots, k, mean_nnz, values, sweeps=4, graph=True):
+    os.environ["SFM_ALS_GRAPH"] = "1" if graph else "0"
     from oracle.capi import OracleFM
     from sparkfm_b200 import Handle, synth
     rng = np.random.default_rng(1)
@@ -40,7 +41,7 @@ def run(name, n_rows, n_slots, k, mean_nnz, values, sweeps=4):
     want, _ = orc.als_sweep(rp, idx, dval, y.astype(np.float64), store_f32=True)
     t_cpu = time.perf_counter() - t0
     hd.close()
-    return {"config": name, "rows": n_rows, "n_slots": n_slots, "k": k, "nnz": int(rp[-1]),
+    return {"config": name, "cuda_graph": graph, "rows": n_rows, "n_slots": n_slots, "k": k, "nnz": int(rp[-1]),
             "first_sweep_s_incl_build": t_first, "sweep_s": t_gpu, "launches_per_sweep": launches,
             "levels": round((launches - 6 - k) / (k + 1)), "rmse": [r_first] + hist,
             "cpu_oracle_sweep_s": t_cpu, "first_sweep_rmse_vs_oracle": [r_first, want],
@@ -48,7 +49,9 @@ def run(name, n_rows, n_slots, k, mean_nnz, values, sweeps=4):
 
 
 if __name__ == "__main__":
-    out = [run("C1 shape: 100k rows x 10k features, nnz~20, k=8, all ones", 100_000, 10_000, 8, 20, "ones"),
+    out = [run("C1 shape: 100k rows x 10k features, nnz~20, k=8, all ones", 100_000, 10_000, 8, 20, "ones",
+               graph=False),
+           run("C1 shape: 100k rows x 10k features, nnz~20, k=8, all ones", 100_000, 10_000, 8, 20, "ones"),
            run("C2 shape / 4: 250k rows x 100k features, nnz~50, k=16, N(0,1) values", 250_000, 100_000,
                16, 50, "normal", sweeps=2)]
     print(json.dumps(out, indent=1))

@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "sfm_common.h"
 
@@ -51,6 +53,10 @@ struct AlsState {
     Buf e, q;     // double [n_rows]
     Buf part;     // double [ALS_PARTS + 8]: reduction partials, then scalars
     std::vector<int32_t> lvl_off;   // host: start of level l in `order`, size max_level + 2
+    cudaGraphExec_t exec = nullptr; // the sweep's launches, captured once
+    float graph_key[4] = {-1.f, 0.f, 0.f, 0.f};   // flags, reg0, regw, regv the graph was built for
+    int64_t graph_launches = 0;
+    bool graph_failed = false;
 };
 
 constexpr int ALS_PARTS = 512;
@@ -318,6 +324,7 @@ als_level_kernel(const uint32_t* __restrict__ order, int first, const int32_t* _
 void als_free(sfm_handle* h) {
     AlsState* s = h->als;
     if (!s) return;
+    if (s->exec) cudaGraphExecDestroy(s->exec);
     Buf* all[] = {&s->pay, &s->colptr, &s->order, &s->lvl, &s->lvl_sorted, &s->rowlvl, &s->e, &s->q,
                   &s->part};
     for (Buf* b : all)
@@ -434,13 +441,10 @@ static int als_build(sfm_handle* h, const BatchView& b) {
     return SFM_OK;
 }
 
-// One ALS sweep over the resident data set `b` (every row, identity order).
-int als_sweep(sfm_handle* h, const BatchView& b, int32_t flags, double* rmse_out) {
+// Queues the kernels of one sweep on the compute stream (directly, or into a stream capture).
+static cudaError_t als_enqueue(sfm_handle* h, AlsState* s, const BatchView& b, int32_t flags,
+                               int64_t* n_launches) {
     const ModelView& m = h->m;
-    if (!h->als || !h->als->built || h->als->n_rows != b.n_rows || h->als->nnz != b.nnz)
-        RC(als_build(h, b));
-    AlsState* s = h->als;
-    int64_t* L = &h->stats.kernel_launches;
     const bool quirks = (flags & SFM_ALS_REF_QUIRKS) != 0;
     const int n_rows = (int)b.n_rows;
     const int skip_id = quirks ? (int)m.n_slots - 1 : -1;
@@ -451,19 +455,19 @@ int als_sweep(sfm_handle* h, const BatchView& b, int32_t flags, double* rmse_out
     const int32_t* colptr = (const int32_t*)s->colptr.p;
     const uint32_t* order = (const uint32_t*)s->order.p;
     const int n_levels = (int)s->lvl_off.size() - 2;   // levels 1 .. n_levels hold columns
-    if (m.k > 128) return set_err(h, SFM_ERR_ARG, "ALS: at most 128 factors");
     int64_t rb64 = ((int64_t)n_rows + 7) / 8;
     if (rb64 > (int64_t)h->sm_count * 16) rb64 = (int64_t)h->sm_count * 16;
     const unsigned rb = (unsigned)(rb64 > 0 ? rb64 : 1);
+    int64_t nl = 0;
     als_residual_kernel<<<rb, 256, 0, h->stream>>>(m.v, m.w, m.w0, m.k, m.kp, m.k0, m.k1, b.row_ptr,
                                                    b.idx, b.val, b.label, b.uniform_m, n_rows, e);
-    ++*L;
+    ++nl;
     if (m.k0) {
         als_sum_kernel<false><<<ALS_PARTS, 256, 0, h->stream>>>(e, n_rows, part);
         als_w0_kernel<<<1, 32, 0, h->stream>>>(part, m.w0, (double)h->cfg.reg0, n_rows, quirks ? 0 : 1,
                                                scal);
         als_shift_kernel<<<(unsigned)(h->sm_count * 4), 256, 0, h->stream>>>(e, n_rows, scal);
-        *L += 3;
+        nl += 3;
     }
 #define ALS_LEVELS(ISV, BASE, STRIDE, OFF, REG)                                                   \
     for (int l = 1; l <= n_levels; ++l) {                                                         \
@@ -475,20 +479,68 @@ int als_sweep(sfm_handle* h, const BatchView& b, int32_t flags, double* rmse_out
         else                                                                                      \
             als_level_kernel<ISV, false><<<(unsigned)cntl, ALS_CTA, 0, h->stream>>>(             \
                 order, first, colptr, s->pay.p, BASE, STRIDE, OFF, REG, skip_id, e, q);           \
-        ++*L;                                                                                     \
+        ++nl;                                                                                     \
     }
     if (m.k1) ALS_LEVELS(false, m.w, 1, 0, (double)h->cfg.regw)
     for (int f = 0; f < m.k; ++f) {
         als_q_kernel<<<(unsigned)(h->sm_count * 8), 256, 0, h->stream>>>(
             m.v, m.kp, f, b.row_ptr, b.idx, b.val, b.uniform_m, n_rows, q);
-        ++*L;
+        ++nl;
         ALS_LEVELS(true, m.v, m.kp, f, (double)h->cfg.regv)
     }
 #undef ALS_LEVELS
     als_sum_kernel<true><<<ALS_PARTS, 256, 0, h->stream>>>(e, n_rows, part);
     als_w0_kernel<<<1, 32, 0, h->stream>>>(part, nullptr, 0.0, n_rows, 0, scal);
-    *L += 2;
-    CU(cudaGetLastError());
+    nl += 2;
+    *n_launches = nl;
+    return cudaGetLastError();
+}
+
+// One ALS sweep over the resident data set `b` (every row, identity order).  The sweep is
+// (k + 1) * levels tiny dependent kernels: they are captured once into a CUDA graph per
+// (data set, flags, regularisation) and replayed (SFM_ALS_GRAPH=0: plain stream launches).
+int als_sweep(sfm_handle* h, const BatchView& b, int32_t flags, double* rmse_out) {
+    const ModelView& m = h->m;
+    if (m.k > 128) return set_err(h, SFM_ERR_ARG, "ALS: at most 128 factors");
+    if (!h->als || !h->als->built || h->als->n_rows != b.n_rows || h->als->nnz != b.nnz)
+        RC(als_build(h, b));
+    AlsState* s = h->als;
+    const int n_rows = (int)b.n_rows;
+    const char* genv = getenv("SFM_ALS_GRAPH");
+    const bool want_graph = !(genv && genv[0] == '0') && !s->graph_failed;
+    const float key[4] = {(float)flags, h->cfg.reg0, h->cfg.regw, h->cfg.regv};
+    int64_t nl = 0;
+    if (want_graph) {
+        if (!s->exec || memcmp(key, s->graph_key, sizeof key) != 0) {
+            if (s->exec) cudaGraphExecDestroy(s->exec);
+            s->exec = nullptr;
+            cudaGraph_t g = nullptr;
+            cudaError_t ce = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+            if (ce == cudaSuccess) {
+                const cudaError_t ke = als_enqueue(h, s, b, flags, &nl);
+                ce = cudaStreamEndCapture(h->stream, &g);
+                if (ce == cudaSuccess) ce = ke;
+            }
+            if (ce == cudaSuccess) ce = cudaGraphInstantiate(&s->exec, g, 0);
+            if (g) cudaGraphDestroy(g);
+            if (ce != cudaSuccess) {   // fall back to stream launches for this data set
+                cudaGetLastError();
+                s->exec = nullptr;
+                s->graph_failed = true;
+            } else {
+                memcpy(s->graph_key, key, sizeof key);
+                s->graph_launches = nl;
+            }
+        }
+    }
+    if (want_graph && s->exec) {
+        CU(cudaGraphLaunch(s->exec, h->stream));
+        nl = s->graph_launches;
+    } else {
+        CU(als_enqueue(h, s, b, flags, &nl));
+    }
+    h->stats.kernel_launches += nl;
+    double* scal = (double*)s->part.p + ALS_PARTS;
     CU(cudaMemcpyAsync(h->h_scal, scal, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     if (rmse_out) *rmse_out = n_rows > 0 ? sqrt(h->h_scal[0] / (double)n_rows) : 0.0;
