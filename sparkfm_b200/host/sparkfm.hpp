@@ -162,6 +162,32 @@ private:
     int64_t iteration_ = 0;
 };
 
+// fm/lib/ALS.scala:11-208: the learner the reference ships.  One learn() = one sweep over w0, w, V
+// with the model's own reg0 / regw / regv; refQuirks = bug-compatible with the reference
+// (see sfm_als_sweep in include/sparkfm_b200.h).
+class ALS : public FMLearn {
+public:
+    std::vector<double> rmseHistory;
+    explicit ALS(bool refQuirks = false) : quirks_(refQuirks) {}
+    static std::unique_ptr<ALS> run(bool refQuirks = false) {            // ALS.scala:202-208
+        return std::unique_ptr<ALS>(new ALS(refQuirks));
+    }
+    FMModel& learn(FMModel& fm, const DataSet& dataset) override {
+        fm.cache(dataset);
+        sfm_config cfg;
+        check(sfm_get_config(fm.handle(), &cfg), fm.handle());
+        check(sfm_set_hyper(fm.handle(), (float)fm.reg0, (float)fm.regw, (float)fm.regv, cfg.step_size,
+                            cfg.mini_batch_fraction), fm.handle());
+        double rmse = 0;
+        check(sfm_als_sweep(fm.handle(), quirks_ ? SFM_ALS_REF_QUIRKS : 0, &rmse), fm.handle());
+        rmseHistory.push_back(rmse);
+        return fm;
+    }
+
+private:
+    bool quirks_;
+};
+
 // fm/FM.scala:25-33 + fm/impl/FactorizationMachines.scala:30-51
 class FM {
 public:
