@@ -204,3 +204,48 @@ def test_parser_multithreaded_chunks_are_seamless():
     with pytest.raises(ValueError) as ei:
         parse_libfm(text2)
     assert f"line {bad_at + 1}" in str(ei.value)
+
+
+def test_parser_number_grammar_fuzz_against_correctly_rounded_python():
+    """30,000 random decimal tokens (long mantissas, huge / tiny exponents, halfway cases, subnormals,
+    Java d/f suffixes, leading zeros, signs) through the C++ parser's exact fast path + from_chars
+    fallback: every value must have the same 64 bits as Python's correctly rounded float()."""
+    import random
+    rnd = random.Random(20260105)
+    special = ["1e400", "1e-400", "4.9e-324", "2.4703282292062327e-324", "2.4703282292062328e-324",
+               "1.7976931348623157e308", "1.7976931348623159e308", "00012", "1E+5", "9007199254740993",
+               "9007199254740992.5", "123456789012345678901234567890", "5e-324", "3e-324", "2e-324",
+               "1.00000000000000011102230246251565404236316680908203125",
+               "1.00000000000000011102230246251565404236316680908203124",
+               "1.00000000000000011102230246251565404236316680908203126", "1e23", "8.5e22",
+               "9.999999999999999e22", "8.41e21", "2.2250738585072011e-308", "7.2057594037927933e16"]
+    digits = "0123456789"
+
+    def tok():
+        r = rnd.random()
+        sign = rnd.choice(["", "-", "+"]) if rnd.random() < 0.5 else ""
+        if r < 0.25:
+            s = str(rnd.randint(0, 10 ** rnd.randint(1, 25)))
+        elif r < 0.5:
+            s = "%d.%s" % (rnd.randint(0, 10 ** rnd.randint(0, 20)),
+                           "".join(rnd.choice(digits) for _ in range(rnd.randint(0, 25))))
+        elif r < 0.75:
+            s = "%d.%se%s%d" % (rnd.randint(0, 10 ** rnd.randint(0, 18)),
+                                "".join(rnd.choice(digits) for _ in range(rnd.randint(1, 20))),
+                                rnd.choice(["", "-", "+"]), rnd.randint(0, 330))
+        elif r < 0.8:
+            s = "." + "".join(rnd.choice(digits) for _ in range(rnd.randint(1, 30)))
+        elif r < 0.88:
+            s = repr(abs(rnd.uniform(-1, 1)) * 10.0 ** rnd.randint(-320, 308))
+        elif r < 0.94:
+            s = str(rnd.randint(0, 999)) + rnd.choice(["d", "D", "f", "F", ".0d", ".5f", "e3f", "E-2D"])
+        else:
+            s = rnd.choice(special)
+        return sign + s
+
+    toks = [tok() for _ in range(30_000)]
+    lines = ["1 %d:%s" % (i % 100, t) for i, t in enumerate(toks)]
+    _, _, _, val, _ = parse_libfm(("\n".join(lines) + "\n").encode(), num_features=200)
+    _, _, _, oval, _ = fn.parse_libfm_lines(lines, 200)
+    diff = np.nonzero(val.view(np.uint64) != oval.view(np.uint64))[0]
+    assert len(diff) == 0, [(toks[j], val[j].hex(), oval[j].hex()) for j in diff[:5]]
