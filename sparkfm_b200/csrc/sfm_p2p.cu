@@ -208,6 +208,10 @@ p2p_reduce_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_
     }
 }
 
+// Called from sfm_destroy before the model buffers are freed.  Every rank has seen every peer's
+// "done" word of the last step by then (the step's wait kernel), so no peer still reads or writes
+// this rank's buffers; the imported mappings are closed first, the own allocations freed after.
+// Hosts are expected to destroy the handles of all ranks together, as they create them.
 void p2p_teardown(sfm_handle* h) {
     P2PState* s = h->p2p;
     if (!s) return;
