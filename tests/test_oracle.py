@@ -246,3 +246,35 @@ def test_als_rejects_a_repeated_feature_in_a_row():
     orc = OracleFM(5, 2, task=0)
     with pytest.raises(ValueError):
         orc.als_sweep([0, 2], np.array([3, 3], np.int32), [1.0, 2.0], [0.5])
+
+
+def test_als_update_is_the_coordinate_minimiser():
+    """Independent of any transliteration: the closed form of ALS.scala:167-176 minimises
+    sum_r (yhat_r - y_r)^2 + lambda * theta^2 over ONE coordinate.  After a sweep the last coordinate
+    touched (last factor of the highest feature id) is therefore stationary:
+    sum_r e_r * d yhat_r / d theta + lambda * theta = 0, with the derivative taken numerically."""
+    rp, idx, val, y, (w0, w, v) = _als_problem(21, n_rows=200, n_slots=15, k=3, mean_nnz=4)
+    n_slots, k = v.shape
+    reg = (0.0, 0.05, 0.3)
+    orc = OracleFM(n_slots, k, task=0, reg=reg)
+    orc.set_model(w0, w, v)
+    for _ in range(2):
+        _, e = orc.als_sweep(rp, idx, val, y)
+    last = int(idx.max())
+    f = k - 1
+    theta = orc.v[last, f]
+    h = 1e-6
+    vp, vm = orc.v.copy(), orc.v.copy()
+    vp[last, f] += h
+    vm[last, f] -= h
+    dy = (fn.predict(orc.w0.value, orc.w, vp, rp, idx, val)
+          - fn.predict(orc.w0.value, orc.w, vm, rp, idx, val)) / (2 * h)
+    grad = float(np.dot(e, dy) + reg[2] * theta)
+    scale = float(np.abs(e).dot(np.abs(dy)) + abs(reg[2] * theta))
+    assert abs(grad) <= 1e-7 * scale
+    # and a coordinate that was updated earlier in the sweep is generally NOT stationary any more
+    dy0 = np.zeros(len(y))
+    for r in range(len(y)):
+        seg = slice(rp[r], rp[r + 1])
+        dy0[r] = val[seg][idx[seg] == idx[0]].sum()
+    assert abs(float(np.dot(e, dy0) + reg[1] * orc.w[idx[0]])) > 1e-9
