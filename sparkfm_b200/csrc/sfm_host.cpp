@@ -217,7 +217,18 @@ static void parse_chunk(const char* p, const char* end, ChunkStat* st, double* l
             // "3:" -> split drops the trailing empty string -> only one part -> throws
             bool rest_empty = true;
             for (const char* z = v0; z < te; ++z) if (*z != ':') { rest_empty = false; break; }
-            if (rest_empty || !java_int(t, c0, &id) || !java_double(v0, v1, &x)) {
+            bool ok_tok = !rest_empty && java_int(t, c0, &id);
+            if (ok_tok) {
+                // "id:1", "id:37": up to 15 plain digits are an exact double, no grammar walk needed
+                const size_t vl = (size_t)(v1 - v0);
+                uint64_t mant = 0;
+                size_t z = 0;
+                if (vl >= 1 && vl <= 15)
+                    for (; z < vl && (unsigned)(v0[z] - '0') <= 9u; ++z) mant = mant * 10 + (uint64_t)(v0[z] - '0');
+                if (z == vl && vl >= 1 && vl <= 15) x = (double)mant;
+                else ok_tok = java_double(v0, v1, &x);
+            }
+            if (!ok_tok) {
                 st->err_line = line_no;
                 return;
             }
@@ -237,6 +248,39 @@ static void parse_chunk(const char* p, const char* end, ChunkStat* st, double* l
     st->lines = line_no;
     st->max_index = max_index;
     st->empty_row = empty_row;
+}
+
+// Counting pass of a filling call: rows, entries and physical lines of a chunk from the line /
+// token structure alone (no number is parsed; malformed input is reported by the filling pass,
+// which walks the same structure).
+static void count_chunk(const char* p, const char* end, ChunkStat* st) {
+    int64_t rows = 0, ents = 0, line_no = 0;
+    while (p < end) {
+        const char* le = p;
+        while (le < end && *le != '\n' && *le != '\r') ++le;
+        const char* next = le;
+        if (next < end) next += (*next == '\r' && next + 1 < end && next[1] == '\n') ? 2 : 1;
+        ++line_no;
+        const char* b = p;
+        const char* e = le;
+        p = next;
+        while (b < e && (unsigned char)*b <= ' ') ++b;
+        while (e > b && (unsigned char)e[-1] <= ' ') --e;
+        if (b == e || *b == '#') continue;
+        ++rows;
+        const char* t = b;
+        while (t < e && *t != ' ') ++t;          // the label
+        while (t < e) {
+            ++t;
+            const char* te = t;
+            while (te < e && *te != ' ') ++te;
+            if (te != t) ++ents;                  // .filter(_.nonEmpty)
+            t = te;
+        }
+    }
+    st->rows = rows;
+    st->ents = ents;
+    st->lines = line_no;
 }
 
 }  // namespace
@@ -277,6 +321,8 @@ extern "C" int32_t sfm_parse_libfm(const char* text, uint64_t len, int32_t num_f
                 if (filling)
                     parse_chunk(cut[t], cut[t + 1], &st[t], label, row_ptr, idx, val, (*row0)[t],
                                 (*ent0)[t]);
+                else if (fill)
+                    count_chunk(cut[t], cut[t + 1], &st[t]);      // sizes only; the fill validates
                 else
                     parse_chunk(cut[t], cut[t + 1], &st[t], nullptr, nullptr, nullptr, nullptr, 0, 0);
             });
@@ -303,6 +349,18 @@ extern "C" int32_t sfm_parse_libfm(const char* text, uint64_t len, int32_t num_f
     if (fill) {
         if (row_ptr) row_ptr[0] = 0;
         run(true, &row0, &ent0);
+        lines_before = 0;
+        max_index = INT32_MIN;
+        empty_row = false;
+        for (unsigned t = 0; t < nt; ++t) {
+            if (st[t].err_line >= 0) {
+                if (err_line) *err_line = lines_before + st[t].err_line;
+                return SFM_ERR_IO;
+            }
+            lines_before += st[t].lines;
+            if (st[t].max_index > max_index) max_index = st[t].max_index;
+            empty_row = empty_row || st[t].empty_row;
+        }
     }
     *n_rows = rows;
     *nnz = ents;

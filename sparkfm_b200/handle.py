@@ -337,23 +337,34 @@ def partition_rows(seed, n_parts, part, row_lo, row_hi):
 
 
 def parse_libfm(text: bytes, num_features: int = -1):
-    """FMUtils.loadLibFMFile on a bytes buffer -> (label f64, row_ptr i64, idx i32, val f64, d)."""
+    """FMUtils.loadLibFMFile on a bytes buffer -> (label f64, row_ptr i64, idx i32, val f64, d).
+    One library call: the output arrays are sized from what the grammar allows per byte (a row
+    needs a label and a terminator, an entry " i:x" four bytes; untouched pages of the
+    over-allocation are never resident), the library counts exactly and fills, the arrays are
+    trimmed.  Falls back to count-then-fill if the bounds cannot be allocated."""
     L = _lib.load()
     n, nnz, d, el = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int64(-1)
-    st = L.sfm_parse_libfm(text, len(text), int(num_features), C.byref(n), C.byref(nnz),
-                           C.byref(d), None, None, None, None, C.byref(el))
-    if st != _lib.SFM_OK:
-        raise ValueError(f"LibFM parse error at line {el.value}")
-    label = np.empty(n.value, dtype=np.float64)
-    row_ptr = np.empty(n.value + 1, dtype=np.int64)
-    idx = np.empty(nnz.value, dtype=np.int32)
-    val = np.empty(nnz.value, dtype=np.float64)
+    try:
+        max_rows, max_nnz = len(text) // 2 + 1, len(text) // 4 + 1
+        label = np.empty(max_rows, dtype=np.float64)
+        row_ptr = np.empty(max_rows + 1, dtype=np.int64)
+        idx = np.empty(max_nnz, dtype=np.int32)
+        val = np.empty(max_nnz, dtype=np.float64)
+    except MemoryError:
+        st = L.sfm_parse_libfm(text, len(text), int(num_features), C.byref(n), C.byref(nnz),
+                               C.byref(d), None, None, None, None, C.byref(el))
+        if st != _lib.SFM_OK:
+            raise ValueError(f"LibFM parse error at line {el.value}")
+        label = np.empty(n.value, dtype=np.float64)
+        row_ptr = np.empty(n.value + 1, dtype=np.int64)
+        idx = np.empty(max(nnz.value, 1), dtype=np.int32)
+        val = np.empty(max(nnz.value, 1), dtype=np.float64)
     st = L.sfm_parse_libfm(text, len(text), int(num_features), C.byref(n), C.byref(nnz),
                            C.byref(d), _p(label, C.c_double), _p(row_ptr, C.c_int64),
                            _p(idx, C.c_int32), _p(val, C.c_double), C.byref(el))
     if st != _lib.SFM_OK:
         raise ValueError(f"LibFM parse error at line {el.value}")
-    return label, row_ptr, idx, val, int(d.value)
+    return (label[:n.value], row_ptr[:n.value + 1], idx[:nnz.value], val[:nnz.value], int(d.value))
 
 
 def format_libfm(label, row_ptr, idx, val) -> bytes:
