@@ -158,6 +158,17 @@ using namespace sfm;
 
 namespace {
 
+// First '\n' or '\r' at or after p (or end): two library scans instead of a byte loop.
+static inline const char* line_end(const char* p, const char* end) {
+    const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
+    const char* stop = nl ? nl : end;
+    const char* cr = static_cast<const char*>(memchr(p, '\r', (size_t)(stop - p)));
+    return cr ? cr : stop;
+}
+
+static const double kPow10[] = {1e0, 1e1, 1e2,  1e3,  1e4,  1e5,  1e6,  1e7,
+                                1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15};
+
 struct ChunkStat {
     int64_t rows = 0, ents = 0, lines = 0, err_line = -1;   // err_line: 1-based inside the chunk
     int32_t max_index = INT32_MIN;
@@ -174,8 +185,7 @@ static void parse_chunk(const char* p, const char* end, ChunkStat* st, double* l
     bool empty_row = false;
     while (p < end) {
         // one physical line: terminated by \n, \r\n or \r (Hadoop LineReader, used by sc.textFile)
-        const char* le = p;
-        while (le < end && *le != '\n' && *le != '\r') ++le;
+        const char* le = line_end(p, end);
         const char* next = le;
         if (next < end) next += (*next == '\r' && next + 1 < end && next[1] == '\n') ? 2 : 1;
         ++line_no;
@@ -199,6 +209,36 @@ static void parse_chunk(const char* p, const char* end, ChunkStat* st, double* l
         t = te;
         while (t < e) {
             ++t;  // skip the separating space
+            {
+                // fast path, one scan: "<digits>:<digits>" followed by a space or the line end --
+                // the shape of every token of one-hot / count data.  Anything else (signs, '.',
+                // exponents, suffixes, extra ':' parts, out-of-range ids) takes the general path
+                // below, which restates the Scala's split / toInt / toDouble literally.
+                const char* z = t;
+                uint64_t id64 = 0;
+                while (z < e && (unsigned)(*z - '0') <= 9u && z - t < 10) id64 = id64 * 10 + (uint64_t)(*z++ - '0');
+                if (z > t && z < e && *z == ':' && id64 <= 2147483647ull) {
+                    // value: digits [. digits], at most 15 digits in all: the mantissa and the
+                    // power of ten are exact doubles, one division is correctly rounded (Clinger)
+                    const char* y = z + 1;
+                    uint64_t mant = 0;
+                    int nd = 0, frac = 0;
+                    while (y < e && (unsigned)(*y - '0') <= 9u && nd < 15) { mant = mant * 10 + (uint64_t)(*y++ - '0'); ++nd; }
+                    if (y < e && *y == '.') {
+                        ++y;
+                        while (y < e && (unsigned)(*y - '0') <= 9u && nd < 15) { mant = mant * 10 + (uint64_t)(*y++ - '0'); ++nd; ++frac; }
+                    }
+                    if (nd > 0 && (y == e || *y == ' ')) {
+                        if (idx) idx[ent0 + ents] = (int32_t)id64;
+                        if (val) val[ent0 + ents] = frac ? (double)mant / kPow10[frac] : (double)mant;
+                        if ((int32_t)id64 > max_index) max_index = (int32_t)id64;
+                        ++ents;
+                        ++row_ents;
+                        t = y;
+                        continue;
+                    }
+                }
+            }
             te = t;
             while (te < e && *te != ' ') ++te;
             if (te == t) continue;                            // .filter(_.nonEmpty)         :30
@@ -256,8 +296,7 @@ static void parse_chunk(const char* p, const char* end, ChunkStat* st, double* l
 static void count_chunk(const char* p, const char* end, ChunkStat* st) {
     int64_t rows = 0, ents = 0, line_no = 0;
     while (p < end) {
-        const char* le = p;
-        while (le < end && *le != '\n' && *le != '\r') ++le;
+        const char* le = line_end(p, end);
         const char* next = le;
         if (next < end) next += (*next == '\r' && next + 1 < end && next[1] == '\n') ? 2 : 1;
         ++line_no;
@@ -268,15 +307,12 @@ static void count_chunk(const char* p, const char* end, ChunkStat* st) {
         while (e > b && (unsigned char)e[-1] <= ' ') --e;
         if (b == e || *b == '#') continue;
         ++rows;
-        const char* t = b;
-        while (t < e && *t != ' ') ++t;          // the label
-        while (t < e) {
-            ++t;
-            const char* te = t;
-            while (te < e && *te != ' ') ++te;
-            if (te != t) ++ents;                  // .filter(_.nonEmpty)
-            t = te;
-        }
+        const char* t = static_cast<const char*>(memchr(b, ' ', (size_t)(e - b)));   // the label
+        if (!t) continue;
+        // non-empty items = characters that are not a space and follow a space (branch-free)
+        int64_t c = 0;
+        for (const char* z = t + 1; z < e; ++z) c += (int64_t)((z[-1] == ' ') & (z[0] != ' '));
+        ents += c;
     }
     st->rows = rows;
     st->ents = ents;

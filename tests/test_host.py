@@ -249,3 +249,24 @@ def test_parser_number_grammar_fuzz_against_correctly_rounded_python():
     _, _, _, oval, _ = fn.parse_libfm_lines(lines, 200)
     diff = np.nonzero(val.view(np.uint64) != oval.view(np.uint64))[0]
     assert len(diff) == 0, [(toks[j], val[j].hex(), oval[j].hex()) for j in diff[:5]]
+
+
+def test_parser_fast_token_path_edges():
+    """The one-scan "<digits>:<digits[.digits]>" path and its hand-over to the general grammar:
+    digit-count limits (10 for the id, 15 for the value), leading zeros, bare '.', '5.' and '.5',
+    values whose nearest double needs the correctly rounded division."""
+    toks = ["0:0", "007:1.", "5:.5", "5:00000000000000.1", "5:0.000000000000001", "5:123456789012345",
+            "5:1234567890123456", "5:1.23456789012345", "5:1.234567890123456", "5:0.1", "5:0.3",
+            "5:4.35", "5:1e5", "2147483647:1", "0000000005:2", "00000000005:2", "5:0.000000", "5:000",
+            "5:99999999999999.9", "5:9.99999999999999", "5:1.0", "9:3.14159", "5:2.5d", "5:7f",
+            "5:0.1:9", "+5:1", "5:+1", "5:-0.0", "5:1.7976931348623157e308"]
+    lines = ["1 " + t for t in toks] + ["0.5 " + " ".join(toks[:12])]
+    lab, rp, idx, val, d = parse_libfm(("\n".join(lines) + "\n").encode(), num_features=10)
+    olab, orp, oidx, oval, od = fn.parse_libfm_lines(lines, 10)
+    assert np.array_equal(rp, orp) and np.array_equal(idx, oidx) and lab.tobytes() == olab.tobytes()
+    assert val.tobytes() == oval.tobytes()
+    for bad in ("1 5:.", "1 5:", "1 :5", "1 5:1x", "1 2147483648:1", "1 5:1..2", "1 5 :1", "1 5: 1"):
+        with pytest.raises(ValueError):
+            parse_libfm((bad + "\n").encode())
+        with pytest.raises(ValueError):
+            fn.parse_libfm_lines([bad])
