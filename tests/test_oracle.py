@@ -278,3 +278,25 @@ def test_als_update_is_the_coordinate_minimiser():
         seg = slice(rp[r], rp[r + 1])
         dy0[r] = val[seg][idx[seg] == idx[0]].sum()
     assert abs(float(np.dot(e, dy0) + reg[1] * orc.w[idx[0]])) > 1e-9
+
+
+def test_als_known_answers_exact_rational():
+    """tests/golden/als_kat.json: one sweep computed in exact rational arithmetic from the formulas of
+    fm/lib/ALS.scala:15-75 (tests/golden/make_als_kat.py, independent of oracle/); both fp64
+    restatements must land on it up to rounding, with and without the reference quirks."""
+    kat = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "als_kat.json")))
+    rp = np.cumsum([0] + [len(r) for r in kat["rows"]]).astype(np.int64)
+    idx = np.array([i for r in kat["rows"] for i, _ in r], np.int32)
+    val = np.array([x for r in kat["rows"] for _, x in r], np.float64)
+    y = np.array(kat["y"])
+    for case in kat["cases"]:
+        orc = OracleFM(kat["n_slots"], kat["k"], task=0, reg=kat["reg"])
+        orc.set_model(kat["w0"], kat["w"], kat["v"])
+        _, e = orc.als_sweep(rp, idx, val, y, ref_quirks=case["ref_quirks"])
+        pw0, pw, pv, pe = fn.als_sweep(kat["w0"], kat["w"], kat["v"], rp, idx, val, y, reg=kat["reg"],
+                                       ref_quirks=case["ref_quirks"])
+        for got_w0, got_w, got_v, got_e in ((orc.w0.value, orc.w, orc.v, e), (pw0, pw, pv, pe)):
+            assert abs(got_w0 - case["w0"]) <= 1e-12
+            assert np.allclose(got_w, case["w"], rtol=1e-12, atol=1e-13)
+            assert np.allclose(got_v, case["v"], rtol=1e-12, atol=1e-13)
+            assert np.allclose(got_e, case["e"], rtol=1e-12, atol=1e-13)
