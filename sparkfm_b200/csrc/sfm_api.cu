@@ -16,6 +16,20 @@ using namespace sfm;
 
 namespace sfm {
 
+static Knobs g_knobs;
+const Knobs& knobs() { return g_knobs; }
+void knobs_refresh() {
+    Knobs k;
+    const char* e;
+    if ((e = getenv("SFM_SORT")) && e[0] == 'c') k.sort_cub = true;
+    if (((e = getenv("SFM_BUCKET")) && e[0] == '0') || k.sort_cub) k.bucket = false;
+    if (getenv("SFM_NO_FASTPATH")) k.no_fastpath = true;
+    if ((e = getenv("SFM_PULL_BLOCK_MB"))) k.pull_block_mb = atoi(e);
+    if ((e = getenv("SFM_AR_SLICES"))) k.ar_slices = atoi(e) < 1 ? 1 : (atoi(e) > 8 ? 8 : atoi(e));
+    if ((e = getenv("SFM_SORT_AHEAD"))) k.sort_ahead = atoi(e);
+    g_knobs = k;
+}
+
 int set_err(sfm_handle* h, int code, const std::string& msg) {
     if (h) h->err = msg;
     return code;
@@ -298,14 +312,29 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     int blk_bits = 0;
     while (((int64_t)1 << blk_bits) < n_blocks) ++blk_bits;
     if (key_bits + blk_bits > 32) return set_err(h, SFM_ERR_ARG, "sort key does not fit 32 bits");
-    RC(ensure(h, h->b_seg, sizeof(int32_t) * 2 * (size_t)m.n_slots * n_blocks));  // seg_lo | seg_hi
+    // bucket form of the transposition + reduce (sfm_bucket.cu) whenever it applies; otherwise the
+    // two-pass global sort + chunked reduce
+    BucketGeom bg;
+    bool bucket = false;
+    if (pc) {
+        bucket = pc->bucket;
+        bg = pc->geom;
+    } else {
+        bucket = n_blocks == 1 && bucket_geometry(m, key_bits, n, nnz, &bg);
+    }
     RC(ensure(h, h->b_partials, sizeof(double) * 4 * 512));
-    RC(ensure(h, h->b_pull, pull_scratch_bytes(m, nnz, n_blocks)));
     const int end_bit = key_bits + blk_bits;
     size_t sort_bytes = 0;
-    if (nnz > 0 && !pc) {
-        sort_bytes = binary ? sort_pairs32_temp_bytes(nnz, end_bit) : sort_pairs_temp_bytes(nnz, end_bit);
-        RC(ensure(h, h->b_sort_tmp, sort_bytes));
+    if (bucket) {
+        RC(ensure(h, h->b_bkt_work, bucket_work_bytes(m, bg, h->sm_count)));
+        if (!pc) RC(ensure(h, h->b_bkt_tables, bucket_tables_bytes(bg)));
+    } else {
+        RC(ensure(h, h->b_seg, sizeof(int32_t) * 2 * (size_t)m.n_slots * n_blocks));  // seg_lo | seg_hi
+        RC(ensure(h, h->b_pull, pull_scratch_bytes(m, nnz, n_blocks)));
+        if (nnz > 0 && !pc) {
+            sort_bytes = binary ? sort_pairs32_temp_bytes(nnz, end_bit) : sort_pairs_temp_bytes(nnz, end_bit);
+            RC(ensure(h, h->b_sort_tmp, sort_bytes));
+        }
     }
     const bool multi = h->world > 1;
     const bool fused = !multi && !grad_keep;
@@ -326,7 +355,7 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     // all-ones rows of m entries in row order: entry i belongs to batch row i / m, so the forward
     // kernel writes no payload and the first sort pass derives it (saves 8 bytes per entry)
     const int implicit_div = (!pc && binary && b.uniform_m > 0 && b.uniform_m < 512 && !b.out_ptr &&
-                              b.out_base == 0 && nnz > 0 && radix_usable(nnz, end_bit))
+                              b.out_base == 0 && nnz > 0 && (bucket || radix_usable(nnz, end_bit)))
                                  ? b.uniform_m : 0;
     if (implicit_div) o.pay = nullptr;
     o.key_bits = key_bits;
@@ -338,15 +367,8 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     // slices; slice q's gradient is all-reduced and applied on the comm stream while the reduce of
     // slice q+1 runs on the compute stream.
     int n_slices = 1;
-    if (multi && !p2p && !grad_keep && n_blocks == 1 && nnz > 0 && !h->phase_timing) {
-        static int q_env = -1;
-        if (q_env < 0) {
-            const char* e = getenv("SFM_AR_SLICES");
-            q_env = e ? atoi(e) : 1;   // off by default: pays only when the all-reduce is long
-            if (q_env < 1) q_env = 1;
-            if (q_env > 8) q_env = 8;
-        }
-        n_slices = q_env;
+    if (multi && !p2p && !grad_keep && n_blocks == 1 && nnz > 0 && !h->phase_timing && !bucket) {
+        n_slices = knobs().ar_slices;   // off by default: pays only when the all-reduce is long
         if (m.n_slots < 64 * n_slices) n_slices = 1;
     }
     const bool sliced = n_slices > 1;
@@ -363,7 +385,11 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     }
     const uint32_t* keys_sorted = pc ? (const uint32_t*)pc->keys.p : (const uint32_t*)h->b_keys[1].p;
     const uint2* pay_sorted = pc ? (const uint2*)pc->pay.p : (const uint2*)h->b_pay[1].p;
-    if (nnz > 0 && !pc) {
+    if (nnz > 0 && !pc && bucket) {
+        CU(bucket_transpose(m, b, bg, o.keys, o.pay, implicit_div, h->b_bkt_work.p,
+                            h->b_bkt_tables.p, (uint32_t*)h->b_keys[1].p,
+                            binary ? nullptr : (uint32_t*)h->b_pay[1].p, h->sm_count, h->stream, L));
+    } else if (nnz > 0 && !pc) {
         if (binary)
             CU(sort_pairs32(h->b_sort_tmp.p, sort_bytes, o.keys, (uint32_t*)h->b_keys[1].p,
                             (const uint32_t*)o.pay, (uint32_t*)h->b_pay[1].p, nnz, end_bit,
@@ -428,10 +454,15 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
         h->stats.train_nnz += nnz;
         return SFM_OK;
     }
-    CU(launch_pull(m, (int32_t*)h->b_seg.p, key_bits, n_blocks, keys_sorted, pay_sorted, nnz, binary,
-                   o.S, o.mult, (float*)h->b_pull.p, h->d_scal, h->d_err, up, fused,
-                   fused ? nullptr : (p2p ? p2p_grad_buffer(h) : (float*)h->b_grad.p), h->sm_count,
-                   h->stream, L));
+    float* grad_out = fused ? nullptr : (p2p ? p2p_grad_buffer(h) : (float*)h->b_grad.p);
+    if (bucket)
+        CU(bucket_pull(m, bg, keys_sorted, binary ? nullptr : (const uint32_t*)pay_sorted,
+                       pc ? pc->tables.p : h->b_bkt_tables.p, h->b_bkt_work.p, o.S, o.mult, h->d_scal,
+                       h->d_err, up, fused, grad_out, h->sm_count, h->stream, L));
+    else
+        CU(launch_pull(m, (int32_t*)h->b_seg.p, key_bits, n_blocks, keys_sorted, pay_sorted, nnz,
+                       binary, o.S, o.mult, (float*)h->b_pull.p, h->d_scal, h->d_err, up, fused,
+                       grad_out, h->sm_count, h->stream, L));
     pt.lap(&h->stats.ms_reduce);
     if (p2p) {
         RC(p2p_reduce_update(h, up));
@@ -542,6 +573,7 @@ static void free_parts(sfm_handle* h) {
         free_buf(pc.row_ids);
         free_buf(pc.keys);
         free_buf(pc.pay);
+        free_buf(pc.tables);
     }
     h->parts.clear();
 }
@@ -607,7 +639,18 @@ static int partition_batch(sfm_handle* h, int64_t iter, BatchView* b, const Part
             RC(ensure(h, pc.keys, sizeof(uint32_t) * cnt));
             RC(ensure(h, pc.pay, pay_sz * cnt));
         }
-        if (v.nnz > 0 && !is_sharded(h)) {   // row-sharded models cache their own plan (sfm_shard.cu)
+        pc.bucket = !is_sharded(h) && pc.n_blocks == 1 &&
+                    bucket_geometry(h->m, pc.key_bits, n, v.nnz, &pc.geom);
+        if (pc.bucket) {   // entries grouped by bucket once; the reduce ranks them per tile
+            CU(launch_emit(v, pc.key_bits, pc.blk_shift, h->m.n_slots, (uint32_t*)h->b_keys[0].p,
+                           (uint2*)h->b_pay[0].p, h->sm_count, h->stream, L));
+            RC(ensure(h, h->b_bkt_work, bucket_work_bytes(h->m, pc.geom, h->sm_count)));
+            RC(ensure(h, pc.tables, bucket_tables_bytes(pc.geom)));
+            CU(bucket_transpose(h->m, v, pc.geom, (const uint32_t*)h->b_keys[0].p,
+                                (const uint2*)h->b_pay[0].p, 0, h->b_bkt_work.p, pc.tables.p,
+                                (uint32_t*)pc.keys.p, binary ? nullptr : (uint32_t*)pc.pay.p,
+                                h->sm_count, h->stream, L));
+        } else if (v.nnz > 0 && !is_sharded(h)) {   // row-sharded models cache their own plan (sfm_shard.cu)
             CU(launch_emit(v, pc.key_bits, pc.blk_shift, h->m.n_slots, (uint32_t*)h->b_keys[0].p,
                            (uint2*)h->b_pay[0].p, h->sm_count, h->stream, L));
             const int end_bit = pc.key_bits + blk_bits;
@@ -746,6 +789,7 @@ int32_t sfm_host_free(void* ptr) {
 int32_t sfm_create(const sfm_config* cfg, sfm_handle** out) {
     if (!cfg || !out) return SFM_ERR_ARG;
     *out = nullptr;
+    knobs_refresh();   // experiment knobs are (re)read here, never in a launch path
     if (cfg->abi_version != SFM_ABI_VERSION) return SFM_ERR_ARG;
     if (cfg->k < 0 || cfg->k > 128 || cfg->n_slots < 1 || cfg->n_slots >= 2147483647LL)
         return SFM_ERR_ARG;
@@ -838,7 +882,7 @@ int32_t sfm_destroy(sfm_handle* h) {
     Buf* bufs[] = {&h->b_row_ids, &h->b_out_ptr, &h->b_S, &h->b_mult, &h->b_loss, &h->b_yhat,
                    &h->b_keys[0], &h->b_keys[1], &h->b_pay[0], &h->b_pay[1], &h->b_seg,
                    &h->b_sort_tmp, &h->b_grad, &h->b_partials, &h->b_sel_tmp, &h->b_lens,
-                   &h->b_pull};
+                   &h->b_pull, &h->b_bkt_work, &h->b_bkt_tables};
     for (Buf* b : bufs) free_buf(*b);
     if (h->shard) {
         ShardState& ss = *h->shard;
@@ -1680,11 +1724,7 @@ int32_t sfm_train(sfm_handle* h, int64_t first_iter, int64_t n_iters, double* lo
     const bool parts = use_partitions(h);
     const bool sampled = !parts && frac < 1.0 && frac > 0.0 && ds.n_rows > 0;
     // uniform rows: the whole transposition of the next batch is built ahead on the copy stream
-    static int ahead_env = -1;
-    if (ahead_env < 0) {
-        const char* e = getenv("SFM_SORT_AHEAD");
-        ahead_env = e ? atoi(e) : 0;   // measured: co-scheduling the sort with the gather kernels does not pay
-    }
+    const int ahead_env = knobs().sort_ahead;   // measured: co-scheduling the sort with the gather kernels does not pay
     const bool ahead = sampled && ds.uniform_m >= 0 && !is_sharded(h) && !h->phase_timing &&
                        ahead_env != 0;
     if (sampled) {

@@ -1,0 +1,971 @@
+// sfm_bucket.cu -- transposition + deterministic reduce-by-feature of the SGD step, bucket form
+// (DESIGN.md 3.3).  Replaces the two-pass global radix sort + fm_pull_chunks + fm_pull_finalize
+// on the hot path; those stay for the row-sharded model and as the SFM_SORT=cub / SFM_BUCKET=0
+// cross-check.
+//
+// The feature id is split into a BUCKET (top HB <= 11 bits) and a LOCAL id (low LB bits, 2^LB
+// features whose gradient accumulators fit in shared memory).  One global pass groups the batch's
+// entries by bucket; the second half of the sort never touches HBM: the reduce kernel ranks every
+// tile of a bucket by local id inside shared memory and walks the runs.
+//
+//   bkt_count_kernel    per contiguous row range c (one per scatter CTA): bucket histogram
+//                       -> counts[c][bucket]
+//   bkt_offsets_kernel  column sums: counts[c][b] <- entries of bucket b in ranges < c; totals[b]
+//   bkt_plan_kernel     bucket starts, work items (a bucket is cut into items of <= 32768
+//                       entries), item table
+//   bkt_scatter_kernel  persistent, one CTA per range, tiles of 8192 entries in order: stable
+//                       rank of every entry inside the tile (peer masks from ballots over the
+//                       digit bits, warp-private counters, prefix over warps and digits), entries
+//                       re-ordered in shared memory, written as ONE packed word
+//                       (local id << RB | batch row) (+ the value for non-binary data) to
+//                       start(range, bucket) + running offset.  Ranges and tiles are visited in
+//                       order, so rows ascend inside a bucket: the pass is a stable partition.
+//   bkt_pull_kernel     persistent over work items (atomic ticket): per tile of 4096 entries
+//                       stable rank by local id (same scheme), re-order into shared memory, walk
+//                       the runs (level 0: a group of LPR lanes adds 8*LPR consecutive entries in
+//                       order, gathering the rows' factor sums S_r; level 1: a run spanning
+//                       several groups is summed by the group where it starts), add the run sums
+//                       to the item's shared-memory accumulators (one owner per (tile, feature):
+//                       no atomics).  Item end: a single-item bucket is finalised in place
+//                       (g = A - v D, then the SGD update or the dense gradient); the items of a
+//                       multi-item bucket leave their touched accumulator rows in scratch and
+//                       the LAST item to finish adds them in item order.
+//
+// Every sum has a fixed shape that depends on entry positions only: bitwise reproducible, no float
+// atomics (the only atomics are the integer ticket / arrival counters).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "sfm_common.h"
+
+namespace sfm {
+
+#define FULL 0xffffffffu
+
+constexpr int BK_MAX_HB = 11;
+constexpr int BK_MAX_LB = 10;
+constexpr int SC_THREADS = 256;              // scatter: 8 warps x 32 entries per thread
+constexpr int SC_WARPS = SC_THREADS / 32;
+constexpr int SC_IPT = 32;
+constexpr int SC_TILE = SC_THREADS * SC_IPT;   // 8192
+constexpr int PL_THREADS = 512;              // pull: 16 warps x 8 entries per thread
+constexpr int PL_WARPS = PL_THREADS / 32;
+constexpr int PL_IPT = 8;
+constexpr int PL_TILE = PL_THREADS * PL_IPT;   // 4096
+constexpr int PL_ITEM_TILES = 8;
+constexpr int PL_ITEM = PL_TILE * PL_ITEM_TILES;   // 32768 entries per work item
+constexpr int PL_U = 4;                      // S-row gathers in flight per lane
+constexpr uint32_t NO_DIGIT = 0xFFFFFFFFu;
+
+__device__ __forceinline__ int64_t ent_of(const int64_t* __restrict__ out_ptr, int64_t out_base,
+                                          int m, int64_t row) {
+    return out_ptr ? __ldg(out_ptr + row) - out_base : row * (int64_t)m;
+}
+
+// peers = lanes of the warp (among `valid`) that hold the same digit.  Every lane stores its lane
+// id into the warp's byte table at its digit (one of the lanes sharing a digit wins), reads the
+// winner back, and the lanes with the same winner find each other with 5 ballots over the winner's
+// bits -- instead of one ballot per digit bit (up to 11).  The table is never cleared: every
+// reader has just written its own slot.
+__device__ __forceinline__ uint32_t peer_mask(uint8_t* __restrict__ tab, uint32_t d, bool valid,
+                                              int lane) {
+    if (valid) tab[d] = (uint8_t)lane;
+    __syncwarp();
+    const uint32_t leader = valid ? (uint32_t)tab[d] : 0u;
+    uint32_t m = __ballot_sync(FULL, valid);
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        const uint32_t bit = (leader >> b) & 1u;
+        const uint32_t bal = __ballot_sync(FULL, bit != 0u);
+        m &= bal ^ (bit - 1u);   // bit ? bal : ~bal
+    }
+    __syncwarp();   // every read is done before the next round's writes
+    return m;
+}
+
+// block-wide exclusive scan of one value per thread (THREADS a multiple of 32, <= 1024)
+template <int THREADS>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* wsum /* [THREADS/32] */,
+                                                    uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    uint32_t excl = incl - v, tot = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) {
+        const uint32_t s = wsum[w];
+        if (w < warp) excl += s;
+        tot += s;
+    }
+    if (total) *total = tot;
+    return excl;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+bkt_count_kernel(const uint32_t* __restrict__ keys, int n_rows, int m,
+                 const int64_t* __restrict__ out_ptr, int64_t out_base, int LB, int NB,
+                 uint32_t* __restrict__ counts) {
+    extern __shared__ uint32_t bk_hist[];
+    for (int d = threadIdx.x; d < NB; d += 512) bk_hist[d] = 0;
+    __syncthreads();
+    const int c = blockIdx.x, G = gridDim.x;
+    const int64_t r0 = (int64_t)c * n_rows / G, r1 = (int64_t)(c + 1) * n_rows / G;
+    const int64_t lo = ent_of(out_ptr, out_base, m, r0), hi = ent_of(out_ptr, out_base, m, r1);
+    for (int64_t i0 = lo; i0 < hi; i0 += 512 * 8) {
+        uint32_t k[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int64_t i = i0 + u * 512 + threadIdx.x;
+            k[u] = i < hi ? __ldg(keys + i) : NO_DIGIT;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (k[u] != NO_DIGIT) atomicAdd(&bk_hist[k[u] >> LB], 1u);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < NB; d += 512) counts[(size_t)c * NB + d] = bk_hist[d];
+}
+
+// counts[c][d] <- sum over ranges c' < c; totals[d] = sum over all ranges.  Grid: NB/32 (>= 1)
+// CTAs of 1024 threads = 32 bucket lanes x 32 blocks of ranges.
+__global__ void __launch_bounds__(1024)
+bkt_offsets_kernel(uint32_t* __restrict__ counts, int G, int NB, uint32_t* __restrict__ totals) {
+    __shared__ uint32_t part[32][33];
+    const int dl = threadIdx.x & 31, rb = threadIdx.x >> 5;
+    const int d = blockIdx.x * 32 + dl;
+    const int per = (G + 31) / 32;
+    const int c0 = min(G, rb * per), c1 = min(G, c0 + per);
+    uint32_t sum = 0;
+    if (d < NB)
+        for (int c = c0; c < c1; ++c) sum += counts[(size_t)c * NB + d];
+    part[rb][dl] = sum;
+    __syncthreads();
+    uint32_t run = 0;
+    for (int r = 0; r < rb; ++r) run += part[r][dl];
+    if (d < NB) {
+        for (int c = c0; c < c1; ++c) {
+            const uint32_t t = counts[(size_t)c * NB + d];
+            counts[(size_t)c * NB + d] = run;
+            run += t;
+        }
+        if (rb == 31) totals[d] = run;
+    }
+}
+
+// bucket_off[b] (exclusive scan of totals), item_start[b] (exclusive scan of the items per
+// bucket, >= 1 each so that untouched buckets still get their L2 decay); [NB] = grand totals;
+// item_bucket[item] = its bucket.
+__global__ void __launch_bounds__(1024)
+bkt_plan_kernel(const uint32_t* __restrict__ totals, int NB, uint32_t* __restrict__ bucket_off,
+                uint32_t* __restrict__ item_start, uint32_t* __restrict__ item_bucket) {
+    __shared__ uint32_t wsum[32];
+    const int b0 = threadIdx.x * 2;
+    const uint32_t t0 = b0 < NB ? totals[b0] : 0u, t1 = b0 + 1 < NB ? totals[b0 + 1] : 0u;
+    const uint32_t n0 = b0 < NB ? max(1u, (t0 + PL_ITEM - 1) / PL_ITEM) : 0u;
+    const uint32_t n1 = b0 + 1 < NB ? max(1u, (t1 + PL_ITEM - 1) / PL_ITEM) : 0u;
+    uint32_t tot_e = 0, tot_i = 0;
+    const uint32_t ex_e = block_excl_scan<1024>(t0 + t1, wsum, &tot_e);
+    __syncthreads();
+    const uint32_t ex_i = block_excl_scan<1024>(n0 + n1, wsum, &tot_i);
+    if (b0 < NB) {
+        bucket_off[b0] = ex_e;
+        item_start[b0] = ex_i;
+        for (uint32_t j = 0; j < n0; ++j) item_bucket[ex_i + j] = (uint32_t)b0;
+    }
+    if (b0 + 1 < NB) {
+        bucket_off[b0 + 1] = ex_e + t0;
+        item_start[b0 + 1] = ex_i + n0;
+        for (uint32_t j = 0; j < n1; ++j) item_bucket[ex_i + n0 + j] = (uint32_t)(b0 + 1);
+    }
+    if (threadIdx.x == 0) {
+        bucket_off[NB] = tot_e;
+        item_start[NB] = tot_i;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Stable partition of the entries by bucket.  PAYMODE 0: all-ones rows of m entries in row
+// order, batch row of input position i = i / m (magic division, exact for i < 2^31, m < 512);
+// 1: batch rows in rows_in (uint32); 2: {batch row, x bits} in pay2 (uint2).
+// ------------------------------------------------------------------------------------------
+template <int PAYMODE>
+__global__ void __launch_bounds__(SC_THREADS, 2)
+bkt_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rows_in,
+                   const uint2* __restrict__ pay2, uint32_t* __restrict__ packed_out,
+                   uint32_t* __restrict__ vals_out, int n_rows, int m,
+                   const int64_t* __restrict__ out_ptr, int64_t out_base, int LB, int HB,
+                   const uint32_t* __restrict__ colpre, const uint32_t* __restrict__ bucket_off,
+                   unsigned long long magic) {
+    constexpr bool HAS_VAL = PAYMODE == 2;
+    extern __shared__ __align__(16) unsigned char sc_smem[];
+    const int NB = 1 << HB;
+    const int RB = 32 - LB;
+    const uint32_t lowmask = (1u << LB) - 1u;
+    uint32_t* ent_s = reinterpret_cast<uint32_t*>(sc_smem);                      // [TILE]
+    uint32_t* val_s = ent_s + SC_TILE;                                            // [TILE] (HAS_VAL)
+    uint16_t* dig_s = reinterpret_cast<uint16_t*>(val_s + (HAS_VAL ? SC_TILE : 0));   // [TILE]
+    uint16_t* whist = dig_s + SC_TILE;                                            // [WARPS][NB]
+    uint32_t* goff = reinterpret_cast<uint32_t*>(whist + SC_WARPS * NB);          // [NB]
+    uint16_t* lstart = reinterpret_cast<uint16_t*>(goff + NB);                    // [NB]
+    uint8_t* ltab = reinterpret_cast<uint8_t*>(lstart + NB) + (threadIdx.x >> 5) * NB;   // [WARPS][NB]
+    __shared__ uint32_t wsum[SC_WARPS];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = blockIdx.x, G = gridDim.x;
+    const int64_t r0 = (int64_t)c * n_rows / G, r1 = (int64_t)(c + 1) * n_rows / G;
+    const int lo = (int)ent_of(out_ptr, out_base, m, r0), hi = (int)ent_of(out_ptr, out_base, m, r1);
+
+    // digits owned by this thread in the prefix phase: words [w0, w0 + cw) of row_words
+    const int row_words = NB >= 2 ? NB / 2 : 1;
+    const int cw = row_words >= SC_THREADS ? row_words / SC_THREADS : 1;   // <= 4
+    const int w0 = tid * cw;
+    const bool has = w0 < row_words;
+    uint32_t R[8];   // running global offset of my digits (start of this range's run in the bucket)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        R[2 * j] = R[2 * j + 1] = 0;
+        if (has && j < cw) {
+            const int b = 2 * (w0 + j);
+            if (b < NB) R[2 * j] = __ldg(bucket_off + b) + __ldg(colpre + (size_t)c * NB + b);
+            if (b + 1 < NB) R[2 * j + 1] = __ldg(bucket_off + b + 1) + __ldg(colpre + (size_t)c * NB + b + 1);
+        }
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    uint16_t* wh = whist + warp * NB;
+    const int strip = warp * (32 * SC_IPT);
+
+    for (int tile_base = lo; tile_base < hi; tile_base += SC_TILE) {
+        const int n_valid = min(SC_TILE, hi - tile_base);
+        {   // zero the warp histograms
+            uint32_t* z = reinterpret_cast<uint32_t*>(whist);
+            const int words = SC_WARPS * NB / 2;
+            for (int i = tid; i < words; i += SC_THREADS) z[i] = 0;
+            if (NB == 1 && tid < SC_WARPS) whist[tid] = 0;
+        }
+        uint32_t key[SC_IPT];
+#pragma unroll
+        for (int r = 0; r < SC_IPT; ++r) {
+            const int p = strip + r * 32 + lane;
+            key[r] = p < n_valid ? __ldg(keys + tile_base + p) : 0u;
+        }
+        __syncthreads();
+        // ---- stable rank inside the warp's strip, in entry order
+        uint32_t rk2[SC_IPT / 2];
+#pragma unroll
+        for (int r = 0; r < SC_IPT; ++r) {
+            if (strip + r * 32 < n_valid) {   // warp-uniform
+                const bool valid = strip + r * 32 + lane < n_valid;
+                const uint32_t d = key[r] >> LB;
+                const uint32_t pm = peer_mask(ltab, d, valid, lane);
+                uint32_t old = 0;
+                if (valid && (pm & lt) == 0u) {   // first lane of the group owns the counter
+                    old = wh[d];
+                    wh[d] = (uint16_t)(old + __popc(pm));
+                }
+                old = __shfl_sync(FULL, old, valid ? __ffs(pm) - 1 : lane);
+                const uint32_t rank = old + __popc(pm & lt);
+                if (r & 1) rk2[r / 2] |= rank << 16; else rk2[r / 2] = rank;
+            } else {
+                if (!(r & 1)) rk2[r / 2] = 0;
+            }
+        }
+        __syncthreads();
+        // ---- per digit: exclusive prefix over the warps (two u16 counters per word; a tile has
+        // 8192 entries, so the halves never carry), then over the digits
+        {
+            uint32_t* wrows = reinterpret_cast<uint32_t*>(whist);
+            uint32_t cnt2[4] = {0, 0, 0, 0};
+            uint32_t local = 0;
+            if (NB >= 2) {
+                if (has) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (j < cw) {
+                            uint32_t run = 0;
+#pragma unroll
+                            for (int w = 0; w < SC_WARPS; ++w) {
+                                const uint32_t t = wrows[w * row_words + w0 + j];
+                                wrows[w * row_words + w0 + j] = run;
+                                run += t;
+                            }
+                            cnt2[j] = run;
+                            local += (run & 0xffffu) + (run >> 16);
+                        }
+                    }
+                }
+            } else if (tid == 0) {   // single bucket
+                uint32_t run = 0;
+                for (int w = 0; w < SC_WARPS; ++w) {
+                    const uint32_t t = whist[w];
+                    whist[w] = (uint16_t)run;
+                    run += t;
+                }
+                cnt2[0] = run;
+                local = run;
+            }
+            const uint32_t excl0 = block_excl_scan<SC_THREADS>(local, wsum, nullptr);
+            uint32_t excl = excl0;
+            if (has) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j < cw) {
+                        const int b = 2 * (w0 + j);
+                        const uint32_t c_lo = cnt2[j] & 0xffffu, c_hi = cnt2[j] >> 16;
+                        if (b < NB) {
+                            lstart[b] = (uint16_t)excl;
+                            goff[b] = R[2 * j] - excl;
+                            R[2 * j] += c_lo;
+                        }
+                        if (b + 1 < NB) {
+                            lstart[b + 1] = (uint16_t)(excl + c_lo);
+                            goff[b + 1] = R[2 * j + 1] - (excl + c_lo);
+                            R[2 * j + 1] += c_hi;
+                        }
+                        excl += c_lo + c_hi;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- re-order inside the tile
+#pragma unroll
+        for (int r0i = 0; r0i < SC_IPT; r0i += 8) {
+            uint32_t rowv[8], xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int p = strip + (r0i + u) * 32 + lane;
+                rowv[u] = 0;
+                xv[u] = 0;
+                if (p < n_valid) {
+                    if (PAYMODE == 0)
+                        rowv[u] = (uint32_t)(((unsigned long long)(uint32_t)(tile_base + p) * magic) >> 40);
+                    else if (PAYMODE == 1)
+                        rowv[u] = __ldg(rows_in + tile_base + p);
+                    else {
+                        const uint2 pl = __ldg(pay2 + tile_base + p);
+                        rowv[u] = pl.x;
+                        xv[u] = pl.y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0i + u;
+                const int p = strip + r * 32 + lane;
+                if (p < n_valid) {
+                    const uint32_t d = key[r] >> LB;
+                    const uint32_t rank = (r & 1) ? (rk2[r / 2] >> 16) : (rk2[r / 2] & 0xffffu);
+                    const int q = (int)lstart[d] + (int)wh[d] + (int)rank;
+                    ent_s[q] = (LB ? (key[r] & lowmask) << RB : 0u) | rowv[u];
+                    dig_s[q] = (uint16_t)d;
+                    if (HAS_VAL) val_s[q] = xv[u];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- contiguous runs per bucket go out
+#pragma unroll 8
+        for (int j = 0; j < SC_IPT; ++j) {
+            const int q = j * SC_THREADS + tid;
+            if (q < n_valid) {
+                const uint32_t g = goff[dig_s[q]] + (uint32_t)q;
+                packed_out[g] = ent_s[q];
+                if (HAS_VAL) vals_out[g] = val_s[q];
+            }
+        }
+        // the next tile's prefix phase (which rewrites goff / lstart) and re-order (ent_s) come
+        // after its own barriers, which every thread reaches only after this write-out
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Reduce + update.
+// ------------------------------------------------------------------------------------------
+template <int LPR>
+struct Pl {
+    static constexpr int G = PL_THREADS / LPR;      // lane groups per CTA
+    static constexpr int SUB = PL_TILE / G;         // consecutive sorted entries per group (8*LPR)
+    static constexpr int SUBSHIFT = LPR == 1 ? 3 : LPR == 2 ? 4 : LPR == 4 ? 5 : LPR == 8 ? 6 : LPR == 16 ? 7 : 8;
+    static constexpr int TILE_PAD = PL_TILE + G;    // phys(q) = q + (q >> SUBSHIFT)
+    static constexpr int REC = LPR * 4 + 4;         // [A (kp) | D | C | 0 | 0]
+};
+
+struct PullArgs {
+    const uint32_t* packed;
+    const uint32_t* vals;        // x bits per entry (non-binary) or nullptr
+    const uint32_t* bucket_off;  // [NB+1]
+    const uint32_t* item_start;  // [NB+1]
+    const uint32_t* item_bucket; // [items]
+    uint32_t* work;              // [0] ticket, [1 + b] arrivals of bucket b (zeroed per step)
+    float* part;                 // [items][2^LB][REC] partial accumulators of multi-item buckets
+    uint32_t* part_bits;         // [items][2^LB / 32 (>= 1)] touched bitmaps
+    const float4* S4;
+    const float* mult;
+    float4* V4;
+    float* W;
+    float* W0;
+    float4* G4;                  // dense gradient out (not FUSED)
+    float* Gw;
+    float* Gw0;
+    const double* d_scal;
+    const int32_t* err;
+    int64_t n_slots;
+    int NB, LB, k0, k1;
+    UpdateParams up;
+};
+
+template <int LPR, bool BINARY, bool FUSED>
+__global__ void __launch_bounds__(PL_THREADS, 2)
+bkt_pull_kernel(const PullArgs a) {
+    using C = Pl<LPR>;
+    constexpr int G = C::G, SUB = C::SUB, SS = C::SUBSHIFT, REC = C::REC;
+    extern __shared__ __align__(16) unsigned char pl_smem[];
+    const int LB = a.LB, RB = 32 - LB, NBL = 1 << LB;
+    const uint32_t rowmask = RB >= 32 ? 0xffffffffu : (1u << RB) - 1u;
+    // shared-memory carve-up (pull_smem() mirrors it)
+    float4* accA = reinterpret_cast<float4*>(pl_smem);                   // [NBL][LPR]
+    float4* headA = accA + (size_t)NBL * LPR;                             // [G][LPR]
+    float2* headDC = reinterpret_cast<float2*>(headA + G * LPR);          // [G]
+    int* nxt = reinterpret_cast<int*>(headDC + G);                        // [G] level-1 chain links
+    float* accC = reinterpret_cast<float*>(nxt + G);                      // [NBL]
+    float* accD = accC + NBL;                                             // [NBL]
+    uint32_t* ent_s = reinterpret_cast<uint32_t*>(accD + NBL);            // [TILE_PAD]
+    float* val_s = reinterpret_cast<float*>(ent_s + C::TILE_PAD);         // [TILE_PAD] x (!BINARY)
+    uint32_t* tch = reinterpret_cast<uint32_t*>(val_s + (BINARY ? 0 : C::TILE_PAD));   // [NBL]
+    uint16_t* lstart = reinterpret_cast<uint16_t*>(tch + NBL);            // [NBL]
+    uint16_t* whist = lstart + (NBL + (NBL & 1));                         // [WARPS][NBL]
+    uint8_t* ltab0 = reinterpret_cast<uint8_t*>(whist + PL_WARPS * NBL);  // [WARPS][NBL]
+    __shared__ uint32_t wsum[PL_WARPS];
+    __shared__ uint32_t s_item, s_last;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = tid / LPR, fq = tid % LPR;
+    const unsigned lt = (1u << lane) - 1u;
+    uint16_t* wh = whist + warp * NBL;
+    uint8_t* ltab = ltab0 + warp * NBL;
+    const int strip = warp * (32 * PL_IPT);
+    const uint32_t total_items = __ldg(a.item_start + a.NB);
+    const double count = a.d_scal[SC_COUNT];
+    const float inv = count > 0.0 ? (float)(1.0 / count) : 0.f;
+    const bool active = count > 0.0 && !(FUSED && *a.err);
+    auto phys = [](int q) { return q + (q >> SS); };
+
+    for (;;) {
+        __syncthreads();   // previous item fully finished (shared scalars, accumulators)
+        if (tid == 0) s_item = atomicAdd(a.work, 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= total_items) break;
+        const int b = (int)__ldg(a.item_bucket + item);
+        const uint32_t it0 = __ldg(a.item_start + b), it1 = __ldg(a.item_start + b + 1);
+        const uint32_t boff = __ldg(a.bucket_off + b), bend = __ldg(a.bucket_off + b + 1);
+        const uint32_t e_lo = boff + (item - it0) * (uint32_t)PL_ITEM;
+        const uint32_t e_hi = min(bend, e_lo + (uint32_t)PL_ITEM);
+
+        // the item's first tile is requested before the accumulators are cleared
+        uint32_t ent[PL_IPT];
+        float xv[PL_IPT];
+        auto load_tile = [&](uint32_t tb) {
+            const int nv = (int)min((uint32_t)PL_TILE, e_hi - tb);
+#pragma unroll
+            for (int r = 0; r < PL_IPT; ++r) {
+                const int p = strip + r * 32 + lane;
+                ent[r] = p < nv ? __ldg(a.packed + tb + p) : 0u;
+                if (!BINARY) xv[r] = p < nv ? __uint_as_float(__ldg(a.vals + tb + p)) : 0.f;
+            }
+        };
+        if (e_lo < e_hi) load_tile(e_lo);
+        for (int i = tid; i < NBL * LPR; i += PL_THREADS) accA[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < NBL; i += PL_THREADS) {
+            accC[i] = 0.f;
+            accD[i] = 0.f;
+            tch[i] = 0u;
+        }
+
+        for (uint32_t tb = e_lo; tb < e_hi; tb += PL_TILE) {
+            const int n_valid = (int)min((uint32_t)PL_TILE, e_hi - tb);
+            {   // zero the warp histograms
+                uint32_t* z = reinterpret_cast<uint32_t*>(whist);
+                const int words = PL_WARPS * NBL / 2;
+                for (int i = tid; i < words; i += PL_THREADS) z[i] = 0;
+                if (NBL == 1 && tid < PL_WARPS) whist[tid] = 0;
+            }
+            __syncthreads();   // histograms zero; the previous tile's walk is over
+            uint32_t rk[PL_IPT];
+#pragma unroll
+            for (int r = 0; r < PL_IPT; ++r) {
+                rk[r] = 0;
+                if (strip + r * 32 < n_valid) {   // warp-uniform
+                    const bool valid = strip + r * 32 + lane < n_valid;
+                    const uint32_t d = LB ? ent[r] >> RB : 0u;
+                    const uint32_t pm = peer_mask(ltab, d, valid, lane);
+                    uint32_t old = 0;
+                    if (valid && (pm & lt) == 0u) {   // first lane of the group owns the counter
+                        old = wh[d];
+                        wh[d] = (uint16_t)(old + __popc(pm));
+                    }
+                    old = __shfl_sync(FULL, old, valid ? __ffs(pm) - 1 : lane);
+                    rk[r] = old + __popc(pm & lt);
+                }
+            }
+            __syncthreads();
+            {   // exclusive prefix over the warps per digit, then over the digits
+                const int row_words = NBL >= 2 ? NBL / 2 : 1;
+                uint32_t* wrows = reinterpret_cast<uint32_t*>(whist);
+                uint32_t cnt2 = 0, local = 0;
+                const bool has = tid < row_words;   // row_words <= 512 = PL_THREADS
+                if (NBL >= 2) {
+                    if (has) {
+                        uint32_t run = 0;
+#pragma unroll
+                        for (int w = 0; w < PL_WARPS; ++w) {
+                            const uint32_t t = wrows[w * row_words + tid];
+                            wrows[w * row_words + tid] = run;
+                            run += t;
+                        }
+                        cnt2 = run;
+                        local = (run & 0xffffu) + (run >> 16);
+                    }
+                } else if (tid == 0) {
+                    uint32_t run = 0;
+                    for (int w = 0; w < PL_WARPS; ++w) {
+                        const uint32_t t = whist[w];
+                        whist[w] = (uint16_t)run;
+                        run += t;
+                    }
+                    cnt2 = run;
+                    local = run;
+                }
+                const uint32_t excl = block_excl_scan<PL_THREADS>(local, wsum, nullptr);
+                if (has) {
+                    const int d0 = 2 * tid;
+                    if (d0 < NBL) lstart[d0] = (uint16_t)excl;
+                    if (d0 + 1 < NBL) lstart[d0 + 1] = (uint16_t)(excl + (cnt2 & 0xffffu));
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < PL_IPT; ++r) {
+                const int p = strip + r * 32 + lane;
+                if (p < n_valid) {
+                    const uint32_t d = LB ? ent[r] >> RB : 0u;
+                    const int q = phys((int)lstart[d] + (int)wh[d] + (int)rk[r]);
+                    ent_s[q] = ent[r];
+                    if (!BINARY) val_s[q] = xv[r];
+                }
+            }
+            __syncthreads();
+            // the next tile's entries travel while this one is walked
+            if (tb + PL_TILE < e_hi) load_tile(tb + PL_TILE);
+
+            // ---- level 0: walk my SUB sorted entries
+            const int q0 = g * SUB;
+            auto digit_at = [&](int q) -> uint32_t {
+                if (q < 0 || q >= n_valid) return NO_DIGIT;
+                return LB ? ent_s[phys(q)] >> RB : 0u;
+            };
+            auto flush = [&](uint32_t d, const float4& A, float D, float Cc) {
+                float4 t = accA[d * LPR + fq];
+                t.x += A.x; t.y += A.y; t.z += A.z; t.w += A.w;
+                accA[d * LPR + fq] = t;
+                if (fq == 0) {
+                    accC[d] += Cc;
+                    if (!BINARY) accD[d] += D;
+                    tch[d] = 1u;
+                }
+            };
+            uint32_t cur = digit_at(q0);
+            bool cur_is_head = cur != NO_DIGIT && g > 0 && digit_at(q0 - 1) == cur;
+            float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
+            float D = 0.f, Cc = 0.f;
+#pragma unroll 1
+            for (int base = 0; base < SUB; base += PL_U) {
+                uint32_t dd[PL_U];
+                float cc[PL_U], xx[PL_U];
+                float4 sv[PL_U];
+#pragma unroll
+                for (int u = 0; u < PL_U; ++u) {
+                    const int q = q0 + base + u;
+                    const bool ok = q < n_valid;
+                    const uint32_t e = ok ? ent_s[phys(q)] : 0u;
+                    const uint32_t row = e & rowmask;
+                    dd[u] = ok ? (LB ? e >> RB : 0u) : NO_DIGIT;
+                    const float mu = ok ? __ldg(a.mult + row) : 0.f;
+                    if (BINARY) {
+                        cc[u] = mu;
+                        xx[u] = 1.f;
+                    } else {
+                        xx[u] = ok ? val_s[phys(q)] : 0.f;
+                        cc[u] = mu * xx[u];
+                    }
+                    sv[u] = ok ? __ldg(a.S4 + ((size_t)row * LPR + fq)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < PL_U; ++u) {
+                    if (dd[u] != cur) {
+                        if (cur != NO_DIGIT) {
+                            if (cur_is_head) {
+                                headA[g * LPR + fq] = A;
+                                if (fq == 0) headDC[g] = make_float2(D, Cc);
+                            } else {
+                                flush(cur, A, D, Cc);
+                            }
+                        }
+                        cur = dd[u];
+                        cur_is_head = false;
+                        A = make_float4(0.f, 0.f, 0.f, 0.f);
+                        D = 0.f;
+                        Cc = 0.f;
+                    }
+                    const float c = dd[u] == NO_DIGIT ? 0.f : cc[u];
+                    A.x = fmaf(c, sv[u].x, A.x);
+                    A.y = fmaf(c, sv[u].y, A.y);
+                    A.z = fmaf(c, sv[u].z, A.z);
+                    A.w = fmaf(c, sv[u].w, A.w);
+                    D = BINARY ? D : fmaf(c, xx[u], D);
+                    Cc += c;
+                }
+            }
+            // ---- level 1: runs that span several groups.  A group whose FIRST run continues
+            // the previous group's last one holds a "head" partial; a head that fills its whole
+            // group and continues links to the next group's head.  The chains are summed by
+            // pointer jumping (fixed tree shape: depends on the run's position only), then the
+            // group where the run starts adds the chain that follows it.
+            const bool open = cur != NO_DIGIT;
+            const bool continues = open && g < G - 1 && digit_at(q0 + SUB) == cur;
+            const bool owner = open && !cur_is_head;
+            if (open && cur_is_head) {
+                headA[g * LPR + fq] = A;   // the whole group is a middle / final piece of a run
+                if (fq == 0) headDC[g] = make_float2(D, Cc);
+            }
+            if (fq == 0) nxt[g] = (open && cur_is_head && continues) ? g + 1 : -1;
+            __syncthreads();
+            for (;;) {
+                const int n = nxt[g];
+                float4 addA = make_float4(0.f, 0.f, 0.f, 0.f);
+                float2 addDC = make_float2(0.f, 0.f);
+                int n2 = -1;
+                if (n >= 0) {
+                    addA = headA[n * LPR + fq];
+                    addDC = headDC[n];
+                    n2 = nxt[n];
+                }
+                if (!__syncthreads_or(n >= 0)) break;   // also: every read is done
+                if (n >= 0) {
+                    float4 t = headA[g * LPR + fq];
+                    t.x += addA.x; t.y += addA.y; t.z += addA.z; t.w += addA.w;
+                    headA[g * LPR + fq] = t;
+                    if (fq == 0) {
+                        const float2 dc = headDC[g];
+                        headDC[g] = make_float2(dc.x + addDC.x, dc.y + addDC.y);
+                        nxt[g] = n2;
+                    }
+                }
+                __syncthreads();
+            }
+            if (owner) {
+                if (continues) {
+                    const float4 h4 = headA[(g + 1) * LPR + fq];
+                    const float2 dc = headDC[g + 1];
+                    A.x += h4.x; A.y += h4.y; A.z += h4.z; A.w += h4.w;
+                    D += dc.x;
+                    Cc += dc.y;
+                }
+                flush(cur, A, D, Cc);
+            }
+            // next tile: its first barrier orders these shared-memory updates
+        }
+        __syncthreads();
+
+        // ---- item end
+        const bool single = it1 - it0 == 1u;
+        const int bw = NBL >= 32 ? NBL / 32 : 1;
+        if (!single) {
+            float* P = a.part + (size_t)item * NBL * REC;
+            for (int d = g; d < NBL; d += G) {
+                if (tch[d]) {
+                    reinterpret_cast<float4*>(P + (size_t)d * REC)[fq] = accA[d * LPR + fq];
+                    if (fq == 0)
+                        reinterpret_cast<float4*>(P + (size_t)d * REC)[LPR] =
+                            make_float4(accD[d], accC[d], 0.f, 0.f);
+                }
+            }
+            for (int wd = tid; wd < bw; wd += PL_THREADS) {
+                uint32_t bits = 0;
+                for (int j = 0; j < 32; ++j)
+                    if (wd * 32 + j < NBL && tch[wd * 32 + j]) bits |= 1u << j;
+                a.part_bits[(size_t)item * bw + wd] = bits;
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t prev = atomicAdd(a.work + 1 + b, 1u);
+                s_last = prev == it1 - it0 - 1u;
+            }
+            __syncthreads();
+            if (!s_last) continue;
+            __threadfence();
+        }
+        // finalize the bucket's features: one lane group per feature
+        if (b == 0 && tid == 0) {
+            const float g0 = (float)a.d_scal[SC_GW0];
+            if (FUSED) {
+                if (a.k0 && active) *a.W0 = sgd_step(*a.W0, g0, inv, a.up.eta, a.up.reg0);
+            } else {
+                *a.Gw0 = a.k0 ? g0 : 0.f;
+            }
+        }
+        for (int d = g; d < NBL; d += G) {
+            const int64_t f = (int64_t)b * NBL + d;
+            if (f >= a.n_slots) break;
+            float4 v = a.V4[f * LPR + fq];
+            const float wi = (fq == 0 && a.k1) ? a.W[f] : 0.f;
+            float4 A;
+            float D, Cc;
+            if (single) {
+                A = accA[d * LPR + fq];
+                D = accD[d];
+                Cc = accC[d];
+            } else {
+                A = make_float4(0.f, 0.f, 0.f, 0.f);
+                D = 0.f;
+                Cc = 0.f;
+                for (uint32_t it = it0; it < it1; ++it) {   // item order: fixed summation order
+                    const uint32_t bits = __ldcg(a.part_bits + (size_t)it * bw + (d >> 5));
+                    if ((bits >> (d & 31)) & 1u) {
+                        const float* P = a.part + ((size_t)it * NBL + d) * REC;
+                        const float4 pa = __ldcg(reinterpret_cast<const float4*>(P) + fq);
+                        const float4 dc = __ldcg(reinterpret_cast<const float4*>(P) + LPR);
+                        A.x += pa.x; A.y += pa.y; A.z += pa.z; A.w += pa.w;
+                        D += dc.x;
+                        Cc += dc.y;
+                    }
+                }
+            }
+            if (BINARY) D = Cc;
+            float4 gr;
+            gr.x = __fmaf_rn(-v.x, D, A.x);
+            gr.y = __fmaf_rn(-v.y, D, A.y);
+            gr.z = __fmaf_rn(-v.z, D, A.z);
+            gr.w = __fmaf_rn(-v.w, D, A.w);
+            if (FUSED) {
+                if (active) {
+                    v.x = sgd_step(v.x, gr.x, inv, a.up.eta, a.up.regv);
+                    v.y = sgd_step(v.y, gr.y, inv, a.up.eta, a.up.regv);
+                    v.z = sgd_step(v.z, gr.z, inv, a.up.eta, a.up.regv);
+                    v.w = sgd_step(v.w, gr.w, inv, a.up.eta, a.up.regv);
+                    a.V4[f * LPR + fq] = v;
+                    if (fq == 0 && a.k1) a.W[f] = sgd_step(wi, Cc, inv, a.up.eta, a.up.regw);
+                }
+            } else {
+                a.G4[f * LPR + fq] = gr;
+                if (fq == 0) a.Gw[f] = a.k1 ? Cc : 0.f;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side.
+// ------------------------------------------------------------------------------------------
+static inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
+
+bool bucket_geometry(const ModelView& m, int key_bits, int64_t n_rows, int64_t nnz, BucketGeom* g) {
+    if (!knobs().bucket) return false;
+    if (key_bits < 1) key_bits = 1;
+    int lb = 0;
+    while (lb < BK_MAX_LB && ((size_t)2 << lb) * (size_t)(m.kp + 2) * 4 <= 37000) ++lb;
+    if (lb > key_bits - 1) lb = key_bits - 1;   // at least one bucket bit
+    if (lb < 0) lb = 0;
+    const int hb = key_bits - lb;
+    if (hb < 1 || hb > BK_MAX_HB) return false;
+    if (n_rows <= 0 || nnz <= 0) return false;
+    if (n_rows >= ((int64_t)1 << (32 - lb)) || nnz >= 2147483647LL - 2 * SC_TILE) return false;
+    g->LB = lb;
+    g->HB = hb;
+    g->NB = 1 << hb;
+    g->max_items = (int64_t)g->NB + nnz / PL_ITEM + 1;
+    return true;
+}
+
+size_t bucket_tables_bytes(const BucketGeom& g) {   // bucket_off | item_start | item_bucket
+    return al256(sizeof(uint32_t) * (size_t)(g.NB + 1)) * 2 + al256(sizeof(uint32_t) * (size_t)g.max_items);
+}
+
+struct TablePtrs {
+    uint32_t *bucket_off, *item_start, *item_bucket;
+};
+
+static TablePtrs carve_tables(const BucketGeom& g, const void* base) {
+    unsigned char* p = static_cast<unsigned char*>(const_cast<void*>(base));
+    TablePtrs t;
+    t.bucket_off = reinterpret_cast<uint32_t*>(p);
+    p += al256(sizeof(uint32_t) * (size_t)(g.NB + 1));
+    t.item_start = reinterpret_cast<uint32_t*>(p);
+    p += al256(sizeof(uint32_t) * (size_t)(g.NB + 1));
+    t.item_bucket = reinterpret_cast<uint32_t*>(p);
+    return t;
+}
+
+size_t bucket_work_bytes(const ModelView& m, const BucketGeom& g, int sm_count) {
+    const int G = 2 * sm_count;
+    const size_t nbl = (size_t)1 << g.LB;
+    size_t b = al256(sizeof(uint32_t) * (size_t)G * g.NB);          // counts / column prefixes
+    b += al256(sizeof(uint32_t) * (size_t)g.NB);                      // totals
+    b += al256(sizeof(uint32_t) * (size_t)(g.NB + 1));                // ticket + arrivals
+    b += al256(sizeof(float) * (size_t)g.max_items * nbl * (m.kp + 4));
+    b += al256(sizeof(uint32_t) * (size_t)g.max_items * (nbl >= 32 ? nbl / 32 : 1));
+    return b;
+}
+
+struct WorkPtrs {
+    uint32_t *counts, *totals, *work, *part_bits;
+    float* part;
+};
+
+static WorkPtrs carve_work(const ModelView& m, const BucketGeom& g, int sm_count, void* base) {
+    const int G = 2 * sm_count;
+    const size_t nbl = (size_t)1 << g.LB;
+    unsigned char* p = static_cast<unsigned char*>(base);
+    WorkPtrs w;
+    w.counts = reinterpret_cast<uint32_t*>(p);
+    p += al256(sizeof(uint32_t) * (size_t)G * g.NB);
+    w.totals = reinterpret_cast<uint32_t*>(p);
+    p += al256(sizeof(uint32_t) * (size_t)g.NB);
+    w.work = reinterpret_cast<uint32_t*>(p);
+    p += al256(sizeof(uint32_t) * (size_t)(g.NB + 1));
+    w.part = reinterpret_cast<float*>(p);
+    p += al256(sizeof(float) * (size_t)g.max_items * nbl * (m.kp + 4));
+    w.part_bits = reinterpret_cast<uint32_t*>(p);
+    return w;
+}
+
+static size_t scatter_smem(int hb, bool has_val) {
+    const size_t nb = (size_t)1 << hb;
+    return (size_t)SC_TILE * 4 * (has_val ? 2 : 1) + (size_t)SC_TILE * 2 + (size_t)SC_WARPS * nb * 2 +
+           nb * 4 + nb * 2 + (size_t)SC_WARPS * nb + 64;
+}
+
+cudaError_t bucket_transpose(const ModelView& m, const BatchView& b, const BucketGeom& g,
+                             const uint32_t* keys, const uint2* pay, int implicit_div, void* work,
+                             void* tables, uint32_t* packed, uint32_t* vals, int sm_count,
+                             cudaStream_t st, int64_t* launches) {
+    const WorkPtrs w = carve_work(m, g, sm_count, work);
+    const TablePtrs tp = carve_tables(g, tables);
+    uint32_t* bucket_off = tp.bucket_off;
+    const int G = 2 * sm_count;
+    const bool has_val = b.val != nullptr;
+    const int mm = b.uniform_m >= 0 ? b.uniform_m : 0;
+    const int64_t* optr = b.uniform_m >= 0 && !b.out_ptr ? nullptr : b.out_ptr;
+    if (!optr && b.uniform_m < 0) return cudaErrorInvalidValue;
+    bkt_count_kernel<<<G, 512, sizeof(uint32_t) * g.NB, st>>>(keys, (int)b.n_rows, mm, optr,
+                                                               b.out_base, g.LB, g.NB, w.counts);
+    bkt_offsets_kernel<<<(g.NB + 31) / 32, 1024, 0, st>>>(w.counts, G, g.NB, w.totals);
+    bkt_plan_kernel<<<1, 1024, 0, st>>>(w.totals, g.NB, bucket_off, tp.item_start, tp.item_bucket);
+    const size_t smem = scatter_smem(g.HB, has_val);
+    const unsigned long long magic =
+        implicit_div ? ((1ULL << 40) + (unsigned long long)implicit_div - 1) / (unsigned long long)implicit_div : 0ULL;
+    cudaError_t e;
+#define SC_LAUNCH(PM)                                                                           \
+    e = cudaFuncSetAttribute(bkt_scatter_kernel<PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int)smem);                                                        \
+    if (e != cudaSuccess) return e;                                                             \
+    bkt_scatter_kernel<PM><<<G, SC_THREADS, smem, st>>>(                                        \
+        keys, reinterpret_cast<const uint32_t*>(pay), pay, packed, vals, (int)b.n_rows, mm, optr, \
+        b.out_base, g.LB, g.HB, w.counts, bucket_off, magic)
+    if (has_val) {
+        SC_LAUNCH(2);
+    } else if (implicit_div) {
+        SC_LAUNCH(0);
+    } else {
+        SC_LAUNCH(1);
+    }
+#undef SC_LAUNCH
+    *launches += 4;
+    return cudaGetLastError();
+}
+
+template <int LPR>
+static size_t pull_smem(int lb, bool binary) {
+    using C = Pl<LPR>;
+    const size_t nbl = (size_t)1 << lb;
+    return nbl * LPR * 16 + (size_t)C::G * LPR * 16 + (size_t)C::G * 8 + (size_t)C::G * 4 + nbl * 4 * 2 +
+           (size_t)C::TILE_PAD * 4 * (binary ? 1 : 2) + nbl * 4 + (nbl + (nbl & 1)) * 2 +
+           (size_t)PL_WARPS * nbl * 2 + (size_t)PL_WARPS * nbl + 64;
+}
+
+template <int LPR>
+static cudaError_t pull_dispatch2(const ModelView& m, const BucketGeom& g, const PullArgs& a,
+                                  bool binary, bool fused, int sm_count, cudaStream_t st) {
+    const size_t smem = pull_smem<LPR>(g.LB, binary);
+    cudaError_t e;
+#define PL_LAUNCH(B, F)                                                                          \
+    e = cudaFuncSetAttribute(bkt_pull_kernel<LPR, B, F>,                                         \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+    if (e != cudaSuccess) return e;                                                              \
+    bkt_pull_kernel<LPR, B, F><<<2 * sm_count, PL_THREADS, smem, st>>>(a)
+    if (binary) {
+        if (fused) { PL_LAUNCH(true, true); } else { PL_LAUNCH(true, false); }
+    } else {
+        if (fused) { PL_LAUNCH(false, true); } else { PL_LAUNCH(false, false); }
+    }
+#undef PL_LAUNCH
+    return cudaGetLastError();
+}
+
+cudaError_t bucket_pull(const ModelView& m, const BucketGeom& g, const uint32_t* packed,
+                        const uint32_t* vals, const void* tables, void* work, const float* S,
+                        const float* mult, const double* d_scal, const int32_t* d_err,
+                        UpdateParams up, bool fused, float* grad, int sm_count, cudaStream_t st,
+                        int64_t* launches) {
+    const WorkPtrs w = carve_work(m, g, sm_count, work);
+    cudaError_t e = cudaMemsetAsync(w.work, 0, sizeof(uint32_t) * (size_t)(g.NB + 1), st);
+    if (e != cudaSuccess) return e;
+    PullArgs a;
+    a.packed = packed;
+    a.vals = vals;
+    const TablePtrs tp = carve_tables(g, tables);
+    a.bucket_off = tp.bucket_off;
+    a.item_start = tp.item_start;
+    a.item_bucket = tp.item_bucket;
+    a.work = w.work;
+    a.part = w.part;
+    a.part_bits = w.part_bits;
+    a.S4 = reinterpret_cast<const float4*>(S);
+    a.mult = mult;
+    a.V4 = reinterpret_cast<float4*>(m.v);
+    a.W = m.w;
+    a.W0 = m.w0;
+    a.G4 = reinterpret_cast<float4*>(grad);
+    a.Gw = grad ? grad + m.n_slots * m.kp : nullptr;
+    a.Gw0 = grad ? a.Gw + m.n_slots : nullptr;
+    a.d_scal = d_scal;
+    a.err = d_err;
+    a.n_slots = m.n_slots;
+    a.NB = g.NB;
+    a.LB = g.LB;
+    a.k0 = m.k0;
+    a.k1 = m.k1;
+    a.up = up;
+    const bool binary = vals == nullptr;
+    *launches += 1;
+    switch (m.lpr) {
+        case 1: return pull_dispatch2<1>(m, g, a, binary, fused, sm_count, st);
+        case 2: return pull_dispatch2<2>(m, g, a, binary, fused, sm_count, st);
+        case 4: return pull_dispatch2<4>(m, g, a, binary, fused, sm_count, st);
+        case 8: return pull_dispatch2<8>(m, g, a, binary, fused, sm_count, st);
+        case 16: return pull_dispatch2<16>(m, g, a, binary, fused, sm_count, st);
+        case 32: return pull_dispatch2<32>(m, g, a, binary, fused, sm_count, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace sfm

@@ -43,11 +43,21 @@ struct Stage {
 // Resident transposition of one fixed mini-batch (PARTITION sampler / full batch): the batch's
 // entries sorted by (feature, batch position), built at first use -- the analogue of the
 // reference's cached `transposeInput` (DataSet.scala:48).
+// Bucket form of the transposition (sfm_bucket.cu): feature id = bucket (top HB bits) | local id
+// (low LB bits); NB = 2^HB buckets; a bucket is reduced in work items of <= 32768 entries.
+struct BucketGeom {
+    int LB = 0, HB = 0, NB = 0;
+    int64_t max_items = 0;
+};
+
 struct PartCache {
     bool built = false;
     int64_t n_rows = 0, nnz = 0;
     int key_bits = 0, blk_shift = 30, n_blocks = 1;
     Buf row_ids, keys, pay;
+    bool bucket = false;        // keys = packed entries grouped by bucket, pay = x bits (or unused)
+    BucketGeom geom;
+    Buf tables;                 // bucket_off | item_start
     int n_slices = 0;           // multi-GPU overlap: sorted position where each feature slice starts
     int32_t slice_pos[16] = {0};
 };
@@ -118,7 +128,7 @@ struct sfm_handle {
     sfm::Dataset ds;
     // batch scratch (all growable)
     sfm::Buf b_row_ids, b_out_ptr, b_S, b_mult, b_loss, b_yhat, b_keys[2], b_pay[2], b_seg,
-        b_sort_tmp, b_grad, b_partials, b_sel_tmp, b_lens, b_pull;
+        b_sort_tmp, b_grad, b_partials, b_sel_tmp, b_lens, b_pull, b_bkt_work, b_bkt_tables;
     sfm::Stage stage[3];
     std::vector<sfm::PartCache> parts;  // PARTITION sampler caches (size P)
     sfm::PartCache pre[2];              // Bernoulli sampler: transposition built one step ahead
@@ -153,6 +163,19 @@ struct sfm_handle {
 };
 
 namespace sfm {
+
+// ---- experiment knobs: environment variables, read when a handle is created
+// (never inside a launch path)
+struct Knobs {
+    bool bucket = true;        // SFM_BUCKET=0: two-pass global sort + chunked reduce instead of sfm_bucket.cu
+    bool sort_cub = false;     // SFM_SORT=cub: library radix sort (implies !bucket)
+    bool no_fastpath = false;  // SFM_NO_FASTPATH: generic forward kernel only
+    int pull_block_mb = 0;     // SFM_PULL_BLOCK_MB
+    int ar_slices = 1;         // SFM_AR_SLICES
+    int sort_ahead = 0;        // SFM_SORT_AHEAD
+};
+const Knobs& knobs();
+void knobs_refresh();
 
 // ---- helpers (sfm_api.cu)
 int set_err(sfm_handle* h, int code, const std::string& msg);
@@ -238,6 +261,26 @@ cudaError_t launch_synth_ctr(int64_t n_rows, int64_t row_off, int n_fields,
                              const int64_t* d_cdf_off, uint64_t seed, int64_t n_slots,
                              int32_t* idx, float* label, int64_t* row_ptr, cudaStream_t st,
                              int64_t* launches);
+
+// ---- bucket-form transposition + reduce (sfm_bucket.cu)
+// false: not applicable (SFM_BUCKET=0 / SFM_SORT=cub, more than 2^11 buckets needed, batch too large)
+bool bucket_geometry(const ModelView& m, int key_bits, int64_t n_rows, int64_t nnz, BucketGeom* g);
+size_t bucket_tables_bytes(const BucketGeom& g);
+size_t bucket_work_bytes(const ModelView& m, const BucketGeom& g, int sm_count);
+// entries (keys[i], payload) in row order -> packed (local id << (32-LB) | batch row) grouped by
+// bucket, rows ascending inside a bucket (+ vals: x bits, non-binary data); fills `tables`.
+// pay: nullptr with implicit_div = m (batch row of entry i = i / m), uint32 rows (binary data) or
+// uint2 {row, x bits}.
+cudaError_t bucket_transpose(const ModelView& m, const BatchView& b, const BucketGeom& g,
+                             const uint32_t* keys, const uint2* pay, int implicit_div, void* work,
+                             void* tables, uint32_t* packed, uint32_t* vals, int sm_count,
+                             cudaStream_t st, int64_t* launches);
+// reduce-by-feature over the bucketed entries + SGD update (fused) or dense gradient
+cudaError_t bucket_pull(const ModelView& m, const BucketGeom& g, const uint32_t* packed,
+                        const uint32_t* vals, const void* tables, void* work, const float* S,
+                        const float* mult, const double* d_scal, const int32_t* d_err,
+                        UpdateParams up, bool fused, float* grad, int sm_count, cudaStream_t st,
+                        int64_t* launches);
 
 // ---- CUB wrappers (sfm_sort.cu)
 size_t sort_pairs_temp_bytes(int64_t n, int end_bit);

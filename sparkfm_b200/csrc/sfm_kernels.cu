@@ -433,7 +433,7 @@ static cudaError_t forward_dispatch(const ModelView& m, const BatchView& b, cons
     const dim3 g((unsigned)blocks), t(256);
     const bool un = b.uniform_m >= 0;
     if (LPR == 4 && un && !b.val && b.validated && b.uniform_m <= 64 && b.n_rows < (1 << 26) &&
-        !getenv("SFM_NO_FASTPATH")) {
+        !knobs().no_fastpath) {
         if (train)
             fm_forward_onehot16_kernel<true><<<g, t, 0, st>>>(
                 (const float4*)m.v, m.w, m.w0, (int)m.n_slots, m.k0, m.k1, m.task, b.idx, b.label,
@@ -955,11 +955,7 @@ static int64_t pull_chunks_for(int64_t nnz) {
 // S rows fit in ~16 MB (so a block stays L2 resident while the reduce sweeps it); the number of
 // blocks is capped so that the per-(block, feature) records stay within ~2 GB.
 void pull_plan(const ModelView& m, int64_t n_rows, int* blk_shift, int* n_blocks) {
-    static int block_mb = -1;  // SFM_PULL_BLOCK_MB: S bytes per row block (0 = no blocking)
-    if (block_mb < 0) {
-        const char* e = getenv("SFM_PULL_BLOCK_MB");
-        block_mb = e ? atoi(e) : 0;  // measured on C3: blocking does not pay (profiles/)
-    }
+    const int block_mb = knobs().pull_block_mb;  // measured on C3: blocking does not pay (profiles/)
     if (block_mb <= 0) {
         *blk_shift = 30;
         *n_blocks = 1;

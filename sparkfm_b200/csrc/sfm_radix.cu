@@ -265,8 +265,7 @@ static void rx_plan(int end_bit, int* passes, int bits[4]) {
 }
 
 bool radix_usable(int64_t n, int end_bit) {
-    const char* e = getenv("SFM_SORT");
-    if (e && e[0] == 'c') return false;   // "cub"
+    if (knobs().sort_cub) return false;
     return n > 0 && n < 2000000000LL && end_bit >= 1 && end_bit <= 3 * RX_MAX_BITS;
 }
 
