@@ -27,6 +27,7 @@ void knobs_refresh() {
     if ((e = getenv("SFM_PULL_BLOCK_MB"))) k.pull_block_mb = atoi(e);
     if ((e = getenv("SFM_AR_SLICES"))) k.ar_slices = atoi(e) < 1 ? 1 : (atoi(e) > 8 ? 8 : atoi(e));
     if ((e = getenv("SFM_SORT_AHEAD"))) k.sort_ahead = atoi(e);
+    if ((e = getenv("SFM_BUCKET_CACHE")) && e[0] == '1') k.bucket_cache = true;
     g_knobs = k;
 }
 
@@ -639,7 +640,9 @@ static int partition_batch(sfm_handle* h, int64_t iter, BatchView* b, const Part
             RC(ensure(h, pc.keys, sizeof(uint32_t) * cnt));
             RC(ensure(h, pc.pay, pay_sz * cnt));
         }
-        pc.bucket = !is_sharded(h) && pc.n_blocks == 1 &&
+        // a cached batch is sorted ONCE, so the fully sorted form + the chunked reduce (no ranking
+        // in the steady state) is the faster steady state; SFM_BUCKET_CACHE=1 caches the bucket form
+        pc.bucket = knobs().bucket_cache && !is_sharded(h) && pc.n_blocks == 1 &&
                     bucket_geometry(h->m, pc.key_bits, n, v.nnz, &pc.geom);
         if (pc.bucket) {   // entries grouped by bucket once; the reduce ranks them per tile
             CU(launch_emit(v, pc.key_bits, pc.blk_shift, h->m.n_slots, (uint32_t*)h->b_keys[0].p,

@@ -37,6 +37,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "sfm_common.h"
 
 namespace sfm {
@@ -49,14 +51,36 @@ constexpr int SC_THREADS = 256;              // scatter: 8 warps x 32 entries pe
 constexpr int SC_WARPS = SC_THREADS / 32;
 constexpr int SC_IPT = 32;
 constexpr int SC_TILE = SC_THREADS * SC_IPT;   // 8192
-constexpr int PL_THREADS = 512;              // pull: 16 warps x 8 entries per thread
+#ifndef BK_PL_THREADS
+#define BK_PL_THREADS 512
+#endif
+#ifndef BK_PL_IPT
+#define BK_PL_IPT 8
+#endif
+constexpr int PL_THREADS = BK_PL_THREADS;    // pull: 16 warps x 8 entries per thread
 constexpr int PL_WARPS = PL_THREADS / 32;
-constexpr int PL_IPT = 8;
+constexpr int PL_IPT = BK_PL_IPT;
+constexpr int PL_CTAS_PER_SM = 1024 / PL_THREADS;
 constexpr int PL_TILE = PL_THREADS * PL_IPT;   // 4096
 constexpr int PL_ITEM_TILES = 8;
 constexpr int PL_ITEM = PL_TILE * PL_ITEM_TILES;   // 32768 entries per work item
 constexpr int PL_U = 4;                      // S-row gathers in flight per lane
 constexpr uint32_t NO_DIGIT = 0xFFFFFFFFu;
+#ifndef BK_STAGE_MULT
+#define BK_STAGE_MULT 0   // all-ones data: mult_r staged in shared memory with the entries (else gathered in the walk)
+#endif
+#ifndef BK_LDCG
+#define BK_LDCG 1         // S-row gathers bypass L1 (ld.global.cg): no L1 line is allocated per gather
+#endif
+constexpr bool STAGE_MULT = BK_STAGE_MULT != 0;
+
+__device__ __forceinline__ float4 ld_gather4(const float4* p) {
+#if BK_LDCG
+    return __ldcg(p);
+#else
+    return __ldg(p);
+#endif
+}
 
 __device__ __forceinline__ int64_t ent_of(const int64_t* __restrict__ out_ptr, int64_t out_base,
                                           int m, int64_t row) {
@@ -393,10 +417,19 @@ template <int LPR>
 struct Pl {
     static constexpr int G = PL_THREADS / LPR;      // lane groups per CTA
     static constexpr int SUB = PL_TILE / G;         // consecutive sorted entries per group (8*LPR)
-    static constexpr int SUBSHIFT = LPR == 1 ? 3 : LPR == 2 ? 4 : LPR == 4 ? 5 : LPR == 8 ? 6 : LPR == 16 ? 7 : 8;
+    static constexpr int SUBSHIFT = SUB == 4 ? 2 : SUB == 8 ? 3 : SUB == 16 ? 4 : SUB == 32 ? 5 : SUB == 64 ? 6 : SUB == 128 ? 7 : SUB == 256 ? 8 : 9;
+    static_assert((1 << SUBSHIFT) == SUB, "SUB must be a power of two in [4, 512]");
     static constexpr int TILE_PAD = PL_TILE + G;    // phys(q) = q + (q >> SUBSHIFT)
     static constexpr int REC = LPR * 4 + 4;         // [A (kp) | D | C | 0 | 0]
 };
+
+template <int LPR>
+__host__ __device__ constexpr size_t pull_union_bytes(int lb) {
+    const size_t nbl = (size_t)1 << lb;
+    const size_t heads = (size_t)Pl<LPR>::G * LPR * 16 + (size_t)Pl<LPR>::G * 8 + (size_t)Pl<LPR>::G * 4;
+    const size_t rank = (size_t)PL_WARPS * nbl + (nbl + (nbl & 1)) * 2;
+    return ((heads > rank ? heads : rank) + 15) / 16 * 16;
+}
 
 struct PullArgs {
     const uint32_t* packed;
@@ -423,7 +456,7 @@ struct PullArgs {
 };
 
 template <int LPR, bool BINARY, bool FUSED>
-__global__ void __launch_bounds__(PL_THREADS, 2)
+__global__ void __launch_bounds__(PL_THREADS, PL_CTAS_PER_SM)
 bkt_pull_kernel(const PullArgs a) {
     using C = Pl<LPR>;
     constexpr int G = C::G, SUB = C::SUB, SS = C::SUBSHIFT, REC = C::REC;
@@ -432,17 +465,20 @@ bkt_pull_kernel(const PullArgs a) {
     const uint32_t rowmask = RB >= 32 ? 0xffffffffu : (1u << RB) - 1u;
     // shared-memory carve-up (pull_smem() mirrors it)
     float4* accA = reinterpret_cast<float4*>(pl_smem);                   // [NBL][LPR]
-    float4* headA = accA + (size_t)NBL * LPR;                             // [G][LPR]
+    // union U: {headA, headDC, nxt} (walk phase) / {ltab, lstart} (ranking phase; both are first
+    // written after the tile's first barrier, i.e. after every owner has read the heads)
+    unsigned char* U = reinterpret_cast<unsigned char*>(accA + (size_t)NBL * LPR);
+    float4* headA = reinterpret_cast<float4*>(U);                         // [G][LPR]
     float2* headDC = reinterpret_cast<float2*>(headA + G * LPR);          // [G]
     int* nxt = reinterpret_cast<int*>(headDC + G);                        // [G] level-1 chain links
-    float* accC = reinterpret_cast<float*>(nxt + G);                      // [NBL]
+    uint8_t* ltab0 = U;                                                   // [WARPS][NBL]
+    uint16_t* lstart = reinterpret_cast<uint16_t*>(U + (size_t)PL_WARPS * NBL);   // [NBL]
+    float* accC = reinterpret_cast<float*>(U + pull_union_bytes<LPR>(LB));   // [NBL]
     float* accD = accC + NBL;                                             // [NBL]
     uint32_t* ent_s = reinterpret_cast<uint32_t*>(accD + NBL);            // [TILE_PAD]
-    float* val_s = reinterpret_cast<float*>(ent_s + C::TILE_PAD);         // [TILE_PAD] x (!BINARY)
-    uint32_t* tch = reinterpret_cast<uint32_t*>(val_s + (BINARY ? 0 : C::TILE_PAD));   // [NBL]
-    uint16_t* lstart = reinterpret_cast<uint16_t*>(tch + NBL);            // [NBL]
-    uint16_t* whist = lstart + (NBL + (NBL & 1));                         // [WARPS][NBL]
-    uint8_t* ltab0 = reinterpret_cast<uint8_t*>(whist + PL_WARPS * NBL);  // [WARPS][NBL]
+    float* val_s = reinterpret_cast<float*>(ent_s + C::TILE_PAD);         // [TILE_PAD] mult_r or x
+    uint32_t* tch = reinterpret_cast<uint32_t*>(val_s + ((BINARY && !STAGE_MULT) ? 0 : C::TILE_PAD));   // [NBL]
+    uint16_t* whist = reinterpret_cast<uint16_t*>(tch + NBL);             // [WARPS][NBL]
     __shared__ uint32_t wsum[PL_WARPS];
     __shared__ uint32_t s_item, s_last;
 
@@ -492,6 +528,15 @@ bkt_pull_kernel(const PullArgs a) {
 
         for (uint32_t tb = e_lo; tb < e_hi; tb += PL_TILE) {
             const int n_valid = (int)min((uint32_t)PL_TILE, e_hi - tb);
+            // all-ones data: the rows' multipliers (4 MB array, L2 resident) are fetched while
+            // the tile is ranked and ride along into shared memory
+            float second[PL_IPT];
+#pragma unroll
+            for (int r = 0; r < PL_IPT; ++r) {
+                const int p = strip + r * 32 + lane;
+                second[r] = BINARY ? ((STAGE_MULT && p < n_valid) ? __ldg(a.mult + (ent[r] & rowmask)) : 0.f)
+                                   : xv[r];
+            }
             {   // zero the warp histograms
                 uint32_t* z = reinterpret_cast<uint32_t*>(whist);
                 const int words = PL_WARPS * NBL / 2;
@@ -559,19 +604,18 @@ bkt_pull_kernel(const PullArgs a) {
                     const uint32_t d = LB ? ent[r] >> RB : 0u;
                     const int q = phys((int)lstart[d] + (int)wh[d] + (int)rk[r]);
                     ent_s[q] = ent[r];
-                    if (!BINARY) val_s[q] = xv[r];
+                    if (!BINARY || STAGE_MULT) val_s[q] = second[r];
                 }
             }
             __syncthreads();
             // the next tile's entries travel while this one is walked
             if (tb + PL_TILE < e_hi) load_tile(tb + PL_TILE);
 
-            // ---- level 0: walk my SUB sorted entries
+            // ---- level 0: walk my SUB sorted entries (group g owns sorted positions
+            // [g * SUB, (g + 1) * SUB): physical words g * (SUB + 1) + j)
             const int q0 = g * SUB;
-            auto digit_at = [&](int q) -> uint32_t {
-                if (q < 0 || q >= n_valid) return NO_DIGIT;
-                return LB ? ent_s[phys(q)] >> RB : 0u;
-            };
+            const uint32_t* my_e = ent_s + g * (SUB + 1);
+            const float* my_v = val_s + g * (SUB + 1);
             auto flush = [&](uint32_t d, const float4& A, float D, float Cc) {
                 float4 t = accA[d * LPR + fq];
                 t.x += A.x; t.y += A.y; t.z += A.z; t.w += A.w;
@@ -582,65 +626,73 @@ bkt_pull_kernel(const PullArgs a) {
                     tch[d] = 1u;
                 }
             };
-            uint32_t cur = digit_at(q0);
-            bool cur_is_head = cur != NO_DIGIT && g > 0 && digit_at(q0 - 1) == cur;
+            const bool full = n_valid == PL_TILE;
+            auto dig = [&](uint32_t e) -> uint32_t { return LB ? e >> RB : 0u; };
+            uint32_t cur = (full || q0 < n_valid) ? dig(my_e[0]) : NO_DIGIT;
+            bool cur_is_head = cur != NO_DIGIT && g > 0 && dig(my_e[-2]) == cur;
             float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
             float D = 0.f, Cc = 0.f;
+            auto walk = [&](auto full_tag) {
+                constexpr bool FULLT = decltype(full_tag)::value;
 #pragma unroll 1
-            for (int base = 0; base < SUB; base += PL_U) {
-                uint32_t dd[PL_U];
-                float cc[PL_U], xx[PL_U];
-                float4 sv[PL_U];
+                for (int base = 0; base < SUB; base += PL_U) {
+                    uint32_t dd[PL_U];
+                    float cc[PL_U], xx[PL_U];
+                    float4 sv[PL_U];
 #pragma unroll
-                for (int u = 0; u < PL_U; ++u) {
-                    const int q = q0 + base + u;
-                    const bool ok = q < n_valid;
-                    const uint32_t e = ok ? ent_s[phys(q)] : 0u;
-                    const uint32_t row = e & rowmask;
-                    dd[u] = ok ? (LB ? e >> RB : 0u) : NO_DIGIT;
-                    const float mu = ok ? __ldg(a.mult + row) : 0.f;
-                    if (BINARY) {
-                        cc[u] = mu;
-                        xx[u] = 1.f;
-                    } else {
-                        xx[u] = ok ? val_s[phys(q)] : 0.f;
-                        cc[u] = mu * xx[u];
-                    }
-                    sv[u] = ok ? __ldg(a.S4 + ((size_t)row * LPR + fq)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int u = 0; u < PL_U; ++u) {
-                    if (dd[u] != cur) {
-                        if (cur != NO_DIGIT) {
-                            if (cur_is_head) {
-                                headA[g * LPR + fq] = A;
-                                if (fq == 0) headDC[g] = make_float2(D, Cc);
-                            } else {
-                                flush(cur, A, D, Cc);
-                            }
+                    for (int u = 0; u < PL_U; ++u) {
+                        const bool ok = FULLT || q0 + base + u < n_valid;
+                        const uint32_t e = ok ? my_e[base + u] : 0u;
+                        const uint32_t row = e & rowmask;
+                        const float sec = (BINARY && !STAGE_MULT) ? (ok ? __ldg(a.mult + row) : 0.f)
+                                                                   : (ok ? my_v[base + u] : 0.f);
+                        dd[u] = ok ? dig(e) : NO_DIGIT;
+                        if (BINARY) {
+                            cc[u] = sec;
+                            xx[u] = 1.f;
+                        } else {
+                            xx[u] = sec;
+                            cc[u] = ok ? __ldg(a.mult + row) * sec : 0.f;
                         }
-                        cur = dd[u];
-                        cur_is_head = false;
-                        A = make_float4(0.f, 0.f, 0.f, 0.f);
-                        D = 0.f;
-                        Cc = 0.f;
+                        // row * LPR + fq < 2^32: checked by the caller (train_core)
+                        sv[u] = ok ? ld_gather4(a.S4 + (uint32_t)(row * (uint32_t)LPR + (uint32_t)fq))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    const float c = dd[u] == NO_DIGIT ? 0.f : cc[u];
-                    A.x = fmaf(c, sv[u].x, A.x);
-                    A.y = fmaf(c, sv[u].y, A.y);
-                    A.z = fmaf(c, sv[u].z, A.z);
-                    A.w = fmaf(c, sv[u].w, A.w);
-                    D = BINARY ? D : fmaf(c, xx[u], D);
-                    Cc += c;
+#pragma unroll
+                    for (int u = 0; u < PL_U; ++u) {
+                        if (dd[u] != cur) {
+                            if (cur != NO_DIGIT) {
+                                if (cur_is_head) {
+                                    headA[g * LPR + fq] = A;
+                                    if (fq == 0) headDC[g] = make_float2(D, Cc);
+                                } else {
+                                    flush(cur, A, D, Cc);
+                                }
+                            }
+                            cur = dd[u];
+                            cur_is_head = false;
+                            A = make_float4(0.f, 0.f, 0.f, 0.f);
+                            D = 0.f;
+                            Cc = 0.f;
+                        }
+                        const float c = cc[u];   // 0 for slots past the end of a partial tile
+                        A.x = fmaf(c, sv[u].x, A.x);
+                        A.y = fmaf(c, sv[u].y, A.y);
+                        A.z = fmaf(c, sv[u].z, A.z);
+                        A.w = fmaf(c, sv[u].w, A.w);
+                        D = BINARY ? D : fmaf(c, xx[u], D);
+                        Cc += c;
+                    }
                 }
-            }
+            };
+            if (full) walk(std::true_type{}); else walk(std::false_type{});
             // ---- level 1: runs that span several groups.  A group whose FIRST run continues
             // the previous group's last one holds a "head" partial; a head that fills its whole
             // group and continues links to the next group's head.  The chains are summed by
             // pointer jumping (fixed tree shape: depends on the run's position only), then the
             // group where the run starts adds the chain that follows it.
             const bool open = cur != NO_DIGIT;
-            const bool continues = open && g < G - 1 && digit_at(q0 + SUB) == cur;
+            const bool continues = open && g < G - 1 && q0 + SUB < n_valid && dig(my_e[SUB + 1]) == cur;
             const bool owner = open && !cur_is_head;
             if (open && cur_is_head) {
                 headA[g * LPR + fq] = A;   // the whole group is a middle / final piece of a run
@@ -897,9 +949,9 @@ template <int LPR>
 static size_t pull_smem(int lb, bool binary) {
     using C = Pl<LPR>;
     const size_t nbl = (size_t)1 << lb;
-    return nbl * LPR * 16 + (size_t)C::G * LPR * 16 + (size_t)C::G * 8 + (size_t)C::G * 4 + nbl * 4 * 2 +
-           (size_t)C::TILE_PAD * 4 * (binary ? 1 : 2) + nbl * 4 + (nbl + (nbl & 1)) * 2 +
-           (size_t)PL_WARPS * nbl * 2 + (size_t)PL_WARPS * nbl + 64;
+    return nbl * LPR * 16 + pull_union_bytes<LPR>(lb) + nbl * 4 * 2 +
+           (size_t)C::TILE_PAD * 4 * ((binary && !STAGE_MULT) ? 1 : 2) + nbl * 4 +
+           (size_t)PL_WARPS * nbl * 2 + 64;
 }
 
 template <int LPR>
@@ -911,7 +963,7 @@ static cudaError_t pull_dispatch2(const ModelView& m, const BucketGeom& g, const
     e = cudaFuncSetAttribute(bkt_pull_kernel<LPR, B, F>,                                         \
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
     if (e != cudaSuccess) return e;                                                              \
-    bkt_pull_kernel<LPR, B, F><<<2 * sm_count, PL_THREADS, smem, st>>>(a)
+    bkt_pull_kernel<LPR, B, F><<<PL_CTAS_PER_SM * sm_count, PL_THREADS, smem, st>>>(a)
     if (binary) {
         if (fused) { PL_LAUNCH(true, true); } else { PL_LAUNCH(true, false); }
     } else {

@@ -173,6 +173,7 @@ struct Knobs {
     int pull_block_mb = 0;     // SFM_PULL_BLOCK_MB
     int ar_slices = 1;         // SFM_AR_SLICES
     int sort_ahead = 0;        // SFM_SORT_AHEAD
+    bool bucket_cache = false; // SFM_BUCKET_CACHE=1: PARTITION caches keep the bucket form
 };
 const Knobs& knobs();
 void knobs_refresh();

@@ -20,7 +20,7 @@ from sparkfm_b200 import Handle, synth
 
 pytestmark = pytest.mark.gpu
 
-KNOBS = ("SFM_SORT", "SFM_BUCKET")
+KNOBS = ("SFM_SORT", "SFM_BUCKET", "SFM_BUCKET_CACHE")
 
 
 def _case(kind, n_slots, k, n_rows, fields, seed):
@@ -101,14 +101,14 @@ def test_bucket_form_matches_sorted_form_and_is_reproducible(kind, n_slots, k, n
     assert la[-1][0] < la[0][0]
 
 
-@pytest.mark.parametrize("env", [{}, {"SFM_BUCKET": "0"}])
+@pytest.mark.parametrize("env", [{"SFM_BUCKET_CACHE": "1"}, {}])
 def test_partition_cache_path(env):
     """The cached transposition of the PARTITION sampler: bucket form (entries grouped by bucket
     once, ranked per tile every step) and sorted form, against the library sort."""
     data = _case("onehot", 200_000, 16, 50_000, 20, seed=5)
     la, ma = _run(env, 200_000, 16, data, 0.25, iters=6, mode=1)
     lb, mb = _run({"SFM_SORT": "cub"}, 200_000, 16, data, 0.25, iters=6, mode=1)
-    if env:
+    if not env:   # default: cached batches keep the fully sorted form (own radix sort)
         assert la == lb and np.array_equal(ma[2], mb[2]) and np.array_equal(ma[1], mb[1])
     else:
         for (x, bx), (y, by) in zip(la, lb):
