@@ -67,6 +67,20 @@ def lib():
         L.fmo_als_sweep.restype = C.c_double
         L.fmo_als_sweep.argtypes = [pp, dp, dp, dp, lp, ip, dp, dp, C.c_int64, C.c_int32, dp]
         L.fmo_max_threads.restype = C.c_int
+        fp = C.POINTER(C.c_float)
+        L.fmo_train_step_faithful_mt.restype = C.c_double
+        L.fmo_train_step_faithful_mt.argtypes = L.fmo_train_step_mt.argtypes
+        L.fmo_fast32_create.restype = C.c_void_p
+        L.fmo_fast32_create.argtypes = [pp, C.c_int]
+        L.fmo_fast32_destroy.restype = None
+        L.fmo_fast32_destroy.argtypes = [C.c_void_p]
+        L.fmo_fast32_set_model.restype = None
+        L.fmo_fast32_set_model.argtypes = [C.c_void_p, C.c_double, dp, dp]
+        L.fmo_fast32_get_model.restype = None
+        L.fmo_fast32_get_model.argtypes = [C.c_void_p, dp, dp, dp]
+        L.fmo_fast32_train_step.restype = C.c_double
+        L.fmo_fast32_train_step.argtypes = [C.c_void_p, lp, ip, fp, fp, lp, C.c_int64, C.c_int64,
+                                            C.c_double, C.c_int64]
         _lib = L
     return _lib
 
@@ -130,13 +144,22 @@ class OracleFM:
         return g[:nk].reshape(self.n_slots, self.k), g[nk:nk + self.n_slots], g[-1], loss
 
     def train_step(self, row_ptr, idx, val, label, row_ids, it, step_size, batch_count=None,
-                   threads=1):
-        """Returns the loss SUM over row_ids; updates the model in place."""
+                   threads=1, faithful=False):
+        """Returns the loss SUM over row_ids; updates the model in place.  faithful: the
+        baseline variant whose forward makes k passes over the row (FMModel.scala:48-51)."""
         row_ptr, idx, val = _c(row_ptr, np.int64), _c(idx, np.int32), _c(val, np.float64)
         label, row_ids = _c(label, np.float64), _c(row_ids, np.int64)
         if batch_count is None:
             batch_count = len(row_ids)
         glen = self.n_slots * (self.k + 1) + 1
+        if faithful:
+            threads = max(threads, 1)
+            if self._scratch is None or self._scratch.size < threads * glen:
+                self._scratch = np.empty(threads * glen, dtype=np.float64)
+            return lib().fmo_train_step_faithful_mt(
+                C.byref(self.p), C.byref(self.w0), _d(self.w), _d(self.v), _l(row_ptr), _i(idx),
+                _d(val), _d(label), _l(row_ids), len(row_ids), it, step_size, batch_count,
+                _d(self._scratch), threads)
         if threads <= 1:
             if self._grad is None:
                 self._grad = np.empty(glen, dtype=np.float64)
@@ -164,6 +187,42 @@ class OracleFM:
         if rmse < 0:
             raise ValueError("fmo_als_sweep: a row stores the same feature twice (or out of memory)")
         return rmse, e[:n]
+
+
+class OracleFast32:
+    """Tuned CPU baseline (fp32, single pass, touched-only reduction): bench.py only."""
+
+    def __init__(self, orc: "OracleFM", threads: int):
+        self.h = lib().fmo_fast32_create(C.byref(orc.p), threads)
+        if not self.h:
+            raise MemoryError("fmo_fast32_create")
+        self.orc = orc
+        lib().fmo_fast32_set_model(self.h, orc.w0.value, _d(orc.w), _d(orc.v))
+
+    def train_step(self, row_ptr, idx, val, label, row_ids, it, step_size, batch_count=None):
+        row_ptr, idx = _c(row_ptr, np.int64), _c(idx, np.int32)
+        label, row_ids = _c(label, np.float32), _c(row_ids, np.int64)
+        fp = C.POINTER(C.c_float)
+        vp = None if val is None else _c(val, np.float32).ctypes.data_as(fp)
+        self._keep = (row_ptr, idx, label, row_ids, val)
+        if batch_count is None:
+            batch_count = len(row_ids)
+        return lib().fmo_fast32_train_step(self.h, _l(row_ptr), _i(idx), vp,
+                                           label.ctypes.data_as(fp), _l(row_ids), len(row_ids),
+                                           it, step_size, batch_count)
+
+    def get_model(self):
+        n, k = self.orc.n_slots, self.orc.k
+        w0 = C.c_double(0)
+        w = np.empty(n, np.float64)
+        v = np.empty((n, max(k, 1)), np.float64)
+        lib().fmo_fast32_get_model(self.h, C.byref(w0), _d(w), _d(v))
+        return w0.value, w, v[:, :k]
+
+    def close(self):
+        if self.h:
+            lib().fmo_fast32_destroy(self.h)
+            self.h = None
 
 
 def sample_rows(seed, it, fraction, row_lo, row_hi):

@@ -247,6 +247,260 @@ double fmo_train_step_mt(const fmo_params* p, double* w0, double* w, double* v,
     return loss_sum;
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * CPU baseline variants.  Both are timed by bench.py; neither is used as
+ * a checker.
+ *   (i)  fmo_train_step_faithful_mt: fp64, the forward of every row makes k passes over the row's
+ *        stored entries exactly as FMModel.scala:48-51 does (computeFactorComponents per factor);
+ *        gradient / reduction / update as fmo_train_step_mt.
+ *   (ii) fmo_fast32_*: single pass per row, fp32 parameters and gradients, per-thread gradient
+ *        rows zeroed and reduced only where touched (iteration stamps), dense decay pass only when
+ *        a regulariser is non-zero: what a tuned CPU implementation of the same spec looks like.
+ * ------------------------------------------------------------------------------------------- */
+double fmo_train_step_faithful_mt(const fmo_params* p, double* w0, double* w, double* v,
+                                  const int64_t* row_ptr, const int32_t* idx, const double* val,
+                                  const double* label, const int64_t* row_ids, int64_t n_ids,
+                                  int64_t iter, double step_size, int64_t batch_count,
+                                  double* scratch, int n_threads) {
+    if (n_threads < 1) n_threads = 1;
+    const int32_t k = p->k;
+    const int64_t n = p->n_slots;
+    const int64_t len = n * (k + 1) + 1;
+    double* losses = (double*)calloc((size_t)n_threads, sizeof(double));
+    const double w0v = *w0;
+#pragma omp parallel num_threads(n_threads)
+    {
+#ifdef _OPENMP
+        const int t = omp_get_thread_num();
+#else
+        const int t = 0;
+#endif
+        double* g = scratch + (int64_t)t * len;
+        memset(g, 0, sizeof(double) * (size_t)len);
+        double* s = (double*)malloc(sizeof(double) * (size_t)(k > 0 ? k : 1));
+        const int64_t lo = n_ids * t / n_threads, hi = n_ids * (t + 1) / n_threads;
+        double ls = 0.0;
+        for (int64_t u = lo; u < hi; ++u) {
+            const int64_t r = row_ids ? row_ids[u] : u;
+            const int64_t b = row_ptr[r], nnz = row_ptr[r + 1] - b;
+            const int32_t* ri = idx + b;
+            const double* rv = val + b;
+            /* FMModel.predict, k passes (FMModel.scala:34-55) */
+            double yhat = p->k0 ? w0v : 0.0;
+            if (nnz > 0) {
+                if (p->k1) {
+                    double lin = w[ri[0]] * rv[0];
+                    for (int64_t j = 1; j < nnz; ++j) lin = lin + w[ri[j]] * rv[j];
+                    yhat += lin;
+                }
+                for (int32_t f = 0; f < k; ++f) {
+                    double sf, qf;
+                    factor_components(v, k, f, ri, rv, nnz, &sf, &qf);
+                    s[f] = sf;
+                    yhat += 0.5 * (sf * sf - qf);
+                }
+            } else {
+                for (int32_t f = 0; f < k; ++f) s[f] = 0.0;
+            }
+            double loss, mult;
+            fmo_loss_mult(p->task, yhat, label[r], &loss, &mult);
+            ls += loss;
+            if (p->k0) g[n * k + n] += mult;
+            for (int64_t j = 0; j < nnz; ++j) {
+                const int64_t i = ri[j];
+                const double x = rv[j];
+                if (p->k1) g[n * k + i] += x * mult;
+                const double* vi = v + i * k;
+                double* gi = g + i * k;
+                for (int32_t f = 0; f < k; ++f) gi[f] += (x * s[f] - vi[f] * x * x) * mult;
+            }
+        }
+        losses[t] = ls;
+        free(s);
+#pragma omp barrier
+        if (batch_count > 0) {
+            const double eta = step_size / sqrt((double)iter);
+            const double inv = 1.0 / (double)batch_count;
+#pragma omp for schedule(static)
+            for (int64_t e = 0; e < len; ++e) {
+                double acc = scratch[e];
+                for (int u = 1; u < n_threads; ++u) acc += scratch[(int64_t)u * len + e];
+                if (e < n * k) v[e] -= eta * (acc * inv + p->regv * v[e]);
+                else if (e < n * k + n) {
+                    if (p->k1) w[e - n * k] -= eta * (acc * inv + p->regw * w[e - n * k]);
+                } else if (p->k0) *w0 -= eta * (acc * inv + p->reg0 * *w0);
+            }
+        }
+    }
+    double loss_sum = 0.0;
+    for (int t = 0; t < n_threads; ++t) loss_sum += losses[t];
+    free(losses);
+    return loss_sum;
+}
+
+struct fmo_fast32 {
+    fmo_params p;
+    int n_threads;
+    float w0;
+    float* w;          /* [n_slots] */
+    float* v;          /* [n_slots][k] */
+    float** g;         /* per thread: [n_slots][k+1] (V row | w) */
+    uint32_t** stamp;  /* per thread: [n_slots] iteration stamp of the last touch */
+    double* loss;      /* per thread */
+    double* gw0;       /* per thread */
+    uint32_t tick;
+};
+
+fmo_fast32* fmo_fast32_create(const fmo_params* p, int n_threads) {
+    if (n_threads < 1) n_threads = 1;
+    fmo_fast32* f = (fmo_fast32*)calloc(1, sizeof(fmo_fast32));
+    if (!f) return NULL;
+    f->p = *p;
+    f->n_threads = n_threads;
+    const size_t n = (size_t)p->n_slots, k = (size_t)p->k;
+    f->w = (float*)calloc(n, sizeof(float));
+    f->v = (float*)calloc(n * (k > 0 ? k : 1), sizeof(float));
+    f->g = (float**)calloc((size_t)n_threads, sizeof(float*));
+    f->stamp = (uint32_t**)calloc((size_t)n_threads, sizeof(uint32_t*));
+    f->loss = (double*)calloc((size_t)n_threads, sizeof(double));
+    f->gw0 = (double*)calloc((size_t)n_threads, sizeof(double));
+    for (int t = 0; t < n_threads; ++t) {
+        f->g[t] = (float*)malloc(sizeof(float) * n * (k + 1));
+        f->stamp[t] = (uint32_t*)calloc(n, sizeof(uint32_t));
+    }
+    return f;
+}
+
+void fmo_fast32_destroy(fmo_fast32* f) {
+    if (!f) return;
+    for (int t = 0; t < f->n_threads; ++t) {
+        free(f->g[t]);
+        free(f->stamp[t]);
+    }
+    free(f->g); free(f->stamp); free(f->loss); free(f->gw0); free(f->w); free(f->v);
+    free(f);
+}
+
+void fmo_fast32_set_model(fmo_fast32* f, double w0, const double* w, const double* v) {
+    const int64_t n = f->p.n_slots, k = f->p.k;
+    f->w0 = (float)w0;
+    for (int64_t i = 0; i < n; ++i) f->w[i] = (float)w[i];
+    for (int64_t e = 0; e < n * k; ++e) f->v[e] = (float)v[e];
+}
+
+void fmo_fast32_get_model(const fmo_fast32* f, double* w0, double* w, double* v) {
+    const int64_t n = f->p.n_slots, k = f->p.k;
+    *w0 = f->w0;
+    for (int64_t i = 0; i < n; ++i) w[i] = f->w[i];
+    for (int64_t e = 0; e < n * k; ++e) v[e] = f->v[e];
+}
+
+/* val may be NULL (all ones).  Returns the loss sum. */
+double fmo_fast32_train_step(fmo_fast32* f, const int64_t* row_ptr, const int32_t* idx,
+                             const float* val, const float* label, const int64_t* row_ids,
+                             int64_t n_ids, int64_t iter, double step_size, int64_t batch_count) {
+    const fmo_params* p = &f->p;
+    const int32_t k = p->k;
+    const int64_t n = p->n_slots;
+    const int T = f->n_threads;
+    const uint32_t tick = ++f->tick;
+    const float w0v = f->w0;
+    const float* w = f->w;
+    const float* v = f->v;
+#pragma omp parallel num_threads(T)
+    {
+#ifdef _OPENMP
+        const int t = omp_get_thread_num();
+#else
+        const int t = 0;
+#endif
+        float* g = f->g[t];
+        uint32_t* st = f->stamp[t];
+        float s[128], q[128];
+        const int64_t lo = n_ids * t / T, hi = n_ids * (t + 1) / T;
+        double ls = 0.0, g0 = 0.0;
+        for (int64_t u = lo; u < hi; ++u) {
+            const int64_t r = row_ids ? row_ids[u] : u;
+            const int64_t b = row_ptr[r], nnz = row_ptr[r + 1] - b;
+            const int32_t* ri = idx + b;
+            const float* rv = val ? val + b : NULL;
+            for (int32_t c = 0; c < k; ++c) { s[c] = 0.f; q[c] = 0.f; }
+            float lin = 0.f;
+            for (int64_t j = 0; j < nnz; ++j) {
+                const float x = rv ? rv[j] : 1.f;
+                const float* vi = v + (int64_t)ri[j] * k;
+                lin += w[ri[j]] * x;
+                for (int32_t c = 0; c < k; ++c) {
+                    const float a = vi[c] * x;
+                    s[c] += a;
+                    q[c] += a * a;
+                }
+            }
+            float yhat = p->k0 ? w0v : 0.f;
+            if (nnz > 0) {
+                if (p->k1) yhat += lin;
+                float pair = 0.f;
+                for (int32_t c = 0; c < k; ++c) pair += s[c] * s[c] - q[c];
+                yhat += 0.5f * pair;
+            }
+            double loss, mult;
+            fmo_loss_mult(p->task, (double)yhat, (double)label[r], &loss, &mult);
+            ls += loss;
+            g0 += mult;
+            const float mu = (float)mult;
+            for (int64_t j = 0; j < nnz; ++j) {
+                const int64_t i = ri[j];
+                const float x = rv ? rv[j] : 1.f;
+                float* gi = g + i * (k + 1);
+                if (st[i] != tick) {   /* first touch in this iteration: clear the row */
+                    st[i] = tick;
+                    for (int32_t c = 0; c <= k; ++c) gi[c] = 0.f;
+                }
+                const float* vi = v + i * k;
+                const float xm = x * mu, xxm = x * x * mu;
+                for (int32_t c = 0; c < k; ++c) gi[c] += xm * s[c] - vi[c] * xxm;
+                gi[k] += xm;
+            }
+        }
+        f->loss[t] = ls;
+        f->gw0[t] = g0;
+#pragma omp barrier
+        if (batch_count > 0) {
+            const float eta = (float)(step_size / sqrt((double)iter));
+            const float inv = (float)(1.0 / (double)batch_count);
+            const float rv_ = (float)p->regv, rw_ = (float)p->regw;
+            const int decay = rv_ != 0.f || rw_ != 0.f;
+            float acc[129];
+#pragma omp for schedule(static)
+            for (int64_t i = 0; i < n; ++i) {
+                int touched = 0;
+                for (int u = 0; u < T; ++u) {
+                    if (f->stamp[u][i] == tick) {
+                        const float* gi = f->g[u] + i * (k + 1);
+                        if (!touched) { for (int32_t c = 0; c <= k; ++c) acc[c] = gi[c]; touched = 1; }
+                        else for (int32_t c = 0; c <= k; ++c) acc[c] += gi[c];
+                    }
+                }
+                float* vi = f->v + i * k;
+                if (touched) {
+                    for (int32_t c = 0; c < k; ++c) vi[c] -= eta * (acc[c] * inv + rv_ * vi[c]);
+                    if (p->k1) f->w[i] -= eta * (acc[k] * inv + rw_ * f->w[i]);
+                } else if (decay) {
+                    for (int32_t c = 0; c < k; ++c) vi[c] -= eta * rv_ * vi[c];
+                    if (p->k1) f->w[i] -= eta * rw_ * f->w[i];
+                }
+            }
+        }
+    }
+    double loss_sum = 0.0, g0 = 0.0;
+    for (int t = 0; t < T; ++t) { loss_sum += f->loss[t]; g0 += f->gw0[t]; }
+    if (batch_count > 0 && p->k0) {
+        const float eta = (float)(step_size / sqrt((double)iter));
+        f->w0 -= eta * ((float)(g0 / (double)batch_count) + (float)p->reg0 * f->w0);
+    }
+    return loss_sum;
+}
+
 int64_t fmo_sample_rows(uint64_t seed, int64_t iter, double fraction, int64_t row_lo,
                         int64_t row_hi, int64_t* out) {
     int64_t n = 0;

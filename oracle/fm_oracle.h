@@ -100,6 +100,23 @@ double fmo_train_step_mt(const fmo_params* p, double* w0, double* w, double* v,
                          int64_t iter, double step_size, int64_t batch_count,
                          double* scratch, int n_threads);
 
+/* CPU baseline variants timed by bench.py; never used as checkers.
+ * (i) faithful structure: fp64, k passes over the row per forward (FMModel.scala:48-51). */
+double fmo_train_step_faithful_mt(const fmo_params* p, double* w0, double* w, double* v,
+                                  const int64_t* row_ptr, const int32_t* idx, const double* val,
+                                  const double* label, const int64_t* row_ids, int64_t n_ids,
+                                  int64_t iter, double step_size, int64_t batch_count,
+                                  double* scratch, int n_threads);
+/* (ii) tuned: single pass, fp32 model and gradients, touched-only zeroing / reduction. */
+typedef struct fmo_fast32 fmo_fast32;
+fmo_fast32* fmo_fast32_create(const fmo_params* p, int n_threads);
+void fmo_fast32_destroy(fmo_fast32* f);
+void fmo_fast32_set_model(fmo_fast32* f, double w0, const double* w, const double* v);
+void fmo_fast32_get_model(const fmo_fast32* f, double* w0, double* w, double* v);
+double fmo_fast32_train_step(fmo_fast32* f, const int64_t* row_ptr, const int32_t* idx,
+                             const float* val, const float* label, const int64_t* row_ids,
+                             int64_t n_ids, int64_t iter, double step_size, int64_t batch_count);
+
 /* Mini-batch sampler: row r of the GLOBAL dataset is in iteration
  * iter's batch iff (mix64(mix64(seed + iter) ^ mix64(r)) >> 11) < floor(fraction * 2^53);
  * fraction >= 1 selects every row.  Writes the selected global row ids of [row_lo, row_hi)

@@ -300,3 +300,33 @@ def test_als_known_answers_exact_rational():
             assert np.allclose(got_w, case["w"], rtol=1e-12, atol=1e-13)
             assert np.allclose(got_v, case["v"], rtol=1e-12, atol=1e-13)
             assert np.allclose(got_e, case["e"], rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("task", [0, 1])
+def test_cpu_baseline_variants_agree_with_the_oracle(task):
+    """bench.py times two CPU variants: the faithful k-pass fp64 one must
+    equal the single-pass oracle up to fp64 summation order, the tuned fp32 one within fp32
+    round-off -- so both are baselines of the SAME computation."""
+    from oracle.capi import OracleFast32
+    n_slots, k, n_rows = 400, 6, 900
+    row_ptr, idx, val = synth.ragged_rows(n_rows, n_slots, 9, seed=3, values="normal")
+    rng = np.random.default_rng(5)
+    label = rng.normal(0, 1, n_rows) if task == 0 else np.where(rng.random(n_rows) < 0.4, 1.0, -1.0)
+    w, v = rng.normal(0, 0.1, n_slots), rng.normal(0, 0.1, (n_slots, k))
+    reg = (0.01, 0.02, 0.03)
+    a, b, c = (OracleFM(n_slots, k, task=task, reg=reg) for _ in range(3))
+    for o in (a, b, c):
+        o.set_model(0.05, w, v)
+    fast = OracleFast32(c, threads=3)
+    for it in (1, 2, 3):
+        ids = np.sort(rng.choice(n_rows, 500, replace=False)).astype(np.int64)
+        la = a.train_step(row_ptr, idx, val, label, ids, it, 0.2, threads=2)
+        lb = b.train_step(row_ptr, idx, val, label, ids, it, 0.2, threads=3, faithful=True)
+        lc = fast.train_step(row_ptr, idx, val.astype(np.float32), label.astype(np.float32), ids, it, 0.2)
+        assert abs(la - lb) <= 1e-11 * abs(la)
+        assert abs(la - lc) <= 2e-5 * abs(la)
+    assert np.allclose(a.v, b.v, rtol=0, atol=1e-12) and np.allclose(a.w, b.w, rtol=0, atol=1e-12)
+    w0c, wc, vc = fast.get_model()
+    assert np.allclose(a.v, vc, rtol=0, atol=2e-6) and np.allclose(a.w, wc, rtol=0, atol=2e-6)
+    assert abs(a.w0.value - w0c) <= 2e-6
+    fast.close()
