@@ -357,8 +357,9 @@ def parity_n(args, rank, world, local_rank, torch, dist, card, cdf, off):
     lo, hi = shard_range(rows_total, rank, world)
     out = {"world": world, "rows_total": rows_total, "fraction": frac, "steps": k_steps}
     models, losses = {}, {}
-    for mode, env in (("peer", "1"), ("nccl", "0")):
+    for mode, env, sparse in (("peer", "1", "1"), ("peer_dense", "1", "0"), ("nccl", "0", "1")):
         os.environ["SFM_P2P"] = env
+        os.environ["SFM_P2P_SPARSE"] = sparse
         h = Handle(N_SLOTS, K, task=1, reg=REG, step_size=STEP_SIZE, mini_batch_fraction=frac,
                    sampler_seed=SAMPLER_SEED, device=local_rank)
         h.init_model(0.0, 0.01, INIT_SEED)
@@ -374,7 +375,10 @@ def parity_n(args, rank, world, local_rank, torch, dist, card, cdf, off):
         out[f"{mode}_replicas_bitwise_equal"] = len(set(gathered)) == 1
         h.close()
     os.environ.pop("SFM_P2P", None)
-    (_, wa, va), (_, wb, vb) = models["peer"], models["nccl"]
+    os.environ.pop("SFM_P2P_SPARSE", None)
+    (_, wa, va), (_, wd, vd), (_, wb, vb) = models["peer"], models["peer_dense"], models["nccl"]
+    # sparse (touched rows only) and dense peer-memory exchange add the same values in rank order
+    out["peer_sparse_vs_dense_bitwise"] = bool(np.array_equal(wa, wd) and np.array_equal(va, vd))
     out["peer_vs_nccl_bitwise"] = bool(np.array_equal(wa, wb) and np.array_equal(va, vb))
     out["peer_vs_nccl_max_abs_diff"] = float(max(np.max(np.abs(wa - wb)), np.max(np.abs(va - vb))))
     out["loss_peer"], out["loss_nccl"] = losses["peer"], losses["nccl"]
@@ -392,6 +396,8 @@ def parity_n(args, rank, world, local_rank, torch, dist, card, cdf, off):
         out["loss_oracle"] = ref
         out["loss_rel_err_vs_oracle"] = float(max(abs(a - b) / abs(b) for a, b in zip(losses["peer"], ref)))
         out["ok"] = bool(out["peer_replicas_bitwise_equal"] and out["nccl_replicas_bitwise_equal"] and
+                         out["peer_dense_replicas_bitwise_equal"] and
+                         out["peer_sparse_vs_dense_bitwise"] and
                          out["loss_rel_err_vs_oracle"] <= 1e-4 and
                          (out["peer_vs_nccl_bitwise"] or world > 2) and
                          out["peer_vs_nccl_max_abs_diff"] <= 1e-6)

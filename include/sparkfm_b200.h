@@ -212,6 +212,24 @@ int32_t sfm_stage_csr(sfm_handle* h, int32_t slot, const int64_t* row_ptr, const
                       const float* val, const float* label, int64_t n_rows);
 int32_t sfm_train_step_staged(sfm_handle* h, int32_t slot, int64_t iter, double* mean_loss_out,
                               int64_t* batch_out);
+/* Compact staging for uniform all-ones mini-batches (one-hot CTR rows packed by the host from
+ * RDD[LabeledPoint] whose rows all hold exactly m entries of value 1): no row_ptr, no values,
+ * the n_rows*m feature ids bit-packed at id_bits (1..32) bits each -- entry e occupies bits
+ * [e*id_bits, (e+1)*id_bits) of the little-endian uint32 stream packed_idx, which must hold
+ * (n_rows*m*id_bits + 31)/32 + 1 words (one word of slack) -- and labels either 1 bit per row in
+ * label_bits (bit r%32 of word r/32; set = positive, stored as 1.0f / 0.0f) or fp32 in label_f32
+ * (exactly one of the two non-NULL).  A device kernel unpacks into the same staging slot
+ * sfm_stage_csr fills, checking every id against n_slots (SFM_ERR_INDEX from the step).  Cuts the
+ * host->device bytes of a Criteo-shaped batch (m = 39, 20-bit ids) from 168 to 98 per row.
+ * Consumed by sfm_train_step_staged like any other staged slot. */
+int32_t sfm_stage_onehot(sfm_handle* h, int32_t slot, const uint32_t* packed_idx,
+                         const uint32_t* label_bits, const float* label_f32, int64_t n_rows,
+                         int32_t m, int32_t id_bits);
+/* Host-side packer for sfm_stage_onehot (multi-threaded; no device needed): idx[n_rows*m] ->
+ * packed_idx, label[n_rows] -> label_bits (NULL: skip).  SFM_ERR_INDEX if an id needs more than
+ * id_bits bits or is negative. */
+int32_t sfm_pack_onehot(const int32_t* idx, const float* label, int64_t n_rows, int32_t m,
+                        int32_t id_bits, uint32_t* packed_idx, uint32_t* label_bits);
 /* The loop of FM.learnWith (fm/impl/FactorizationMachines.scala:42-46) with the built-in
  * sampler: iterations first_iter .. first_iter + n_iters - 1 on the resident data set, no host
  * round trip in between.  loss_history[n_iters] (may be NULL) gets each iteration's mean loss. */

@@ -4,9 +4,9 @@ this package is the ctypes binding plus a Python mirror of the reference's opera
 from . import _lib  # noqa: F401
 from .api import (ALS, DataSet, FM, FMLearn, FMModel, FMUtils, FMWithSGD, FactorizationMachines,  # noqa: F401
                   LabeledPoint, Model, SGD, SparseVector, Task)
-from .handle import (Handle, device_count, format_libfm, parse_libfm, partition_rows,  # noqa: F401
-                     sample_rows)
+from .handle import (Handle, device_count, format_libfm, pack_onehot, parse_libfm,  # noqa: F401
+                     partition_rows, sample_rows)
 
 __all__ = ["ALS", "DataSet", "FM", "FMLearn", "FMModel", "FMUtils", "FMWithSGD", "FactorizationMachines",
            "LabeledPoint", "Model", "SGD", "SparseVector", "Task", "Handle", "device_count",
-           "format_libfm", "parse_libfm", "partition_rows", "sample_rows"]
+           "format_libfm", "pack_onehot", "parse_libfm", "partition_rows", "sample_rows"]

@@ -80,6 +80,9 @@ SIGNATURES = {
                                        _f64p, _i64p]),
     "sfm_stage_csr": (C.c_int32, [_H, C.c_int32, _i64p, _i32p, _f32p, _f32p, C.c_int64]),
     "sfm_train_step_staged": (C.c_int32, [_H, C.c_int32, C.c_int64, _f64p, _i64p]),
+    "sfm_stage_onehot": (C.c_int32, [_H, C.c_int32, _u32p, _u32p, _f32p, C.c_int64, C.c_int32,
+                                     C.c_int32]),
+    "sfm_pack_onehot": (C.c_int32, [_i32p, _f32p, C.c_int64, C.c_int32, C.c_int32, _u32p, _u32p]),
     "sfm_train": (C.c_int32, [_H, C.c_int64, C.c_int64, _f64p]),
     "sfm_sample_rows": (C.c_int32, [C.c_uint64, C.c_int64, C.c_double, C.c_int64, C.c_int64,
                                     _i64p, _i64p]),

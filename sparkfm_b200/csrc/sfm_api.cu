@@ -28,6 +28,7 @@ void knobs_refresh() {
     if ((e = getenv("SFM_AR_SLICES"))) k.ar_slices = atoi(e) < 1 ? 1 : (atoi(e) > 8 ? 8 : atoi(e));
     if ((e = getenv("SFM_SORT_AHEAD"))) k.sort_ahead = atoi(e);
     if ((e = getenv("SFM_BUCKET_CACHE")) && e[0] == '1') k.bucket_cache = true;
+    if ((e = getenv("SFM_P2P_SPARSE")) && e[0] == '0') k.p2p_sparse = false;
     g_knobs = k;
 }
 
@@ -227,11 +228,73 @@ static int stage_csr(sfm_handle* h, Stage& sg, cudaStream_t st, const int64_t* r
     sg.nnz = nnz;
     sg.has_val = val != nullptr;
     sg.has_label = label != nullptr;
+    sg.uniform_m = -1;
+    sg.valid = true;
+    return SFM_OK;
+}
+
+// Compact form (sfm_stage_onehot): copy the bit-packed ids and the labels, unpack on `st`.
+static int stage_onehot(sfm_handle* h, Stage& sg, cudaStream_t st, const uint32_t* packed_idx,
+                        const uint32_t* label_bits, const float* label_f32, int64_t n_rows, int m,
+                        int id_bits) {
+    sg.valid = false;
+    if (n_rows < 0 || m < 1 || m > 64 || id_bits < 1 || id_bits > 32)
+        return set_err(h, SFM_ERR_ARG, "sfm_stage_onehot: need n_rows >= 0, 1 <= m <= 64, 1 <= id_bits <= 32");
+    if (n_rows > 0 && (!packed_idx || (label_bits == nullptr) == (label_f32 == nullptr)))
+        return set_err(h, SFM_ERR_ARG, "sfm_stage_onehot: packed_idx and exactly one label array are required");
+    const int64_t nnz = n_rows * m;
+    if (nnz >= 2147483647LL) return set_err(h, SFM_ERR_ARG, "batch nnz out of range [0, 2^31-1)");
+    const size_t words = (size_t)(((uint64_t)nnz * (uint64_t)id_bits + 31) / 32) + 1;
+    const size_t lwords = (size_t)((n_rows + 31) / 32);
+    RC(ensure(h, sg.packed, sizeof(uint32_t) * words));
+    RC(ensure(h, sg.idx, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1)));
+    RC(ensure(h, sg.label, sizeof(float) * (size_t)(n_rows > 0 ? n_rows : 1)));
+    if (label_bits) RC(ensure(h, sg.lbits, sizeof(uint32_t) * (lwords > 0 ? lwords : 1)));
+    if (!sg.d_bad) CU(cudaMalloc(&sg.d_bad, sizeof(int32_t)));
+    CU(cudaMemsetAsync(sg.d_bad, 0, sizeof(int32_t), st));
+    if (n_rows > 0) {
+        CU(cudaMemcpyAsync(sg.packed.p, packed_idx, sizeof(uint32_t) * words, cudaMemcpyHostToDevice, st));
+        h->stats.h2d_bytes += (int64_t)(sizeof(uint32_t) * words);
+        if (label_bits) {
+            CU(cudaMemcpyAsync(sg.lbits.p, label_bits, sizeof(uint32_t) * lwords, cudaMemcpyHostToDevice, st));
+            h->stats.h2d_bytes += (int64_t)(sizeof(uint32_t) * lwords);
+        } else {
+            CU(cudaMemcpyAsync(sg.label.p, label_f32, sizeof(float) * (size_t)n_rows, cudaMemcpyHostToDevice, st));
+            h->stats.h2d_bytes += (int64_t)sizeof(float) * n_rows;
+        }
+        CU(launch_unpack_onehot((const uint32_t*)sg.packed.p,
+                                label_bits ? (const uint32_t*)sg.lbits.p : nullptr, nnz, n_rows, id_bits,
+                                h->m.n_slots, (int32_t*)sg.idx.p, (float*)sg.label.p, sg.d_bad, st,
+                                &h->stats.kernel_launches));
+    }
+    sg.n_rows = n_rows;
+    sg.nnz = nnz;
+    sg.has_val = false;
+    sg.has_label = true;
+    sg.uniform_m = m;
     sg.valid = true;
     return SFM_OK;
 }
 
 static void stage_view(const Stage& sg, BatchView* out) {
+    if (sg.uniform_m >= 0) {   // unpacked one-hot batch: uniform rows, ids already range-checked
+        out->row_ptr = nullptr;
+        out->idx = (const int32_t*)sg.idx.p;
+        out->val = nullptr;
+        out->label = (const float*)sg.label.p;
+        out->row_ids = nullptr;
+        out->row_lo = 0;
+        out->n_rows = sg.n_rows;
+        out->nnz = sg.nnz;
+        out->idx_len = sg.nnz;
+        out->out_ptr = nullptr;
+        out->out_base = 0;
+        out->uniform_m = sg.uniform_m;
+        out->validated = true;
+        out->pre_err = sg.d_bad;
+        return;
+    }
+    out->pre_err = nullptr;
     out->row_ptr = (const int64_t*)sg.rowptr.p;
     out->idx = (const int32_t*)sg.idx.p;
     out->val = sg.has_val ? (const float*)sg.val.p : nullptr;
@@ -254,6 +317,14 @@ static int read_err_flag(sfm_handle* h) {
         CU(cudaMemcpyAsync(h->h_flags + 1, p2p_timeout_flag(h), sizeof(int32_t),
                            cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    if (h->comm) {   // a dead peer / failed transport shows up here, not in the enqueue calls
+        std::string msg;
+        if (nccl_async_error(h->nccl, h->comm, &msg) != SFM_OK) {
+            nccl_abort(h->nccl, h->comm);
+            h->comm = nullptr;   // world stays > 1: train_core refuses to run without the communicator
+            return set_err(h, SFM_ERR_NCCL, msg + " (communicator aborted)");
+        }
+    }
     if (h->h_flags[1])
         return set_err(h, SFM_ERR_NCCL, "peer-memory gradient exchange timed out waiting for a rank");
     if (h->h_flags[0])
@@ -284,6 +355,8 @@ static int validate_view(sfm_handle* h, const BatchView& b) {
 static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad_keep,
                       const PartCache* pc = nullptr) {
     NEED_MODEL(h);
+    if (h->world > 1 && !h->comm)
+        return set_err(h, SFM_ERR_NCCL, "the communicator was aborted after an asynchronous NCCL error");
     if (is_sharded(h)) {
         if (grad_keep) return set_err(h, SFM_ERR_STATE, "sfm_gradient is not available with SFM_FLAG_SHARD_V");
         RC(validate_view(h, b));
@@ -345,7 +418,10 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     if ((n + 1) * (int64_t)m.lpr >= 4294967296LL)
         return set_err(h, SFM_ERR_ARG, "batch too large: rows * kp/4 must stay below 2^32");
     PhaseTimer pt(h);
-    CU(cudaMemsetAsync(h->d_err, 0, sizeof(int32_t), h->stream));
+    if (b.pre_err)   // the staging kernel already range-checked the ids: its flag is the step's
+        CU(cudaMemcpyAsync(h->d_err, b.pre_err, sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+    else
+        CU(cudaMemsetAsync(h->d_err, 0, sizeof(int32_t), h->stream));
     FwdOut o;
     o.S = (float*)h->b_S.p;
     o.mult = (float*)h->b_mult.p;
@@ -362,7 +438,8 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     o.key_bits = key_bits;
     o.blk_shift = blk_shift;
     CU(launch_forward(m, b, o, true, h->d_err, h->sm_count, h->stream, L));
-    CU(launch_scalar_reduce(o.loss, o.mult, n, (double*)h->b_partials.p, h->d_scal, h->stream, L));
+    CU(launch_scalar_reduce(o.loss, o.mult, n, (double*)h->b_partials.p, h->d_scal, h->d_err,
+                            h->stream, L));
     pt.lap(&h->stats.ms_forward);
     // Multi-GPU, reduce / all-reduce overlap: the feature range is cut into Q
     // slices; slice q's gradient is all-reduced and applied on the comm stream while the reduce of
@@ -456,17 +533,29 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
         return SFM_OK;
     }
     float* grad_out = fused ? nullptr : (p2p ? p2p_grad_buffer(h) : (float*)h->b_grad.p);
+    // Sparse peer-memory exchange: whether it is used depends on the model geometry only (the same
+    // on every rank); a rank whose own batch cannot take the bucket path this step (empty batch,
+    // cached sorted form) publishes a dense gradient with an all-ones touched bitmap instead.
+    const bool sparse_x = p2p && knobs().p2p_sparse && bucket_sparse_capable(m, key_bits);
+    uint32_t* touch = nullptr;
+    if (sparse_x) {
+        if (bucket)
+            touch = p2p_touch_bits(h);
+        else
+            CU(cudaMemsetAsync(p2p_touch_bits(h), 0xff, sizeof(uint32_t) * (size_t)((m.n_slots + 31) / 32),
+                               h->stream));
+    }
     if (bucket)
         CU(bucket_pull(m, bg, keys_sorted, binary ? nullptr : (const uint32_t*)pay_sorted,
                        pc ? pc->tables.p : h->b_bkt_tables.p, h->b_bkt_work.p, o.S, o.mult, h->d_scal,
-                       h->d_err, up, fused, grad_out, h->sm_count, h->stream, L));
+                       h->d_err, up, fused, grad_out, touch, h->sm_count, h->stream, L));
     else
         CU(launch_pull(m, (int32_t*)h->b_seg.p, key_bits, n_blocks, keys_sorted, pay_sorted, nnz,
                        binary, o.S, o.mult, (float*)h->b_pull.p, h->d_scal, h->d_err, up, fused,
                        grad_out, h->sm_count, h->stream, L));
     pt.lap(&h->stats.ms_reduce);
     if (p2p) {
-        RC(p2p_reduce_update(h, up));
+        RC(p2p_reduce_update(h, up, sparse_x));
         pt.lap(&h->stats.ms_allreduce);
         h->stats.train_steps += 1;
         h->stats.train_rows += n;
@@ -722,6 +811,9 @@ static int finish_step(sfm_handle* h, double* mean_loss_out, int64_t* batch_out)
                        h->stream));
     h->stats.d2h_bytes += (int64_t)sizeof(double) * SC_N + 4;
     RC(read_err_flag(h));
+    if (h->world > 1 && !is_sharded(h) && h->h_scal[SC_ERR] != 0.0)
+        return set_err(h, SFM_ERR_INDEX,
+                       "another rank saw a feature index outside [0, n_slots): every rank skipped this update");
     const double cnt = h->h_scal[SC_COUNT];
     if (mean_loss_out) *mean_loss_out = cnt > 0.0 ? h->h_scal[SC_LOSS] / cnt : 0.0;
     if (batch_out) *batch_out = (int64_t)cnt;
@@ -931,6 +1023,9 @@ int32_t sfm_destroy(sfm_handle* h) {
         free_buf(sg.idx);
         free_buf(sg.val);
         free_buf(sg.label);
+        free_buf(sg.packed);
+        free_buf(sg.lbits);
+        if (sg.d_bad) cudaFree(sg.d_bad);
         if (sg.ready) cudaEventDestroy(sg.ready);
     }
     if (h->m.v) cudaFree(h->m.v);
@@ -1602,6 +1697,20 @@ int32_t sfm_stage_csr(sfm_handle* h, int32_t slot, const int64_t* row_ptr, const
     return SFM_OK;
 }
 
+int32_t sfm_stage_onehot(sfm_handle* h, int32_t slot, const uint32_t* packed_idx,
+                         const uint32_t* label_bits, const float* label_f32, int64_t n_rows,
+                         int32_t m, int32_t id_bits) {
+    if (!h) return SFM_ERR_ARG;
+    if (slot < 0 || slot > 1) return set_err(h, SFM_ERR_ARG, "slot must be 0 or 1");
+    if (is_sharded(h) || h->shard_requested)
+        return set_err(h, SFM_ERR_STATE, "sfm_stage_onehot is not available with SFM_FLAG_SHARD_V");
+    CU(cudaSetDevice(h->device));
+    Stage& sg = h->stage[slot];
+    RC(stage_onehot(h, sg, h->copy_stream, packed_idx, label_bits, label_f32, n_rows, m, id_bits));
+    CU(cudaEventRecord(sg.ready, h->copy_stream));
+    return SFM_OK;
+}
+
 int32_t sfm_train_step_staged(sfm_handle* h, int32_t slot, int64_t iter, double* mean_loss_out,
                               int64_t* batch_out) {
     if (!h) return SFM_ERR_ARG;
@@ -1806,6 +1915,13 @@ int32_t sfm_train(sfm_handle* h, int64_t first_iter, int64_t n_iters, double* lo
     if (rc == SFM_OK) rc = read_err_flag(h);
     else cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->copy_stream);
+    if (rc == SFM_OK && h->world > 1 && !is_sharded(h))
+        for (int64_t t = 0; t < n_iters; ++t)
+            if (hist[SC_N * t + SC_ERR] != 0.0) {
+                rc = set_err(h, SFM_ERR_INDEX,
+                             "a rank saw a feature index outside [0, n_slots): every rank skipped that update");
+                break;
+            }
     if (rc == SFM_OK && loss_history)
         for (int64_t t = 0; t < n_iters; ++t) {
             const double c = hist[SC_N * t + SC_COUNT];

@@ -448,6 +448,7 @@ struct PullArgs {
     float4* G4;                  // dense gradient out (not FUSED)
     float* Gw;
     float* Gw0;
+    uint32_t* touch_bits;        // [ceil(n_slots / 32)] (MODE 2)
     const double* d_scal;
     const int32_t* err;
     int64_t n_slots;
@@ -455,9 +456,13 @@ struct PullArgs {
     UpdateParams up;
 };
 
-template <int LPR, bool BINARY, bool FUSED>
+// MODE 0: SGD update in place (one GPU); 1: dense gradient [gV | gw | gw0]; 2: sparse gradient --
+// rows are written only for the features this rank's batch touched, plus one bit per feature in
+// touch_bits (the peer-memory exchange then moves touched rows only, sfm_p2p.cu).
+template <int LPR, bool BINARY, int MODE>
 __global__ void __launch_bounds__(PL_THREADS, PL_CTAS_PER_SM)
 bkt_pull_kernel(const PullArgs a) {
+    constexpr bool FUSED = MODE == 0;
     using C = Pl<LPR>;
     constexpr int G = C::G, SUB = C::SUB, SS = C::SUBSHIFT, REC = C::REC;
     extern __shared__ __align__(16) unsigned char pl_smem[];
@@ -782,17 +787,21 @@ bkt_pull_kernel(const PullArgs a) {
             const float wi = (fq == 0 && a.k1) ? a.W[f] : 0.f;
             float4 A;
             float D, Cc;
+            bool touched;
             if (single) {
                 A = accA[d * LPR + fq];
                 D = accD[d];
                 Cc = accC[d];
+                touched = tch[d] != 0u;
             } else {
                 A = make_float4(0.f, 0.f, 0.f, 0.f);
                 D = 0.f;
                 Cc = 0.f;
+                touched = false;
                 for (uint32_t it = it0; it < it1; ++it) {   // item order: fixed summation order
                     const uint32_t bits = __ldcg(a.part_bits + (size_t)it * bw + (d >> 5));
                     if ((bits >> (d & 31)) & 1u) {
+                        touched = true;
                         const float* P = a.part + ((size_t)it * NBL + d) * REC;
                         const float4 pa = __ldcg(reinterpret_cast<const float4*>(P) + fq);
                         const float4 dc = __ldcg(reinterpret_cast<const float4*>(P) + LPR);
@@ -817,9 +826,21 @@ bkt_pull_kernel(const PullArgs a) {
                     a.V4[f * LPR + fq] = v;
                     if (fq == 0 && a.k1) a.W[f] = sgd_step(wi, Cc, inv, a.up.eta, a.up.regw);
                 }
-            } else {
+            } else if (MODE == 1 || touched) {
                 a.G4[f * LPR + fq] = gr;
                 if (fq == 0) a.Gw[f] = a.k1 ? Cc : 0.f;
+            }
+            if (MODE == 2 && !single && fq == 0) tch[d] = touched ? 1u : 0u;
+        }
+        if (MODE == 2) {   // the bucket's touched bitmap (buckets are multiples of 32 features)
+            __syncthreads();
+            for (int wd = tid; wd < bw; wd += PL_THREADS) {
+                const int64_t f0 = (int64_t)b * NBL + wd * 32;
+                if (f0 >= a.n_slots) break;
+                uint32_t bits = 0;
+                for (int j = 0; j < 32; ++j)
+                    if (wd * 32 + j < NBL && f0 + j < a.n_slots && tch[wd * 32 + j]) bits |= 1u << j;
+                a.touch_bits[f0 >> 5] = bits;
             }
         }
     }
@@ -830,7 +851,7 @@ bkt_pull_kernel(const PullArgs a) {
 // ------------------------------------------------------------------------------------------
 static inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
-bool bucket_geometry(const ModelView& m, int key_bits, int64_t n_rows, int64_t nnz, BucketGeom* g) {
+static bool model_geometry(const ModelView& m, int key_bits, int* lb_out, int* hb_out) {
     if (!knobs().bucket) return false;
     if (key_bits < 1) key_bits = 1;
     int lb = 0;
@@ -839,6 +860,19 @@ bool bucket_geometry(const ModelView& m, int key_bits, int64_t n_rows, int64_t n
     if (lb < 0) lb = 0;
     const int hb = key_bits - lb;
     if (hb < 1 || hb > BK_MAX_HB) return false;
+    *lb_out = lb;
+    *hb_out = hb;
+    return true;
+}
+
+bool bucket_sparse_capable(const ModelView& m, int key_bits) {
+    int lb, hb;
+    return model_geometry(m, key_bits, &lb, &hb) && lb >= 5;
+}
+
+bool bucket_geometry(const ModelView& m, int key_bits, int64_t n_rows, int64_t nnz, BucketGeom* g) {
+    int lb, hb;
+    if (!model_geometry(m, key_bits, &lb, &hb)) return false;
     if (n_rows <= 0 || nnz <= 0) return false;
     if (n_rows >= ((int64_t)1 << (32 - lb)) || nnz >= 2147483647LL - 2 * SC_TILE) return false;
     g->LB = lb;
@@ -956,18 +990,18 @@ static size_t pull_smem(int lb, bool binary) {
 
 template <int LPR>
 static cudaError_t pull_dispatch2(const ModelView& m, const BucketGeom& g, const PullArgs& a,
-                                  bool binary, bool fused, int sm_count, cudaStream_t st) {
+                                  bool binary, int mode, int sm_count, cudaStream_t st) {
     const size_t smem = pull_smem<LPR>(g.LB, binary);
     cudaError_t e;
-#define PL_LAUNCH(B, F)                                                                          \
-    e = cudaFuncSetAttribute(bkt_pull_kernel<LPR, B, F>,                                         \
+#define PL_LAUNCH(B, M)                                                                          \
+    e = cudaFuncSetAttribute(bkt_pull_kernel<LPR, B, M>,                                         \
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
     if (e != cudaSuccess) return e;                                                              \
-    bkt_pull_kernel<LPR, B, F><<<PL_CTAS_PER_SM * sm_count, PL_THREADS, smem, st>>>(a)
+    bkt_pull_kernel<LPR, B, M><<<PL_CTAS_PER_SM * sm_count, PL_THREADS, smem, st>>>(a)
     if (binary) {
-        if (fused) { PL_LAUNCH(true, true); } else { PL_LAUNCH(true, false); }
+        if (mode == 0) { PL_LAUNCH(true, 0); } else if (mode == 1) { PL_LAUNCH(true, 1); } else { PL_LAUNCH(true, 2); }
     } else {
-        if (fused) { PL_LAUNCH(false, true); } else { PL_LAUNCH(false, false); }
+        if (mode == 0) { PL_LAUNCH(false, 0); } else if (mode == 1) { PL_LAUNCH(false, 1); } else { PL_LAUNCH(false, 2); }
     }
 #undef PL_LAUNCH
     return cudaGetLastError();
@@ -976,9 +1010,11 @@ static cudaError_t pull_dispatch2(const ModelView& m, const BucketGeom& g, const
 cudaError_t bucket_pull(const ModelView& m, const BucketGeom& g, const uint32_t* packed,
                         const uint32_t* vals, const void* tables, void* work, const float* S,
                         const float* mult, const double* d_scal, const int32_t* d_err,
-                        UpdateParams up, bool fused, float* grad, int sm_count, cudaStream_t st,
-                        int64_t* launches) {
+                        UpdateParams up, bool fused, float* grad, uint32_t* touch_bits,
+                        int sm_count, cudaStream_t st, int64_t* launches) {
     const WorkPtrs w = carve_work(m, g, sm_count, work);
+    if (touch_bits && g.LB < 5) return cudaErrorInvalidValue;   // bitmap words must not straddle buckets
+    const int mode = fused ? 0 : (touch_bits ? 2 : 1);
     cudaError_t e = cudaMemsetAsync(w.work, 0, sizeof(uint32_t) * (size_t)(g.NB + 1), st);
     if (e != cudaSuccess) return e;
     PullArgs a;
@@ -999,6 +1035,7 @@ cudaError_t bucket_pull(const ModelView& m, const BucketGeom& g, const uint32_t*
     a.G4 = reinterpret_cast<float4*>(grad);
     a.Gw = grad ? grad + m.n_slots * m.kp : nullptr;
     a.Gw0 = grad ? a.Gw + m.n_slots : nullptr;
+    a.touch_bits = touch_bits;
     a.d_scal = d_scal;
     a.err = d_err;
     a.n_slots = m.n_slots;
@@ -1010,12 +1047,12 @@ cudaError_t bucket_pull(const ModelView& m, const BucketGeom& g, const uint32_t*
     const bool binary = vals == nullptr;
     *launches += 1;
     switch (m.lpr) {
-        case 1: return pull_dispatch2<1>(m, g, a, binary, fused, sm_count, st);
-        case 2: return pull_dispatch2<2>(m, g, a, binary, fused, sm_count, st);
-        case 4: return pull_dispatch2<4>(m, g, a, binary, fused, sm_count, st);
-        case 8: return pull_dispatch2<8>(m, g, a, binary, fused, sm_count, st);
-        case 16: return pull_dispatch2<16>(m, g, a, binary, fused, sm_count, st);
-        case 32: return pull_dispatch2<32>(m, g, a, binary, fused, sm_count, st);
+        case 1: return pull_dispatch2<1>(m, g, a, binary, mode, sm_count, st);
+        case 2: return pull_dispatch2<2>(m, g, a, binary, mode, sm_count, st);
+        case 4: return pull_dispatch2<4>(m, g, a, binary, mode, sm_count, st);
+        case 8: return pull_dispatch2<8>(m, g, a, binary, mode, sm_count, st);
+        case 16: return pull_dispatch2<16>(m, g, a, binary, mode, sm_count, st);
+        case 32: return pull_dispatch2<32>(m, g, a, binary, mode, sm_count, st);
     }
     return cudaErrorInvalidValue;
 }

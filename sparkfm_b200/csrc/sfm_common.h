@@ -13,7 +13,7 @@ namespace sfm {
 
 // ---- device scalar block (doubles): written by the forward reduction, all-reduced across
 // ranks, read by the update kernels.
-enum { SC_LOSS = 0, SC_COUNT = 1, SC_GW0 = 2, SC_N = 4 };
+enum { SC_LOSS = 0, SC_COUNT = 1, SC_GW0 = 2, SC_ERR = 3, SC_N = 4 };   // SC_ERR: ranks that saw a bad index
 
 struct Buf {  // growable device allocation
     void* p = nullptr;
@@ -35,6 +35,9 @@ struct Dataset {
 // synchronous entry points).
 struct Stage {
     Buf rowptr, idx, val, label;
+    Buf packed, lbits;           // sfm_stage_onehot: bit-packed ids / label bits as copied
+    int32_t* d_bad = nullptr;    // sfm_stage_onehot: set by the unpack kernel on an id >= n_slots
+    int32_t uniform_m = -1;      // >= 0: uniform all-ones rows (no row_ptr), ids validated
     int64_t n_rows = 0, nnz = 0;
     bool has_val = false, has_label = false, valid = false;
     cudaEvent_t ready = nullptr;
@@ -100,6 +103,7 @@ struct BatchView {
     int64_t out_base;
     int32_t uniform_m;
     bool validated = false;  // idx already checked against n_slots (resident data set)
+    const int32_t* pre_err = nullptr;   // device flag raised while the batch was staged (or null)
 };
 
 struct ModelView {
@@ -174,6 +178,7 @@ struct Knobs {
     int ar_slices = 1;         // SFM_AR_SLICES
     int sort_ahead = 0;        // SFM_SORT_AHEAD
     bool bucket_cache = false; // SFM_BUCKET_CACHE=1: PARTITION caches keep the bucket form
+    bool p2p_sparse = true;    // SFM_P2P_SPARSE=0: peer-memory exchange moves the dense gradient
 };
 const Knobs& knobs();
 void knobs_refresh();
@@ -197,7 +202,8 @@ cudaError_t launch_forward(const ModelView& m, const BatchView& b, const FwdOut&
                            int32_t* d_err, int sm_count, cudaStream_t st, int64_t* launches);
 // loss / mult -> d_scal[SC_LOSS], [SC_GW0], [SC_COUNT] (fixed-shape fp64 tree, deterministic)
 cudaError_t launch_scalar_reduce(const float* loss, const float* mult, int64_t n, double* partials,
-                                 double* d_scal, cudaStream_t st, int64_t* launches);
+                                 double* d_scal, const int32_t* d_err, cudaStream_t st,
+                                 int64_t* launches);
 struct UpdateParams {
     float eta, reg0, regw, regv;
 };
@@ -255,6 +261,11 @@ cudaError_t launch_row_lens(const int64_t* row_ptr, const int32_t* row_ids, int6
                             int64_t* lens, cudaStream_t st, int64_t* launches);
 cudaError_t launch_idx_range(const int32_t* idx, int64_t nnz, int32_t* d_minmax, cudaStream_t st,
                              int64_t* launches);
+// bit-packed one-hot batch -> idx[n_entries] (ids >= n_slots: *bad = 1, id 0), label[n_rows]
+cudaError_t launch_unpack_onehot(const uint32_t* packed, const uint32_t* label_bits,
+                                 int64_t n_entries, int64_t n_rows, int id_bits, int64_t n_slots,
+                                 int32_t* idx, float* label, int32_t* bad, cudaStream_t st,
+                                 int64_t* launches);
 cudaError_t launch_pad_v(const float* src, float* dst, int64_t n_slots, int k, int kp, bool unpad,
                          cudaStream_t st, int64_t* launches);
 cudaError_t launch_synth_ctr(int64_t n_rows, int64_t row_off, int n_fields,
@@ -266,6 +277,9 @@ cudaError_t launch_synth_ctr(int64_t n_rows, int64_t row_off, int n_fields,
 // ---- bucket-form transposition + reduce (sfm_bucket.cu)
 // false: not applicable (SFM_BUCKET=0 / SFM_SORT=cub, more than 2^11 buckets needed, batch too large)
 bool bucket_geometry(const ModelView& m, int key_bits, int64_t n_rows, int64_t nnz, BucketGeom* g);
+// the bucket geometry of this model gives buckets of whole 32-feature bitmap words (depends on
+// the model only, so every rank answers the same): the sparse gradient exchange can be used
+bool bucket_sparse_capable(const ModelView& m, int key_bits);
 size_t bucket_tables_bytes(const BucketGeom& g);
 size_t bucket_work_bytes(const ModelView& m, const BucketGeom& g, int sm_count);
 // entries (keys[i], payload) in row order -> packed (local id << (32-LB) | batch row) grouped by
@@ -280,8 +294,8 @@ cudaError_t bucket_transpose(const ModelView& m, const BatchView& b, const Bucke
 cudaError_t bucket_pull(const ModelView& m, const BucketGeom& g, const uint32_t* packed,
                         const uint32_t* vals, const void* tables, void* work, const float* S,
                         const float* mult, const double* d_scal, const int32_t* d_err,
-                        UpdateParams up, bool fused, float* grad, int sm_count, cudaStream_t st,
-                        int64_t* launches);
+                        UpdateParams up, bool fused, float* grad, uint32_t* touch_bits,
+                        int sm_count, cudaStream_t st, int64_t* launches);
 
 // ---- CUB wrappers (sfm_sort.cu)
 size_t sort_pairs_temp_bytes(int64_t n, int end_bit);
@@ -338,8 +352,9 @@ void shard_clear_cache(sfm_handle* h);
 int p2p_setup(sfm_handle* h);      // collective; leaves h->p2p null when any rank cannot take part
 void p2p_teardown(sfm_handle* h);
 float* p2p_grad_buffer(sfm_handle* h);
+uint32_t* p2p_touch_bits(sfm_handle* h);   // this rank's touched-feature bitmap (sparse exchange)
 const int32_t* p2p_timeout_flag(sfm_handle* h);
-int p2p_reduce_update(sfm_handle* h, UpdateParams up);
+int p2p_reduce_update(sfm_handle* h, UpdateParams up, bool sparse);
 
 // ---- ALS sweep of the reference's own trainer (sfm_als.cu)
 int als_sweep(sfm_handle* h, const BatchView& all_rows, int32_t flags, double* rmse_out);
@@ -357,6 +372,8 @@ Nccl* nccl_load(std::string* err);
 int nccl_unique_id(Nccl* n, uint8_t* id128, std::string* err);
 int nccl_init(Nccl* n, void** comm, const uint8_t* id128, int rank, int world, std::string* err);
 int nccl_destroy(Nccl* n, void* comm);
+int nccl_async_error(Nccl* n, void* comm, std::string* err);   // ncclCommGetAsyncError
+int nccl_abort(Nccl* n, void* comm);
 int nccl_allreduce_f32(Nccl* n, void* comm, float* buf, size_t count, cudaStream_t st,
                        std::string* err);
 int nccl_allreduce_f64(Nccl* n, void* comm, double* buf, size_t count, cudaStream_t st,

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <charconv>
 #include <string>
 #include <system_error>
@@ -487,5 +488,66 @@ extern "C" int32_t sfm_partition_rows(uint64_t seed, int64_t n_parts, int64_t pa
     for (int64_t r = row_lo; r < row_hi; ++r)
         if ((int64_t)((mix64(key ^ mix64((uint64_t)r)) >> 11) % (uint64_t)n_parts) == part) out[n++] = r;
     *n_out = n;
+    return SFM_OK;
+}
+
+// Host-side packer of the compact one-hot staging format (include/sparkfm_b200.h,
+// sfm_stage_onehot): entry e -> bits [e*id_bits, (e+1)*id_bits) of the little-endian uint32
+// stream.  Threads own disjoint entry ranges whose first bit is word-aligned (ranges start at
+// multiples of 32 entries), so no two threads touch the same word.
+extern "C" int32_t sfm_pack_onehot(const int32_t* idx, const float* label, int64_t n_rows, int32_t m,
+                                   int32_t id_bits, uint32_t* packed_idx, uint32_t* label_bits) {
+    if (n_rows < 0 || m < 1 || id_bits < 1 || id_bits > 32 || (n_rows > 0 && (!idx || !packed_idx)))
+        return SFM_ERR_ARG;
+    const int64_t n = n_rows * (int64_t)m;
+    const int64_t words = (int64_t)(((uint64_t)n * (uint64_t)id_bits + 31) / 32) + 1;
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > 32) nt = 32;
+    if (n < (int64_t)1 << 16) nt = 1;
+    const int64_t groups = (n + 31) / 32;   // 32 entries = id_bits whole words
+    std::vector<int> bad(nt, 0);
+    auto work = [&](unsigned t) {
+        const int64_t e0 = groups * t / nt * 32, e1 = std::min<int64_t>(n, groups * (t + 1) / nt * 32);
+        if (e0 >= e1) return;
+        const uint64_t lim = id_bits >= 32 ? 0x100000000ull : (1ull << id_bits);
+        uint32_t* out = packed_idx + (uint64_t)e0 * (uint64_t)id_bits / 32;
+        uint64_t acc = 0;
+        int fill = 0;
+        for (int64_t e = e0; e < e1; ++e) {
+            const int32_t v = idx[e];
+            if (v < 0 || (uint64_t)(uint32_t)v >= lim) bad[t] = 1;
+            acc |= ((uint64_t)(uint32_t)v & (lim - 1)) << fill;
+            fill += id_bits;
+            if (fill >= 32) {
+                *out++ = (uint32_t)acc;
+                acc >>= 32;
+                fill -= 32;
+            }
+        }
+        if (fill > 0) *out++ = (uint32_t)acc;
+    };
+    if (nt == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    // the trailing slack word(s) the unpack kernel may touch
+    const int64_t used = (int64_t)(((uint64_t)n * (uint64_t)id_bits + 31) / 32);
+    for (int64_t w = used; w < words; ++w) packed_idx[w] = 0u;
+    if (label && label_bits) {
+        const int64_t lw = (n_rows + 31) / 32;
+        for (int64_t w = 0; w < lw; ++w) {
+            uint32_t bits = 0;
+            const int64_t r1 = std::min<int64_t>(n_rows, (w + 1) * 32);
+            for (int64_t r = w * 32; r < r1; ++r)
+                if (label[r] > 0.f) bits |= 1u << (r & 31);
+            label_bits[w] = bits;
+        }
+    }
+    for (int b : bad)
+        if (b) return SFM_ERR_INDEX;
     return SFM_OK;
 }

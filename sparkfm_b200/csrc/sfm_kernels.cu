@@ -517,7 +517,7 @@ scalar_reduce1_kernel(const float* __restrict__ loss, const float* __restrict__ 
 
 __global__ void __launch_bounds__(RED_THREADS)
 scalar_reduce2_kernel(const double* __restrict__ partials, int nblocks, int64_t n,
-                      double* __restrict__ d_scal) {
+                      double* __restrict__ d_scal, const int32_t* __restrict__ err) {
     __shared__ double sm[2 * RED_THREADS];
     double acc[2] = {0.0, 0.0};
     for (int i = threadIdx.x; i < nblocks; i += RED_THREADS) {
@@ -529,15 +529,16 @@ scalar_reduce2_kernel(const double* __restrict__ partials, int nblocks, int64_t 
         d_scal[SC_LOSS] = acc[0];
         d_scal[SC_GW0] = acc[1];
         d_scal[SC_COUNT] = (double)n;
-        d_scal[3] = 0.0;
+        d_scal[SC_ERR] = (err && *err) ? 1.0 : 0.0;   // summed over the ranks: everybody skips the update
     }
 }
 
 cudaError_t launch_scalar_reduce(const float* loss, const float* mult, int64_t n, double* partials,
-                                 double* d_scal, cudaStream_t st, int64_t* launches) {
+                                 double* d_scal, const int32_t* d_err, cudaStream_t st,
+                                 int64_t* launches) {
     *launches += 2;
     scalar_reduce1_kernel<<<RED_BLOCKS, RED_THREADS, 0, st>>>(loss, mult, n, partials);
-    scalar_reduce2_kernel<<<1, RED_THREADS, 0, st>>>(partials, RED_BLOCKS, n, d_scal);
+    scalar_reduce2_kernel<<<1, RED_THREADS, 0, st>>>(partials, RED_BLOCKS, n, d_scal, d_err);
     return cudaGetLastError();
 }
 
@@ -1112,7 +1113,7 @@ fm_update_kernel(float4* __restrict__ V4, float* __restrict__ W, float* __restri
                  const float4* __restrict__ G4, const float* __restrict__ Gw,
                  const float* __restrict__ Gw0, const double* __restrict__ d_scal,
                  const int32_t* __restrict__ err, UpdateParams up) {
-    if (*err) return;
+    if (*err || d_scal[SC_ERR] != 0.0) return;   // some rank saw a bad index: nobody updates
     const double count = d_scal[SC_COUNT];
     if (!(count > 0.0)) return;
     const float inv = (float)(1.0 / count);
@@ -1277,6 +1278,47 @@ cudaError_t launch_idx_range(const int32_t* idx, int64_t nnz, int32_t* d_minmax,
 }
 
 // [n_slots][k] <-> [n_slots][kp] (zero padded)
+// Unpacks the compact one-hot staging format (sfm_stage_onehot): entry e = bits
+// [e*id_bits, (e+1)*id_bits) of the uint32 stream.  One thread per entry: consecutive threads read
+// the same or neighbouring words (coalesced through L1) and write consecutive ids.
+__global__ void __launch_bounds__(256)
+unpack_onehot_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ label_bits,
+                     int64_t n_entries, int64_t n_rows, int id_bits, uint32_t n_slots,
+                     int32_t* __restrict__ idx, float* __restrict__ label, int32_t* __restrict__ bad) {
+    const uint64_t mask = id_bits >= 32 ? 0xffffffffull : ((1ull << id_bits) - 1ull);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    bool any_bad = false;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_entries; e += stride) {
+        const uint64_t bit = (uint64_t)e * (uint64_t)id_bits;
+        const uint64_t wd = bit >> 5;
+        const uint32_t sh = (uint32_t)(bit & 31u);
+        const uint64_t two = (uint64_t)__ldg(packed + wd) | ((uint64_t)__ldg(packed + wd + 1) << 32);
+        uint32_t id = (uint32_t)((two >> sh) & mask);
+        if (id >= n_slots) {
+            any_bad = true;
+            id = 0u;
+        }
+        idx[e] = (int32_t)id;
+    }
+    if (label_bits)
+        for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride)
+            label[r] = ((__ldg(label_bits + (r >> 5)) >> (r & 31)) & 1u) ? 1.f : 0.f;
+    if (any_bad) atomicExch(bad, 1);
+}
+
+cudaError_t launch_unpack_onehot(const uint32_t* packed, const uint32_t* label_bits,
+                                 int64_t n_entries, int64_t n_rows, int id_bits, int64_t n_slots,
+                                 int32_t* idx, float* label, int32_t* bad, cudaStream_t st,
+                                 int64_t* launches) {
+    if (n_entries <= 0 && n_rows <= 0) return cudaSuccess;
+    int64_t blocks = ((n_entries > n_rows ? n_entries : n_rows) + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    unpack_onehot_kernel<<<(unsigned)blocks, 256, 0, st>>>(packed, label_bits, n_entries, n_rows,
+                                                           id_bits, (uint32_t)n_slots, idx, label, bad);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
 __global__ void pad_v_kernel(const float* __restrict__ src, float* __restrict__ dst,
                              int64_t n_slots, int k, int kp, int unpad) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;

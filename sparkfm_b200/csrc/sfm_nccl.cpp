@@ -31,6 +31,8 @@ struct Nccl {
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
+    int (*CommGetAsyncError)(ncclComm_t, int*) = nullptr;   // optional
+    int (*CommAbort)(ncclComm_t) = nullptr;                 // optional
 };
 
 static std::string nerr(Nccl* n, const char* what, int rc) {
@@ -74,6 +76,8 @@ Nccl* nccl_load(std::string* err) {
     SYM(GroupEnd, "ncclGroupEnd")
     SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
+    *(void**)(&n->CommGetAsyncError) = dlsym(dl, "ncclCommGetAsyncError");
+    *(void**)(&n->CommAbort) = dlsym(dl, "ncclCommAbort");
     inst = n;
     return n;
 }
@@ -99,6 +103,23 @@ int nccl_init(Nccl* n, void** comm, const uint8_t* id128, int rank, int world, s
         return SFM_ERR_NCCL;
     }
     *comm = c;
+    return SFM_OK;
+}
+
+// Asynchronous communicator errors (a peer died, a transport failed) never surface through the
+// enqueue calls; every step's read-back polls this.  On error the
+// communicator is aborted so that queued collectives fail instead of hanging.
+int nccl_async_error(Nccl* n, void* comm, std::string* err) {
+    if (!n || !comm || !n->CommGetAsyncError) return SFM_OK;
+    int async = ncclSuccess;
+    const int rc = n->CommGetAsyncError((ncclComm_t)comm, &async);
+    if (rc == ncclSuccess && async == ncclSuccess) return SFM_OK;
+    if (err) *err = nerr(n, "ncclCommGetAsyncError", rc != ncclSuccess ? rc : async);
+    return SFM_ERR_NCCL;
+}
+
+int nccl_abort(Nccl* n, void* comm) {
+    if (n && comm && n->CommAbort) n->CommAbort((ncclComm_t)comm);
     return SFM_OK;
 }
 

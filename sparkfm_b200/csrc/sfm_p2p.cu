@@ -49,12 +49,14 @@ struct DevPeers {
     float* w[P2P_MAXG];
     const float4* g4[P2P_MAXG];
     const float* gw[P2P_MAXG];
-    const double* scal[P2P_MAXG];   // [SC_N] per-rank loss / count / gw0 sums of this step
+    const double* scal[P2P_MAXG];   // [SC_N] per-rank loss / count / gw0 / error sums of this step
+    const uint32_t* tb[P2P_MAXG];   // touched-feature bitmap of this step (sparse exchange)
     uint32_t* sig[P2P_MAXG];   // [2][P2P_MAXG]: ready words, done words
 };
 
 struct P2PState {
     float* grad = nullptr;
+    uint32_t* touch = nullptr;   // inside the grad allocation
     uint32_t* sig = nullptr;
     uint32_t* done_ctr = nullptr;
     void* opened[P2P_MAXG][4];
@@ -154,7 +156,8 @@ p2p_reduce_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_
     }
     __syncthreads();
     const double count = tot[SC_COUNT];
-    const bool active = ok && count > 0.0 && *err == 0;
+    // tot[SC_ERR] = number of ranks that saw a bad index: everybody skips the update together
+    const bool active = ok && count > 0.0 && tot[SC_ERR] == 0.0;
     if (ok && blockIdx.x == 0 && threadIdx.x < SC_N) d_scal[threadIdx.x] = tot[threadIdx.x];
     if (active) {
         const float inv = (float)(1.0 / count);
@@ -208,6 +211,136 @@ p2p_reduce_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_
     }
 }
 
+// Sparse form of the same exchange: every rank publishes one bit per feature its batch touched
+// (written by bkt_pull_kernel<MODE 2> next to the gradient rows of exactly those features).
+//   part 1, own slice of bitmap words: for every feature some rank touched, the touching ranks'
+//           rows are loaded (peer loads), added in rank order, the update is applied and the new
+//           row is stored into all G replicas;
+//   part 2, ALL features: a feature nobody touched only receives its L2 decay, which every rank
+//           applies to its own replica -- no NVLink traffic (skipped when lambda_w = lambda_V = 0).
+// Same bits as the dense kernel (an untouched rank contributes +0 there) up to the sign of a zero.
+template <int W>
+__global__ void __launch_bounds__(256)
+p2p_sparse_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_t n_slots, int lsh,
+                         int wd_lo, int wd_hi, int wd_total, int k0, int k1,
+                         float* __restrict__ W0, const uint32_t* sig, double* __restrict__ d_scal,
+                         UpdateParams up, unsigned long long timeout_ns, uint32_t* done_ctr) {
+    __shared__ int ok;
+    __shared__ double tot[SC_N];
+    if (threadIdx.x == 0) {
+        ok = p2p_wait(sig, 0, world, epoch, timeout_ns, done_ctr + 1) ? 1 : 0;
+        for (int j = 0; j < SC_N; ++j) {
+            double a = 0.0;
+            if (ok)
+                for (int p = 0; p < world; ++p) {
+                    double x;
+                    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(x) : "l"(P.scal[p] + j));
+                    a += x;
+                }
+            tot[j] = a;
+        }
+    }
+    __syncthreads();
+    const double count = tot[SC_COUNT];
+    const bool active = ok && count > 0.0 && tot[SC_ERR] == 0.0;
+    if (ok && blockIdx.x == 0 && threadIdx.x < SC_N) d_scal[threadIdx.x] = tot[threadIdx.x];
+    if (active) {
+        const float inv = (float)(1.0 / count);
+        const int lane = threadIdx.x & 31;
+        const int lpr = 1 << lsh, fpp = 32 >> lsh;   // float4 per row, features per pass
+        const int fq = lane & (lpr - 1), jl = lane >> lsh;
+        const int warps = (gridDim.x * blockDim.x) >> 5;
+        const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        float4* Vme = P.v[rank];
+        float* Wme = P.w[rank];
+        for (int wd = wd_lo + gw; wd < wd_hi; wd += warps) {
+            uint32_t mine = 0;
+#pragma unroll
+            for (int p = 0; p < W; ++p)
+                if (lane == p && p < world) mine = ld_volatile_u32(P.tb[p] + wd);
+            uint32_t bits[W];
+            uint32_t uni = 0;
+#pragma unroll
+            for (int p = 0; p < W; ++p) {
+                bits[p] = __shfl_sync(0xffffffffu, mine, p);
+                uni |= bits[p];
+            }
+            if (!uni) continue;
+            for (int pass = 0; pass < lpr; ++pass) {
+                const int j = pass * fpp + jl;
+                const int64_t f = (int64_t)wd * 32 + j;
+                if (!((uni >> j) & 1u) || f >= n_slots) continue;
+                const int64_t e = (f << lsh) + fq;
+                float4 x[W];
+#pragma unroll
+                for (int p = 0; p < W; ++p)
+                    x[p] = ((bits[p] >> j) & 1u) ? ld_peer4(P.g4[p] + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float gs = 0.f;
+                if (fq == 0 && k1) {
+#pragma unroll
+                    for (int p = 0; p < W; ++p) gs += ((bits[p] >> j) & 1u) ? ld_peer1(P.gw[p] + f) : 0.f;
+                }
+                float4 g = x[0];
+#pragma unroll
+                for (int p = 1; p < W; ++p) {   // rank order: fixed summation order
+                    g.x += x[p].x; g.y += x[p].y; g.z += x[p].z; g.w += x[p].w;
+                }
+                float4 v = Vme[e];
+                v.x = sgd_step(v.x, g.x, inv, up.eta, up.regv);
+                v.y = sgd_step(v.y, g.y, inv, up.eta, up.regv);
+                v.z = sgd_step(v.z, g.z, inv, up.eta, up.regv);
+                v.w = sgd_step(v.w, g.w, inv, up.eta, up.regv);
+#pragma unroll
+                for (int p = 0; p < W; ++p)
+                    if (p < world) P.v[p][e] = v;
+                if (fq == 0 && k1) {
+                    const float wn = sgd_step(Wme[f], gs, inv, up.eta, up.regw);
+#pragma unroll
+                    for (int p = 0; p < W; ++p)
+                        if (p < world) P.w[p][f] = wn;
+                }
+            }
+        }
+        if (up.regv != 0.f || (k1 && up.regw != 0.f)) {
+            for (int wd = gw; wd < wd_total; wd += warps) {
+                uint32_t mine = 0;
+#pragma unroll
+                for (int p = 0; p < W; ++p)
+                    if (lane == p && p < world) mine = ld_volatile_u32(P.tb[p] + wd);
+                const uint32_t uni = __reduce_or_sync(0xffffffffu, mine);
+                if (uni == 0xffffffffu) continue;
+                for (int pass = 0; pass < lpr; ++pass) {
+                    const int j = pass * fpp + jl;
+                    const int64_t f = (int64_t)wd * 32 + j;
+                    if (((uni >> j) & 1u) || f >= n_slots) continue;
+                    const int64_t e = (f << lsh) + fq;
+                    float4 v = Vme[e];
+                    v.x = sgd_step(v.x, 0.f, inv, up.eta, up.regv);
+                    v.y = sgd_step(v.y, 0.f, inv, up.eta, up.regv);
+                    v.z = sgd_step(v.z, 0.f, inv, up.eta, up.regv);
+                    v.w = sgd_step(v.w, 0.f, inv, up.eta, up.regv);
+                    Vme[e] = v;
+                    if (fq == 0 && k1) Wme[f] = sgd_step(Wme[f], 0.f, inv, up.eta, up.regw);
+                }
+            }
+        }
+        if (k0 && blockIdx.x == 0 && threadIdx.x == 0) {
+            const float w0 = *W0;
+            *W0 = sgd_step(w0, (float)tot[SC_GW0], inv, up.eta, up.reg0);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned ticket = atomicAdd(done_ctr, 1u);
+        if (ticket == gridDim.x - 1) {
+            *done_ctr = 0;
+            __threadfence_system();
+            for (int p = 0; p < world; ++p) st_volatile_u32(P.sig[p] + P2P_MAXG + rank, epoch);
+        }
+    }
+}
+
 // Called from sfm_destroy before the model buffers are freed.  Every rank has seen every peer's
 // "done" word of the last step by then (the step's wait kernel), so no peer still reads or writes
 // this rank's buffers; the imported mappings are closed first, the own allocations freed after.
@@ -238,10 +371,13 @@ int p2p_setup(sfm_handle* h) {
     memset(&s->peers, 0, sizeof s->peers);
     const size_t glen = (size_t)m.n_slots * (m.kp + 1) + 1;
     const size_t scal_off = (glen + 3) / 4 * 4;   // floats; the [SC_N] doubles sit 16-byte aligned
+    const size_t touch_off = scal_off + 2 * SC_N; // floats; then one bit per feature
+    const size_t touch_words = (size_t)(m.n_slots + 31) / 32;
     bool ok = want != 0;
     cudaIpcMemHandle_t mine[4];
     memset(mine, 0, sizeof mine);
-    if (ok) ok = cudaMalloc(&s->grad, sizeof(float) * scal_off + sizeof(double) * SC_N) == cudaSuccess;
+    if (ok) ok = cudaMalloc(&s->grad, sizeof(float) * (touch_off + touch_words)) == cudaSuccess;
+    if (ok) s->touch = reinterpret_cast<uint32_t*>(s->grad + touch_off);
     if (ok) ok = cudaMalloc(&s->sig, sizeof(uint32_t) * 2 * P2P_MAXG) == cudaSuccess;
     if (ok) ok = cudaMalloc(&s->done_ctr, sizeof(uint32_t) * 4) == cudaSuccess;
     if (ok) {
@@ -323,6 +459,7 @@ int p2p_setup(sfm_handle* h) {
             s->peers.g4[p] = (const float4*)ptr[2];
             s->peers.gw[p] = (const float*)ptr[2] + (size_t)m.n_slots * m.kp;
             s->peers.scal[p] = (const double*)((const float*)ptr[2] + scal_off);
+            s->peers.tb[p] = (const uint32_t*)((const float*)ptr[2] + touch_off);
             s->peers.sig[p] = (uint32_t*)ptr[3];
         }
     }
@@ -346,31 +483,52 @@ int p2p_setup(sfm_handle* h) {
 }
 
 float* p2p_grad_buffer(sfm_handle* h) { return h->p2p ? h->p2p->grad : nullptr; }
+uint32_t* p2p_touch_bits(sfm_handle* h) { return h->p2p ? h->p2p->touch : nullptr; }
 const int32_t* p2p_timeout_flag(sfm_handle* h) {
     return h->p2p ? (const int32_t*)(h->p2p->done_ctr + 1) : nullptr;
 }
 
-// Steps 1-3 above, queued on the compute stream after the finalize kernel wrote p2p grad.
-int p2p_reduce_update(sfm_handle* h, UpdateParams up) {
+// Steps 1-3 above, queued on the compute stream after the reduce kernel wrote p2p grad.
+// sparse: the reduce wrote touched rows + the touched bitmap only (bkt_pull_kernel<MODE 2>).
+int p2p_reduce_update(sfm_handle* h, UpdateParams up, bool sparse) {
     P2PState* s = h->p2p;
     const ModelView& m = h->m;
     const int G = h->world, r = h->rank;
     int64_t* L = &h->stats.kernel_launches;
     const uint32_t epoch = ++s->epoch;
-    const int64_t f_lo = (int64_t)r * m.n_slots / G, f_hi = (int64_t)(r + 1) * m.n_slots / G;
     p2p_signal_kernel<<<1, 32, 0, h->stream>>>(s->peers, G, r, 0, epoch, h->d_scal);
-    int64_t blocks = ((f_hi - f_lo) * m.lpr + 255) / 256;
-    const int64_t cap = (int64_t)h->sm_count * 8;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
+    if (sparse) {
+        const int64_t words = (m.n_slots + 31) / 32;
+        const int wd_lo = (int)((int64_t)r * words / G), wd_hi = (int)((int64_t)(r + 1) * words / G);
+        int lsh = 0;
+        while ((1 << lsh) < m.lpr) ++lsh;
+        int64_t blocks = (words + 7) / 8;   // one warp per word at most
+        const int64_t cap = (int64_t)h->sm_count * 8;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+#define SP_ARGS                                                                                \
+    s->peers, G, r, epoch, m.n_slots, lsh, wd_lo, wd_hi, (int)words, m.k0, m.k1, m.w0, s->sig, \
+        h->d_scal, up, s->timeout_ns, s->done_ctr
+        if (G <= 2)      p2p_sparse_update_kernel<2><<<(unsigned)blocks, 256, 0, h->stream>>>(SP_ARGS);
+        else if (G <= 4) p2p_sparse_update_kernel<4><<<(unsigned)blocks, 256, 0, h->stream>>>(SP_ARGS);
+        else if (G <= 8) p2p_sparse_update_kernel<8><<<(unsigned)blocks, 256, 0, h->stream>>>(SP_ARGS);
+        else             p2p_sparse_update_kernel<16><<<(unsigned)blocks, 256, 0, h->stream>>>(SP_ARGS);
+#undef SP_ARGS
+    } else {
+        const int64_t f_lo = (int64_t)r * m.n_slots / G, f_hi = (int64_t)(r + 1) * m.n_slots / G;
+        int64_t blocks = ((f_hi - f_lo) * m.lpr + 255) / 256;
+        const int64_t cap = (int64_t)h->sm_count * 8;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
 #define RU_ARGS                                                                                \
     s->peers, G, r, epoch, f_lo * m.lpr, f_hi * m.lpr, f_lo, f_hi, m.k0, m.k1, m.w0,          \
         s->sig, h->d_scal, h->d_err, up, s->timeout_ns, s->done_ctr
-    if (G <= 2)      p2p_reduce_update_kernel<2><<<(unsigned)blocks, 256, 0, h->stream>>>(RU_ARGS);
-    else if (G <= 4) p2p_reduce_update_kernel<4><<<(unsigned)blocks, 256, 0, h->stream>>>(RU_ARGS);
-    else if (G <= 8) p2p_reduce_update_kernel<8><<<(unsigned)blocks, 256, 0, h->stream>>>(RU_ARGS);
-    else             p2p_reduce_update_kernel<16><<<(unsigned)blocks, 256, 0, h->stream>>>(RU_ARGS);
+        if (G <= 2)      p2p_reduce_update_kernel<2><<<(unsigned)blocks, 256, 0, h->stream>>>(RU_ARGS);
+        else if (G <= 4) p2p_reduce_update_kernel<4><<<(unsigned)blocks, 256, 0, h->stream>>>(RU_ARGS);
+        else if (G <= 8) p2p_reduce_update_kernel<8><<<(unsigned)blocks, 256, 0, h->stream>>>(RU_ARGS);
+        else             p2p_reduce_update_kernel<16><<<(unsigned)blocks, 256, 0, h->stream>>>(RU_ARGS);
 #undef RU_ARGS
+    }
     p2p_wait_kernel<<<1, 32, 0, h->stream>>>(s->sig, 1, G, epoch, s->timeout_ns, s->done_ctr + 1);
     *L += 3;
     CU(cudaGetLastError());

@@ -237,6 +237,25 @@ class Handle:
                                        _p(arrs[1], C.c_int32), _p(arrs[2], C.c_float),
                                        _p(arrs[3], C.c_float), len(arrs[0]) - 1))
 
+    def stage_onehot_raw(self, slot, packed_p, label_bits_p, label_f32_p, n_rows, m, id_bits):
+        """Queue the H2D copy + device unpack of a compact one-hot batch (raw pinned addresses)."""
+        self._ck(self._L.sfm_stage_onehot(
+            self._h, int(slot), C.cast(packed_p, C.POINTER(C.c_uint32)),
+            C.cast(label_bits_p, C.POINTER(C.c_uint32)) if label_bits_p else None,
+            C.cast(label_f32_p, C.POINTER(C.c_float)) if label_f32_p else None,
+            int(n_rows), int(m), int(id_bits)))
+
+    def stage_onehot(self, slot, packed, label_bits, n_rows, m, id_bits, label_f32=None):
+        """numpy form; the arrays must stay alive and unchanged until the slot is consumed."""
+        packed = _arr(packed, np.uint32)
+        label_bits = _arr(label_bits, np.uint32)
+        label_f32 = _arr(label_f32, np.float32)
+        self._keep = getattr(self, "_keep", {})
+        self._keep[slot] = (packed, label_bits, label_f32)
+        self._ck(self._L.sfm_stage_onehot(self._h, int(slot), _p(packed, C.c_uint32),
+                                          _p(label_bits, C.c_uint32), _p(label_f32, C.c_float),
+                                          int(n_rows), int(m), int(id_bits)))
+
     def train_step_staged(self, slot, it):
         loss, batch = C.c_double(), C.c_int64()
         self._ck(self._L.sfm_train_step_staged(self._h, int(slot), int(it), C.byref(loss),
@@ -314,6 +333,21 @@ class Handle:
         ms = C.c_float()
         self._ck(self._L.sfm_timer_stop(self._h, C.byref(ms)))
         return float(ms.value)
+
+
+def pack_onehot(idx, label, m, id_bits):
+    """Host packer of the compact one-hot staging format: (packed uint32 words, label bit words)."""
+    idx = _arr(np.asarray(idx).reshape(-1), np.int32)
+    n_rows = len(idx) // m
+    assert n_rows * m == len(idx)
+    label = _arr(label, np.float32)
+    words = (n_rows * m * id_bits + 31) // 32 + 1
+    packed = np.empty(words, dtype=np.uint32)
+    lbits = np.zeros(max(1, (n_rows + 31) // 32), dtype=np.uint32)
+    check(_lib.load().sfm_pack_onehot(_p(idx, C.c_int32), _p(label, C.c_float), n_rows, int(m),
+                                 int(id_bits), _p(packed, C.c_uint32),
+                                 _p(lbits, C.c_uint32) if label is not None else None))
+    return packed, lbits
 
 
 def sample_rows(seed, it, fraction, row_lo, row_hi):

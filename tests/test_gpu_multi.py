@@ -1,4 +1,4 @@
-"""2-GPU data-parallel test (skipped with fewer than 2 GPUs): one process per GPU, rows block-
+"""2/4/8-GPU data-parallel tests (skipped with fewer GPUs): one process per GPU, rows block-
 sharded, gradient all-reduced by the library over NCCL (sfm_comm_init).  Checks (SURVEY.md
 section 4 item 4): per-iteration loss on 2 GPUs == 1 GPU within the 1e-4 tolerance, replicas stay
 bitwise identical across ranks, and a rerun at the same GPU count reproduces the same bits."""
@@ -32,15 +32,17 @@ def _data():
                             rng.normal(0, 0.05, (N_SLOTS, K)).astype(np.float32))
 
 
-def _worker(rank, world, port, out_dir, p2p="1"):
+def _worker(rank, world, port, out_dir, p2p="1", sparse="1", bad_rank=-1):
     import torch.distributed as dist
     os.environ["SFM_P2P"] = p2p
+    os.environ["SFM_P2P_SPARSE"] = sparse
     os.environ["SFM_P2P_TIMEOUT_S"] = "20"
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)  # rendezvous only
     try:
         from sparkfm_b200 import Handle
+        from sparkfm_b200._lib import SfmError
         from sparkfm_b200.dist import init_comm, shard_range
         rp, idx, label, (w0, w, v) = _data()
         lo, hi = shard_range(N_ROWS, rank, world)
@@ -55,38 +57,67 @@ def _worker(rank, world, port, out_dir, p2p="1"):
         hd.load_dataset(rp[lo:hi + 1] - rp[lo], sub, None, label[lo:hi], global_row_offset=lo)
         losses = [hd.train_step(it) for it in range(1, ITERS + 1)]
         m = hd.get_model()
+        bad_seen = -1
+        if bad_rank >= 0:
+            # one rank feeds a host batch with an out-of-range index: EVERY rank must report the
+            # step as failed and leave its replica untouched (no silent divergence)
+            brp = np.arange(0, 5 * FIELDS + 1, FIELDS, dtype=np.int64)
+            bidx = sub[:5 * FIELDS].copy()
+            if rank == bad_rank:
+                bidx[7] = N_SLOTS + 3
+            try:
+                hd.train_step_csr(ITERS + 1, brp, bidx, None, label[lo:lo + 5])
+                bad_seen = 0
+            except SfmError:
+                bad_seen = 1
+            m2 = hd.get_model()
+            assert m2[0] == m[0] and np.array_equal(m2[1], m[1]) and np.array_equal(m2[2], m[2])
+            # and the job carries on afterwards
+            losses.append(hd.train_step(ITERS + 2))
+            m = hd.get_model()
         ev = hd.evaluate()
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), loss=np.array([l for l, _ in losses]),
                  batch=np.array([b for _, b in losses]), w0=m[0], w=m[1], v=m[2], rmse=ev["rmse"],
-                 n=ev["n"], mode=mode)
+                 n=ev["n"], mode=mode, bad_seen=bad_seen)
         hd.close()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpus_match_one_gpu(tmp_path):
-    """Run 0 and 1: default gradient exchange (the fused sum + update kernel over NVLink peer
-    memory when the GPUs can map each other, see `mode`); run 2: SFM_P2P=0, the NCCL all-reduce
-    path.  With two ranks both sum a + b, so all three runs must agree bit for bit."""
+def _need(world):
+    if device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_n_gpus_match_one_gpu(tmp_path, world):
+    """Runs 0 and 1: default gradient exchange (sparse sum + update kernel over NVLink peer memory
+    when the GPUs can map each other, see `mode`); run 2: the dense peer-memory kernel
+    (SFM_P2P_SPARSE=0); run 3: SFM_P2P=0, the NCCL all-reduce path.  Both peer-memory kernels add the
+    ranks' rows in rank order, so runs 0-2 agree bit for bit at every world size; NCCL's order is
+    its own, so run 3 is bitwise only at two ranks (a + b) and within 1e-6 otherwise."""
+    _need(world)
     import torch.multiprocessing as mp
     from sparkfm_b200 import Handle
     runs = []
-    for rep in range(3):
+    for rep, (p2p, sparse) in enumerate([("1", "1"), ("1", "1"), ("1", "0"), ("0", "1")]):
         d = tmp_path / f"rep{rep}"
         d.mkdir()
-        mp.spawn(_worker, args=(2, _free_port(), str(d), "0" if rep == 2 else "1"), nprocs=2,
-                 join=True)
-        runs.append([np.load(d / f"r{r}.npz") for r in range(2)])
-    a, b = runs[0]
+        mp.spawn(_worker, args=(world, _free_port(), str(d), p2p, sparse), nprocs=world, join=True)
+        runs.append([np.load(d / f"r{r}.npz") for r in range(world)])
+    a = runs[0][0]
     print("gradient exchange mode:", str(a["mode"]))
-    assert str(runs[2][0]["mode"]) == "nccl"
+    assert str(runs[3][0]["mode"]) == "nccl"
     for key in ("loss", "batch", "w0", "w", "v"):
-        assert np.array_equal(a[key], runs[2][0][key]), key   # peer-memory path == NCCL path
-    # replicas identical across ranks, and reproducible across reruns
-    for key in ("loss", "batch", "w0", "w", "v"):
-        assert np.array_equal(a[key], b[key]), key
-        assert np.array_equal(a[key], runs[1][0][key]), key
+        for r in range(1, world):                                  # replicas identical across ranks
+            assert np.array_equal(a[key], runs[0][r][key]), (key, r)
+            assert np.array_equal(runs[3][0][key], runs[3][r][key]), (key, r)
+        assert np.array_equal(a[key], runs[1][0][key]), key         # reproducible across reruns
+        assert np.array_equal(a[key], runs[2][0][key]), key         # sparse == dense peer-memory kernel
+        if world == 2:
+            assert np.array_equal(a[key], runs[3][0][key]), key     # == NCCL path
+        else:
+            assert np.max(np.abs(a[key] - runs[3][0][key])) <= 1e-6, key
     assert a["n"] == N_ROWS
     # same trajectory as one GPU holding every row
     rp, idx, label, (w0, w, v) = _data()
@@ -101,6 +132,19 @@ def test_two_gpus_match_one_gpu(tmp_path):
     assert np.max(np.abs(m1[2] - a["v"])) <= 1e-4 * np.abs(m1[2]).max()
     assert abs(hd.evaluate()["rmse"] - float(a["rmse"])) < 1e-5
     hd.close()
+
+
+@pytest.mark.parametrize("p2p,sparse", [("1", "1"), ("1", "0"), ("0", "1")])
+def test_bad_index_on_one_rank_stops_every_rank(tmp_path, p2p, sparse):
+    """A feature index outside [0, n_slots) seen by ONE rank: the error travels with the summed
+    scalars, every rank skips that update and reports SFM_ERR_INDEX; replicas stay identical."""
+    _need(2)
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), p2p, sparse, 1), nprocs=2, join=True)
+    a, b = [np.load(tmp_path / f"r{r}.npz") for r in range(2)]
+    assert int(a["bad_seen"]) == 1 and int(b["bad_seen"]) == 1
+    for key in ("loss", "w0", "w", "v"):
+        assert np.array_equal(a[key], b[key]), key
 
 
 # ------------------------------------------------------------------------------ row-sharded V

@@ -19,9 +19,12 @@ from sparkfm_b200._lib import SFM_ERR_INDEX, SFM_ERR_STATE, SfmError
 
 pytestmark = pytest.mark.gpu
 
-PRED_RTOL = 1e-5   # |got - want| <= 1e-5 * max(|want|, mean |want| of the batch): fp32 cannot
-                   # hold a RELATIVE bound on predictions that cancel to ~0, so values below the
-                   # batch's typical magnitude are held to the same absolute error instead
+PRED_RTOL = 1e-5   # gate 1: |got - want| <= 1e-5 * max(|want|, floor), floor = mean |want| of the
+                   # batch unless a test passes its own: fp32 cannot hold a RELATIVE bound on
+                   # predictions that cancel to ~0, so values below the batch's typical magnitude
+                   # are held to the same absolute error instead.  gate 2 (strict_rel): the STRICT
+                   # relative error |got - want| / |want| is reported for every row, and the rows
+                   # that miss 1e-5 must be few and must all be the small-magnitude ones.
 LOSS_RTOL = 1e-4
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "predict_kat.json")
 
@@ -30,8 +33,25 @@ def rel_err(got, want, floor=None):
     want = np.asarray(want, dtype=np.float64)
     if not len(want):
         return 0.0
-    floor = max(float(np.mean(np.abs(want))), 1e-30)
+    if floor is None:
+        floor = float(np.mean(np.abs(want)))
+    floor = max(float(floor), 1e-30)
     return np.max(np.abs(np.asarray(got, dtype=np.float64) - want) / np.maximum(np.abs(want), floor))
+
+
+def strict_rel(got, want):
+    """(max strict relative error, fraction of rows above PRED_RTOL, largest |want| among them
+    relative to the batch mean |want|) -- no floor anywhere."""
+    want = np.asarray(want, dtype=np.float64)
+    got = np.asarray(got, dtype=np.float64)
+    nz = want != 0.0
+    if not nz.any():
+        return 0.0, 0.0, 0.0
+    r = np.abs(got[nz] - want[nz]) / np.abs(want[nz])
+    over = r > PRED_RTOL
+    mean_abs = max(float(np.mean(np.abs(want))), 1e-30)
+    worst_mag = float(np.max(np.abs(want[nz][over])) / mean_abs) if over.any() else 0.0
+    return float(r.max()), float(over.mean()), worst_mag
 
 
 def make_model(rng, n_slots, k, w_std=0.1, v_std=0.1):
@@ -71,7 +91,13 @@ def test_predict_matches_oracle_all_k(k):
     orc.set_model(w0, w, v)
     got = hd.predict(row_ptr, idx, val)
     want = orc.predict(row_ptr, idx, val.astype(np.float64))
-    assert rel_err(got, want, 1e-2) < PRED_RTOL
+    assert rel_err(got, want) < PRED_RTOL
+    smax, frac_over, worst_mag = strict_rel(got, want)
+    print(f"k={k}: strict relative max {smax:.3e}, rows above 1e-5: {100 * frac_over:.3f} %, "
+          f"largest |want| among them = {worst_mag:.3f} x batch mean")
+    # strict 1e-5 relative holds except for predictions that cancel to a small fraction of the
+    # batch's typical magnitude (fp32 sums of ~25 terms cannot do better there)
+    assert frac_over <= 0.02 and worst_mag <= 0.5
     hd.close()
 
 
@@ -481,6 +507,56 @@ def test_pipelined_staging_matches_synchronous_csr_path():
     with pytest.raises(SfmError) as ei:
         b.train_step_staged(0, 6)           # slot already consumed
     assert ei.value.status == SFM_ERR_STATE
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize("m,id_bits,n_slots", [(13, 12, 3000), (39, 20, 1_000_000), (5, 32, 70_000)])
+def test_compact_onehot_staging_matches_csr_path(m, id_bits, n_slots):
+    """sfm_pack_onehot + sfm_stage_onehot (bit-packed ids, 1-bit labels, unpacked on the device)
+    + sfm_train_step_staged must give the same bits as sfm_train_step_csr on the same batches;
+    an id >= n_slots inside the packed stream is reported as SFM_ERR_INDEX and skips the update."""
+    from sparkfm_b200 import pack_onehot
+    rng = np.random.default_rng(5 + m)
+    k = 16
+    w0, w, v = make_model(rng, n_slots, k, 0.05, 0.05)
+    kw = dict(task=1, reg=(0.0, 1e-4, 1e-4), step_size=0.2)
+    a, b = Handle(n_slots, k, **kw), Handle(n_slots, k, **kw)
+    for h in (a, b):
+        h.set_model(w0, w, v)
+    batches = []
+    for s in range(4):
+        n = 3000 + 37 * s
+        idx = rng.integers(0, n_slots, size=(n, m)).astype(np.int32)
+        lab = (rng.random(n) < 0.3).astype(np.float32)
+        batches.append((idx, lab))
+    la, lb = [], []
+    packed = [pack_onehot(i, l, m, id_bits) for i, l in batches]
+    b.stage_onehot(0, packed[0][0], packed[0][1], len(batches[0][1]), m, id_bits)
+    for s, (idx, lab) in enumerate(batches):
+        rp = np.arange(len(lab) + 1, dtype=np.int64) * m
+        la.append(a.train_step_csr(s + 1, rp, idx.reshape(-1), None, lab))
+        if s + 1 < len(batches):
+            b.stage_onehot((s + 1) & 1, packed[s + 1][0], packed[s + 1][1], len(batches[s + 1][1]), m, id_bits)
+        lb.append(b.train_step_staged(s & 1, s + 1))
+    assert la == lb
+    ma, mb = a.get_model(), b.get_model()
+    assert ma[0] == mb[0] and np.array_equal(ma[1], mb[1]) and np.array_equal(ma[2], mb[2])
+    # fp32 labels instead of label bits
+    b.stage_onehot(0, packed[0][0], None, len(batches[0][1]), m, id_bits, label_f32=batches[0][1])
+    rp = np.arange(len(batches[0][1]) + 1, dtype=np.int64) * m
+    assert a.train_step_csr(5, rp, batches[0][0].reshape(-1), None, batches[0][1]) == b.train_step_staged(0, 5)
+    if (1 << id_bits) > n_slots:            # an id the packed width can hold but the model cannot
+        bad = batches[1][0].copy()
+        bad[17, m - 1] = n_slots
+        pk, lbits = pack_onehot(bad, batches[1][1], m, id_bits)
+        before = b.get_model()
+        b.stage_onehot(1, pk, lbits, len(bad), m, id_bits)
+        with pytest.raises(SfmError) as ei:
+            b.train_step_staged(1, 6)
+        assert ei.value.status == SFM_ERR_INDEX
+        after = b.get_model()
+        assert before[0] == after[0] and np.array_equal(before[2], after[2])
     a.close()
     b.close()
 

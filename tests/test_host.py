@@ -270,3 +270,28 @@ def test_parser_fast_token_path_edges():
             parse_libfm((bad + "\n").encode())
         with pytest.raises(ValueError):
             fn.parse_libfm_lines([bad])
+
+
+def test_pack_onehot_matches_bitstream_definition():
+    """sfm_pack_onehot: entry e occupies bits [e*id_bits, (e+1)*id_bits) of the little-endian
+    uint32 stream, labels one bit per row; ids wider than id_bits are SFM_ERR_INDEX."""
+    from sparkfm_b200 import pack_onehot
+    from sparkfm_b200._lib import SFM_ERR_INDEX, SfmError
+    rng = np.random.default_rng(0)
+    for m, bits, n in [(39, 20, 1000), (13, 15, 77), (3, 32, 50), (64, 1, 33), (39, 20, 100_000), (1, 7, 0)]:
+        lim = (1 << bits) if bits < 32 else (1 << 31)
+        idx = rng.integers(0, lim, size=(n, m)).astype(np.int32)
+        lab = (rng.random(n) < 0.3).astype(np.float32)
+        pk, lb = pack_onehot(idx, lab, m, bits)
+        flat = idx.reshape(-1).astype(np.uint64)
+        stream = np.zeros(len(pk) * 32, dtype=np.uint8)
+        b = ((flat[:, None] >> np.arange(bits, dtype=np.uint64)) & 1).astype(np.uint8).reshape(-1)
+        stream[:len(b)] = b
+        want = np.packbits(stream.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).reshape(-1)
+        assert np.array_equal(pk, want), (m, bits, n)
+        wl = np.zeros(len(lb) * 32, dtype=np.uint8)
+        wl[:n] = lab > 0
+        assert np.array_equal(lb, np.packbits(wl.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).reshape(-1))
+    with pytest.raises(SfmError) as ei:
+        pack_onehot(np.array([[1, 2, 1 << 12]], np.int32), np.array([1.0], np.float32), 3, 12)
+    assert ei.value.status == SFM_ERR_INDEX
