@@ -436,7 +436,7 @@ def main():
 
     import torch  # plumbing only: rendezvous + cross-rank max of the timings
     import torch.distributed as dist
-    from sparkfm_b200 import Handle, synth
+    from sparkfm_b200 import Handle, pack_onehot, synth
     from sparkfm_b200.dist import init_comm, shard_range
 
     torch.cuda.set_device(local_rank)
@@ -549,63 +549,96 @@ def main():
                 / (wms / wsteps * 1e-3) / 1e9 / (peak * world)}
         hd.set_hyper(REG[0], REG[1], REG[2], STEP_SIZE, frac)
 
-    # ---- e2e arm: host CSR mini-batches through sfm_stage_csr + sfm_train_step_staged
+    # ---- e2e arm: host mini-batches through the C ABI, H2D + D2H inside the timed region.
+    #      Headline: the compact one-hot staging format (sfm_stage_onehot: ids bit-packed at
+    #      ID_BITS, 1-bit labels, unpacked by a device kernel); beside it the generic CSR form
+    #      (sfm_stage_csr: int64 row_ptr, int32 ids, fp32 labels).
     e2e = None
+    e2e_csr = None
     if not args.no_e2e:
         L = hd._L
         nb = 3
-        bufs = []
+        id_bits = max(1, int(N_SLOTS - 1).bit_length())
         e2e_rows = batch_per_gpu
+        csr_bufs, oh_bufs = [], []
+
+        def pinned(a_):
+            p_ = ctypes.c_void_p()
+            assert L.sfm_host_alloc(ctypes.byref(p_), max(a_.nbytes, 4)) == 0
+            ctypes.memmove(p_, a_.ctypes.data, a_.nbytes)
+            return p_
+
+        pack_s = 0.0
         for b in range(nb):
             idx, label = synth.ctr_rows(rows_lo + b * e2e_rows, rows_lo + (b + 1) * e2e_rows, card,
                                         cdf, off, N_SLOTS, DATA_SEED)
             arrs = (np.arange(e2e_rows + 1, dtype=np.int64) * N_FIELDS, idx.reshape(-1), label)
-            ptrs = []
-            for a_ in arrs:
-                p_ = ctypes.c_void_p()
-                assert L.sfm_host_alloc(ctypes.byref(p_), a_.nbytes) == 0
-                ctypes.memmove(p_, a_.ctypes.data, a_.nbytes)
-                ptrs.append(p_)
-            bufs.append(ptrs)
-        h2d = (e2e_rows + 1) * 8 + e2e_rows * N_FIELDS * 4 + e2e_rows * 4
+            csr_bufs.append([pinned(a_) for a_ in arrs])
+            tp = time.perf_counter()
+            packed, lbits = pack_onehot(idx, label, N_FIELDS, id_bits)
+            pack_s += time.perf_counter() - tp
+            oh_bufs.append([pinned(packed), pinned(lbits), packed.nbytes + lbits.nbytes])
+        h2d_csr = (e2e_rows + 1) * 8 + e2e_rows * N_FIELDS * 4 + e2e_rows * 4
+        h2d_oh = oh_bufs[0][2]
 
-        def run_pipelined(n_steps, it0):
+        def stage(kind, slot, b_):
+            if kind == "onehot":
+                q_ = oh_bufs[b_]
+                hd.stage_onehot_raw(slot, q_[0], q_[1], None, e2e_rows, N_FIELDS, id_bits)
+            else:
+                q_ = csr_bufs[b_]
+                hd.stage_csr_raw(slot, q_[0], q_[1], None, q_[2], e2e_rows)
+
+        def run_pipelined(kind, n_steps, it0):
             # stage batch s+1 (async H2D on the copy stream) while batch s trains
-            p_ = bufs[0]
-            hd.stage_csr_raw(0, p_[0], p_[1], None, p_[2], e2e_rows)
+            stage(kind, 0, 0)
             for s_ in range(n_steps):
                 if s_ + 1 < n_steps:
-                    q_ = bufs[(s_ + 1) % nb]
-                    hd.stage_csr_raw((s_ + 1) & 1, q_[0], q_[1], None, q_[2], e2e_rows)
+                    stage(kind, (s_ + 1) & 1, (s_ + 1) % nb)
                 hd.train_step_staged(s_ & 1, it0 + s_)
             return it0 + n_steps
 
-        it = run_pipelined(3, it)
-        e2e_steps = args.e2e_steps
-        barrier()
-        t0 = time.perf_counter()
-        it = run_pipelined(e2e_steps, it)
-        barrier()
-        dt = time.perf_counter() - t0
-        if dt < args.min_seconds:   # short steps (small per-GPU batch): time a longer run
-            e2e_steps = int(e2e_steps * args.min_seconds / max(dt, 1e-6)) + 1
+        def time_e2e(kind, it0):
+            it1 = run_pipelined(kind, 3, it0)
+            n_steps = args.e2e_steps
             barrier()
             t0 = time.perf_counter()
-            it = run_pipelined(e2e_steps, it)
+            it1 = run_pipelined(kind, n_steps, it1)
             barrier()
             dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": e2e_rows * world * e2e_steps / float(tt[0]), "unit": UNIT,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 36, "steps": e2e_steps,
-               "rows_per_step_per_gpu": e2e_rows,
-               "api": "sfm_stage_csr (pinned host CSR -> device, copy stream) + "
-                      "sfm_train_step_staged (returns the mean loss)",
-               "timing": "wall clock around the C-ABI calls, every H2D/D2H inside the timed region"}
-        for ptrs in bufs:
+            if dt < args.min_seconds:   # short steps (small per-GPU batch): time a longer run
+                n_steps = int(n_steps * args.min_seconds / max(dt, 1e-6)) + 1
+                barrier()
+                t0 = time.perf_counter()
+                it1 = run_pipelined(kind, n_steps, it1)
+                barrier()
+                dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return e2e_rows * world * n_steps / float(tt[0]), n_steps, it1
+
+        v_oh, n_oh, it = time_e2e("onehot", it)
+        v_csr, n_csr, it = time_e2e("csr", it)
+        e2e = {"value": v_oh, "unit": UNIT, "h2d_bytes_per_step": h2d_oh, "d2h_bytes_per_step": 36,
+               "steps": n_oh, "rows_per_step_per_gpu": e2e_rows,
+               "api": f"sfm_stage_onehot (pinned host buffer: {N_FIELDS} ids per row bit-packed at "
+                      f"{id_bits} bits + 1 label bit per row -> device, copy stream, device unpack) "
+                      "+ sfm_train_step_staged (returns the mean loss)",
+               "timing": "wall clock around the C-ABI calls, every H2D/D2H inside the timed region",
+               "host_packer": {"api": "sfm_pack_onehot (multi-threaded, outside the timed region like "
+                                      "the CSR packing of the other form)",
+                               "rows_per_s": nb * e2e_rows / max(pack_s, 1e-9)},
+               "frac_of_resident_value": None}
+        e2e_csr = {"value": v_csr, "unit": UNIT, "h2d_bytes_per_step": h2d_csr,
+                   "d2h_bytes_per_step": 36, "steps": n_csr,
+                   "api": "sfm_stage_csr (int64 row_ptr, int32 ids, fp32 labels) + sfm_train_step_staged"}
+        for ptrs in csr_bufs:
             for p_ in ptrs:
                 L.sfm_host_free(p_)
+        for q_ in oh_bufs:
+            L.sfm_host_free(q_[0])
+            L.sfm_host_free(q_[1])
 
     # ---- PARTITION sampler (epoch-wise fixed mini-batches, transposition cached at first use):
     #      reported beside the Bernoulli headline, never instead of it
@@ -665,6 +698,8 @@ def main():
         cpu = cpu_baseline_block(min(args.batch, 1_000_000), 10.0)
 
     if rank == 0:
+        if e2e:
+            e2e["frac_of_resident_value"] = e2e["value"] / value
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -678,7 +713,8 @@ def main():
                        "parallelism": f"dp{world}", "gradient_exchange": comm_mode,
                        "l2": "inputs larger than L2: each step streams a fresh sampled batch "
                              "out of a 7 GB resident set; model 68 MB + per-batch scratch"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "predict": predict,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_csr": e2e_csr,
+            "predict": predict,
             "partition_sampler": part, "weak_scaling": weak, "parity_n": par,
             "comm_mode": comm_mode, "gpu_launches": int(launches),
             "clocks": clk, "loss_first_last": [float(hist[0]), float(hist[-1])],

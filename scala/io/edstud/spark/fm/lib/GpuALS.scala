@@ -1,7 +1,5 @@
 package io.edstud.spark.fm.lib
 
-import java.lang.foreign._
-import java.lang.foreign.ValueLayout._
 import io.edstud.spark.DataSet
 import io.edstud.spark.fm._
 import io.edstud.spark.fm.gpu._
@@ -9,9 +7,9 @@ import io.edstud.spark.fm.gpu._
 /** The reference's own learner (fm/lib/ALS.scala:11-208) with the sweep on the GPU: same plugin
   * boundary, same coordinate order, same closed-form update, the residual map `e` and the
   * per-factor map `q` kept on the device instead of in driver hash maps.  Used like the
-  * original: `FM(dataset, k, task, iters).learnWith(GpuALS.run())`.  `refQuirks = true` gives the
-  * bug-compatible behaviour described at sfm_als_sweep (include/sparkfm_b200.h).
-  * UNVERIFIED SOURCE (no JVM in the build image). */
+  * original: `FM(dataset, k, task, iters).learnWith(GpuALS.run())`.  `refQuirks = true` skips the
+  * last slot like `0 until num_attribute` does (ALS.scala:38,52; see sfm_als_sweep in
+  * include/sparkfm_b200.h).  UNVERIFIED SOURCE (no JVM in the build image). */
 class GpuALS protected (val refQuirks: Boolean) extends FMLearn {
 
     val rmseHistory = scala.collection.mutable.ArrayBuffer[Double]()
@@ -23,16 +21,13 @@ class GpuALS protected (val refQuirks: Boolean) extends FMLearn {
         }
         gpu.cache(dataset)
         // the model's own regularisation (FMModel.scala:29-31), as ALS.scala:21,40,56 reads it
-        SfmNative.check(SfmNative.setHyper.invoke(gpu.handle, fm.reg0.toFloat, fm.regw.toFloat,
-            fm.regv.toFloat, 0.1f, 1.0f).asInstanceOf[Int], gpu.handle)
-        val a = Arena.ofConfined()
-        try {
-            val rmse = a.allocate(JAVA_DOUBLE)
-            SfmNative.check(SfmNative.alsSweep.invoke(gpu.handle, if (refQuirks) 1 else 0, rmse)
-                .asInstanceOf[Int], gpu.handle)
-            rmseHistory += rmse.get(JAVA_DOUBLE, 0)
-            logInfo("Finish")
-        } finally a.close()
+        SfmJni.check(SfmJni.setHyper(gpu.handle, fm.reg0.toFloat, fm.regw.toFloat, fm.regv.toFloat,
+            0.1f, 1.0f), gpu.handle)
+        val rmse = new Array[Double](1)
+        SfmJni.check(SfmJni.alsSweep(gpu.handle, if (refQuirks) 1 else 0, rmse), gpu.handle)
+        gpu.markStale()
+        rmseHistory += rmse(0)
+        logInfo("Finish")
         gpu
     }
 }

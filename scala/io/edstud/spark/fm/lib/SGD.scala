@@ -1,7 +1,5 @@
 package io.edstud.spark.fm.lib
 
-import java.lang.foreign._
-import java.lang.foreign.ValueLayout._
 import io.edstud.spark.DataSet
 import io.edstud.spark.fm._
 import io.edstud.spark.fm.gpu._
@@ -22,18 +20,15 @@ class SGD protected (val stepSize: Double, val regParam: (Double, Double, Double
             case _ => throw new Exception("SGD needs a GpuFMModel (build it with FMWithSGD or GpuFM)")
         }
         gpu.cache(dataset)
-        SfmNative.check(SfmNative.setHyper.invoke(gpu.handle, regParam._1.toFloat, regParam._2.toFloat,
-            regParam._3.toFloat, stepSize.toFloat, miniBatchFraction.toFloat).asInstanceOf[Int], gpu.handle)
+        SfmJni.check(SfmJni.setHyper(gpu.handle, regParam._1.toFloat, regParam._2.toFloat,
+            regParam._3.toFloat, stepSize.toFloat, miniBatchFraction.toFloat), gpu.handle)
         iteration += 1
-        val a = Arena.ofConfined()
-        try {
-            val loss = a.allocate(JAVA_DOUBLE); val batch = a.allocate(JAVA_LONG)
-            // row_ids = NULL, n_ids = -1: the built-in sampler
-            SfmNative.check(SfmNative.trainStep.invoke(gpu.handle, MemorySegment.NULL, -1L, iteration,
-                loss, batch).asInstanceOf[Int], gpu.handle)
-            lossHistory += loss.get(JAVA_DOUBLE, 0)
-            logDebug("SGD iteration " + iteration + ": mean loss " + lossHistory.last)
-        } finally a.close()
+        val loss = new Array[Double](1); val batch = new Array[Long](1)
+        // row_ids = NULL, n_ids = -1: the built-in sampler
+        SfmJni.check(SfmJni.trainStep(gpu.handle, null, -1L, iteration, loss, batch), gpu.handle)
+        gpu.markStale()                                   // predict / computeMAE re-read the device model
+        lossHistory += loss(0)
+        logDebug("SGD iteration " + iteration + ": mean loss " + lossHistory.last)
         gpu
     }
 }

@@ -1,5 +1,7 @@
 package io.edstud.spark.fm.gpu
 
+// ALTERNATIVE binding for a JDK 22+ build (NOT what build.sbt:7-11 pins -- the JNI binding
+// scala/io/edstud/spark/fm/gpu/SfmJni.scala + jni/sfm_jni.c is the one the shim uses).
 // Panama (java.lang.foreign, JDK 22+) binding of libsparkfm_b200.so -- the reference-side stub a
 // maintainer adds; one MethodHandle per C-ABI export used by the Scala layer.
 // UNVERIFIED SOURCE: no JVM / scalac exists in the build image (SURVEY.md F3); the same ABI is

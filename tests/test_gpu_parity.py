@@ -119,11 +119,11 @@ def test_predict_edge_rows():
     orc.set_model(w0, w, v)
     got = hd.predict(rp, idx, val)
     want = orc.predict(rp, idx, val.astype(np.float64))
-    assert rel_err(got, want, 1e-2) < PRED_RTOL
+    assert rel_err(got, want) < PRED_RTOL
     assert got[0] == np.float32(w0) and got[6] == np.float32(w0)
     got1 = hd.predict(rp, idx, None)  # val == NULL means all ones
     want1 = orc.predict(rp, idx, np.ones(len(idx)))
-    assert rel_err(got1, want1, 1e-2) < PRED_RTOL
+    assert rel_err(got1, want1) < PRED_RTOL
     assert hd.predict([0], np.zeros(0, np.int32), None).shape == (0,)  # empty batch
     hd.close()
 
@@ -142,7 +142,7 @@ def test_predict_dominant_feature_no_cancellation():
     orc.set_model(w0, w, v)
     got = hd.predict(row_ptr, idx, val)
     want = orc.predict(row_ptr, idx, val.astype(np.float64))
-    assert rel_err(got, want, 1e-2) < PRED_RTOL
+    assert rel_err(got, want) < PRED_RTOL
     hd.close()
 
 
@@ -377,7 +377,7 @@ def test_evaluate_matches_oracle_metrics():
     agree = np.mean(((y >= 0) & (p >= 0)) | ((y < 0) & (p < 0)))           # Model.scala:29
     assert abs(m["accuracy"] - agree) < 2e-4  # sign flips of |p| ~ 1e-7 are allowed
     assert m["n"] == n_rows
-    assert rel_err(hd.predict_resident(100, 900), p[100:900], 1e-2) < PRED_RTOL
+    assert rel_err(hd.predict_resident(100, 900), p[100:900]) < PRED_RTOL
     hd.close()
 
 

@@ -295,3 +295,24 @@ def test_pack_onehot_matches_bitstream_definition():
     with pytest.raises(SfmError) as ei:
         pack_onehot(np.array([[1, 2, 1 << 12]], np.int32), np.array([1.0], np.float32), 3, 12)
     assert ei.value.status == SFM_ERR_INDEX
+
+
+def test_jni_glue_binds_every_export_and_matches_the_scala_declarations():
+    """jni/sfm_jni.c (the binding for the reference's Scala 2.10 / Java 7-8 toolchain): valid C
+    against a stand-in jni.h (no JDK in the image), one call of every export the header declares,
+    and one `@native def` in SfmJni.scala per JNI function (and vice versa)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "jni", "sfm_jni.c")
+    subprocess.check_call(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-Wno-unused-parameter",
+                           "-DSFM_JNI_COMPILE_CHECK_ONLY", "-I" + os.path.join(root, "jni", "compile_check"),
+                           "-I" + os.path.join(root, "include"), src])
+    text = open(src).read()
+    header = open(os.path.join(root, "include", "sparkfm_b200.h")).read()
+    declared = set(re.findall(r"\b(sfm_[a-z0-9_]+)\s*\(", header))
+    called = set(re.findall(r"\b(sfm_[a-z0-9_]+)\s*\(", text))
+    assert declared <= called, sorted(declared - called)
+    c_names = set(re.findall(r"FN\((\w+)\)", text)) - {"name"}
+    scala = open(os.path.join(root, "scala", "io", "edstud", "spark", "fm", "gpu", "SfmJni.scala")).read()
+    s_names = set(re.findall(r"@native def (\w+)", scala))
+    assert c_names == s_names, (sorted(c_names - s_names), sorted(s_names - c_names))
