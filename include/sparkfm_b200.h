@@ -255,9 +255,10 @@ int32_t sfm_gradient(sfm_handle* h, const int64_t* row_ids, int64_t n_ids, float
  * coordinate order, residual cache e and per-factor cache q in fp64 on the device.  The
  * transposed input and the level schedule that makes the sequential sweep parallel are built at
  * the first call and kept (the reference's cached `transposeInput`, DataSet.scala:48).
- * flags: SFM_ALS_REF_QUIRKS reproduces two reference bugs (the last slot is never trained,
- * ALS.scala:38,52; the residuals are not corrected after the w0 step, :24); 0 = the algorithm as
- * written down.  rmse_out: sqrt(mean e^2) of the residuals after the sweep (the per-iteration
+ * flags: SFM_ALS_REF_QUIRKS reproduces the reference's one bug (`0 until num_attribute`,
+ * ALS.scala:38,52, never trains the last slot) and is what a drop-in for ALS.run() passes; 0 trains
+ * every slot.  (The residuals after the w0 step are yhat_new - y in both modes: the reference's
+ * lazy RDD is re-evaluated with the new w0, ALS.scala:27,31,142-144.)  rmse_out: sqrt(mean e^2) of the residuals after the sweep (the per-iteration
  * train RMSE FactorizationMachines.scala:43 computes with an extra pass).  One GPU, replicated
  * model; rows must not store a feature index twice (SFM_ERR_ARG). */
 #define SFM_ALS_REF_QUIRKS 1

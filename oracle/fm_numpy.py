@@ -197,7 +197,9 @@ def als_sweep(w0, w, v, row_ptr, idx, val, label, k0=True, k1=True, reg=(0.0, 0.
         for r in range(n):
             total = e[r] if r == 0 else total + e[r]
         nw0 = rnd(compute_theta(w0, r0, total, float(n)))
-        if updatable(nw0, w0) and not ref_quirks:             # quirk (ii): lazily evaluated to + 0
+        # :24 is lazily evaluated to "+ 0" at :31, but the same re-evaluation runs fm.predict with
+        # the new w0 (:27, :142-144): the materialised residuals are shifted either way
+        if updatable(nw0, w0):
             for r in range(n):
                 e[r] = e[r] + (nw0 - w0)
         w0 = nw0
@@ -205,7 +207,7 @@ def als_sweep(w0, w, v, row_ptr, idx, val, label, k0=True, k1=True, reg=(0.0, 0.
     for r in range(n):
         for j in range(int(row_ptr[r]), int(row_ptr[r + 1])):
             features.setdefault(int(idx[j]), []).append((r, float(val[j])))
-    id_end = n_slots - 1 if ref_quirks else n_slots           # quirk (i): `0 until num_attribute`
+    id_end = n_slots - 1 if ref_quirks else n_slots           # the one quirk: `0 until num_attribute`
 
     def draw_theta(theta, lam, h):                            # :156-165, h = [(row, value)]
         sum_h_sqr = sum_e_h = 0.0

@@ -594,7 +594,11 @@ double fmo_als_sweep(const fmo_params* p, double* w0, double* w, double* v,
         }
         double nw0 = als_theta(*w0, p->reg0, sum, (double)n_rows);   /* drawGlobalBias :152-154 */
         if (f32) nw0 = (double)(float)nw0;
-        if (als_updatable(nw0, *w0) && !quirks)                      /* quirk (ii): no correction */
+        /* :24 adds (w0* - fm.w0) inside a lazy, uncached RDD (:142-144) that is first materialised
+         * at :31, after `fm.w0 = w0` (:27): the added term is then 0, but the re-evaluation runs
+         * fm.predict with the NEW w0 -- the residuals the sweep uses are yhat_new - y, i.e. the
+         * old ones shifted by the w0 step, with or without FMO_ALS_REF_QUIRKS. */
+        if (als_updatable(nw0, *w0))
             for (int64_t r = 0; r < n_rows; ++r) e[r] = e[r] + (nw0 - *w0);
         *w0 = nw0;
     }

@@ -147,11 +147,13 @@ void fmo_init_v(double* v, int64_t count, double mean, double stdev, uint64_t se
  * Columns are the transposed input (DataSet.scala:31-38): rows ascending; a column without
  * stored entries is skipped (`features.contains(id)`).  A row must not store the same feature
  * twice (the transposition would carry a duplicate index; the CUDA path rejects it).
- * flags: FMO_ALS_REF_QUIRKS reproduces two behaviours of the reference that are bugs:
- *   (i)  `for (id <- 0 until fm.num_attribute)` (:38, :52) never trains the last slot
- *        id = n_slots - 1;
- *   (ii) the residual correction after the w0 step (:24) is a lazy RDD closure over the mutable
- *        model and evaluates to e + (w0* - w0*) = e: e is NOT corrected.
+ * flags: FMO_ALS_REF_QUIRKS reproduces the one behaviour of the reference that is a bug:
+ *   `for (id <- 0 until fm.num_attribute)` (:38, :52) never trains the last slot id = n_slots - 1.
+ *   (The residual correction after the w0 step, :24, is NOT a second quirk: it is a lazy RDD
+ *   closure over the mutable model that evaluates to e + (w0* - w0*) = e + 0, but the same lazy
+ *   re-evaluation, first materialised at :31 after `fm.w0 = w0` at :27, runs fm.predict with
+ *   the new w0 (:142-144) -- the residuals come out shifted, exactly as the plain algorithm has
+ *   them.  Round 1 modelled this wrongly as "e stays stale".)
  *   FMO_ALS_STORE_F32: every accepted parameter is rounded to fp32 before it is stored and
  *   before the residual update uses it (what the fp32 device model does), so the CUDA path can
  *   be compared tightly.

@@ -296,8 +296,8 @@ class SGD(FMLearn):
 class ALS(FMLearn):
     """fm/lib/ALS.scala:11-200 -- the learner the reference ships: one `learn` call is one sweep of
     closed-form coordinate updates over w0, w and V for squared loss, using the model's own
-    reg0 / regw / regv (FMModel.scala:29-31).  `refQuirks=True` reproduces the two reference bugs
-    described at `sfm_als_sweep` in include/sparkfm_b200.h."""
+    reg0 / regw / regv (FMModel.scala:29-31).  `refQuirks=True` reproduces the reference's one bug
+    (the last slot is never trained, ALS.scala:38,52; see `sfm_als_sweep` in include/sparkfm_b200.h)."""
 
     def __init__(self, refQuirks=False):
         self.refQuirks = bool(refQuirks)

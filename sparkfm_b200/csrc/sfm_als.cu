@@ -232,7 +232,10 @@ __global__ void als_w0_kernel(const double* __restrict__ part, float* __restrict
     if (w0) {
         double delta;
         *w0 = als_theta(*w0, reg0, s, (double)n_rows, &delta);
-        scal[1] = correct_e ? delta : 0.0;   // reference quirk: the residuals are not corrected
+        // The reference adds (w0* - fm.w0) inside a LAZY RDD that is first materialised after
+        // `fm.w0 = w0` (ALS.scala:17,24,27,31,142-144): the term is 0 there, but the same
+        // re-evaluation runs fm.predict with the NEW w0, so its residuals do carry the shift.
+        scal[1] = correct_e ? delta : 0.0;
     }
 }
 
@@ -464,8 +467,7 @@ static cudaError_t als_enqueue(sfm_handle* h, AlsState* s, const BatchView& b, i
     ++nl;
     if (m.k0) {
         als_sum_kernel<false><<<ALS_PARTS, 256, 0, h->stream>>>(e, n_rows, part);
-        als_w0_kernel<<<1, 32, 0, h->stream>>>(part, m.w0, (double)h->cfg.reg0, n_rows, quirks ? 0 : 1,
-                                               scal);
+        als_w0_kernel<<<1, 32, 0, h->stream>>>(part, m.w0, (double)h->cfg.reg0, n_rows, 1, scal);
         als_shift_kernel<<<(unsigned)(h->sm_count * 4), 256, 0, h->stream>>>(e, n_rows, scal);
         nl += 3;
     }

@@ -57,14 +57,25 @@ constexpr int SC_TILE = SC_THREADS * SC_IPT;   // 8192
 #ifndef BK_PL_IPT
 #define BK_PL_IPT 8
 #endif
+#ifndef BK_ITEM_TILES
+#define BK_ITEM_TILES 8
+#endif
 constexpr int PL_THREADS = BK_PL_THREADS;    // pull: 16 warps x 8 entries per thread
 constexpr int PL_WARPS = PL_THREADS / 32;
 constexpr int PL_IPT = BK_PL_IPT;
-constexpr int PL_CTAS_PER_SM = 1024 / PL_THREADS;
+#ifndef BK_PL_CTAS
+#define BK_PL_CTAS (1024 / BK_PL_THREADS)
+#endif
+constexpr int PL_CTAS_PER_SM = BK_PL_CTAS;   // launch bound (register budget); the grid uses the real occupancy
 constexpr int PL_TILE = PL_THREADS * PL_IPT;   // 4096
-constexpr int PL_ITEM_TILES = 8;
+static_assert(PL_IPT % 2 == 0 && 32 * PL_IPT <= 65536, "strip ranks are packed two per word");
+constexpr int PL_ITEM_TILES = BK_ITEM_TILES;
 constexpr int PL_ITEM = PL_TILE * PL_ITEM_TILES;   // 32768 entries per work item
-constexpr int PL_U = 4;                      // S-row gathers in flight per lane
+constexpr int PL_ORDER_CLASSES = 64;               // size classes of the largest-first item order
+#ifndef BK_PL_U
+#define BK_PL_U 4
+#endif
+constexpr int PL_U = BK_PL_U;                // S-row gathers in flight per lane
 constexpr uint32_t NO_DIGIT = 0xFFFFFFFFu;
 #ifndef BK_STAGE_MULT
 #define BK_STAGE_MULT 0   // all-ones data: mult_r staged in shared memory with the entries (else gathered in the walk)
@@ -92,8 +103,19 @@ __device__ __forceinline__ int64_t ent_of(const int64_t* __restrict__ out_ptr, i
 // winner back, and the lanes with the same winner find each other with 5 ballots over the winner's
 // bits -- instead of one ballot per digit bit (up to 11).  The table is never cleared: every
 // reader has just written its own slot.
+#ifndef BK_MATCH
+#define BK_MATCH 0        // scatter: 1 = one MATCH.ANY instead of the leader table + 5 ballots (A/B knob)
+#endif
+#ifndef BK_MATCH_PULL
+#define BK_MATCH_PULL 1   // the same choice for the reduce kernel's tile ranking (measured: 0.669 -> 0.638 ms)
+#endif
+template <bool MATCH>
 __device__ __forceinline__ uint32_t peer_mask(uint8_t* __restrict__ tab, uint32_t d, bool valid,
                                               int lane) {
+    if (MATCH) {
+        const uint32_t mm = __match_any_sync(FULL, valid ? d : 0xFFFFFFFFu);
+        return valid ? mm : 0u;
+    }
     if (valid) tab[d] = (uint8_t)lane;
     __syncwarp();
     const uint32_t leader = valid ? (uint32_t)tab[d] : 0u;
@@ -189,8 +211,10 @@ bkt_offsets_kernel(uint32_t* __restrict__ counts, int G, int NB, uint32_t* __res
 // item_bucket[item] = its bucket.
 __global__ void __launch_bounds__(1024)
 bkt_plan_kernel(const uint32_t* __restrict__ totals, int NB, uint32_t* __restrict__ bucket_off,
-                uint32_t* __restrict__ item_start, uint32_t* __restrict__ item_bucket) {
+                uint32_t* __restrict__ item_start, uint32_t* __restrict__ item_bucket,
+                uint32_t* __restrict__ item_order) {
     __shared__ uint32_t wsum[32];
+    __shared__ uint32_t cls_cnt[PL_ORDER_CLASSES];
     const int b0 = threadIdx.x * 2;
     const uint32_t t0 = b0 < NB ? totals[b0] : 0u, t1 = b0 + 1 < NB ? totals[b0 + 1] : 0u;
     const uint32_t n0 = b0 < NB ? max(1u, (t0 + PL_ITEM - 1) / PL_ITEM) : 0u;
@@ -213,6 +237,41 @@ bkt_plan_kernel(const uint32_t* __restrict__ totals, int NB, uint32_t* __restric
         bucket_off[NB] = tot_e;
         item_start[NB] = tot_i;
     }
+    // item_order: the work items largest first (counting sort by size class), so that the
+    // persistent CTAs of the reduce end together instead of one of them starting a 32 K-entry item
+    // last.  The order inside a class comes from integer atomics and is free to vary: it only
+    // schedules work, every sum keeps its fixed shape.
+    for (int c = threadIdx.x; c < PL_ORDER_CLASSES; c += 1024) cls_cnt[c] = 0;
+    __syncthreads();
+    auto cls_of = [](uint32_t entries) -> int {   // class 0 = largest
+        const int c = (int)((PL_ITEM - min(entries, (uint32_t)PL_ITEM)) / (PL_ITEM / PL_ORDER_CLASSES));
+        return min(c, PL_ORDER_CLASSES - 1);
+    };
+    auto for_my_items = [&](auto fn) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int b = b0 + h;
+            if (b >= NB) continue;
+            const uint32_t t = h ? t1 : t0, n = h ? n1 : n0, first = h ? ex_i + n0 : ex_i;
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint32_t lo = j * (uint32_t)PL_ITEM;
+                const uint32_t sz = t > lo ? min((uint32_t)PL_ITEM, t - lo) : 0u;
+                fn(first + j, sz);
+            }
+        }
+    };
+    for_my_items([&](uint32_t, uint32_t sz) { atomicAdd(&cls_cnt[cls_of(sz)], 1u); });
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int c = 0; c < PL_ORDER_CLASSES; ++c) {
+            const uint32_t t = cls_cnt[c];
+            cls_cnt[c] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+    for_my_items([&](uint32_t item, uint32_t sz) { item_order[atomicAdd(&cls_cnt[cls_of(sz)], 1u)] = item; });
 }
 
 // ------------------------------------------------------------------------------------------
@@ -288,7 +347,7 @@ bkt_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict
             if (strip + r * 32 < n_valid) {   // warp-uniform
                 const bool valid = strip + r * 32 + lane < n_valid;
                 const uint32_t d = key[r] >> LB;
-                const uint32_t pm = peer_mask(ltab, d, valid, lane);
+                const uint32_t pm = peer_mask<BK_MATCH != 0>(ltab, d, valid, lane);
                 uint32_t old = 0;
                 if (valid && (pm & lt) == 0u) {   // first lane of the group owns the counter
                     old = wh[d];
@@ -437,6 +496,7 @@ struct PullArgs {
     const uint32_t* bucket_off;  // [NB+1]
     const uint32_t* item_start;  // [NB+1]
     const uint32_t* item_bucket; // [items]
+    const uint32_t* item_order;  // [items] ticket -> item, largest items first
     uint32_t* work;              // [0] ticket, [1 + b] arrivals of bucket b (zeroed per step)
     float* part;                 // [items][2^LB][REC] partial accumulators of multi-item buckets
     uint32_t* part_bits;         // [items][2^LB / 32 (>= 1)] touched bitmaps
@@ -484,6 +544,8 @@ bkt_pull_kernel(const PullArgs a) {
     float* val_s = reinterpret_cast<float*>(ent_s + C::TILE_PAD);         // [TILE_PAD] mult_r or x
     uint32_t* tch = reinterpret_cast<uint32_t*>(val_s + ((BINARY && !STAGE_MULT) ? 0 : C::TILE_PAD));   // [NBL]
     uint16_t* whist = reinterpret_cast<uint16_t*>(tch + NBL);             // [WARPS][NBL]
+    // one bit per sorted position of the tile: set where a run (a new local id) begins
+    uint32_t* bflag = reinterpret_cast<uint32_t*>(whist + (size_t)PL_WARPS * NBL);   // [PL_TILE / 32]
     __shared__ uint32_t wsum[PL_WARPS];
     __shared__ uint32_t s_item, s_last;
 
@@ -503,8 +565,8 @@ bkt_pull_kernel(const PullArgs a) {
         __syncthreads();   // previous item fully finished (shared scalars, accumulators)
         if (tid == 0) s_item = atomicAdd(a.work, 1u);
         __syncthreads();
-        const uint32_t item = s_item;
-        if (item >= total_items) break;
+        if (s_item >= total_items) break;
+        const uint32_t item = __ldg(a.item_order + s_item);
         const int b = (int)__ldg(a.item_bucket + item);
         const uint32_t it0 = __ldg(a.item_start + b), it1 = __ldg(a.item_start + b + 1);
         const uint32_t boff = __ldg(a.bucket_off + b), bend = __ldg(a.bucket_off + b + 1);
@@ -523,7 +585,8 @@ bkt_pull_kernel(const PullArgs a) {
                 if (!BINARY) xv[r] = p < nv ? __uint_as_float(__ldg(a.vals + tb + p)) : 0.f;
             }
         };
-        if (e_lo < e_hi) load_tile(e_lo);
+        // (the tile's entries are only live from here to the re-order: the NEXT tile is pulled
+        // into L2 by prefetch instructions during the walk, not held in registers)
         for (int i = tid; i < NBL * LPR; i += PL_THREADS) accA[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int i = tid; i < NBL; i += PL_THREADS) {
             accC[i] = 0.f;
@@ -533,6 +596,7 @@ bkt_pull_kernel(const PullArgs a) {
 
         for (uint32_t tb = e_lo; tb < e_hi; tb += PL_TILE) {
             const int n_valid = (int)min((uint32_t)PL_TILE, e_hi - tb);
+            load_tile(tb);
             // all-ones data: the rows' multipliers (4 MB array, L2 resident) are fetched while
             // the tile is ranked and ride along into shared memory
             float second[PL_IPT];
@@ -549,21 +613,22 @@ bkt_pull_kernel(const PullArgs a) {
                 if (NBL == 1 && tid < PL_WARPS) whist[tid] = 0;
             }
             __syncthreads();   // histograms zero; the previous tile's walk is over
-            uint32_t rk[PL_IPT];
+            if (tid < PL_TILE / 32) bflag[tid] = 0u;   // read next after two more barriers
+            uint32_t rk2[PL_IPT / 2];   // ranks inside the warp's strip (< 32 * PL_IPT), two per word
 #pragma unroll
             for (int r = 0; r < PL_IPT; ++r) {
-                rk[r] = 0;
+                if (!(r & 1)) rk2[r / 2] = 0;
                 if (strip + r * 32 < n_valid) {   // warp-uniform
                     const bool valid = strip + r * 32 + lane < n_valid;
                     const uint32_t d = LB ? ent[r] >> RB : 0u;
-                    const uint32_t pm = peer_mask(ltab, d, valid, lane);
+                    const uint32_t pm = peer_mask<BK_MATCH_PULL != 0>(ltab, d, valid, lane);
                     uint32_t old = 0;
                     if (valid && (pm & lt) == 0u) {   // first lane of the group owns the counter
                         old = wh[d];
                         wh[d] = (uint16_t)(old + __popc(pm));
                     }
                     old = __shfl_sync(FULL, old, valid ? __ffs(pm) - 1 : lane);
-                    rk[r] = old + __popc(pm & lt);
+                    rk2[r / 2] |= (old + __popc(pm & lt)) << ((r & 1) * 16);
                 }
             }
             __syncthreads();
@@ -607,20 +672,33 @@ bkt_pull_kernel(const PullArgs a) {
                 const int p = strip + r * 32 + lane;
                 if (p < n_valid) {
                     const uint32_t d = LB ? ent[r] >> RB : 0u;
-                    const int q = phys((int)lstart[d] + (int)wh[d] + (int)rk[r]);
+                    const uint32_t within = (uint32_t)wh[d] + ((rk2[r / 2] >> ((r & 1) * 16)) & 0xffffu);   // rank inside the local id's run
+                    const int ql = (int)lstart[d] + (int)within;
+                    if (within == 0u) atomicOr(&bflag[ql >> 5], 1u << (ql & 31));   // <= 2^LB per tile
+                    const int q = phys(ql);
                     ent_s[q] = ent[r];
                     if (!BINARY || STAGE_MULT) val_s[q] = second[r];
                 }
             }
             __syncthreads();
-            // the next tile's entries travel while this one is walked
-            if (tb + PL_TILE < e_hi) load_tile(tb + PL_TILE);
+            // the next tile's entries travel to L2 while this one is walked
+            if (lane == 0 && tb + PL_TILE < e_hi) {
+#pragma unroll
+                for (int r = 0; r < PL_IPT; ++r) {
+                    const uint32_t p = tb + PL_TILE + strip + r * 32;
+                    if (p < e_hi) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.packed + p));
+                        if (!BINARY) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vals + p));
+                    }
+                }
+            }
 
             // ---- level 0: walk my SUB sorted entries (group g owns sorted positions
             // [g * SUB, (g + 1) * SUB): physical words g * (SUB + 1) + j)
             const int q0 = g * SUB;
             const uint32_t* my_e = ent_s + g * (SUB + 1);
             const float* my_v = val_s + g * (SUB + 1);
+            const char* Sq = reinterpret_cast<const char*>(a.S4 + fq);   // this lane's quarter of a row
             auto flush = [&](uint32_t d, const float4& A, float D, float Cc) {
                 float4 t = accA[d * LPR + fq];
                 t.x += A.x; t.y += A.y; t.z += A.z; t.w += A.w;
@@ -641,7 +719,7 @@ bkt_pull_kernel(const PullArgs a) {
                 constexpr bool FULLT = decltype(full_tag)::value;
 #pragma unroll 1
                 for (int base = 0; base < SUB; base += PL_U) {
-                    uint32_t dd[PL_U];
+                    uint32_t ee[PL_U];
                     float cc[PL_U], xx[PL_U];
                     float4 sv[PL_U];
 #pragma unroll
@@ -651,7 +729,7 @@ bkt_pull_kernel(const PullArgs a) {
                         const uint32_t row = e & rowmask;
                         const float sec = (BINARY && !STAGE_MULT) ? (ok ? __ldg(a.mult + row) : 0.f)
                                                                    : (ok ? my_v[base + u] : 0.f);
-                        dd[u] = ok ? dig(e) : NO_DIGIT;
+                        ee[u] = e;
                         if (BINARY) {
                             cc[u] = sec;
                             xx[u] = 1.f;
@@ -660,12 +738,32 @@ bkt_pull_kernel(const PullArgs a) {
                             cc[u] = ok ? __ldg(a.mult + row) * sec : 0.f;
                         }
                         // row * LPR + fq < 2^32: checked by the caller (train_core)
-                        sv[u] = ok ? ld_gather4(a.S4 + (uint32_t)(row * (uint32_t)LPR + (uint32_t)fq))
+                        sv[u] = ok ? ld_gather4(reinterpret_cast<const float4*>(
+                                         Sq + (size_t)row * (size_t)(LPR * 16)))
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    // no run starts inside this chunk (the common case on skewed ids, where runs
+                    // are long): plain accumulation, no digit compares
+                    const int qb = q0 + base;
+                    const uint32_t starts = FULLT ? ((bflag[qb >> 5] >> (qb & 31)) & ((1u << PL_U) - 1u)) : 1u;
+                    if (starts == 0u) {
+#pragma unroll
+                        for (int u = 0; u < PL_U; ++u) {
+                            const float c = cc[u];
+                            A.x = fmaf(c, sv[u].x, A.x);
+                            A.y = fmaf(c, sv[u].y, A.y);
+                            A.z = fmaf(c, sv[u].z, A.z);
+                            A.w = fmaf(c, sv[u].w, A.w);
+                            D = BINARY ? D : fmaf(c, xx[u], D);
+                            Cc += c;
+                        }
+                        continue;
                     }
 #pragma unroll
                     for (int u = 0; u < PL_U; ++u) {
-                        if (dd[u] != cur) {
+                        const bool ok = FULLT || q0 + base + u < n_valid;
+                        const uint32_t du = ok ? dig(ee[u]) : NO_DIGIT;
+                        if (du != cur) {
                             if (cur != NO_DIGIT) {
                                 if (cur_is_head) {
                                     headA[g * LPR + fq] = A;
@@ -674,7 +772,7 @@ bkt_pull_kernel(const PullArgs a) {
                                     flush(cur, A, D, Cc);
                                 }
                             }
-                            cur = dd[u];
+                            cur = du;
                             cur_is_head = false;
                             A = make_float4(0.f, 0.f, 0.f, 0.f);
                             D = 0.f;
@@ -882,12 +980,12 @@ bool bucket_geometry(const ModelView& m, int key_bits, int64_t n_rows, int64_t n
     return true;
 }
 
-size_t bucket_tables_bytes(const BucketGeom& g) {   // bucket_off | item_start | item_bucket
-    return al256(sizeof(uint32_t) * (size_t)(g.NB + 1)) * 2 + al256(sizeof(uint32_t) * (size_t)g.max_items);
+size_t bucket_tables_bytes(const BucketGeom& g) {   // bucket_off | item_start | item_bucket | item_order
+    return al256(sizeof(uint32_t) * (size_t)(g.NB + 1)) * 2 + al256(sizeof(uint32_t) * (size_t)g.max_items) * 2;
 }
 
 struct TablePtrs {
-    uint32_t *bucket_off, *item_start, *item_bucket;
+    uint32_t *bucket_off, *item_start, *item_bucket, *item_order;
 };
 
 static TablePtrs carve_tables(const BucketGeom& g, const void* base) {
@@ -898,6 +996,8 @@ static TablePtrs carve_tables(const BucketGeom& g, const void* base) {
     t.item_start = reinterpret_cast<uint32_t*>(p);
     p += al256(sizeof(uint32_t) * (size_t)(g.NB + 1));
     t.item_bucket = reinterpret_cast<uint32_t*>(p);
+    p += al256(sizeof(uint32_t) * (size_t)g.max_items);
+    t.item_order = reinterpret_cast<uint32_t*>(p);
     return t;
 }
 
@@ -955,7 +1055,8 @@ cudaError_t bucket_transpose(const ModelView& m, const BatchView& b, const Bucke
     bkt_count_kernel<<<G, 512, sizeof(uint32_t) * g.NB, st>>>(keys, (int)b.n_rows, mm, optr,
                                                                b.out_base, g.LB, g.NB, w.counts);
     bkt_offsets_kernel<<<(g.NB + 31) / 32, 1024, 0, st>>>(w.counts, G, g.NB, w.totals);
-    bkt_plan_kernel<<<1, 1024, 0, st>>>(w.totals, g.NB, bucket_off, tp.item_start, tp.item_bucket);
+    bkt_plan_kernel<<<1, 1024, 0, st>>>(w.totals, g.NB, bucket_off, tp.item_start, tp.item_bucket,
+                                        tp.item_order);
     const size_t smem = scatter_smem(g.HB, has_val);
     const unsigned long long magic =
         implicit_div ? ((1ULL << 40) + (unsigned long long)implicit_div - 1) / (unsigned long long)implicit_div : 0ULL;
@@ -985,7 +1086,7 @@ static size_t pull_smem(int lb, bool binary) {
     const size_t nbl = (size_t)1 << lb;
     return nbl * LPR * 16 + pull_union_bytes<LPR>(lb) + nbl * 4 * 2 +
            (size_t)C::TILE_PAD * 4 * ((binary && !STAGE_MULT) ? 1 : 2) + nbl * 4 +
-           (size_t)PL_WARPS * nbl * 2 + 64;
+           (size_t)PL_WARPS * nbl * 2 + PL_TILE / 8 + 64;
 }
 
 template <int LPR>
@@ -993,11 +1094,16 @@ static cudaError_t pull_dispatch2(const ModelView& m, const BucketGeom& g, const
                                   bool binary, int mode, int sm_count, cudaStream_t st) {
     const size_t smem = pull_smem<LPR>(g.LB, binary);
     cudaError_t e;
+    int occ = 0;   // resident CTAs per SM: the grid of the persistent kernel
 #define PL_LAUNCH(B, M)                                                                          \
     e = cudaFuncSetAttribute(bkt_pull_kernel<LPR, B, M>,                                         \
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
     if (e != cudaSuccess) return e;                                                              \
-    bkt_pull_kernel<LPR, B, M><<<PL_CTAS_PER_SM * sm_count, PL_THREADS, smem, st>>>(a)
+    occ = 0;                                                                                     \
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bkt_pull_kernel<LPR, B, M>, PL_THREADS, smem); \
+    if (e != cudaSuccess) return e;                                                              \
+    if (occ < 1) occ = 1;                                                                        \
+    bkt_pull_kernel<LPR, B, M><<<occ * sm_count, PL_THREADS, smem, st>>>(a)
     if (binary) {
         if (mode == 0) { PL_LAUNCH(true, 0); } else if (mode == 1) { PL_LAUNCH(true, 1); } else { PL_LAUNCH(true, 2); }
     } else {
@@ -1024,6 +1130,7 @@ cudaError_t bucket_pull(const ModelView& m, const BucketGeom& g, const uint32_t*
     a.bucket_off = tp.bucket_off;
     a.item_start = tp.item_start;
     a.item_bucket = tp.item_bucket;
+    a.item_order = tp.item_order;
     a.work = w.work;
     a.part = w.part;
     a.part_bits = w.part_bits;

@@ -28,7 +28,7 @@ def als_sweep(w0, w, v, rows, y, k, reg, quirks):
     r0, rw, rv = reg
     e = [predict(w0, w, v, row, k) - yy for row, yy in zip(rows, y)]
     new = -(sum(e) - w0 * len(rows)) / (r0 + len(rows))
-    if new != w0 and not quirks:
+    if new != w0:   # the reference's lazily re-evaluated residuals carry the shift too (ALS.scala:27,31,142-144)
         e = [x + (new - w0) for x in e]
     w0 = new
     cols = {}

@@ -58,9 +58,9 @@ def test_als_sweeps_match_the_scala_restatement(kind, n_rows, n_slots, k, fields
         e = hd.als_residuals(n_rows)
         assert np.max(np.abs(e - e_want)) <= 1e-5 * max(np.abs(e_want).max(), 1e-3)
     assert hist[-1] < hist[0]
-    if not quirks:   # the residual cache is yhat - y of the model the sweep left behind
-        pred = hd.predict_resident(0, n_rows)
-        assert np.max(np.abs(e - (pred.astype(np.float64) - y))) < 1e-4
+    # the residual cache is yhat - y of the model the sweep left behind, quirk mode or not
+    pred = hd.predict_resident(0, n_rows)
+    assert np.max(np.abs(e - (pred.astype(np.float64) - y))) < 1e-4
     hd.close()
 
 

@@ -450,10 +450,14 @@ def test_partition_sampler_matches_oracle_and_explicit_rows():
         lb, nb = b.train_step(it, ids)                      # explicit rows: per-iteration sort
         lo = orc.train_step(row_ptr, idx, val.astype(np.float64), label, ids, it,
                             float(np.float32(0.4))) / len(ids)
-        assert nb == len(ids) and la == lb
+        # a: cached batches keep the fully sorted form (chunked reduce); b: explicit rows go through
+        # the bucket form every iteration -- the same sums with a different (fixed) tree for runs
+        # that span several lane groups, so the two agree to fp32 rounding, not bit for bit
+        assert nb == len(ids) and abs(la - lb) <= 1e-6 * abs(lb)
         assert abs(la - lo) <= LOSS_RTOL * abs(lo), (it, la, lo)
     ma, mb = a.get_model(), b.get_model()
-    assert ma[0] == mb[0] and np.array_equal(ma[1], mb[1]) and np.array_equal(ma[2], mb[2])
+    assert abs(ma[0] - mb[0]) <= 1e-6 and np.max(np.abs(ma[1] - mb[1])) <= 1e-6
+    assert np.max(np.abs(ma[2] - mb[2])) <= 1e-6
     a.close()
     b.close()
 
@@ -472,9 +476,9 @@ def test_partition_sampler_uniform_all_ones_rows():
     la = a.train(1, 12)
     for it in range(1, 13):
         lb, _ = b.train_step(it, ocapi.partition_rows(5, P, (it - 1) % P, 0, n_rows))
-        assert la[it - 1] == lb
+        assert abs(la[it - 1] - lb) <= 1e-6 * abs(lb)      # sorted form vs bucket form: same sums, other tree
     ma, mb = a.get_model(), b.get_model()
-    assert np.array_equal(ma[2], mb[2]) and np.array_equal(ma[1], mb[1])
+    assert np.max(np.abs(ma[2] - mb[2])) <= 1e-6 and np.max(np.abs(ma[1] - mb[1])) <= 1e-6
     a.close()
     b.close()
 

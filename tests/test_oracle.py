@@ -223,7 +223,7 @@ def test_als_sweeps_fit_a_planted_model_and_keep_residuals_consistent():
     assert hist[-1] < 0.5 * hist[0] and all(b <= a + 1e-9 for a, b in zip(hist, hist[1:]))
 
 
-def test_als_reference_quirks_are_reproduced_on_request():
+def test_als_reference_quirk_is_reproduced_on_request():
     rp, idx, val, y, (w0, w, v) = _als_problem(7)
     n_slots, k = v.shape
     last = n_slots - 1
@@ -237,9 +237,10 @@ def test_als_reference_quirks_are_reproduced_on_request():
     # (i) `0 until num_attribute` never trains the last slot (ALS.scala:38,52)
     assert b.w[last] == w[last] and np.array_equal(b.v[last], v[last])
     assert a.w[last] != w[last]
-    # (ii) residuals are not corrected for the w0 step (ALS.scala:24): they drift from yhat - y
+    # the residual cache is yhat - y of the model the sweep left behind in BOTH modes: the
+    # reference's lazy `error` RDD is re-evaluated with the new w0 (ALS.scala:27,31,142-144)
     assert np.allclose(ea, a.predict(rp, idx, val) - y, atol=1e-9)
-    assert not np.allclose(eb, b.predict(rp, idx, val) - y, atol=1e-6)
+    assert np.allclose(eb, b.predict(rp, idx, val) - y, atol=1e-9)
 
 
 def test_als_rejects_a_repeated_feature_in_a_row():
