@@ -438,7 +438,8 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     o.key_bits = key_bits;
     o.blk_shift = blk_shift;
     CU(launch_forward(m, b, o, true, h->d_err, h->sm_count, h->stream, L));
-    CU(launch_scalar_reduce(o.loss, o.mult, n, (double*)h->b_partials.p, h->d_scal, h->d_err,
+    CU(launch_scalar_reduce(o.loss, o.mult, n, (double*)h->b_partials.p,
+                            reinterpret_cast<unsigned int*>(h->d_count + 3), h->d_scal, h->d_err,
                             h->stream, L));
     pt.lap(&h->stats.ms_forward);
     // Multi-GPU, reduce / all-reduce overlap: the feature range is cut into Q
@@ -466,7 +467,8 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     if (nnz > 0 && !pc && bucket) {
         CU(bucket_transpose(m, b, bg, o.keys, o.pay, implicit_div, h->b_bkt_work.p,
                             h->b_bkt_tables.p, (uint32_t*)h->b_keys[1].p,
-                            binary ? nullptr : (uint32_t*)h->b_pay[1].p, h->sm_count, h->stream, L));
+                            binary ? nullptr : (uint32_t*)h->b_pay[1].p,
+                            reinterpret_cast<unsigned int*>(h->d_count + 4), h->sm_count, h->stream, L));
     } else if (nnz > 0 && !pc) {
         if (binary)
             CU(sort_pairs32(h->b_sort_tmp.p, sort_bytes, o.keys, (uint32_t*)h->b_keys[1].p,
@@ -548,7 +550,7 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     if (bucket)
         CU(bucket_pull(m, bg, keys_sorted, binary ? nullptr : (const uint32_t*)pay_sorted,
                        pc ? pc->tables.p : h->b_bkt_tables.p, h->b_bkt_work.p, o.S, o.mult, h->d_scal,
-                       h->d_err, up, fused, grad_out, touch, h->sm_count, h->stream, L));
+                       h->d_err, up, fused, grad_out, touch, nnz > 0 && !pc, h->sm_count, h->stream, L));
     else
         CU(launch_pull(m, (int32_t*)h->b_seg.p, key_bits, n_blocks, keys_sorted, pay_sorted, nnz,
                        binary, o.S, o.mult, (float*)h->b_pull.p, h->d_scal, h->d_err, up, fused,
@@ -741,7 +743,7 @@ static int partition_batch(sfm_handle* h, int64_t iter, BatchView* b, const Part
             CU(bucket_transpose(h->m, v, pc.geom, (const uint32_t*)h->b_keys[0].p,
                                 (const uint2*)h->b_pay[0].p, 0, h->b_bkt_work.p, pc.tables.p,
                                 (uint32_t*)pc.keys.p, binary ? nullptr : (uint32_t*)pc.pay.p,
-                                h->sm_count, h->stream, L));
+                                reinterpret_cast<unsigned int*>(h->d_count + 4), h->sm_count, h->stream, L));
         } else if (v.nnz > 0 && !is_sharded(h)) {   // row-sharded models cache their own plan (sfm_shard.cu)
             CU(launch_emit(v, pc.key_bits, pc.blk_shift, h->m.n_slots, (uint32_t*)h->b_keys[0].p,
                            (uint2*)h->b_pay[0].p, h->sm_count, h->stream, L));
@@ -953,12 +955,13 @@ int32_t sfm_create(const sfm_config* cfg, sfm_handle** out) {
     CK(cudaMalloc(&m.w0, sizeof(float) * 4));
     CK(cudaMalloc(&h->d_scal, sizeof(double) * 8));
     CK(cudaMalloc(&h->d_err, sizeof(int32_t) * 4));
-    CK(cudaMalloc(&h->d_count, sizeof(int32_t) * 4));
+    CK(cudaMalloc(&h->d_count, sizeof(int32_t) * 8));
     CK(cudaMallocHost(&h->h_scal, sizeof(double) * 8));
     CK(cudaMallocHost(&h->h_flags, sizeof(int32_t) * 16));
     if (m.v) CK(cudaMemsetAsync(m.v, 0, sizeof(float) * (size_t)(m.n_slots + 1) * m.kp, h->stream));
     if (m.w) CK(cudaMemsetAsync(m.w, 0, sizeof(float) * (size_t)(m.n_slots + 1), h->stream));
     CK(cudaMemsetAsync(m.w0, 0, sizeof(float) * 4, h->stream));
+    CK(cudaMemsetAsync(h->d_count, 0, sizeof(int32_t) * 8, h->stream));   // [3], [4]: tickets (scalar reduce, bucket plan)
     CK(cudaMemsetAsync(h->d_scal, 0, sizeof(double) * 8, h->stream));
     CK(cudaMemsetAsync(h->d_err, 0, sizeof(int32_t) * 4, h->stream));
     CK(cudaStreamSynchronize(h->stream));

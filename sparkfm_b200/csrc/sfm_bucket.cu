@@ -10,9 +10,10 @@
 //
 //   bkt_count_kernel    per contiguous row range c (one per scatter CTA): bucket histogram
 //                       -> counts[c][bucket]
-//   bkt_offsets_kernel  column sums: counts[c][b] <- entries of bucket b in ranges < c; totals[b]
-//   bkt_plan_kernel     bucket starts, work items (a bucket is cut into items of <= 32768
-//                       entries), item table
+//   bkt_offsets_plan_kernel  column sums: counts[c][b] <- entries of bucket b in ranges < c;
+//                       totals[b]; the CTA that finishes last builds the plan: bucket starts,
+//                       work items (a bucket is cut into items of <= 32768 entries), the item
+//                       table and the largest-first item order
 //   bkt_scatter_kernel  persistent, one CTA per range, tiles of 8192 entries in order: stable
 //                       rank of every entry inside the tile (peer masks from ballots over the
 //                       digit bits, warp-private counters, prefix over warps and digits), entries
@@ -47,10 +48,21 @@ namespace sfm {
 
 constexpr int BK_MAX_HB = 11;
 constexpr int BK_MAX_LB = 10;
-constexpr int SC_THREADS = 256;              // scatter: 8 warps x 32 entries per thread
+#ifndef BK_SC_IPT
+#define BK_SC_IPT 32
+#endif
+#ifndef BK_SC_CTAS
+#define BK_SC_CTAS 2
+#endif
+#ifndef BK_SC_RANK
+#define BK_SC_RANK 2      // scatter ranking: 0 leader byte table + ballots, 1 MATCH.ANY, 2 leader id packed
+#endif                    // into the top bits of the warp's digit counter (measured 0.440 / 0.53 / 0.389 ms)
+constexpr int SC_THREADS = 256;              // scatter: 8 warps x SC_IPT entries per thread
 constexpr int SC_WARPS = SC_THREADS / 32;
-constexpr int SC_IPT = 32;
+constexpr int SC_IPT = BK_SC_IPT;
 constexpr int SC_TILE = SC_THREADS * SC_IPT;   // 8192
+constexpr int SC_RANK = BK_SC_RANK;
+static_assert(SC_RANK != 2 || 32 * SC_IPT < 2048, "packed leader: strip counts must fit 11 bits");
 #ifndef BK_PL_THREADS
 #define BK_PL_THREADS 512
 #endif
@@ -104,11 +116,13 @@ __device__ __forceinline__ int64_t ent_of(const int64_t* __restrict__ out_ptr, i
 // bits -- instead of one ballot per digit bit (up to 11).  The table is never cleared: every
 // reader has just written its own slot.
 #ifndef BK_MATCH
-#define BK_MATCH 0        // scatter: 1 = one MATCH.ANY instead of the leader table + 5 ballots (A/B knob)
+#define BK_MATCH (BK_SC_RANK == 1)
 #endif
-#ifndef BK_MATCH_PULL
-#define BK_MATCH_PULL 1   // the same choice for the reduce kernel's tile ranking (measured: 0.669 -> 0.638 ms)
+#ifndef BK_PL_RANK
+#define BK_PL_RANK 1      // reduce kernel's tile ranking: 0 table, 1 MATCH.ANY (0.669 -> 0.638 ms), 2 packed leader
 #endif
+#define BK_MATCH_PULL (BK_PL_RANK == 1)
+static_assert(BK_PL_RANK != 2 || 32 * PL_IPT < 2048, "packed leader: strip counts must fit 11 bits");
 template <bool MATCH>
 __device__ __forceinline__ uint32_t peer_mask(uint8_t* __restrict__ tab, uint32_t d, bool valid,
                                               int lane) {
@@ -181,42 +195,51 @@ bkt_count_kernel(const uint32_t* __restrict__ keys, int n_rows, int m,
 }
 
 // counts[c][d] <- sum over ranges c' < c; totals[d] = sum over all ranges.  Grid: NB/32 (>= 1)
-// CTAs of 1024 threads = 32 bucket lanes x 32 blocks of ranges.
+// CTAs of 1024 threads = 32 bucket lanes x 32 blocks of ranges.  The CTA that finishes last
+// (integer ticket, reset for the next launch) then builds the plan: bucket_off[b] (exclusive scan
+// of totals), item_start[b] (exclusive scan of the items per bucket, >= 1 each so that untouched
+// buckets still get their L2 decay); [NB] = grand totals; item_bucket[item] = its bucket;
+// item_order = the items largest first; and it zeroes the reduce kernel's ticket / arrival words.
 __global__ void __launch_bounds__(1024)
-bkt_offsets_kernel(uint32_t* __restrict__ counts, int G, int NB, uint32_t* __restrict__ totals) {
+bkt_offsets_plan_kernel(uint32_t* __restrict__ counts, int G, int NB, uint32_t* __restrict__ totals,
+                        unsigned int* __restrict__ ticket, uint32_t* __restrict__ bucket_off,
+                        uint32_t* __restrict__ item_start, uint32_t* __restrict__ item_bucket,
+                        uint32_t* __restrict__ item_order, uint32_t* __restrict__ pull_work) {
     __shared__ uint32_t part[32][33];
-    const int dl = threadIdx.x & 31, rb = threadIdx.x >> 5;
-    const int d = blockIdx.x * 32 + dl;
-    const int per = (G + 31) / 32;
-    const int c0 = min(G, rb * per), c1 = min(G, c0 + per);
-    uint32_t sum = 0;
-    if (d < NB)
-        for (int c = c0; c < c1; ++c) sum += counts[(size_t)c * NB + d];
-    part[rb][dl] = sum;
-    __syncthreads();
-    uint32_t run = 0;
-    for (int r = 0; r < rb; ++r) run += part[r][dl];
-    if (d < NB) {
-        for (int c = c0; c < c1; ++c) {
-            const uint32_t t = counts[(size_t)c * NB + d];
-            counts[(size_t)c * NB + d] = run;
-            run += t;
+    __shared__ bool last;
+    {
+        const int dl = threadIdx.x & 31, rb = threadIdx.x >> 5;
+        const int d = blockIdx.x * 32 + dl;
+        const int per = (G + 31) / 32;
+        const int c0 = min(G, rb * per), c1 = min(G, c0 + per);
+        uint32_t sum = 0;
+        if (d < NB)
+            for (int c = c0; c < c1; ++c) sum += counts[(size_t)c * NB + d];
+        part[rb][dl] = sum;
+        __syncthreads();
+        uint32_t run = 0;
+        for (int r = 0; r < rb; ++r) run += part[r][dl];
+        if (d < NB) {
+            for (int c = c0; c < c1; ++c) {
+                const uint32_t t = counts[(size_t)c * NB + d];
+                counts[(size_t)c * NB + d] = run;
+                run += t;
+            }
+            if (rb == 31) totals[d] = run;
         }
-        if (rb == 31) totals[d] = run;
     }
-}
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
 
-// bucket_off[b] (exclusive scan of totals), item_start[b] (exclusive scan of the items per
-// bucket, >= 1 each so that untouched buckets still get their L2 decay); [NB] = grand totals;
-// item_bucket[item] = its bucket.
-__global__ void __launch_bounds__(1024)
-bkt_plan_kernel(const uint32_t* __restrict__ totals, int NB, uint32_t* __restrict__ bucket_off,
-                uint32_t* __restrict__ item_start, uint32_t* __restrict__ item_bucket,
-                uint32_t* __restrict__ item_order) {
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t cls_cnt[PL_ORDER_CLASSES];
+    for (int i = threadIdx.x; i <= NB; i += 1024) pull_work[i] = 0u;
     const int b0 = threadIdx.x * 2;
-    const uint32_t t0 = b0 < NB ? totals[b0] : 0u, t1 = b0 + 1 < NB ? totals[b0 + 1] : 0u;
+    const uint32_t t0 = b0 < NB ? __ldcg(totals + b0) : 0u, t1 = b0 + 1 < NB ? __ldcg(totals + b0 + 1) : 0u;
     const uint32_t n0 = b0 < NB ? max(1u, (t0 + PL_ITEM - 1) / PL_ITEM) : 0u;
     const uint32_t n1 = b0 + 1 < NB ? max(1u, (t1 + PL_ITEM - 1) / PL_ITEM) : 0u;
     uint32_t tot_e = 0, tot_i = 0;
@@ -236,6 +259,7 @@ bkt_plan_kernel(const uint32_t* __restrict__ totals, int NB, uint32_t* __restric
     if (threadIdx.x == 0) {
         bucket_off[NB] = tot_e;
         item_start[NB] = tot_i;
+        *ticket = 0u;
     }
     // item_order: the work items largest first (counting sort by size class), so that the
     // persistent CTAs of the reduce end together instead of one of them starting a 32 K-entry item
@@ -280,7 +304,7 @@ bkt_plan_kernel(const uint32_t* __restrict__ totals, int NB, uint32_t* __restric
 // 1: batch rows in rows_in (uint32); 2: {batch row, x bits} in pay2 (uint2).
 // ------------------------------------------------------------------------------------------
 template <int PAYMODE>
-__global__ void __launch_bounds__(SC_THREADS, 2)
+__global__ void __launch_bounds__(SC_THREADS, BK_SC_CTAS)
 bkt_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rows_in,
                    const uint2* __restrict__ pay2, uint32_t* __restrict__ packed_out,
                    uint32_t* __restrict__ vals_out, int n_rows, int m,
@@ -298,7 +322,7 @@ bkt_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict
     uint16_t* whist = dig_s + SC_TILE;                                            // [WARPS][NB]
     uint32_t* goff = reinterpret_cast<uint32_t*>(whist + SC_WARPS * NB);          // [NB]
     uint16_t* lstart = reinterpret_cast<uint16_t*>(goff + NB);                    // [NB]
-    uint8_t* ltab = reinterpret_cast<uint8_t*>(lstart + NB) + (threadIdx.x >> 5) * NB;   // [WARPS][NB]
+    uint8_t* ltab = reinterpret_cast<uint8_t*>(lstart + NB) + (threadIdx.x >> 5) * NB;   // [WARPS][NB] (SC_RANK 0)
     __shared__ uint32_t wsum[SC_WARPS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -347,14 +371,35 @@ bkt_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict
             if (strip + r * 32 < n_valid) {   // warp-uniform
                 const bool valid = strip + r * 32 + lane < n_valid;
                 const uint32_t d = key[r] >> LB;
-                const uint32_t pm = peer_mask<BK_MATCH != 0>(ltab, d, valid, lane);
-                uint32_t old = 0;
-                if (valid && (pm & lt) == 0u) {   // first lane of the group owns the counter
-                    old = wh[d];
-                    wh[d] = (uint16_t)(old + __popc(pm));
+                uint32_t rank;
+                if (SC_RANK == 2) {
+                    // the warp's counter of digit d carries the count so far in its low 11 bits;
+                    // every lane holding d stamps its lane id into the top 5 bits (one wins), the
+                    // lanes that read the same winner back are peers (5 ballots over its bits)
+                    const uint32_t cnt = valid ? ((uint32_t)wh[d] & 0x7ffu) : 0u;
+                    if (valid) wh[d] = (uint16_t)(cnt | ((uint32_t)lane << 11));
+                    __syncwarp();
+                    const uint32_t leader = valid ? ((uint32_t)wh[d] >> 11) : 0u;
+                    uint32_t pm = __ballot_sync(FULL, valid);
+#pragma unroll
+                    for (int b = 0; b < 5; ++b) {
+                        const uint32_t bit = (leader >> b) & 1u;
+                        const uint32_t bal = __ballot_sync(FULL, bit != 0u);
+                        pm &= bal ^ (bit - 1u);
+                    }
+                    rank = cnt + __popc(pm & lt);
+                    if (valid && (uint32_t)lane == leader) wh[d] = (uint16_t)((cnt + __popc(pm)) | (leader << 11));
+                    __syncwarp();
+                } else {
+                    const uint32_t pm = peer_mask<SC_RANK == 1>(ltab, d, valid, lane);
+                    uint32_t old = 0;
+                    if (valid && (pm & lt) == 0u) {   // first lane of the group owns the counter
+                        old = wh[d];
+                        wh[d] = (uint16_t)(old + __popc(pm));
+                    }
+                    old = __shfl_sync(FULL, old, valid ? __ffs(pm) - 1 : lane);
+                    rank = old + __popc(pm & lt);
                 }
-                old = __shfl_sync(FULL, old, valid ? __ffs(pm) - 1 : lane);
-                const uint32_t rank = old + __popc(pm & lt);
                 if (r & 1) rk2[r / 2] |= rank << 16; else rk2[r / 2] = rank;
             } else {
                 if (!(r & 1)) rk2[r / 2] = 0;
@@ -375,7 +420,8 @@ bkt_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict
                             uint32_t run = 0;
 #pragma unroll
                             for (int w = 0; w < SC_WARPS; ++w) {
-                                const uint32_t t = wrows[w * row_words + w0 + j];
+                                uint32_t t = wrows[w * row_words + w0 + j];
+                                if (SC_RANK == 2) t &= 0x07ff07ffu;   // drop the leader stamps
                                 wrows[w * row_words + w0 + j] = run;
                                 run += t;
                             }
@@ -387,7 +433,7 @@ bkt_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict
             } else if (tid == 0) {   // single bucket
                 uint32_t run = 0;
                 for (int w = 0; w < SC_WARPS; ++w) {
-                    const uint32_t t = whist[w];
+                    const uint32_t t = SC_RANK == 2 ? (whist[w] & 0x7ffu) : whist[w];
                     whist[w] = (uint16_t)run;
                     run += t;
                 }
@@ -621,14 +667,33 @@ bkt_pull_kernel(const PullArgs a) {
                 if (strip + r * 32 < n_valid) {   // warp-uniform
                     const bool valid = strip + r * 32 + lane < n_valid;
                     const uint32_t d = LB ? ent[r] >> RB : 0u;
-                    const uint32_t pm = peer_mask<BK_MATCH_PULL != 0>(ltab, d, valid, lane);
-                    uint32_t old = 0;
-                    if (valid && (pm & lt) == 0u) {   // first lane of the group owns the counter
-                        old = wh[d];
-                        wh[d] = (uint16_t)(old + __popc(pm));
+                    uint32_t rank;
+                    if (BK_PL_RANK == 2) {   // leader id in the top 5 bits of the counter (see bkt_scatter_kernel)
+                        const uint32_t cnt = valid ? ((uint32_t)wh[d] & 0x7ffu) : 0u;
+                        if (valid) wh[d] = (uint16_t)(cnt | ((uint32_t)lane << 11));
+                        __syncwarp();
+                        const uint32_t leader = valid ? ((uint32_t)wh[d] >> 11) : 0u;
+                        uint32_t pm = __ballot_sync(FULL, valid);
+#pragma unroll
+                        for (int bb = 0; bb < 5; ++bb) {
+                            const uint32_t bit = (leader >> bb) & 1u;
+                            const uint32_t bal = __ballot_sync(FULL, bit != 0u);
+                            pm &= bal ^ (bit - 1u);
+                        }
+                        rank = cnt + __popc(pm & lt);
+                        if (valid && (uint32_t)lane == leader) wh[d] = (uint16_t)((cnt + __popc(pm)) | (leader << 11));
+                        __syncwarp();
+                    } else {
+                        const uint32_t pm = peer_mask<BK_PL_RANK == 1>(ltab, d, valid, lane);
+                        uint32_t old = 0;
+                        if (valid && (pm & lt) == 0u) {   // first lane of the group owns the counter
+                            old = wh[d];
+                            wh[d] = (uint16_t)(old + __popc(pm));
+                        }
+                        old = __shfl_sync(FULL, old, valid ? __ffs(pm) - 1 : lane);
+                        rank = old + __popc(pm & lt);
                     }
-                    old = __shfl_sync(FULL, old, valid ? __ffs(pm) - 1 : lane);
-                    rk2[r / 2] |= (old + __popc(pm & lt)) << ((r & 1) * 16);
+                    rk2[r / 2] |= rank << ((r & 1) * 16);
                 }
             }
             __syncthreads();
@@ -642,7 +707,8 @@ bkt_pull_kernel(const PullArgs a) {
                         uint32_t run = 0;
 #pragma unroll
                         for (int w = 0; w < PL_WARPS; ++w) {
-                            const uint32_t t = wrows[w * row_words + tid];
+                            uint32_t t = wrows[w * row_words + tid];
+                            if (BK_PL_RANK == 2) t &= 0x07ff07ffu;   // drop the leader stamps
                             wrows[w * row_words + tid] = run;
                             run += t;
                         }
@@ -652,7 +718,7 @@ bkt_pull_kernel(const PullArgs a) {
                 } else if (tid == 0) {
                     uint32_t run = 0;
                     for (int w = 0; w < PL_WARPS; ++w) {
-                        const uint32_t t = whist[w];
+                        const uint32_t t = BK_PL_RANK == 2 ? (whist[w] & 0x7ffu) : whist[w];
                         whist[w] = (uint16_t)run;
                         run += t;
                     }
@@ -1037,13 +1103,13 @@ static WorkPtrs carve_work(const ModelView& m, const BucketGeom& g, int sm_count
 static size_t scatter_smem(int hb, bool has_val) {
     const size_t nb = (size_t)1 << hb;
     return (size_t)SC_TILE * 4 * (has_val ? 2 : 1) + (size_t)SC_TILE * 2 + (size_t)SC_WARPS * nb * 2 +
-           nb * 4 + nb * 2 + (size_t)SC_WARPS * nb + 64;
+           nb * 4 + nb * 2 + (SC_RANK == 0 ? (size_t)SC_WARPS * nb : 0) + 64;
 }
 
 cudaError_t bucket_transpose(const ModelView& m, const BatchView& b, const BucketGeom& g,
                              const uint32_t* keys, const uint2* pay, int implicit_div, void* work,
-                             void* tables, uint32_t* packed, uint32_t* vals, int sm_count,
-                             cudaStream_t st, int64_t* launches) {
+                             void* tables, uint32_t* packed, uint32_t* vals, unsigned int* ticket,
+                             int sm_count, cudaStream_t st, int64_t* launches) {
     const WorkPtrs w = carve_work(m, g, sm_count, work);
     const TablePtrs tp = carve_tables(g, tables);
     uint32_t* bucket_off = tp.bucket_off;
@@ -1054,9 +1120,9 @@ cudaError_t bucket_transpose(const ModelView& m, const BatchView& b, const Bucke
     if (!optr && b.uniform_m < 0) return cudaErrorInvalidValue;
     bkt_count_kernel<<<G, 512, sizeof(uint32_t) * g.NB, st>>>(keys, (int)b.n_rows, mm, optr,
                                                                b.out_base, g.LB, g.NB, w.counts);
-    bkt_offsets_kernel<<<(g.NB + 31) / 32, 1024, 0, st>>>(w.counts, G, g.NB, w.totals);
-    bkt_plan_kernel<<<1, 1024, 0, st>>>(w.totals, g.NB, bucket_off, tp.item_start, tp.item_bucket,
-                                        tp.item_order);
+    bkt_offsets_plan_kernel<<<(g.NB + 31) / 32, 1024, 0, st>>>(w.counts, G, g.NB, w.totals, ticket,
+                                                               bucket_off, tp.item_start, tp.item_bucket,
+                                                               tp.item_order, w.work);
     const size_t smem = scatter_smem(g.HB, has_val);
     const unsigned long long magic =
         implicit_div ? ((1ULL << 40) + (unsigned long long)implicit_div - 1) / (unsigned long long)implicit_div : 0ULL;
@@ -1076,7 +1142,7 @@ cudaError_t bucket_transpose(const ModelView& m, const BatchView& b, const Bucke
         SC_LAUNCH(1);
     }
 #undef SC_LAUNCH
-    *launches += 4;
+    *launches += 3;
     return cudaGetLastError();
 }
 
@@ -1117,12 +1183,14 @@ cudaError_t bucket_pull(const ModelView& m, const BucketGeom& g, const uint32_t*
                         const uint32_t* vals, const void* tables, void* work, const float* S,
                         const float* mult, const double* d_scal, const int32_t* d_err,
                         UpdateParams up, bool fused, float* grad, uint32_t* touch_bits,
-                        int sm_count, cudaStream_t st, int64_t* launches) {
+                        bool work_zeroed, int sm_count, cudaStream_t st, int64_t* launches) {
     const WorkPtrs w = carve_work(m, g, sm_count, work);
     if (touch_bits && g.LB < 5) return cudaErrorInvalidValue;   // bitmap words must not straddle buckets
     const int mode = fused ? 0 : (touch_bits ? 2 : 1);
-    cudaError_t e = cudaMemsetAsync(w.work, 0, sizeof(uint32_t) * (size_t)(g.NB + 1), st);
-    if (e != cudaSuccess) return e;
+    if (!work_zeroed) {   // (a transposition built in this step left the ticket / arrival words zero)
+        cudaError_t e = cudaMemsetAsync(w.work, 0, sizeof(uint32_t) * (size_t)(g.NB + 1), st);
+        if (e != cudaSuccess) return e;
+    }
     PullArgs a;
     a.packed = packed;
     a.vals = vals;

@@ -202,8 +202,8 @@ cudaError_t launch_forward(const ModelView& m, const BatchView& b, const FwdOut&
                            int32_t* d_err, int sm_count, cudaStream_t st, int64_t* launches);
 // loss / mult -> d_scal[SC_LOSS], [SC_GW0], [SC_COUNT] (fixed-shape fp64 tree, deterministic)
 cudaError_t launch_scalar_reduce(const float* loss, const float* mult, int64_t n, double* partials,
-                                 double* d_scal, const int32_t* d_err, cudaStream_t st,
-                                 int64_t* launches);
+                                 unsigned int* ticket, double* d_scal, const int32_t* d_err,
+                                 cudaStream_t st, int64_t* launches);
 struct UpdateParams {
     float eta, reg0, regw, regv;
 };
@@ -288,14 +288,14 @@ size_t bucket_work_bytes(const ModelView& m, const BucketGeom& g, int sm_count);
 // uint2 {row, x bits}.
 cudaError_t bucket_transpose(const ModelView& m, const BatchView& b, const BucketGeom& g,
                              const uint32_t* keys, const uint2* pay, int implicit_div, void* work,
-                             void* tables, uint32_t* packed, uint32_t* vals, int sm_count,
-                             cudaStream_t st, int64_t* launches);
+                             void* tables, uint32_t* packed, uint32_t* vals, unsigned int* ticket,
+                             int sm_count, cudaStream_t st, int64_t* launches);
 // reduce-by-feature over the bucketed entries + SGD update (fused) or dense gradient
 cudaError_t bucket_pull(const ModelView& m, const BucketGeom& g, const uint32_t* packed,
                         const uint32_t* vals, const void* tables, void* work, const float* S,
                         const float* mult, const double* d_scal, const int32_t* d_err,
                         UpdateParams up, bool fused, float* grad, uint32_t* touch_bits,
-                        int sm_count, cudaStream_t st, int64_t* launches);
+                        bool work_zeroed, int sm_count, cudaStream_t st, int64_t* launches);
 
 // ---- CUB wrappers (sfm_sort.cu)
 size_t sort_pairs_temp_bytes(int64_t n, int end_bit);

@@ -496,10 +496,15 @@ __device__ __forceinline__ void block_tree(double (&acc)[NV], double* sm /* [NV]
     for (int v = 0; v < NV; ++v) acc[v] = sm[v * RED_THREADS];
 }
 
+// One launch: every block reduces its span to a partial; the block that arrives last (integer
+// ticket, reset for the next launch) adds the partials in block order -- the same fixed fp64 tree
+// whichever block that is.
 __global__ void __launch_bounds__(RED_THREADS)
-scalar_reduce1_kernel(const float* __restrict__ loss, const float* __restrict__ mult, int64_t n,
-                      double* __restrict__ partials) {
+scalar_reduce_kernel(const float* __restrict__ loss, const float* __restrict__ mult, int64_t n,
+                     double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                     double* __restrict__ d_scal, const int32_t* __restrict__ err) {
     __shared__ double sm[2 * RED_THREADS];
+    __shared__ bool last;
     const int64_t span = (n + gridDim.x - 1) / gridDim.x;
     const int64_t lo = (int64_t)blockIdx.x * span;
     const int64_t hi = min(n, lo + span);
@@ -512,17 +517,16 @@ scalar_reduce1_kernel(const float* __restrict__ loss, const float* __restrict__ 
     if (threadIdx.x == 0) {
         partials[2 * blockIdx.x] = acc[0];
         partials[2 * blockIdx.x + 1] = acc[1];
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     }
-}
-
-__global__ void __launch_bounds__(RED_THREADS)
-scalar_reduce2_kernel(const double* __restrict__ partials, int nblocks, int64_t n,
-                      double* __restrict__ d_scal, const int32_t* __restrict__ err) {
-    __shared__ double sm[2 * RED_THREADS];
-    double acc[2] = {0.0, 0.0};
-    for (int i = threadIdx.x; i < nblocks; i += RED_THREADS) {
-        acc[0] += partials[2 * i];
-        acc[1] += partials[2 * i + 1];
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    acc[0] = acc[1] = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += RED_THREADS) {
+        acc[0] += __ldcg(partials + 2 * i);
+        acc[1] += __ldcg(partials + 2 * i + 1);
     }
     block_tree<2>(acc, sm);
     if (threadIdx.x == 0) {
@@ -530,15 +534,15 @@ scalar_reduce2_kernel(const double* __restrict__ partials, int nblocks, int64_t 
         d_scal[SC_GW0] = acc[1];
         d_scal[SC_COUNT] = (double)n;
         d_scal[SC_ERR] = (err && *err) ? 1.0 : 0.0;   // summed over the ranks: everybody skips the update
+        *ticket = 0u;
     }
 }
 
 cudaError_t launch_scalar_reduce(const float* loss, const float* mult, int64_t n, double* partials,
-                                 double* d_scal, const int32_t* d_err, cudaStream_t st,
-                                 int64_t* launches) {
-    *launches += 2;
-    scalar_reduce1_kernel<<<RED_BLOCKS, RED_THREADS, 0, st>>>(loss, mult, n, partials);
-    scalar_reduce2_kernel<<<1, RED_THREADS, 0, st>>>(partials, RED_BLOCKS, n, d_scal, d_err);
+                                 unsigned int* ticket, double* d_scal, const int32_t* d_err,
+                                 cudaStream_t st, int64_t* launches) {
+    *launches += 1;   // ticket: one device word, zero at handle creation, reset by the kernel itself
+    scalar_reduce_kernel<<<RED_BLOCKS, RED_THREADS, 0, st>>>(loss, mult, n, partials, ticket, d_scal, d_err);
     return cudaGetLastError();
 }
 

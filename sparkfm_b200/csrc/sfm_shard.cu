@@ -430,7 +430,8 @@ int shard_train(sfm_handle* h, const BatchView& b, int64_t iter, int cache_slot)
     o.mult = (float*)h->b_mult.p;
     o.loss = (float*)h->b_loss.p;
     CU(launch_forward(sp.mc, sp.bc, o, true, h->d_err, h->sm_count, h->stream, L));
-    CU(launch_scalar_reduce(o.loss, o.mult, n, (double*)h->b_partials.p, h->d_scal, h->d_err,
+    CU(launch_scalar_reduce(o.loss, o.mult, n, (double*)h->b_partials.p,
+                            reinterpret_cast<unsigned int*>(h->d_count + 3), h->d_scal, h->d_err,
                             h->stream, L));
     RC(nccl_allreduce_f64(h->nccl, h->comm, h->d_scal, SC_N, h->stream, &h->err));
     // 4c. compact gradient [gV U*kp | gw U | gw0]
