@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() { # name batch env...
+  env "${@:3}" python bench.py --batch $2 --steps 100 --warmup 5 --no-cpu-baseline --no-e2e --no-partition --rows 20000000 > gpurun_out/ab_$1.json 2> gpurun_out/ab_$1.err || tail -3 gpurun_out/ab_$1.err
+  python - "$1" <<'PY'
+import json,sys
+d=json.load(open(f"gpurun_out/ab_{sys.argv[1]}.json"))
+print(f"{sys.argv[1]:14s} step {d['ms_per_step']:.4f} ms  {d['value']/1e6:.0f} M/s  frac {d['roofline']['frac']:.3f} loss {d['loss_first_last'][1]:.6f}")
+PY
+}
+run nograph_64k 64000 SFM_GRAPH=0
+run graph_64k 64000 SFM_GRAPH=1
+run nograph_1m 1000000 SFM_GRAPH=0
+run graph_1m 1000000 SFM_GRAPH=1
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2_graph_tests.log 2>&1; echo "gpu tests rc=$?"; tail -4 gpurun_out/r2_graph_tests.log

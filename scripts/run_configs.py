@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Runs BASELINE.json configs 1, 2 and 4 at FULL size on one B200 through the public API, checks
 the per-iteration loss against the fp64 CPU oracle where the oracle finishes in seconds (C1, C2)
-and size-independent properties elsewhere, and writes gpurun_out/configs_r1.json.
+and size-independent properties elsewhere, and writes gpurun_out/configs_r2.json.
 (Config 3 is bench.py; config 5 is bench.py under torchrun at N = 1, 2, 4, 8.)"""
 import json
 import os
@@ -33,7 +33,7 @@ def timed_steps(hd, it0, n):
     return hist, best / n
 
 
-def config1():
+def config1(n_check=8, n_timed=50):
     """100k x 10k LIBSVM-format binary classification, ~20 nnz/row, k=8, logistic, full batch."""
     row_ptr, idx, val, label = synth.classification_c1()
     t0 = time.perf_counter()
@@ -57,14 +57,14 @@ def config1():
     ids = np.arange(ds.size, dtype=np.int64)
     worst = 0.0
     losses = []
-    for it in range(1, 9):
+    for it in range(1, n_check + 1):
         lo = orc.train_step(ds.row_ptr, ds.idx, ds.val, ds.labels, ids, it, step, threads=8) / ds.size
         lg, batch = hd.train_step(it)
         assert batch == ds.size
         worst = max(worst, abs(lg - lo) / lo)
         losses.append(lg)
     assert worst < 1e-4, worst
-    hist, ms = timed_steps(hd, 9, 50)
+    hist, ms = timed_steps(hd, n_check + 1, n_timed)
     pred = hd.predict_resident(0, ds.size)
     want = orc.predict(ds.row_ptr, ds.idx, ds.val, fast=True, threads=8)
     # models have drifted apart by fp32 rounding over 8+ steps; compare predictions of the SAME model
@@ -75,13 +75,13 @@ def config1():
     assert perr < 1e-5, perr
     OUT["C1"] = {"rows": ds.size, "n_slots": n_slots, "k": k, "nnz": int(ds.row_ptr[-1]),
                  "text_bytes": len(text), "parse_s": t_parse, "parse_MBps": len(text) / t_parse / 1e6,
-                 "loss_rel_err_max_8_iters": worst, "loss_first_last": [losses[0], float(hist[-1])],
+                 "loss_rel_err_max": worst, "loss_iters_checked": n_check, "loss_first_last": [losses[0], float(hist[-1])],
                  "ms_per_full_batch_step": ms, "samples_per_s": ds.size / (ms * 1e-3),
                  "predict_rel_err_max": perr, "accuracy": hd.evaluate()["accuracy"]}
     hd.close()
 
 
-def config2():
+def config2(n_check=10, n_timed=100):
     """1M x 100k regression, ~50 nnz/row, values N(0,1), k=16, squared loss, miniBatchFraction 0.1."""
     row_ptr, idx, val, y = synth.regression_c2()
     n_rows, n_slots, k = len(y), 100_000, 16
@@ -97,7 +97,7 @@ def config2():
     f32 = float(np.float32(frac))
     s32 = float(np.float32(step))
     losses = []
-    for it in range(1, 11):
+    for it in range(1, n_check + 1):
         ids = ocapi.sample_rows(42, it, f32, 0, n_rows)
         lo = orc.train_step(row_ptr, idx, v64, y, ids, it, s32, threads=8) / len(ids)
         lg, batch = hd.train_step(it)
@@ -105,25 +105,25 @@ def config2():
         worst = max(worst, abs(lg - lo) / lo)
         losses.append(lg)
     assert worst < 1e-4, worst
-    hist, ms = timed_steps(hd, 11, 100)
+    hist, ms = timed_steps(hd, n_check + 1, n_timed)
     rows = hd.stats()["train_rows"]
     ev = hd.evaluate()
     OUT["C2"] = {"rows": n_rows, "n_slots": n_slots, "k": k, "nnz": int(row_ptr[-1]),
-                 "loss_rel_err_max_10_iters": worst, "loss_first_last": [losses[0], float(hist[-1])],
+                 "loss_rel_err_max": worst, "loss_iters_checked": n_check, "loss_first_last": [losses[0], float(hist[-1])],
                  "ms_per_step": ms, "batch_rows": int(round(n_rows * frac)),
                  "samples_per_s": n_rows * frac / (ms * 1e-3), "rmse_after": ev["rmse"],
                  "train_rows_total": rows}
     hd.close()
 
 
-def config4():
+def config4(n_timed=20, modes=((0, "bernoulli"), (1, "partition"))):
     """Avazu-shaped: 24 one-hot fields, 10M hashed features, k=64, logistic -- model REPLICATED on
-    one GPU here (row-sharded V is not implemented in round 1)."""
+    one GPU here (the row-sharded form needs >= 2 GPUs: tests/test_gpu_multi.py, scripts/bench_c4.py)."""
     n_fields, n_slots, k, n_rows, batch = 24, 10_000_000, 64, 8_000_000, 500_000
     card = synth.ctr_field_log2_cards(n_fields)
     cdf, off = synth.zipf_tables(card)
     res = {}
-    for mode, name in ((0, "bernoulli"), (1, "partition")):
+    for mode, name in modes:
         hd = Handle(n_slots, k, task=1, reg=(0.0, 0.0, 1e-5), step_size=0.1,
                     mini_batch_fraction=batch / n_rows, sampler_seed=42, sampler_mode=mode)
         hd.init_model(0.0, 0.01, 1)
@@ -131,7 +131,7 @@ def config4():
         n_parts = round(n_rows / batch)
         warm = n_parts if mode == 1 else 3
         h0 = hd.train(1, warm)
-        hist, ms = timed_steps(hd, warm + 1, 20)
+        hist, ms = timed_steps(hd, warm + 1, n_timed)
         res[name] = {"ms_per_step": ms, "samples_per_s": batch / (ms * 1e-3),
                      "loss_first_last": [float(h0[0]), float(hist[-1])]}
         assert hist[-1] < h0[0]
@@ -159,6 +159,6 @@ if __name__ == "__main__":
         fn()
         print(fn.__name__, "ok", f"{time.perf_counter() - t0:.1f}s", flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "configs_r1.json"), "w") as fh:
+    with open(os.path.join(ROOT, "gpurun_out", "configs_r2.json"), "w") as fh:
         json.dump(OUT, fh, indent=1)
     print(json.dumps(OUT, indent=1))

@@ -29,6 +29,7 @@ void knobs_refresh() {
     if ((e = getenv("SFM_SORT_AHEAD"))) k.sort_ahead = atoi(e);
     if ((e = getenv("SFM_BUCKET_CACHE")) && e[0] == '1') k.bucket_cache = true;
     if ((e = getenv("SFM_P2P_SPARSE")) && e[0] == '0') k.p2p_sparse = false;
+    if ((e = getenv("SFM_GRAPH")) && e[0] == '0') k.step_graph = false;
     g_knobs = k;
 }
 
@@ -58,6 +59,10 @@ static int cuda_fail(sfm_handle* h, cudaError_t e, const char* what) {
 
 int ensure(sfm_handle* h, Buf& b, size_t bytes) {
     if (bytes <= b.cap) return SFM_OK;
+    if (h->capturing) {   // no allocation inside a stream capture: the step is re-run uncaptured
+        h->capture_abort = true;
+        return SFM_ERR_STATE;
+    }
     if (b.p) {
         cudaStreamSynchronize(h->stream);
         cudaFree(b.p);
@@ -581,6 +586,62 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     return SFM_OK;
 }
 
+// One SGD iteration as ONE graph launch: train_core's launch sequence is captured
+// from the compute stream, the resident executable graph is updated in place with this step's
+// arguments (cudaGraphExecUpdate: same topology, new batch size / step number / buffers) and
+// launched -- the device runs the ~8 dependent kernels of a step without per-launch gaps, which is
+// what small mini-batches are bound by.  Anything that cannot be captured (a scratch buffer has to
+// grow, NCCL collectives, per-phase timing, the row-sharded model) runs as plain stream launches.
+static int train_step_run(sfm_handle* h, const BatchView& b, int64_t iter, const PartCache* pc = nullptr) {
+    const bool multi = h->world > 1;
+    if (!knobs().step_graph || h->phase_timing || is_sharded(h) || (multi && !h->p2p) ||
+        (h->shard_requested && !h->shard))
+        return train_core(h, b, iter, false, pc);
+    const sfm_stats saved = h->stats;
+    if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return train_core(h, b, iter, false, pc);
+    }
+    h->capturing = true;
+    h->capture_abort = false;
+    int rc = train_core(h, b, iter, false, pc);
+    h->capturing = false;
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+    if (rc != SFM_OK || ce != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        if (h->capture_abort || ce != cudaSuccess) {   // e.g. a scratch buffer must grow: run it uncaptured
+            h->capture_abort = false;
+            h->stats = saved;
+            h->err.clear();
+            return train_core(h, b, iter, false, pc);
+        }
+        return rc;
+    }
+    bool ready = false;
+    if (h->step_exec) {
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(h->step_exec, g, &info) == cudaSuccess) {
+            ready = true;
+        } else {   // another launch sequence (other path / sampler / exchange): new executable
+            cudaGetLastError();
+            cudaGraphExecDestroy(h->step_exec);
+            h->step_exec = nullptr;
+        }
+    }
+    cudaError_t le = cudaSuccess;
+    if (!ready) le = cudaGraphInstantiate(&h->step_exec, g, 0);
+    if (le == cudaSuccess) le = cudaGraphLaunch(h->step_exec, h->stream);
+    cudaGraphDestroy(g);
+    if (le != cudaSuccess) {
+        if (h->step_exec) cudaGraphExecDestroy(h->step_exec);
+        h->step_exec = nullptr;
+        return cuda_fail(h, le, "step graph");
+    }
+    return SFM_OK;
+}
+
 // Builds the view of a batch of resident rows.  ids_dev: device int32 row ids or nullptr (all).
 static int resident_batch(sfm_handle* h, const int32_t* ids_dev, int64_t n_ids, BatchView* b) {
     const Dataset& ds = h->ds;
@@ -974,6 +1035,8 @@ int32_t sfm_destroy(sfm_handle* h) {
     if (!h) return SFM_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->step_exec) cudaGraphExecDestroy(h->step_exec);
+    h->step_exec = nullptr;
     p2p_teardown(h);
     if (h->comm) nccl_destroy(h->nccl, h->comm);
     sfm_unload_dataset(h);
@@ -1223,7 +1286,13 @@ struct SfmFileHeader {
 int32_t sfm_save(sfm_handle* h, const char* path) {
     if (!h || !path) return SFM_ERR_ARG;
     const ModelView& m = h->m;
-    std::vector<float> wf((size_t)m.n_slots), vf((size_t)m.n_slots * m.k);
+    std::vector<float> wf, vf;
+    try {   // no exception may cross the C ABI (the host is a JVM / Python process)
+        wf.resize((size_t)m.n_slots);
+        vf.resize((size_t)m.n_slots * m.k);
+    } catch (const std::exception&) {
+        return set_err(h, SFM_ERR_OOM, "sfm_save: host buffer for the model");
+    }
     float w0 = 0.f;
     RC(sfm_get_model(h, &w0, wf.data(), vf.empty() ? nullptr : vf.data()));
     SfmFileHeader hd;
@@ -1234,7 +1303,7 @@ int32_t sfm_save(sfm_handle* h, const char* path) {
     hd.reg0 = h->cfg.reg0; hd.regw = h->cfg.regw; hd.regv = h->cfg.regv;
     hd.step_size = h->cfg.step_size; hd.mini_batch_fraction = h->cfg.mini_batch_fraction;
     hd.sampler_seed = h->cfg.sampler_seed;
-    hd.pad = (uint32_t)h->cfg.sampler_mode;
+    hd.pad = (uint32_t)(h->cfg.sampler_mode & ~SFM_FLAG_SHARD_V);   // sharding is a property of the run, not of the model
     FILE* f = fopen(path, "wb");
     if (!f) return set_err(h, SFM_ERR_IO, std::string("cannot open for writing: ") + path);
     bool ok = fwrite(&hd, sizeof hd, 1, f) == 1 && fwrite(&w0, sizeof w0, 1, f) == 1 &&
@@ -1250,12 +1319,31 @@ int32_t sfm_load(const char* path, int32_t device, sfm_handle** out) {
     FILE* f = fopen(path, "rb");
     if (!f) return SFM_ERR_IO;
     SfmFileHeader hd;
-    if (fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, "SFMB200", 8) != 0 || hd.version != 1 ||
-        hd.n_slots < 1 || hd.k < 0 || hd.k > 128) {
+    // the header is untrusted input: the same bounds sfm_create applies, and the payload size it
+    // implies must be the size of the rest of the file, before anything is allocated
+    bool good = fread(&hd, sizeof hd, 1, f) == 1 && memcmp(hd.magic, "SFMB200", 8) == 0 &&
+                hd.version == 1 && hd.n_slots >= 1 && hd.n_slots < 2147483647LL && hd.k >= 0 &&
+                hd.k <= 128 && (hd.task == SFM_TASK_REGRESSION || hd.task == SFM_TASK_CLASSIFICATION) &&
+                (hd.k0 == 0 || hd.k0 == 1) && (hd.k1 == 0 || hd.k1 == 1);
+    if (good) {
+        const long pos = ftell(f);
+        good = pos >= 0 && fseek(f, 0, SEEK_END) == 0;
+        const long end = good ? ftell(f) : -1;
+        const unsigned long long want = 4ull * (1ull + (unsigned long long)hd.n_slots * (1ull + (unsigned long long)hd.k));
+        good = good && end >= pos && (unsigned long long)(end - pos) == want && fseek(f, pos, SEEK_SET) == 0;
+    }
+    if (!good) {
         fclose(f);
         return SFM_ERR_IO;
     }
-    std::vector<float> wf((size_t)hd.n_slots), vf((size_t)hd.n_slots * hd.k);
+    std::vector<float> wf, vf;
+    try {
+        wf.resize((size_t)hd.n_slots);
+        vf.resize((size_t)hd.n_slots * hd.k);
+    } catch (const std::exception&) {
+        fclose(f);
+        return SFM_ERR_OOM;
+    }
     float w0 = 0.f;
     const bool ok = fread(&w0, sizeof w0, 1, f) == 1 &&
                     fread(wf.data(), sizeof(float), wf.size(), f) == wf.size() &&
@@ -1269,7 +1357,7 @@ int32_t sfm_load(const char* path, int32_t device, sfm_handle** out) {
     cfg.n_slots = hd.n_slots; cfg.reg0 = hd.reg0; cfg.regw = hd.regw; cfg.regv = hd.regv;
     cfg.step_size = hd.step_size; cfg.mini_batch_fraction = hd.mini_batch_fraction;
     cfg.sampler_seed = hd.sampler_seed;
-    cfg.sampler_mode = (int32_t)hd.pad;
+    cfg.sampler_mode = (int32_t)hd.pad & ~SFM_FLAG_SHARD_V;   // a loaded handle is a plain replicated model
     sfm_handle* h = nullptr;
     RC(sfm_create(&cfg, &h));
     const int rc = sfm_set_model(h, w0, wf.data(), vf.empty() ? nullptr : vf.data());
@@ -1662,7 +1750,7 @@ int32_t sfm_train_step(sfm_handle* h, const int64_t* row_ids, int64_t n_ids, int
         BatchView pb;
         const PartCache* pc = nullptr;
         RC(partition_batch(h, iter, &pb, &pc));
-        RC(train_core(h, pb, iter, false, pc));
+        RC(train_step_run(h, pb, iter, pc));
         return finish_step(h, mean_loss_out, batch_out);
     } else {
         RC(sample_device(h, iter, &ids_dev, &n));
@@ -1670,7 +1758,7 @@ int32_t sfm_train_step(sfm_handle* h, const int64_t* row_ids, int64_t n_ids, int
     BatchView b;
     RC(resident_batch(h, ids_dev, n, &b));
     if (b.nnz >= 2147483647LL) return set_err(h, SFM_ERR_ARG, "batch nnz must be < 2^31-1");
-    RC(train_core(h, b, iter, false));
+    RC(train_step_run(h, b, iter));
     return finish_step(h, mean_loss_out, batch_out);
 }
 
@@ -1684,7 +1772,7 @@ int32_t sfm_train_step_csr(sfm_handle* h, const int64_t* row_ptr, const int32_t*
     BatchView b;
     RC(stage_csr(h, h->stage[2], h->stream, row_ptr, idx, val, label, n_rows));
     stage_view(h->stage[2], &b);
-    RC(train_core(h, b, iter, false));
+    RC(train_step_run(h, b, iter));
     return finish_step(h, mean_loss_out, batch_out);
 }
 
@@ -1725,7 +1813,7 @@ int32_t sfm_train_step_staged(sfm_handle* h, int32_t slot, int64_t iter, double*
     CU(cudaStreamWaitEvent(h->stream, sg.ready, 0));
     BatchView b;
     stage_view(sg, &b);
-    RC(train_core(h, b, iter, false));
+    RC(train_step_run(h, b, iter));
     sg.valid = false;
     return finish_step(h, mean_loss_out, batch_out);
 }
@@ -1875,7 +1963,7 @@ int32_t sfm_train(sfm_handle* h, int64_t first_iter, int64_t n_iters, double* lo
             b.validated = true;
             if (cudaStreamWaitEvent(h->stream, h->ev_samp[slot], 0) != cudaSuccess)
                 rc = set_err(h, SFM_ERR_CUDA, "cudaStreamWaitEvent failed");
-            if (rc == SFM_OK) rc = train_core(h, b, first_iter + t, false, &pre);
+            if (rc == SFM_OK) rc = train_step_run(h, b, first_iter + t, &pre);
             if (rc == SFM_OK && cudaEventRecord(h->ev_used[slot], h->stream) != cudaSuccess)
                 rc = set_err(h, SFM_ERR_CUDA, "cudaEventRecord failed");
             if (rc == SFM_OK &&
@@ -1907,7 +1995,7 @@ int32_t sfm_train(sfm_handle* h, int64_t first_iter, int64_t n_iters, double* lo
             if (rc == SFM_OK) rc = resident_batch(h, ids_dev, n, &b);
             if (rc == SFM_OK && b.nnz >= 2147483647LL) rc = set_err(h, SFM_ERR_ARG, "batch nnz must be < 2^31-1");
         }
-        if (rc == SFM_OK) rc = train_core(h, b, first_iter + t, false, pc);
+        if (rc == SFM_OK) rc = train_step_run(h, b, first_iter + t, pc);
         if (rc == SFM_OK && sampled && cudaEventRecord(h->ev_used[slot], h->stream) != cudaSuccess)
             rc = set_err(h, SFM_ERR_CUDA, "cudaEventRecord failed");
         if (rc == SFM_OK &&

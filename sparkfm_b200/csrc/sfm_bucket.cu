@@ -631,6 +631,15 @@ bkt_pull_kernel(const PullArgs a) {
                 if (!BINARY) xv[r] = p < nv ? __uint_as_float(__ldg(a.vals + tb + p)) : 0.f;
             }
         };
+        // the bucket's parameter rows are needed at the item's end: ask for them now (L2), so
+        // that the finalisation of a small item is not one DRAM round trip per feature
+        {
+            const int64_t f0 = (int64_t)b * NBL;
+            const int64_t nf = min((int64_t)NBL, a.n_slots - f0);
+            const char* vb = reinterpret_cast<const char*>(a.V4 + f0 * LPR);
+            for (int64_t off = (int64_t)tid * 128; off < nf * (LPR * 16); off += (int64_t)PL_THREADS * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + off));
+        }
         // (the tile's entries are only live from here to the re-order: the NEXT tile is pulled
         // into L2 by prefetch instructions during the walk, not held in registers)
         for (int i = tid; i < NBL * LPR; i += PL_THREADS) accA[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -944,11 +953,26 @@ bkt_pull_kernel(const PullArgs a) {
                 *a.Gw0 = a.k0 ? g0 : 0.f;
             }
         }
-        for (int d = g; d < NBL; d += G) {
+        // four features per lane group at a time: their parameter rows are requested together,
+        // before the first of them is updated (the stores would otherwise order the loads)
+        for (int d0 = g; d0 < NBL; d0 += 4 * G) {
+          float4 vv[4];
+          float ww[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+              const int dj = d0 + j * G;
+              const int64_t fj = (int64_t)b * NBL + dj;
+              const bool in = dj < NBL && fj < a.n_slots;
+              vv[j] = in ? a.V4[fj * LPR + fq] : make_float4(0.f, 0.f, 0.f, 0.f);
+              ww[j] = (in && fq == 0 && a.k1) ? a.W[fj] : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int d = d0 + j * G;
             const int64_t f = (int64_t)b * NBL + d;
-            if (f >= a.n_slots) break;
-            float4 v = a.V4[f * LPR + fq];
-            const float wi = (fq == 0 && a.k1) ? a.W[f] : 0.f;
+            if (d >= NBL || f >= a.n_slots) continue;
+            float4 v = vv[j];
+            const float wi = ww[j];
             float4 A;
             float D, Cc;
             bool touched;
@@ -995,6 +1019,7 @@ bkt_pull_kernel(const PullArgs a) {
                 if (fq == 0) a.Gw[f] = a.k1 ? Cc : 0.f;
             }
             if (MODE == 2 && !single && fq == 0) tch[d] = touched ? 1u : 0u;
+          }
         }
         if (MODE == 2) {   // the bucket's touched bitmap (buckets are multiples of 32 features)
             __syncthreads();

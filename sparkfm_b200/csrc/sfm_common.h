@@ -162,6 +162,10 @@ struct sfm_handle {
     void* comm = nullptr;
     int rank = 0, world = 1;
     bool phase_timing = false;
+    // one SGD step replayed as a CUDA graph: the step's launches are captured every step, the
+    // resident executable graph is updated in place (same topology, new arguments) and launched
+    cudaGraphExec_t step_exec = nullptr;
+    bool capturing = false, capture_abort = false;
     sfm_stats stats{};
     std::string err;
 };
@@ -179,6 +183,7 @@ struct Knobs {
     int sort_ahead = 0;        // SFM_SORT_AHEAD
     bool bucket_cache = false; // SFM_BUCKET_CACHE=1: PARTITION caches keep the bucket form
     bool p2p_sparse = true;    // SFM_P2P_SPARSE=0: peer-memory exchange moves the dense gradient
+    bool step_graph = true;    // SFM_GRAPH=0: plain stream launches instead of the per-step CUDA graph
 };
 const Knobs& knobs();
 void knobs_refresh();

@@ -316,3 +316,32 @@ def test_jni_glue_binds_every_export_and_matches_the_scala_declarations():
     scala = open(os.path.join(root, "scala", "io", "edstud", "spark", "fm", "gpu", "SfmJni.scala")).read()
     s_names = set(re.findall(r"@native def (\w+)", scala))
     assert c_names == s_names, (sorted(c_names - s_names), sorted(s_names - c_names))
+
+
+def test_model_file_header_is_validated_before_anything_is_allocated(tmp_path):
+    """sfm_load treats the header as untrusted: absurd sizes, a payload that does not match the
+    header, bad flags -> SFM_ERR_IO, never an exception through the C ABI (no GPU needed: the
+    checks come before the handle is created)."""
+    import struct
+    from sparkfm_b200._lib import SFM_ERR_IO
+    L = _lib.load()
+
+    def header(n_slots, k, task=0, k0=1, k1=1, version=1):
+        return struct.pack("@8sIiiiiqfffffIQ", b"SFMB200\0", version, task, k, k0, k1, n_slots,
+                           0.0, 0.0, 0.0, 0.1, 1.0, 0, 42)
+
+    assert len(header(1, 1)) == 72
+    cases = {
+        "huge": header(1 << 40, 128),                       # would need 2^49 bytes
+        "negative": header(-5, 4),
+        "truncated": header(1000, 8) + b"\0" * 100,       # payload shorter than the header says
+        "trailing": header(2, 1) + b"\0" * (4 * (1 + 2 * 2)) + b"junk",
+        "bad_task": header(2, 1, task=7) + b"\0" * (4 * (1 + 2 * 2)),
+        "bad_version": header(2, 1, version=9) + b"\0" * (4 * (1 + 2 * 2)),
+    }
+    for name, blob in cases.items():
+        p = tmp_path / f"{name}.sfm"
+        p.write_bytes(blob)
+        out = ctypes.c_void_p()
+        assert L.sfm_load(str(p).encode(), 0, ctypes.byref(out)) == SFM_ERR_IO, name
+        assert not out.value
