@@ -268,8 +268,9 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step / val * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32" if cpu["variant"].startswith("tuned") else "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD + " (CPU arm: bounded sample)", "global_batch": per_step,
-                   "n_slots": N_SLOTS, "k": K},
+        "config": {"workload": WORKLOAD, "rows": args.rows, "global_batch_target": args.batch,
+                   "global_batch": per_step, "n_slots": N_SLOTS, "k": K,
+                   "cpu_arm": "each step is a bounded sample of the workload (cpu_baseline.sample)"},
         "cpu_baseline": cpu,
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -5,11 +5,17 @@ run() { # name batch env...
   python - "$1" <<'PY'
 import json,sys
 d=json.load(open(f"gpurun_out/ab_{sys.argv[1]}.json"))
-print(f"{sys.argv[1]:14s} step {d['ms_per_step']:.4f} ms  {d['value']/1e6:.0f} M/s  frac {d['roofline']['frac']:.3f} loss {d['loss_first_last'][1]:.6f}")
+p=d["roofline"]["phase_ms"]
+print(f"{sys.argv[1]:16s} step {d['ms_per_step']:.4f} ms  {d['value']/1e6:.0f} M/s  frac {d['roofline']['frac']:.3f} fwd {p['ms_forward']:.3f} sort {p['ms_sort']:.3f} reduce {p['ms_reduce']:.3f} loss {d['loss_first_last'][1]:.6f}")
 PY
 }
+V=$PWD/sparkfm_b200/variants/libsparkfm_b200_nospread.so
 run nograph_64k 64000 SFM_GRAPH=0
 run graph_64k 64000 SFM_GRAPH=1
+run graph_64k_nospread 64000 SFM_GRAPH=1 SFM_LIB=$V
+run graph_125k 125000 SFM_GRAPH=1
+run graph_256k 256000 SFM_GRAPH=1
 run nograph_1m 1000000 SFM_GRAPH=0
 run graph_1m 1000000 SFM_GRAPH=1
+run graph_1m_nospread 1000000 SFM_GRAPH=1 SFM_LIB=$V
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2_graph_tests.log 2>&1; echo "gpu tests rc=$?"; tail -4 gpurun_out/r2_graph_tests.log

@@ -87,6 +87,9 @@ constexpr int PL_ORDER_CLASSES = 64;               // size classes of the larges
 #ifndef BK_PL_U
 #define BK_PL_U 4
 #endif
+#ifndef BK_SPREAD
+#define BK_SPREAD 1       // partial tiles are spread over all warps / lane groups (A/B knob)
+#endif
 constexpr int PL_U = BK_PL_U;                // S-row gathers in flight per lane
 constexpr uint32_t NO_DIGIT = 0xFFFFFFFFu;
 #ifndef BK_STAGE_MULT
@@ -600,12 +603,10 @@ bkt_pull_kernel(const PullArgs a) {
     const unsigned lt = (1u << lane) - 1u;
     uint16_t* wh = whist + warp * NBL;
     uint8_t* ltab = ltab0 + warp * NBL;
-    const int strip = warp * (32 * PL_IPT);
     const uint32_t total_items = __ldg(a.item_start + a.NB);
     const double count = a.d_scal[SC_COUNT];
     const float inv = count > 0.0 ? (float)(1.0 / count) : 0.f;
     const bool active = count > 0.0 && !(FUSED && *a.err);
-    auto phys = [](int q) { return q + (q >> SS); };
 
     for (;;) {
         __syncthreads();   // previous item fully finished (shared scalars, accumulators)
@@ -619,21 +620,11 @@ bkt_pull_kernel(const PullArgs a) {
         const uint32_t e_lo = boff + (item - it0) * (uint32_t)PL_ITEM;
         const uint32_t e_hi = min(bend, e_lo + (uint32_t)PL_ITEM);
 
-        // the item's first tile is requested before the accumulators are cleared
         uint32_t ent[PL_IPT];
         float xv[PL_IPT];
-        auto load_tile = [&](uint32_t tb) {
-            const int nv = (int)min((uint32_t)PL_TILE, e_hi - tb);
-#pragma unroll
-            for (int r = 0; r < PL_IPT; ++r) {
-                const int p = strip + r * 32 + lane;
-                ent[r] = p < nv ? __ldg(a.packed + tb + p) : 0u;
-                if (!BINARY) xv[r] = p < nv ? __uint_as_float(__ldg(a.vals + tb + p)) : 0.f;
-            }
-        };
         // the bucket's parameter rows are needed at the item's end: ask for them now (L2), so
         // that the finalisation of a small item is not one DRAM round trip per feature
-        {
+        if (MODE != 2) {   // (sparse gradient: only the touched rows are read at all)
             const int64_t f0 = (int64_t)b * NBL;
             const int64_t nf = min((int64_t)NBL, a.n_slots - f0);
             const char* vb = reinterpret_cast<const char*>(a.V4 + f0 * LPR);
@@ -651,14 +642,34 @@ bkt_pull_kernel(const PullArgs a) {
 
         for (uint32_t tb = e_lo; tb < e_hi; tb += PL_TILE) {
             const int n_valid = (int)min((uint32_t)PL_TILE, e_hi - tb);
-            load_tile(tb);
+            const bool full = n_valid == PL_TILE;
+            // A partial tile (the tail of an item; every tile of a small mini-batch) is spread
+            // over ALL warps and lane groups: shorter strips to rank, fewer sequential chunks to
+            // walk.  strip_len: entries per warp (multiple of 32); ssd: log2(entries per group).
+            int strip_len = 32 * PL_IPT, ssd = SS;
+            if (!full && BK_SPREAD) {
+                strip_len = ((n_valid + PL_WARPS - 1) / PL_WARPS + 31) & ~31;
+                const int per_g = (n_valid + G - 1) / G;
+                ssd = 2;
+                while ((1 << ssd) < per_g) ++ssd;
+            }
+            const int strip = warp * strip_len;
+            auto phys = [ssd](int q) { return q + (q >> ssd); };
+#pragma unroll
+            for (int r = 0; r < PL_IPT; ++r) {
+                const int p = strip + r * 32 + lane;
+                const bool in = r * 32 < strip_len && p < n_valid;
+                ent[r] = in ? __ldg(a.packed + tb + p) : 0u;
+                if (!BINARY) xv[r] = in ? __uint_as_float(__ldg(a.vals + tb + p)) : 0.f;
+            }
             // all-ones data: the rows' multipliers (4 MB array, L2 resident) are fetched while
             // the tile is ranked and ride along into shared memory
             float second[PL_IPT];
 #pragma unroll
             for (int r = 0; r < PL_IPT; ++r) {
                 const int p = strip + r * 32 + lane;
-                second[r] = BINARY ? ((STAGE_MULT && p < n_valid) ? __ldg(a.mult + (ent[r] & rowmask)) : 0.f)
+                second[r] = BINARY ? ((STAGE_MULT && r * 32 < strip_len && p < n_valid)
+                                          ? __ldg(a.mult + (ent[r] & rowmask)) : 0.f)
                                    : xv[r];
             }
             {   // zero the warp histograms
@@ -673,7 +684,7 @@ bkt_pull_kernel(const PullArgs a) {
 #pragma unroll
             for (int r = 0; r < PL_IPT; ++r) {
                 if (!(r & 1)) rk2[r / 2] = 0;
-                if (strip + r * 32 < n_valid) {   // warp-uniform
+                if (r * 32 < strip_len && strip + r * 32 < n_valid) {   // warp-uniform
                     const bool valid = strip + r * 32 + lane < n_valid;
                     const uint32_t d = LB ? ent[r] >> RB : 0u;
                     uint32_t rank;
@@ -745,7 +756,7 @@ bkt_pull_kernel(const PullArgs a) {
 #pragma unroll
             for (int r = 0; r < PL_IPT; ++r) {
                 const int p = strip + r * 32 + lane;
-                if (p < n_valid) {
+                if (r * 32 < strip_len && p < n_valid) {
                     const uint32_t d = LB ? ent[r] >> RB : 0u;
                     const uint32_t within = (uint32_t)wh[d] + ((rk2[r / 2] >> ((r & 1) * 16)) & 0xffffu);   // rank inside the local id's run
                     const int ql = (int)lstart[d] + (int)within;
@@ -757,22 +768,18 @@ bkt_pull_kernel(const PullArgs a) {
             }
             __syncthreads();
             // the next tile's entries travel to L2 while this one is walked
-            if (lane == 0 && tb + PL_TILE < e_hi) {
-#pragma unroll
-                for (int r = 0; r < PL_IPT; ++r) {
-                    const uint32_t p = tb + PL_TILE + strip + r * 32;
-                    if (p < e_hi) {
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.packed + p));
-                        if (!BINARY) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vals + p));
-                    }
-                }
+            for (uint32_t i = tb + PL_TILE + (uint32_t)tid * 32u; i < min(e_hi, tb + 2u * PL_TILE);
+                 i += (uint32_t)PL_THREADS * 32u) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.packed + i));
+                if (!BINARY) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vals + i));
             }
 
             // ---- level 0: walk my SUB sorted entries (group g owns sorted positions
             // [g * SUB, (g + 1) * SUB): physical words g * (SUB + 1) + j)
-            const int q0 = g * SUB;
-            const uint32_t* my_e = ent_s + g * (SUB + 1);
-            const float* my_v = val_s + g * (SUB + 1);
+            const int subd = 1 << ssd;             // == SUB on full tiles
+            const int q0 = g << ssd;
+            const uint32_t* my_e = ent_s + g * (subd + 1);
+            const float* my_v = val_s + g * (subd + 1);
             const char* Sq = reinterpret_cast<const char*>(a.S4 + fq);   // this lane's quarter of a row
             auto flush = [&](uint32_t d, const float4& A, float D, float Cc) {
                 float4 t = accA[d * LPR + fq];
@@ -784,7 +791,6 @@ bkt_pull_kernel(const PullArgs a) {
                     tch[d] = 1u;
                 }
             };
-            const bool full = n_valid == PL_TILE;
             auto dig = [&](uint32_t e) -> uint32_t { return LB ? e >> RB : 0u; };
             uint32_t cur = (full || q0 < n_valid) ? dig(my_e[0]) : NO_DIGIT;
             bool cur_is_head = cur != NO_DIGIT && g > 0 && dig(my_e[-2]) == cur;
@@ -792,8 +798,9 @@ bkt_pull_kernel(const PullArgs a) {
             float D = 0.f, Cc = 0.f;
             auto walk = [&](auto full_tag) {
                 constexpr bool FULLT = decltype(full_tag)::value;
+                const int subn = FULLT ? SUB : subd;
 #pragma unroll 1
-                for (int base = 0; base < SUB; base += PL_U) {
+                for (int base = 0; base < subn; base += PL_U) {
                     uint32_t ee[PL_U];
                     float cc[PL_U], xx[PL_U];
                     float4 sv[PL_U];
@@ -870,7 +877,7 @@ bkt_pull_kernel(const PullArgs a) {
             // pointer jumping (fixed tree shape: depends on the run's position only), then the
             // group where the run starts adds the chain that follows it.
             const bool open = cur != NO_DIGIT;
-            const bool continues = open && g < G - 1 && q0 + SUB < n_valid && dig(my_e[SUB + 1]) == cur;
+            const bool continues = open && g < G - 1 && q0 + subd < n_valid && dig(my_e[subd + 1]) == cur;
             const bool owner = open && !cur_is_head;
             if (open && cur_is_head) {
                 headA[g * LPR + fq] = A;   // the whole group is a middle / final piece of a run
@@ -962,7 +969,9 @@ bkt_pull_kernel(const PullArgs a) {
           for (int j = 0; j < 4; ++j) {
               const int dj = d0 + j * G;
               const int64_t fj = (int64_t)b * NBL + dj;
-              const bool in = dj < NBL && fj < a.n_slots;
+              bool in = dj < NBL && fj < a.n_slots;
+              // sparse gradient: a feature this rank did not touch writes nothing -- skip its row
+              if (MODE == 2 && single && in) in = tch[dj] != 0u;
               vv[j] = in ? a.V4[fj * LPR + fq] : make_float4(0.f, 0.f, 0.f, 0.f);
               ww[j] = (in && fq == 0 && a.k1) ? a.W[fj] : 0.f;
           }
