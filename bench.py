@@ -607,6 +607,10 @@ def main():
             it1 = run_pipelined(kind, n_steps, it1)
             barrier()
             dt = time.perf_counter() - t0
+            if world > 1:   # every rank must run the SAME number of steps (each step is a collective)
+                td = torch.tensor([dt], dtype=torch.float64, device="cuda")
+                dist.all_reduce(td, op=dist.ReduceOp.MAX)
+                dt = float(td[0])
             if dt < args.min_seconds:   # short steps (small per-GPU batch): time a longer run
                 n_steps = int(n_steps * args.min_seconds / max(dt, 1e-6)) + 1
                 barrier()

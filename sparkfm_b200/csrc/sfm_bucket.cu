@@ -1162,9 +1162,19 @@ cudaError_t bucket_transpose(const ModelView& m, const BatchView& b, const Bucke
         implicit_div ? ((1ULL << 40) + (unsigned long long)implicit_div - 1) / (unsigned long long)implicit_div : 0ULL;
     cudaError_t e;
 #define SC_LAUNCH(PM)                                                                           \
-    e = cudaFuncSetAttribute(bkt_scatter_kernel<PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                             (int)smem);                                                        \
-    if (e != cudaSuccess) return e;                                                             \
+    {                                                                                           \
+        static size_t set_smem = 0;                                                             \
+        static int set_dev = -1;                                                                \
+        int dev_now = 0;                                                                        \
+        cudaGetDevice(&dev_now);                                                                \
+        if (set_smem != smem || set_dev != dev_now) {                                           \
+            set_dev = dev_now;                                                                  \
+            e = cudaFuncSetAttribute(bkt_scatter_kernel<PM>,                                    \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+            if (e != cudaSuccess) return e;                                                     \
+            set_smem = smem;                                                                    \
+        }                                                                                       \
+    }                                                                                           \
     bkt_scatter_kernel<PM><<<G, SC_THREADS, smem, st>>>(                                        \
         keys, reinterpret_cast<const uint32_t*>(pay), pay, packed, vals, (int)b.n_rows, mm, optr, \
         b.out_base, g.LB, g.HB, w.counts, bucket_off, magic)
@@ -1196,13 +1206,25 @@ static cudaError_t pull_dispatch2(const ModelView& m, const BucketGeom& g, const
     cudaError_t e;
     int occ = 0;   // resident CTAs per SM: the grid of the persistent kernel
 #define PL_LAUNCH(B, M)                                                                          \
-    e = cudaFuncSetAttribute(bkt_pull_kernel<LPR, B, M>,                                         \
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
-    if (e != cudaSuccess) return e;                                                              \
-    occ = 0;                                                                                     \
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bkt_pull_kernel<LPR, B, M>, PL_THREADS, smem); \
-    if (e != cudaSuccess) return e;                                                              \
-    if (occ < 1) occ = 1;                                                                        \
+    {                                                                                            \
+        static size_t set_smem = 0;   /* attribute + occupancy: queried once per kernel, size, device */ \
+        static int set_occ = 0, set_dev = -1;                                                    \
+        int dev_now = 0;                                                                         \
+        cudaGetDevice(&dev_now);                                                                 \
+        if (set_smem != smem || set_occ < 1 || set_dev != dev_now) {                             \
+            set_dev = dev_now;                                                                   \
+            e = cudaFuncSetAttribute(bkt_pull_kernel<LPR, B, M>,                                 \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+            if (e != cudaSuccess) return e;                                                      \
+            occ = 0;                                                                             \
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bkt_pull_kernel<LPR, B, M>,  \
+                                                              PL_THREADS, smem);                 \
+            if (e != cudaSuccess) return e;                                                      \
+            set_occ = occ < 1 ? 1 : occ;                                                         \
+            set_smem = smem;                                                                     \
+        }                                                                                        \
+        occ = set_occ;                                                                           \
+    }                                                                                            \
     bkt_pull_kernel<LPR, B, M><<<occ * sm_count, PL_THREADS, smem, st>>>(a)
     if (binary) {
         if (mode == 0) { PL_LAUNCH(true, 0); } else if (mode == 1) { PL_LAUNCH(true, 1); } else { PL_LAUNCH(true, 2); }

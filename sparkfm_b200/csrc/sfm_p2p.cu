@@ -129,6 +129,27 @@ __device__ __forceinline__ float ld_peer1(const float* p) {
     return r;
 }
 
+// The G ranks' scalar blocks of this step -> tot[SC_N], added in rank order (fp64: the same on
+// every rank).  One peer load per thread, all in flight together: ONE NVLink round trip instead
+// of G * SC_N dependent ones (the round-1 form cost ~0.1 ms at 8 ranks).
+__device__ __forceinline__ void p2p_gather_scalars(const DevPeers& P, int world, bool ok,
+                                                    double (*sc)[SC_N], double* tot) {
+    const int t = threadIdx.x;
+    if (t < world * SC_N) {
+        const int p = t / SC_N, j = t % SC_N;
+        double x = 0.0;
+        if (ok) asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(x) : "l"(P.scal[p] + j));
+        sc[p][j] = x;
+    }
+    __syncthreads();
+    if (t < SC_N) {
+        double a = 0.0;
+        for (int p = 0; p < world; ++p) a += sc[p][t];
+        tot[t] = a;
+    }
+    __syncthreads();
+}
+
 template <int W>   // W = number of ranks rounded up to 2 / 4 / 8 / 16 (loads are issued together)
 __global__ void __launch_bounds__(256)
 p2p_reduce_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_t v4_lo,
@@ -138,23 +159,10 @@ p2p_reduce_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_
                          unsigned long long timeout_ns, uint32_t* done_ctr) {
     __shared__ int ok;
     __shared__ double tot[SC_N];
-    if (threadIdx.x == 0) {
-        ok = p2p_wait(sig, 0, world, epoch, timeout_ns, done_ctr + 1) ? 1 : 0;
-        if (ok) {   // global loss / count / gw0: rank-order fp64 sums, the same on every rank
-            for (int j = 0; j < SC_N; ++j) {
-                double a = 0.0;
-                for (int p = 0; p < world; ++p) {
-                    double x;
-                    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(x) : "l"(P.scal[p] + j));
-                    a += x;
-                }
-                tot[j] = a;
-            }
-        } else {
-            for (int j = 0; j < SC_N; ++j) tot[j] = 0.0;
-        }
-    }
+    __shared__ double sc[P2P_MAXG][SC_N];
+    if (threadIdx.x == 0) ok = p2p_wait(sig, 0, world, epoch, timeout_ns, done_ctr + 1) ? 1 : 0;
     __syncthreads();
+    p2p_gather_scalars(P, world, ok != 0, sc, tot);   // global loss / count / gw0 / error
     const double count = tot[SC_COUNT];
     // tot[SC_ERR] = number of ranks that saw a bad index: everybody skips the update together
     const bool active = ok && count > 0.0 && tot[SC_ERR] == 0.0;
@@ -227,20 +235,10 @@ p2p_sparse_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_
                          UpdateParams up, unsigned long long timeout_ns, uint32_t* done_ctr) {
     __shared__ int ok;
     __shared__ double tot[SC_N];
-    if (threadIdx.x == 0) {
-        ok = p2p_wait(sig, 0, world, epoch, timeout_ns, done_ctr + 1) ? 1 : 0;
-        for (int j = 0; j < SC_N; ++j) {
-            double a = 0.0;
-            if (ok)
-                for (int p = 0; p < world; ++p) {
-                    double x;
-                    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(x) : "l"(P.scal[p] + j));
-                    a += x;
-                }
-            tot[j] = a;
-        }
-    }
+    __shared__ double sc[P2P_MAXG][SC_N];
+    if (threadIdx.x == 0) ok = p2p_wait(sig, 0, world, epoch, timeout_ns, done_ctr + 1) ? 1 : 0;
     __syncthreads();
+    p2p_gather_scalars(P, world, ok != 0, sc, tot);
     const double count = tot[SC_COUNT];
     const bool active = ok && count > 0.0 && tot[SC_ERR] == 0.0;
     if (ok && blockIdx.x == 0 && threadIdx.x < SC_N) d_scal[threadIdx.x] = tot[threadIdx.x];
