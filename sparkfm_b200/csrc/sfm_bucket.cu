@@ -798,7 +798,7 @@ bkt_pull_kernel(const PullArgs a) {
             float D = 0.f, Cc = 0.f;
             auto walk = [&](auto full_tag) {
                 constexpr bool FULLT = decltype(full_tag)::value;
-                const int subn = FULLT ? SUB : subd;
+                const int subn = subd;   // SUB on full tiles
 #pragma unroll 1
                 for (int base = 0; base < subn; base += PL_U) {
                     uint32_t ee[PL_U];
@@ -870,7 +870,9 @@ bkt_pull_kernel(const PullArgs a) {
                     }
                 }
             };
-            if (full) walk(std::true_type{}); else walk(std::false_type{});
+            // a group whose entries all exist takes the unpredicated walk (with the compare-free
+            // chunks), also on a partial tile; only the group that straddles the tile's end checks
+            if (full || q0 + subd <= n_valid) walk(std::true_type{}); else walk(std::false_type{});
             // ---- level 1: runs that span several groups.  A group whose FIRST run continues
             // the previous group's last one holds a "head" partial; a head that fills its whole
             // group and continues links to the next group's head.  The chains are summed by
