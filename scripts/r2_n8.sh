@@ -1,20 +1,18 @@
 #!/bin/bash
-# one 8-GPU lease: parity tests at 4 and 8 ranks, the strong-scaling bench line, small global batches
+# one 8-GPU lease: the strong-scaling bench line (1 M global), small global batches, the reference arm
 mkdir -p gpurun_out
 export SFM_P2P_TIMEOUT_S=30
-timeout 900 python -m pytest tests/test_gpu_multi.py -x -q -k "n_gpus_match" > gpurun_out/r2_n8_tests.log 2>&1; echo "multi tests rc=$?"; tail -4 gpurun_out/r2_n8_tests.log
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29581"
-timeout 600 $TR bench.py --gpus 8 --steps 200 --warmup 10 --no-cpu-baseline > gpurun_out/r2_bench_n8.json 2> gpurun_out/r2_bench_n8.err; echo "bench n8 rc=$?"
+timeout 700 $TR bench.py --gpus 8 --steps 200 --warmup 10 --no-cpu-baseline > gpurun_out/r2_bench_n8.json 2> gpurun_out/r2_bench_n8.err; echo "bench n8 rc=$?"
 for b in 64000 256000; do
 timeout 300 $TR bench.py --gpus 8 --batch $b --steps 200 --warmup 10 --no-cpu-baseline --no-e2e --no-partition --no-parity --weak-batch 0 > gpurun_out/r2_c5_n8_$b.json 2> gpurun_out/r2_c5_n8_$b.err; echo "c5 $b rc=$?"
 done
-SFM_P2P_SPARSE=0 timeout 300 $TR bench.py --gpus 8 --steps 200 --warmup 10 --no-cpu-baseline --no-e2e --no-partition --no-parity --weak-batch 0 > gpurun_out/r2_bench_n8_dense.json 2> gpurun_out/r2_bench_n8_dense.err; echo "dense rc=$?"
 python - <<'PY'
 import json
-for f in ("r2_bench_n8","r2_c5_n8_64000","r2_c5_n8_256000","r2_bench_n8_dense"):
+for f in ("r2_bench_n8","r2_c5_n8_64000","r2_c5_n8_256000"):
     try:
         d=json.loads(open(f"gpurun_out/{f}.json").read().strip().splitlines()[-1])
-        print(f, d["config"]["global_batch"], "step", round(d["ms_per_step"],4), "value", round(d["value"]/1e6,1), "M/s", d["roofline"]["phase_ms"], "e2e", (d.get("e2e") or {}).get("value"), "weak", (d.get("weak_scaling") or {}).get("value"), "parity", (d.get("parity_n") or {}).get("ok"))
+        print(f, d["config"]["global_batch"], "step", round(d["ms_per_step"],4), "value", round(d["value"]/1e6,1), "M/s", "e2e", (d.get("e2e") or {}).get("value"), "weak", (d.get("weak_scaling") or {}).get("value"), "part", (d.get("partition_sampler") or {}).get("value"), "parity", (d.get("parity_n") or {}).get("ok"))
     except Exception as e:
         print(f, "parse failed", e)
 PY

@@ -21,6 +21,7 @@
 // raises the handle's error flag instead of hanging.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -57,12 +58,14 @@ struct DevPeers {
 struct P2PState {
     float* grad = nullptr;
     uint32_t* touch = nullptr;   // inside the grad allocation
+    uint32_t* tball = nullptr;   // [world][words] local copy of every rank's touched bitmap (sparse exchange)
     uint32_t* sig = nullptr;
     uint32_t* done_ctr = nullptr;
     void* opened[P2P_MAXG][4];
     DevPeers peers;
     uint32_t epoch = 0;
     unsigned long long timeout_ns = 0;
+    unsigned long long* trace = nullptr;   // SFM_P2P_TRACE=1: [8] summed stage times (ns) of CTA 0 + step count
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -219,6 +222,35 @@ p2p_reduce_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_
     }
 }
 
+// The ranks' touched bitmaps -> one local array tball[rank][word], with coalesced 16-byte peer
+// loads (a bitmap is 125 KB at 1 M features).  The update kernel then reads bitmaps locally: one
+// 4-byte peer load per (warp, rank, word) -- what the first version did -- is one NVLink request
+// each, and their number, not their bytes, was what an exchange at 8 ranks cost.
+__global__ void __launch_bounds__(256)
+p2p_bitmap_gather_kernel(DevPeers P, int world, uint32_t epoch, int words, const uint32_t* sig,
+                         uint32_t* __restrict__ tball, unsigned long long timeout_ns,
+                         uint32_t* done_ctr) {
+    __shared__ int ok;
+    if (threadIdx.x == 0) ok = p2p_wait(sig, 0, world, epoch, timeout_ns, done_ctr + 1) ? 1 : 0;
+    __syncthreads();
+    if (!ok) return;
+    const int quads = words / 4;   // the bitmap is padded to a multiple of 4 words
+    const int64_t total = (int64_t)world * quads;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int p = (int)(i / quads), q = (int)(i % quads);
+        const uint32_t* src = nullptr;
+#pragma unroll
+        for (int r = 0; r < P2P_MAXG; ++r)
+            if (r == p) src = P.tb[r];
+        uint4 v;
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(reinterpret_cast<const uint4*>(src) + q));
+        reinterpret_cast<uint4*>(tball + (size_t)p * words)[q] = v;
+    }
+}
+
 // Sparse form of the same exchange: every rank publishes one bit per feature its batch touched
 // (written by bkt_pull_kernel<MODE 2> next to the gradient rows of exactly those features).
 //   part 1, own slice of bitmap words: for every feature some rank touched, the touching ranks'
@@ -232,13 +264,20 @@ __global__ void __launch_bounds__(256)
 p2p_sparse_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_t n_slots, int lsh,
                          int wd_lo, int wd_hi, int wd_total, int k0, int k1,
                          float* __restrict__ W0, const uint32_t* sig, double* __restrict__ d_scal,
-                         UpdateParams up, unsigned long long timeout_ns, uint32_t* done_ctr) {
+                         UpdateParams up, unsigned long long timeout_ns, uint32_t* done_ctr,
+                         unsigned long long* __restrict__ trace, const uint32_t* __restrict__ tball,
+                         int tb_words) {
     __shared__ int ok;
     __shared__ double tot[SC_N];
     __shared__ double sc[P2P_MAXG][SC_N];
+    const bool tr = trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    unsigned long long ts[6];
+    if (tr) ts[0] = global_ns();
     if (threadIdx.x == 0) ok = p2p_wait(sig, 0, world, epoch, timeout_ns, done_ctr + 1) ? 1 : 0;
     __syncthreads();
+    if (tr) ts[1] = global_ns();
     p2p_gather_scalars(P, world, ok != 0, sc, tot);
+    if (tr) ts[2] = global_ns();
     const double count = tot[SC_COUNT];
     const bool active = ok && count > 0.0 && tot[SC_ERR] == 0.0;
     if (ok && blockIdx.x == 0 && threadIdx.x < SC_N) d_scal[threadIdx.x] = tot[threadIdx.x];
@@ -253,9 +292,7 @@ p2p_sparse_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_
         float* Wme = P.w[rank];
         for (int wd = wd_lo + gw; wd < wd_hi; wd += warps) {
             uint32_t mine = 0;
-#pragma unroll
-            for (int p = 0; p < W; ++p)
-                if (lane == p && p < world) mine = ld_volatile_u32(P.tb[p] + wd);
+            if (lane < world) mine = __ldcg(tball + (size_t)lane * tb_words + wd);   // local copy
             uint32_t bits[W];
             uint32_t uni = 0;
 #pragma unroll
@@ -264,6 +301,21 @@ p2p_sparse_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_
                 uni |= bits[p];
             }
             if (!uni) continue;
+            if (k1) {   // w: lane <-> feature of the word, so a rank's gw values / the new w values
+                        // of the word travel as ONE request per rank instead of one per feature
+                const int64_t f = (int64_t)wd * 32 + lane;
+                const bool in = f < n_slots;
+                float gs = 0.f;
+#pragma unroll
+                for (int p = 0; p < W; ++p)   // rank order: fixed summation order
+                    gs += (in && ((bits[p] >> lane) & 1u)) ? ld_peer1(P.gw[p] + f) : 0.f;
+                if (in && ((uni >> lane) & 1u)) {
+                    const float wn = sgd_step(Wme[f], gs, inv, up.eta, up.regw);
+#pragma unroll
+                    for (int p = 0; p < W; ++p)
+                        if (p < world) P.w[p][f] = wn;
+                }
+            }
             for (int pass = 0; pass < lpr; ++pass) {
                 const int j = pass * fpp + jl;
                 const int64_t f = (int64_t)wd * 32 + j;
@@ -273,11 +325,6 @@ p2p_sparse_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_
 #pragma unroll
                 for (int p = 0; p < W; ++p)
                     x[p] = ((bits[p] >> j) & 1u) ? ld_peer4(P.g4[p] + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-                float gs = 0.f;
-                if (fq == 0 && k1) {
-#pragma unroll
-                    for (int p = 0; p < W; ++p) gs += ((bits[p] >> j) & 1u) ? ld_peer1(P.gw[p] + f) : 0.f;
-                }
                 float4 g = x[0];
 #pragma unroll
                 for (int p = 1; p < W; ++p) {   // rank order: fixed summation order
@@ -291,22 +338,20 @@ p2p_sparse_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_
 #pragma unroll
                 for (int p = 0; p < W; ++p)
                     if (p < world) P.v[p][e] = v;
-                if (fq == 0 && k1) {
-                    const float wn = sgd_step(Wme[f], gs, inv, up.eta, up.regw);
-#pragma unroll
-                    for (int p = 0; p < W; ++p)
-                        if (p < world) P.w[p][f] = wn;
-                }
             }
         }
+        if (tr) ts[3] = global_ns();
         if (up.regv != 0.f || (k1 && up.regw != 0.f)) {
             for (int wd = gw; wd < wd_total; wd += warps) {
                 uint32_t mine = 0;
-#pragma unroll
-                for (int p = 0; p < W; ++p)
-                    if (lane == p && p < world) mine = ld_volatile_u32(P.tb[p] + wd);
+                if (lane < world) mine = __ldcg(tball + (size_t)lane * tb_words + wd);
                 const uint32_t uni = __reduce_or_sync(0xffffffffu, mine);
                 if (uni == 0xffffffffu) continue;
+                if (k1 && up.regw != 0.f) {
+                    const int64_t f = (int64_t)wd * 32 + lane;
+                    if (f < n_slots && !((uni >> lane) & 1u)) Wme[f] = sgd_step(Wme[f], 0.f, inv, up.eta, up.regw);
+                }
+                if (up.regv == 0.f) continue;
                 for (int pass = 0; pass < lpr; ++pass) {
                     const int j = pass * fpp + jl;
                     const int64_t f = (int64_t)wd * 32 + j;
@@ -318,7 +363,6 @@ p2p_sparse_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_
                     v.z = sgd_step(v.z, 0.f, inv, up.eta, up.regv);
                     v.w = sgd_step(v.w, 0.f, inv, up.eta, up.regv);
                     Vme[e] = v;
-                    if (fq == 0 && k1) Wme[f] = sgd_step(Wme[f], 0.f, inv, up.eta, up.regw);
                 }
             }
         }
@@ -326,9 +370,15 @@ p2p_sparse_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_
             const float w0 = *W0;
             *W0 = sgd_step(w0, (float)tot[SC_GW0], inv, up.eta, up.reg0);
         }
+        if (tr) ts[4] = global_ns();
     }
     __threadfence_system();
     __syncthreads();
+    if (tr && active) {   // stage times of CTA 0: wait for the ranks, scalars, touched rows, decay, fence
+        ts[5] = global_ns();
+        for (int j = 0; j < 5; ++j) atomicAdd(trace + j, ts[j + 1] - ts[j]);
+        atomicAdd(trace + 5, 1ull);
+    }
     if (threadIdx.x == 0) {
         const unsigned ticket = atomicAdd(done_ctr, 1u);
         if (ticket == gridDim.x - 1) {
@@ -346,10 +396,23 @@ p2p_sparse_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_
 void p2p_teardown(sfm_handle* h) {
     P2PState* s = h->p2p;
     if (!s) return;
+    if (s->trace) {
+        unsigned long long t[8] = {0};
+        cudaStreamSynchronize(h->stream);
+        if (cudaMemcpy(t, s->trace, sizeof t, cudaMemcpyDeviceToHost) == cudaSuccess && t[5] > 0) {
+            const double n = (double)t[5] * 1e3;
+            fprintf(stderr, "[sfm p2p trace] rank %d/%d, %llu sparse exchanges, CTA 0 avg us: wait for ranks %.1f, "
+                    "scalars %.1f, touched rows (part 1) %.1f, local decay (part 2) %.1f, fence %.1f\n",
+                    h->rank, h->world, t[5], t[0] / n, t[1] / n, t[2] / n, t[3] / n, t[4] / n);
+        }
+        cudaFree(s->trace);
+        cudaGetLastError();
+    }
     for (int p = 0; p < h->world && p < P2P_MAXG; ++p)
         for (int j = 0; j < 4; ++j)
             if (s->opened[p][j]) cudaIpcCloseMemHandle(s->opened[p][j]);
     if (s->grad) cudaFree(s->grad);
+    if (s->tball) cudaFree(s->tball);
     if (s->sig) cudaFree(s->sig);
     if (s->done_ctr) cudaFree(s->done_ctr);
     delete s;
@@ -370,14 +433,23 @@ int p2p_setup(sfm_handle* h) {
     const size_t glen = (size_t)m.n_slots * (m.kp + 1) + 1;
     const size_t scal_off = (glen + 3) / 4 * 4;   // floats; the [SC_N] doubles sit 16-byte aligned
     const size_t touch_off = scal_off + 2 * SC_N; // floats; then one bit per feature
-    const size_t touch_words = (size_t)(m.n_slots + 31) / 32;
+    const size_t touch_words = ((size_t)(m.n_slots + 31) / 32 + 3) / 4 * 4;   // whole 16-byte quads
     bool ok = want != 0;
     cudaIpcMemHandle_t mine[4];
     memset(mine, 0, sizeof mine);
     if (ok) ok = cudaMalloc(&s->grad, sizeof(float) * (touch_off + touch_words)) == cudaSuccess;
     if (ok) s->touch = reinterpret_cast<uint32_t*>(s->grad + touch_off);
+    if (ok) ok = cudaMalloc(&s->tball, sizeof(uint32_t) * touch_words * (size_t)G) == cudaSuccess;
+    if (ok) cudaMemsetAsync(s->grad + touch_off, 0, sizeof(uint32_t) * touch_words, h->stream);   // pad words stay 0
     if (ok) ok = cudaMalloc(&s->sig, sizeof(uint32_t) * 2 * P2P_MAXG) == cudaSuccess;
     if (ok) ok = cudaMalloc(&s->done_ctr, sizeof(uint32_t) * 4) == cudaSuccess;
+    if (ok && getenv("SFM_P2P_TRACE")) {
+        if (cudaMalloc(&s->trace, sizeof(unsigned long long) * 8) == cudaSuccess)
+            cudaMemsetAsync(s->trace, 0, sizeof(unsigned long long) * 8, h->stream);
+        else
+            s->trace = nullptr;
+        cudaGetLastError();
+    }
     if (ok) {
         cudaMemsetAsync(s->sig, 0, sizeof(uint32_t) * 2 * P2P_MAXG, h->stream);
         cudaMemsetAsync(s->done_ctr, 0, sizeof(uint32_t) * 4, h->stream);
@@ -497,6 +569,15 @@ int p2p_reduce_update(sfm_handle* h, UpdateParams up, bool sparse) {
     p2p_signal_kernel<<<1, 32, 0, h->stream>>>(s->peers, G, r, 0, epoch, h->d_scal);
     if (sparse) {
         const int64_t words = (m.n_slots + 31) / 32;
+        const int tb_words = (int)((words + 3) / 4 * 4);
+        {   // the ranks' bitmaps -> local copy (coalesced peer loads)
+            int64_t gb = ((int64_t)G * (tb_words / 4) + 255) / 256;
+            if (gb > (int64_t)h->sm_count * 4) gb = (int64_t)h->sm_count * 4;
+            if (gb < 1) gb = 1;
+            p2p_bitmap_gather_kernel<<<(unsigned)gb, 256, 0, h->stream>>>(s->peers, G, epoch, tb_words, s->sig,
+                                                                       s->tball, s->timeout_ns, s->done_ctr);
+            *L += 1;
+        }
         const int wd_lo = (int)((int64_t)r * words / G), wd_hi = (int)((int64_t)(r + 1) * words / G);
         int lsh = 0;
         while ((1 << lsh) < m.lpr) ++lsh;
@@ -506,7 +587,7 @@ int p2p_reduce_update(sfm_handle* h, UpdateParams up, bool sparse) {
         if (blocks < 1) blocks = 1;
 #define SP_ARGS                                                                                \
     s->peers, G, r, epoch, m.n_slots, lsh, wd_lo, wd_hi, (int)words, m.k0, m.k1, m.w0, s->sig, \
-        h->d_scal, up, s->timeout_ns, s->done_ctr
+        h->d_scal, up, s->timeout_ns, s->done_ctr, s->trace, s->tball, tb_words
         if (G <= 2)      p2p_sparse_update_kernel<2><<<(unsigned)blocks, 256, 0, h->stream>>>(SP_ARGS);
         else if (G <= 4) p2p_sparse_update_kernel<4><<<(unsigned)blocks, 256, 0, h->stream>>>(SP_ARGS);
         else if (G <= 8) p2p_sparse_update_kernel<8><<<(unsigned)blocks, 256, 0, h->stream>>>(SP_ARGS);
