@@ -59,6 +59,7 @@ struct P2PState {
     float* grad = nullptr;
     uint32_t* touch = nullptr;   // inside the grad allocation
     uint32_t* tball = nullptr;   // [world][words] local copy of every rank's touched bitmap (sparse exchange)
+    double* scal_all = nullptr;  // [world][SC_N] local copy of the ranks' scalar blocks
     uint32_t* sig = nullptr;
     uint32_t* done_ctr = nullptr;
     void* opened[P2P_MAXG][4];
@@ -102,6 +103,30 @@ __device__ bool p2p_wait(const uint32_t* sig, int base, int world, uint32_t epoc
     return true;
 }
 
+// The same wait with one polling thread per rank (the flags are G dependent L2 round trips when
+// one thread reads them in turn).  Every thread of the block must call it.
+__device__ bool p2p_wait_block(const uint32_t* sig, int base, int world, uint32_t epoch,
+                               unsigned long long timeout_ns, uint32_t* timed_out) {
+    bool ok = true;
+    if ((int)threadIdx.x < world) {
+        if (ld_volatile_u32(timed_out)) {
+            ok = false;
+        } else {
+            const unsigned long long t0 = global_ns();
+            while ((int32_t)(ld_volatile_u32(sig + base + threadIdx.x) - epoch) < 0) {
+                if (global_ns() - t0 > timeout_ns) {
+                    st_volatile_u32(timed_out, 1u);
+                    ok = false;
+                    break;
+                }
+                __nanosleep(100);
+            }
+        }
+        __threadfence_system();
+    }
+    return __syncthreads_and(ok) != 0;
+}
+
 __global__ void p2p_signal_kernel(DevPeers P, int world, int rank, int phase, uint32_t epoch,
                                   const double* __restrict__ d_scal) {
     const int p = threadIdx.x;
@@ -115,7 +140,7 @@ __global__ void p2p_signal_kernel(DevPeers P, int world, int rank, int phase, ui
 
 __global__ void p2p_wait_kernel(const uint32_t* sig, int phase, int world, uint32_t epoch,
                                 unsigned long long timeout_ns, uint32_t* timed_out) {
-    if (threadIdx.x == 0) p2p_wait(sig, phase * P2P_MAXG, world, epoch, timeout_ns, timed_out);
+    p2p_wait_block(sig, phase * P2P_MAXG, world, epoch, timeout_ns, timed_out);
 }
 
 __device__ __forceinline__ float4 ld_peer4(const float4* p) {   // no caching of peer data
@@ -163,8 +188,11 @@ p2p_reduce_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_
     __shared__ int ok;
     __shared__ double tot[SC_N];
     __shared__ double sc[P2P_MAXG][SC_N];
-    if (threadIdx.x == 0) ok = p2p_wait(sig, 0, world, epoch, timeout_ns, done_ctr + 1) ? 1 : 0;
-    __syncthreads();
+    {
+        const bool w_ok = p2p_wait_block(sig, 0, world, epoch, timeout_ns, done_ctr + 1);
+        if (threadIdx.x == 0) ok = w_ok ? 1 : 0;
+        __syncthreads();
+    }
     p2p_gather_scalars(P, world, ok != 0, sc, tot);   // global loss / count / gw0 / error
     const double count = tot[SC_COUNT];
     // tot[SC_ERR] = number of ranks that saw a bad index: everybody skips the update together
@@ -228,12 +256,19 @@ p2p_reduce_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_
 // each, and their number, not their bytes, was what an exchange at 8 ranks cost.
 __global__ void __launch_bounds__(256)
 p2p_bitmap_gather_kernel(DevPeers P, int world, uint32_t epoch, int words, const uint32_t* sig,
-                         uint32_t* __restrict__ tball, unsigned long long timeout_ns,
-                         uint32_t* done_ctr) {
-    __shared__ int ok;
-    if (threadIdx.x == 0) ok = p2p_wait(sig, 0, world, epoch, timeout_ns, done_ctr + 1) ? 1 : 0;
-    __syncthreads();
-    if (!ok) return;
+                         uint32_t* __restrict__ tball, double* __restrict__ scal_all,
+                         unsigned long long timeout_ns, uint32_t* done_ctr) {
+    if (!p2p_wait_block(sig, 0, world, epoch, timeout_ns, done_ctr + 1)) return;
+    if (blockIdx.x == 0 && (int)threadIdx.x < world * SC_N) {   // the ranks' scalar blocks, too
+        const int pp = threadIdx.x / SC_N, j = threadIdx.x % SC_N;
+        const double* src = nullptr;
+#pragma unroll
+        for (int r = 0; r < P2P_MAXG; ++r)
+            if (r == pp) src = P.scal[r];
+        double x;
+        asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(x) : "l"(src + j));
+        scal_all[pp * SC_N + j] = x;
+    }
     const int quads = words / 4;   // the bitmap is padded to a multiple of 4 words
     const int64_t total = (int64_t)world * quads;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -266,17 +301,29 @@ p2p_sparse_update_kernel(DevPeers P, int world, int rank, uint32_t epoch, int64_
                          float* __restrict__ W0, const uint32_t* sig, double* __restrict__ d_scal,
                          UpdateParams up, unsigned long long timeout_ns, uint32_t* done_ctr,
                          unsigned long long* __restrict__ trace, const uint32_t* __restrict__ tball,
-                         int tb_words) {
+                         int tb_words, const double* __restrict__ scal_all) {
     __shared__ int ok;
     __shared__ double tot[SC_N];
     __shared__ double sc[P2P_MAXG][SC_N];
     const bool tr = trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     unsigned long long ts[6];
     if (tr) ts[0] = global_ns();
-    if (threadIdx.x == 0) ok = p2p_wait(sig, 0, world, epoch, timeout_ns, done_ctr + 1) ? 1 : 0;
-    __syncthreads();
+    {   // (the flags are already up: the bitmap kernel in front of this one waited for them)
+        const bool w_ok = p2p_wait_block(sig, 0, world, epoch, timeout_ns, done_ctr + 1);
+        if (threadIdx.x == 0) ok = w_ok ? 1 : 0;
+    }
     if (tr) ts[1] = global_ns();
-    p2p_gather_scalars(P, world, ok != 0, sc, tot);
+    {   // global loss / count / gw0 / error from the local copy of the ranks' scalar blocks
+        const int t = threadIdx.x;
+        if (t < world * SC_N) sc[t / SC_N][t % SC_N] = __ldcg(scal_all + t);
+        __syncthreads();
+        if (t < SC_N) {
+            double acc = 0.0;
+            for (int p = 0; p < world; ++p) acc += sc[p][t];   // rank order
+            tot[t] = acc;
+        }
+        __syncthreads();
+    }
     if (tr) ts[2] = global_ns();
     const double count = tot[SC_COUNT];
     const bool active = ok && count > 0.0 && tot[SC_ERR] == 0.0;
@@ -413,6 +460,7 @@ void p2p_teardown(sfm_handle* h) {
             if (s->opened[p][j]) cudaIpcCloseMemHandle(s->opened[p][j]);
     if (s->grad) cudaFree(s->grad);
     if (s->tball) cudaFree(s->tball);
+    if (s->scal_all) cudaFree(s->scal_all);
     if (s->sig) cudaFree(s->sig);
     if (s->done_ctr) cudaFree(s->done_ctr);
     delete s;
@@ -440,6 +488,7 @@ int p2p_setup(sfm_handle* h) {
     if (ok) ok = cudaMalloc(&s->grad, sizeof(float) * (touch_off + touch_words)) == cudaSuccess;
     if (ok) s->touch = reinterpret_cast<uint32_t*>(s->grad + touch_off);
     if (ok) ok = cudaMalloc(&s->tball, sizeof(uint32_t) * touch_words * (size_t)G) == cudaSuccess;
+    if (ok) ok = cudaMalloc(&s->scal_all, sizeof(double) * SC_N * P2P_MAXG) == cudaSuccess;
     if (ok) cudaMemsetAsync(s->grad + touch_off, 0, sizeof(uint32_t) * touch_words, h->stream);   // pad words stay 0
     if (ok) ok = cudaMalloc(&s->sig, sizeof(uint32_t) * 2 * P2P_MAXG) == cudaSuccess;
     if (ok) ok = cudaMalloc(&s->done_ctr, sizeof(uint32_t) * 4) == cudaSuccess;
@@ -575,7 +624,8 @@ int p2p_reduce_update(sfm_handle* h, UpdateParams up, bool sparse) {
             if (gb > (int64_t)h->sm_count * 4) gb = (int64_t)h->sm_count * 4;
             if (gb < 1) gb = 1;
             p2p_bitmap_gather_kernel<<<(unsigned)gb, 256, 0, h->stream>>>(s->peers, G, epoch, tb_words, s->sig,
-                                                                       s->tball, s->timeout_ns, s->done_ctr);
+                                                                       s->tball, s->scal_all, s->timeout_ns,
+                                                                       s->done_ctr);
             *L += 1;
         }
         const int wd_lo = (int)((int64_t)r * words / G), wd_hi = (int)((int64_t)(r + 1) * words / G);
@@ -587,7 +637,7 @@ int p2p_reduce_update(sfm_handle* h, UpdateParams up, bool sparse) {
         if (blocks < 1) blocks = 1;
 #define SP_ARGS                                                                                \
     s->peers, G, r, epoch, m.n_slots, lsh, wd_lo, wd_hi, (int)words, m.k0, m.k1, m.w0, s->sig, \
-        h->d_scal, up, s->timeout_ns, s->done_ctr, s->trace, s->tball, tb_words
+        h->d_scal, up, s->timeout_ns, s->done_ctr, s->trace, s->tball, tb_words, s->scal_all
         if (G <= 2)      p2p_sparse_update_kernel<2><<<(unsigned)blocks, 256, 0, h->stream>>>(SP_ARGS);
         else if (G <= 4) p2p_sparse_update_kernel<4><<<(unsigned)blocks, 256, 0, h->stream>>>(SP_ARGS);
         else if (G <= 8) p2p_sparse_update_kernel<8><<<(unsigned)blocks, 256, 0, h->stream>>>(SP_ARGS);
