@@ -173,6 +173,12 @@ class Handle:
         self._ck(self._L.sfm_predict_resident(self._h, row_lo, row_hi, _p(out, C.c_float)))
         return out
 
+    def predict_resident_raw(self, row_lo, row_hi, out_p):
+        """Same into a caller-owned buffer given by address (e.g. pinned memory from host_alloc,
+        which makes the device->host copy of the predictions a DMA at PCIe speed)."""
+        self._ck(self._L.sfm_predict_resident(self._h, int(row_lo), int(row_hi),
+                                              C.cast(out_p, C.POINTER(C.c_float))))
+
     def evaluate(self):
         m = np.zeros(5, dtype=np.float64)
         self._ck(self._L.sfm_evaluate(self._h, _p(m, C.c_double)))
