@@ -349,8 +349,9 @@ static int als_build(sfm_handle* h, const BatchView& b) {
     h->als = s;
     const ModelView& m = h->m;
     int64_t* L = &h->stats.kernel_launches;
-    if (b.nnz >= 2147483647LL || b.n_rows >= 2147483647LL || m.n_slots >= 2147483647LL)
-        return set_err(h, SFM_ERR_ARG, "ALS: rows, entries and slots must stay below 2^31");
+    // rows below 2^30: the entry emitter ORs (row >> 30) above the feature bits of the sort key
+    if (b.nnz >= 2147483647LL || b.n_rows >= (1LL << 30) || m.n_slots >= 2147483647LL)
+        return set_err(h, SFM_ERR_ARG, "ALS: entries and slots must stay below 2^31, rows below 2^30");
     s->n_rows = b.n_rows;
     s->nnz = b.nnz;
     s->binary = b.val == nullptr;

@@ -393,13 +393,28 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     if (key_bits + blk_bits > 32) return set_err(h, SFM_ERR_ARG, "sort key does not fit 32 bits");
     // bucket form of the transposition + reduce (sfm_bucket.cu) whenever it applies; otherwise the
     // two-pass global sort + chunked reduce
+    const bool multi = h->world > 1;
+    const bool fused = !multi && !grad_keep;
+    const bool p2p = multi && h->p2p && !grad_keep;   // sum + update in one kernel over NVLink
     BucketGeom bg;
     bool bucket = false;
+    // Multi-GPU, reduce / all-reduce overlap (SFM_AR_SLICES): the feature range is
+    // cut into Q slices; slice q's gradient is all-reduced and applied on the comm stream while the
+    // reduce of slice q+1 runs on the compute stream.  The sliced path issues a different sequence
+    // of collectives, so whether it is taken must come out the same on every rank: it is decided
+    // from the knobs, the communicator state and the model geometry only -- never from this rank's
+    // batch (under the Bernoulli sampler the ranks' n / nnz differ; an empty local batch walks the
+    // sliced path with zero chunks).  It uses the fully sorted form of the reduce.
+    int n_slices = 1;
+    if (multi && !p2p && !grad_keep && !h->phase_timing && knobs().ar_slices > 1 &&
+        knobs().pull_block_mb <= 0 && !knobs().bucket_cache && m.n_slots >= 64 * knobs().ar_slices)
+        n_slices = knobs().ar_slices;
+    const bool sliced = n_slices > 1;
     if (pc) {
         bucket = pc->bucket;
         bg = pc->geom;
     } else {
-        bucket = n_blocks == 1 && bucket_geometry(m, key_bits, n, nnz, &bg);
+        bucket = !sliced && n_blocks == 1 && bucket_geometry(m, key_bits, n, nnz, &bg);
     }
     RC(ensure(h, h->b_partials, sizeof(double) * 4 * 512));
     const int end_bit = key_bits + blk_bits;
@@ -415,13 +430,10 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
             RC(ensure(h, h->b_sort_tmp, sort_bytes));
         }
     }
-    const bool multi = h->world > 1;
-    const bool fused = !multi && !grad_keep;
-    const bool p2p = multi && h->p2p && !grad_keep;   // sum + update in one kernel over NVLink
     if (!fused && !p2p) RC(ensure(h, h->b_grad, sizeof(float) * grad_len(h)));
 
-    if ((n + 1) * (int64_t)m.lpr >= 4294967296LL)
-        return set_err(h, SFM_ERR_ARG, "batch too large: rows * kp/4 must stay below 2^32");
+    if ((n + 1) * (int64_t)m.lpr >= 4294967296LL || n >= (1LL << 30))
+        return set_err(h, SFM_ERR_ARG, "batch too large: rows must stay below 2^30 and rows * kp/4 below 2^32");
     PhaseTimer pt(h);
     if (b.pre_err)   // the staging kernel already range-checked the ids: its flag is the step's
         CU(cudaMemcpyAsync(h->d_err, b.pre_err, sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
@@ -447,15 +459,6 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
                             reinterpret_cast<unsigned int*>(h->d_count + 3), h->d_scal, h->d_err,
                             h->stream, L));
     pt.lap(&h->stats.ms_forward);
-    // Multi-GPU, reduce / all-reduce overlap: the feature range is cut into Q
-    // slices; slice q's gradient is all-reduced and applied on the comm stream while the reduce of
-    // slice q+1 runs on the compute stream.
-    int n_slices = 1;
-    if (multi && !p2p && !grad_keep && n_blocks == 1 && nnz > 0 && !h->phase_timing && !bucket) {
-        n_slices = knobs().ar_slices;   // off by default: pays only when the all-reduce is long
-        if (m.n_slots < 64 * n_slices) n_slices = 1;
-    }
-    const bool sliced = n_slices > 1;
     if (multi) {
         if (sliced) {
             CU(cudaEventRecord(h->ev_pool[0], h->stream));
