@@ -1,8 +1,9 @@
 #!/usr/bin/env python
-"""Runs BASELINE.json configs 1, 2 and 4 at FULL size on one B200 through the public API, checks
-the per-iteration loss against the fp64 CPU oracle where the oracle finishes in seconds (C1, C2)
-and size-independent properties elsewhere, and writes gpurun_out/configs_r2.json.
-(Config 3 is bench.py; config 5 is bench.py under torchrun at N = 1, 2, 4, 8.)"""
+"""Runs BASELINE.json configs 1-4 at FULL size on one B200 through the public API, checks the
+per-iteration loss against the fp64 CPU oracle where the oracle finishes in seconds (C1, C2, and
+C3 through its sampled mini-batches) and size-independent properties elsewhere, and writes
+gpurun_out/configs_r2.json.  (Config 3's throughput is bench.py; config 5 is bench.py under
+torchrun at N = 1, 2, 4, 8.)"""
 import json
 import os
 import sys
@@ -153,8 +154,86 @@ def config4(n_timed=20, modes=((0, "bernoulli"), (1, "partition"))):
     OUT["C4_replicated_1gpu"] = res
 
 
+def config3(n_check=3, n_rows=45_000_000, batch=1_000_000):
+    """Criteo-shaped, the HEADLINE config at full size: 39 one-hot fields, 1 M hashed features,
+    Zipf 1.1, k=16, logistic loss, 45 M rows generated on the device, Bernoulli mini-batches of
+    ~1 M rows.  The oracle cannot hold 45 M rows in seconds, but a row depends on its number only,
+    so each iteration's sampled rows are rebuilt on the host (numpy twin of the device generator)
+    and fed to the fp64 oracle: exact batch sizes, per-iteration loss at 1e-4, predictions of the
+    trained model at 1e-5; plus size-independent properties: the device rows at the far end of the
+    data set equal the twin's bit for bit, and a rerun reproduces loss and model bits."""
+    import hashlib
+    n_fields, n_slots, k = 39, 1_000_000, 16
+    reg, step, frac, data_seed = (0.0, 0.0, 1e-5), 0.1, batch / n_rows, 20260103
+    card = synth.ctr_field_log2_cards(n_fields)
+    cdf, off = synth.zipf_tables(card)
+
+    def run(n_iters):
+        hd = Handle(n_slots, k, task=1, reg=reg, step_size=step, mini_batch_fraction=frac, sampler_seed=42)
+        hd.init_model(0.0, 0.01, 1)
+        hd.synth_ctr_dataset(n_rows, 0, card, cdf, off, data_seed)
+        return hd
+
+    def digest(hd):
+        w0, w, v = hd.get_model()
+        h = hashlib.sha256(np.float32(w0).tobytes())
+        h.update(np.ascontiguousarray(w).tobytes())
+        h.update(np.ascontiguousarray(v).tobytes())
+        return h.hexdigest()
+
+    hd = run(n_check)
+    assert hd.dataset_info()[:2] == (n_rows, n_rows * n_fields)
+    # the device generator at the far end of the data set (64-bit row arithmetic) vs the numpy twin
+    lo = n_rows - 4096
+    _, d_idx, _, d_label = hd.get_dataset_rows(lo, n_rows, with_val=False)
+    t_idx, t_label = synth.ctr_rows(lo, n_rows, card, cdf, off, n_slots, data_seed)
+    assert np.array_equal(d_idx.reshape(-1, n_fields), t_idx) and np.array_equal(d_label, t_label)
+    w0, w, v = hd.get_model()
+    orc = OracleFM(n_slots, k, task=1, reg=tuple(float(np.float32(r)) for r in reg))
+    orc.set_model(w0, w, v)
+    f32, s32 = float(np.float32(frac)), float(np.float32(step))
+    worst, losses, batches = 0.0, [], []
+    for it in range(1, n_check + 1):
+        ids = ocapi.sample_rows(42, it, f32, 0, n_rows)
+        idx, label = synth.ctr_rows_at(ids, card, cdf, off, n_slots, data_seed)
+        rp = np.arange(len(ids) + 1, dtype=np.int64) * n_fields
+        lo_ = orc.train_step(rp, idx.reshape(-1), np.ones(idx.size), label,
+                             np.arange(len(ids), dtype=np.int64), it, s32, threads=8) / len(ids)
+        lg, nb = hd.train_step(it)
+        assert nb == len(ids), (nb, len(ids))      # the sampler's batch, exactly
+        worst = max(worst, abs(lg - lo_) / lo_)
+        losses.append(lg)
+        batches.append(int(nb))
+    assert worst < 1e-4, worst
+    # predictions of the trained model on rows from both ends, against the oracle holding the
+    # SAME (device) model
+    o2 = OracleFM(n_slots, k, task=1)
+    o2.set_model(*hd.get_model())
+    perr = 0.0
+    for a, b in ((0, 50_000), (n_rows - 50_000, n_rows)):
+        pred = hd.predict_resident(a, b)
+        idx, _ = synth.ctr_rows(a, b, card, cdf, off, n_slots, data_seed)
+        rp = np.arange(b - a + 1, dtype=np.int64) * n_fields
+        want = o2.predict(rp, idx.reshape(-1), np.ones(idx.size), fast=True, threads=8)
+        perr = max(perr, float(np.max(np.abs(pred - want) / np.maximum(np.abs(want), np.mean(np.abs(want))))))
+    assert perr < 1e-5, perr
+    dig = digest(hd)
+    hd.close()
+    # rerun from the same seeds through the device-side loop (sfm_train): same loss and model bits
+    hb = run(n_check)
+    hist = hb.train(1, n_check)
+    same = bool(np.array_equal(np.asarray(hist, dtype=np.float64), np.asarray(losses, dtype=np.float64))
+                and digest(hb) == dig)
+    hb.close()
+    assert same
+    OUT["C3"] = {"rows": n_rows, "n_slots": n_slots, "k": k, "batch_rows": batches,
+                 "loss_rel_err_max": worst, "loss_iters_checked": n_check, "losses": losses,
+                 "predict_rel_err_max": perr, "bitwise_rerun": same,
+                 "far_end_rows_bit_identical_to_twin": True}
+
+
 if __name__ == "__main__":
-    for fn in (config1, config2, config4):
+    for fn in (config1, config2, config3, config4):
         t0 = time.perf_counter()
         fn()
         print(fn.__name__, "ok", f"{time.perf_counter() - t0:.1f}s", flush=True)

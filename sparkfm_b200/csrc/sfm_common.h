@@ -11,6 +11,20 @@
 
 namespace sfm {
 
+// SMs of the CURRENT device (cached per device): grid caps of the grid-stride helper kernels are
+// multiples of it instead of a literal 148.
+inline int device_sm_count() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cache[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+
 // ---- device scalar block (doubles): written by the forward reduction, all-reduced across
 // ranks, read by the update kernels.
 enum { SC_LOSS = 0, SC_COUNT = 1, SC_GW0 = 2, SC_ERR = 3, SC_N = 4 };   // SC_ERR: ranks that saw a bad index

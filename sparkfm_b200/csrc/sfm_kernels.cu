@@ -646,7 +646,7 @@ cudaError_t launch_iota_u32(uint32_t* p, int64_t n, cudaStream_t st, int64_t* la
     if (n <= 0) return cudaSuccess;
     ++*launches;
     int64_t blocks = (n + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > (int64_t)device_sm_count() * 16) blocks = (int64_t)device_sm_count() * 16;
     iota_u32_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, n);
     return cudaGetLastError();
 }
@@ -1150,7 +1150,7 @@ cudaError_t launch_update_ptrs(const ModelView& m, const float* gv, const float*
     ++*launches;
     const int64_t nv4 = (feat_hi - feat_lo) * m.lpr;
     int64_t blocks = (nv4 + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > (int64_t)device_sm_count() * 16) blocks = (int64_t)device_sm_count() * 16;
     if (blocks < 1) blocks = 1;
     fm_update_kernel<<<(unsigned)blocks, 256, 0, st>>>((float4*)m.v, m.w, m.w0, m.lpr, feat_lo,
                                                        feat_hi, m.k0, m.k1, (const float4*)gv, gw,
@@ -1247,7 +1247,7 @@ cudaError_t launch_row_lens(const int64_t* row_ptr, const int32_t* row_ids, int6
     if (n <= 0) return cudaSuccess;
     ++*launches;
     int64_t blocks = (n + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > (int64_t)device_sm_count() * 16) blocks = (int64_t)device_sm_count() * 16;
     row_lens_kernel<<<(unsigned)blocks, 256, 0, st>>>(row_ptr, row_ids, n, lens);
     return cudaGetLastError();
 }
@@ -1276,7 +1276,7 @@ cudaError_t launch_idx_range(const int32_t* idx, int64_t nnz, int32_t* d_minmax,
     if (nnz <= 0) return cudaSuccess;
     ++*launches;
     int64_t blocks = (nnz + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > (int64_t)device_sm_count() * 16) blocks = (int64_t)device_sm_count() * 16;
     idx_range_kernel<<<(unsigned)blocks, 256, 0, st>>>(idx, nnz, d_minmax);
     return cudaGetLastError();
 }
@@ -1316,7 +1316,7 @@ cudaError_t launch_unpack_onehot(const uint32_t* packed, const uint32_t* label_b
                                  int64_t* launches) {
     if (n_entries <= 0 && n_rows <= 0) return cudaSuccess;
     int64_t blocks = ((n_entries > n_rows ? n_entries : n_rows) + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (blocks > (int64_t)device_sm_count() * 32) blocks = (int64_t)device_sm_count() * 32;
     unpack_onehot_kernel<<<(unsigned)blocks, 256, 0, st>>>(packed, label_bits, n_entries, n_rows,
                                                            id_bits, (uint32_t)n_slots, idx, label, bad);
     *launches += 1;
@@ -1346,7 +1346,7 @@ cudaError_t launch_pad_v(const float* src, float* dst, int64_t n_slots, int k, i
     if (total <= 0) return cudaSuccess;
     ++*launches;
     int64_t blocks = (total + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > (int64_t)device_sm_count() * 16) blocks = (int64_t)device_sm_count() * 16;
     pad_v_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, n_slots, k, kp, unpad ? 1 : 0);
     return cudaGetLastError();
 }
@@ -1413,7 +1413,7 @@ cudaError_t launch_synth_ctr(int64_t n_rows, int64_t row_off, int n_fields,
     if (n_rows <= 0) return cudaSuccess;
     ++*launches;
     int64_t blocks = (n_rows + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > (int64_t)device_sm_count() * 16) blocks = (int64_t)device_sm_count() * 16;
     synth_ctr_kernel<<<(unsigned)blocks, 256, 0, st>>>(n_rows, row_off, n_fields, d_log2card,
                                                        d_cdf, d_cdf_off, mix64_dev(seed), n_slots,
                                                        idx, label, row_ptr);

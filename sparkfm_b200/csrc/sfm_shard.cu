@@ -43,7 +43,7 @@ namespace sfm {
 
 static inline int64_t grid_for(int64_t n, int threads = 256) {
     int64_t b = (n + threads - 1) / threads;
-    if (b > 148 * 32) b = 148 * 32;
+    if (b > (int64_t)device_sm_count() * 32) b = (int64_t)device_sm_count() * 32;
     return b < 1 ? 1 : b;
 }
 

@@ -56,11 +56,18 @@ def zipf_tables(field_log2_card, s: float = 1.1):
 def ctr_rows(row_lo: int, row_hi: int, field_log2_card, cdf, cdf_off, n_slots: int, seed: int):
     """Rows [row_lo, row_hi) of the synthetic CTR data set: idx int32 [n][F] (one id per field,
     values all 1), label float32 [n] in {0, 1}."""
+    return ctr_rows_at(np.arange(row_lo, row_hi, dtype=np.uint64), field_log2_card, cdf, cdf_off,
+                       n_slots, seed)
+
+
+def ctr_rows_at(rows, field_log2_card, cdf, cdf_off, n_slots: int, seed: int):
+    """The same for an arbitrary list of GLOBAL row numbers (a row depends on its number only), e.g.
+    one sampled mini-batch of a 45 M-row data set without materialising the data set on the host."""
     card = np.asarray(field_log2_card, dtype=np.int64)
     F = len(card)
-    n = row_hi - row_lo
+    gr = np.ascontiguousarray(rows).astype(np.uint64)
+    n = len(gr)
     seed_key = mix64(_U64(seed))
-    gr = np.arange(row_lo, row_hi, dtype=np.uint64)
     idx = np.empty((n, F), dtype=np.int32)
     lin = np.zeros(n, dtype=np.int64)
     sb = np.zeros(n, dtype=np.int64)
