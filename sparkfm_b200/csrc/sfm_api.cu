@@ -30,6 +30,7 @@ void knobs_refresh() {
     if ((e = getenv("SFM_BUCKET_CACHE")) && e[0] == '1') k.bucket_cache = true;
     if ((e = getenv("SFM_P2P_SPARSE")) && e[0] == '0') k.p2p_sparse = false;
     if ((e = getenv("SFM_GRAPH")) && e[0] == '0') k.step_graph = false;
+    if ((e = getenv("SFM_STREAM_PRIO"))) k.stream_prio = e[0] != '0';
     g_knobs = k;
 }
 
@@ -992,8 +993,19 @@ int32_t sfm_create(const sfm_config* cfg, sfm_handle** out) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->device));
     h->sm_count = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (knobs().stream_prio) {
+        // compute stream at the greatest priority, copy stream (sampler one iteration ahead,
+        // staging copies + unpack) at the least: the block scheduler hands SM slots to the
+        // sampler's CTAs only where the step's kernels leave them free (kernel tails, beside the
+        // persistent latency-bound scatter / reduce) instead of beside the issue-bound forward
+        int least = 0, greatest = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CK(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, greatest));
+        CK(cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, least));
+    } else {
+        CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    }
     CK(cudaEventCreate(&h->ev_a));
     CK(cudaEventCreate(&h->ev_b));
     CK(cudaEventCreate(&h->ev_t0));

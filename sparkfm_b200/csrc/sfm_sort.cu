@@ -3,7 +3,9 @@
 //     deterministic reduce-by-feature needs.  It is overhead, not counted in
 //     the algorithmic bytes.  sort_pairs / sort_pairs32 dispatch to the wide-digit sort of
 //     sfm_radix.cu; the library sort stays as the SFM_SORT=cub fallback and as the test oracle.
-//   * exclusive scan of row lengths, Bernoulli row sampler (stream compaction).
+//   * ascending sort of float scores (AUC).
+// (The samplers' stream compaction and the exclusive scans were library calls here in round 1;
+// they are own kernels now: sfm_scan.cu.)
 #include <cub/cub.cuh>
 
 #include "sfm_common.h"
@@ -67,81 +69,6 @@ cudaError_t sort_f32_u32(void* tmp, size_t tmp_bytes, const float* keys_in, floa
     *launches += 6;
     return cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, val_in, val_out, n, 0,
                                            32, st);
-}
-
-size_t scan_u32_temp_bytes(int64_t n) {
-    size_t bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, n);
-    return bytes;
-}
-
-cudaError_t exclusive_scan_u32(void* tmp, size_t tmp_bytes, const uint32_t* in, uint32_t* out,
-                               int64_t n, cudaStream_t st, int64_t* launches) {
-    *launches += 2;
-    return cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, n, st);
-}
-
-size_t scan_temp_bytes(int64_t n) {
-    size_t bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int64_t*)nullptr, (int64_t*)nullptr, n);
-    return bytes;
-}
-
-cudaError_t exclusive_scan_i64(void* tmp, size_t tmp_bytes, const int64_t* in, int64_t* out,
-                               int64_t n, cudaStream_t st, int64_t* launches) {
-    *launches += 2;
-    return cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, n, st);
-}
-
-__host__ __device__ __forceinline__ uint64_t mix64_s(uint64_t x) {
-    uint64_t z = x + 0x9E3779B97F4A7C15ULL;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    return z ^ (z >> 31);
-}
-
-// row r (global) is in the batch iff (mix64(key ^ mix64(r)) >> 11) < thr.
-struct InBatch {
-    uint64_t key, thr;
-    int64_t off;
-    __host__ __device__ bool operator()(const int32_t& r) const {
-        return (mix64_s(key ^ mix64_s((uint64_t)(off + r))) >> 11) < thr;
-    }
-};
-
-// PARTITION sampler: row r (global) belongs to part (mix64(key ^ mix64(r)) >> 11) % n_parts.
-struct InPart {
-    uint64_t key, n_parts, part;
-    int64_t off;
-    __host__ __device__ bool operator()(const int32_t& r) const {
-        return ((mix64_s(key ^ mix64_s((uint64_t)(off + r))) >> 11) % n_parts) == part;
-    }
-};
-
-cudaError_t partition_rows_device(void* tmp, size_t tmp_bytes, int64_t n, int64_t global_off,
-                                  uint64_t key, int64_t n_parts, int64_t part, int32_t* out_rows,
-                                  int32_t* d_count, cudaStream_t st, int64_t* launches) {
-    *launches += 2;
-    cub::CountingInputIterator<int32_t> it(0);
-    return cub::DeviceSelect::If(tmp, tmp_bytes, it, out_rows, d_count, (int)n,
-                                 InPart{key, (uint64_t)n_parts, (uint64_t)part, global_off}, st);
-}
-
-size_t select_temp_bytes(int64_t n) {
-    size_t bytes = 0;
-    cub::CountingInputIterator<int32_t> it(0);
-    cub::DeviceSelect::If(nullptr, bytes, it, (int32_t*)nullptr, (int32_t*)nullptr, (int)n,
-                          InBatch{0, 0, 0});
-    return bytes;
-}
-
-cudaError_t sample_rows_device(void* tmp, size_t tmp_bytes, int64_t n, int64_t global_off,
-                               uint64_t key, uint64_t thr, int32_t* out_rows, int32_t* d_count,
-                               cudaStream_t st, int64_t* launches) {
-    *launches += 2;
-    cub::CountingInputIterator<int32_t> it(0);
-    return cub::DeviceSelect::If(tmp, tmp_bytes, it, out_rows, d_count, (int)n,
-                                 InBatch{key, thr, global_off}, st);
 }
 
 }  // namespace sfm
