@@ -2,7 +2,7 @@
 # round-2 closing check on one GPU: GPU tests (incl. the full-size config 3 run), A/B of the own sampler
 # kernels against the previous library-select build and of the stream-priority knob, smoke
 mkdir -p gpurun_out
-timeout 420 python -m pytest tests -m gpu -x -q > gpurun_out/r2f2_tests.log 2>&1; echo "gpu tests rc=$?"; tail -4 gpurun_out/r2f2_tests.log
+timeout 420 python -m pytest tests -m gpu -q > gpurun_out/r2f2_tests.log 2>&1; echo "gpu tests rc=$?"; tail -4 gpurun_out/r2f2_tests.log
 timeout 60 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2f2_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/r2f2_smoke.log
 run() { # name env...
   env "${@:2}" timeout 150 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-partition --e2e-steps 20 > gpurun_out/r2f2_$1.json 2> gpurun_out/r2f2_$1.err || tail -3 gpurun_out/r2f2_$1.err

@@ -31,6 +31,7 @@ void knobs_refresh() {
     if ((e = getenv("SFM_P2P_SPARSE")) && e[0] == '0') k.p2p_sparse = false;
     if ((e = getenv("SFM_GRAPH")) && e[0] == '0') k.step_graph = false;
     if ((e = getenv("SFM_STREAM_PRIO"))) k.stream_prio = e[0] != '0';
+    if ((e = getenv("SFM_PLAN_AHEAD"))) k.plan_ahead = e[0] != '0';
     g_knobs = k;
 }
 
@@ -359,7 +360,7 @@ static int validate_view(sfm_handle* h, const BatchView& b) {
 // synchronises.  If grad_keep, the (all-reduced) dense gradient stays in h->b_grad and no update
 // is applied.
 static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad_keep,
-                      const PartCache* pc = nullptr) {
+                      const PartCache* pc = nullptr, const AheadPlan* ap = nullptr) {
     NEED_MODEL(h);
     if (h->world > 1 && !h->comm)
         return set_err(h, SFM_ERR_NCCL, "the communicator was aborted after an asynchronous NCCL error");
@@ -417,12 +418,19 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     } else {
         bucket = !sliced && n_blocks == 1 && bucket_geometry(m, key_bits, n, nnz, &bg);
     }
+    // the bucket counts + plan of this batch were built one step ahead (sfm_train): usable when the
+    // step takes the bucket path and its work items fit the buffers the plan was carved with
+    const bool planned = ap && !pc && bucket && n <= ap->cap_rows && bg.LB == ap->geom.LB &&
+                         bg.HB == ap->geom.HB && bg.max_items <= ap->geom.max_items;
+    if (planned) bg = ap->geom;
     RC(ensure(h, h->b_partials, sizeof(double) * 4 * 512));
     const int end_bit = key_bits + blk_bits;
     size_t sort_bytes = 0;
     if (bucket) {
-        RC(ensure(h, h->b_bkt_work, bucket_work_bytes(m, bg, h->sm_count)));
-        if (!pc) RC(ensure(h, h->b_bkt_tables, bucket_tables_bytes(bg)));
+        if (!planned) {
+            RC(ensure(h, h->b_bkt_work, bucket_work_bytes(m, bg, h->sm_count)));
+            if (!pc) RC(ensure(h, h->b_bkt_tables, bucket_tables_bytes(bg)));
+        }
     } else {
         RC(ensure(h, h->b_seg, sizeof(int32_t) * 2 * (size_t)m.n_slots * n_blocks));  // seg_lo | seg_hi
         RC(ensure(h, h->b_pull, pull_scratch_bytes(m, nnz, n_blocks)));
@@ -473,7 +481,13 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     }
     const uint32_t* keys_sorted = pc ? (const uint32_t*)pc->keys.p : (const uint32_t*)h->b_keys[1].p;
     const uint2* pay_sorted = pc ? (const uint2*)pc->pay.p : (const uint2*)h->b_pay[1].p;
-    if (nnz > 0 && !pc && bucket) {
+    void* const bk_work = planned ? ap->work : h->b_bkt_work.p;
+    const void* const bk_tables = planned ? ap->tables : (pc ? pc->tables.p : h->b_bkt_tables.p);
+    if (nnz > 0 && !pc && bucket && planned) {
+        CU(bucket_scatter(m, b, bg, o.keys, o.pay, implicit_div, bk_work, bk_tables,
+                          (uint32_t*)h->b_keys[1].p, binary ? nullptr : (uint32_t*)h->b_pay[1].p,
+                          h->sm_count, h->stream, L));
+    } else if (nnz > 0 && !pc && bucket) {
         CU(bucket_transpose(m, b, bg, o.keys, o.pay, implicit_div, h->b_bkt_work.p,
                             h->b_bkt_tables.p, (uint32_t*)h->b_keys[1].p,
                             binary ? nullptr : (uint32_t*)h->b_pay[1].p,
@@ -558,7 +572,7 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
     }
     if (bucket)
         CU(bucket_pull(m, bg, keys_sorted, binary ? nullptr : (const uint32_t*)pay_sorted,
-                       pc ? pc->tables.p : h->b_bkt_tables.p, h->b_bkt_work.p, o.S, o.mult, h->d_scal,
+                       bk_tables, bk_work, o.S, o.mult, h->d_scal,
                        h->d_err, up, fused, grad_out, touch, nnz > 0 && !pc, h->sm_count, h->stream, L));
     else
         CU(launch_pull(m, (int32_t*)h->b_seg.p, key_bits, n_blocks, keys_sorted, pay_sorted, nnz,
@@ -596,19 +610,20 @@ static int train_core(sfm_handle* h, const BatchView& b, int64_t iter, bool grad
 // launched -- the device runs the ~8 dependent kernels of a step without per-launch gaps, which is
 // what small mini-batches are bound by.  Anything that cannot be captured (a scratch buffer has to
 // grow, NCCL collectives, per-phase timing, the row-sharded model) runs as plain stream launches.
-static int train_step_run(sfm_handle* h, const BatchView& b, int64_t iter, const PartCache* pc = nullptr) {
+static int train_step_run(sfm_handle* h, const BatchView& b, int64_t iter, const PartCache* pc = nullptr,
+                          const AheadPlan* ap = nullptr) {
     const bool multi = h->world > 1;
     if (!knobs().step_graph || h->phase_timing || is_sharded(h) || (multi && !h->p2p) ||
         (h->shard_requested && !h->shard))
-        return train_core(h, b, iter, false, pc);
+        return train_core(h, b, iter, false, pc, ap);
     const sfm_stats saved = h->stats;
     if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
         cudaGetLastError();
-        return train_core(h, b, iter, false, pc);
+        return train_core(h, b, iter, false, pc, ap);
     }
     h->capturing = true;
     h->capture_abort = false;
-    int rc = train_core(h, b, iter, false, pc);
+    int rc = train_core(h, b, iter, false, pc, ap);
     h->capturing = false;
     cudaGraph_t g = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
@@ -619,7 +634,7 @@ static int train_step_run(sfm_handle* h, const BatchView& b, int64_t iter, const
             h->capture_abort = false;
             h->stats = saved;
             h->err.clear();
-            return train_core(h, b, iter, false, pc);
+            return train_core(h, b, iter, false, pc, ap);
         }
         return rc;
     }
@@ -1015,6 +1030,7 @@ int32_t sfm_create(const sfm_config* cfg, sfm_handle** out) {
     for (int i = 0; i < 2; ++i) {
         CK(cudaEventCreateWithFlags(&h->ev_samp[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_used[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_plan[i], cudaEventDisableTiming));
     }
     CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
     for (cudaEvent_t& e : h->ev_pool) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1098,6 +1114,9 @@ int32_t sfm_destroy(sfm_handle* h) {
     for (int i = 0; i < 2; ++i) {
         if (h->ev_samp[i]) cudaEventDestroy(h->ev_samp[i]);
         if (h->ev_used[i]) cudaEventDestroy(h->ev_used[i]);
+        if (h->ev_plan[i]) cudaEventDestroy(h->ev_plan[i]);
+        free_buf(h->b_bkt_work2[i]);
+        free_buf(h->b_bkt_tables2[i]);
     }
     for (Stage& sg : h->stage) {
         free_buf(sg.rowptr);
@@ -1835,7 +1854,7 @@ int32_t sfm_train_step_staged(sfm_handle* h, int32_t slot, int64_t iter, double*
 
 // Queues the sampling of iteration `iter` into slot `slot` on the copy stream (it depends on the
 // seed only, so it runs while the previous iteration computes).
-static int sample_prefetch(sfm_handle* h, int64_t iter, int slot) {
+static int sample_prefetch(sfm_handle* h, int64_t iter, int slot, bool plan = false) {
     const Dataset& ds = h->ds;
     const double frac = (double)h->cfg.mini_batch_fraction;
     const uint64_t thr = (uint64_t)floor(frac * 9007199254740992.0);
@@ -1848,6 +1867,15 @@ static int sample_prefetch(sfm_handle* h, int64_t iter, int slot) {
                        cudaMemcpyDeviceToHost, h->copy_stream));
     CU(cudaEventRecord(h->ev_samp[slot], h->copy_stream));
     h->stats.d2h_bytes += 4;
+    if (plan) {
+        // the batch's feature ids do not depend on the model: its bucket counts and work-item plan
+        // are built here, behind the sampler, and the step starts at the scatter
+        CU(bucket_count_plan_rows(h->m, h->ahead_geom, ds.idx, (const int32_t*)h->b_ids2[slot].p,
+                                  h->d_count2 + slot, h->ahead_cap, ds.uniform_m, h->b_bkt_work2[slot].p,
+                                  h->b_bkt_tables2[slot].p, reinterpret_cast<unsigned int*>(h->d_count + 5),
+                                  h->sm_count, h->copy_stream, &h->stats.kernel_launches));
+        CU(cudaEventRecord(h->ev_plan[slot], h->copy_stream));
+    }
     return SFM_OK;
 }
 
@@ -1945,12 +1973,30 @@ int32_t sfm_train(sfm_handle* h, int64_t first_iter, int64_t n_iters, double* lo
     const int ahead_env = knobs().sort_ahead;   // measured: co-scheduling the sort with the gather kernels does not pay
     const bool ahead = sampled && ds.uniform_m >= 0 && !is_sharded(h) && !h->phase_timing &&
                        ahead_env != 0;
+    // plan-ahead: all-ones / valued rows of one length, bucket form -- the next batch's bucket counts
+    // and plan ride behind its sampler on the (low-priority) copy stream; the work buffers are
+    // carved for a batch of up to ahead_cap rows (a larger draw simply plans inside the step)
+    bool plan_ahead = false;
+    if (sampled && !ahead && knobs().plan_ahead && knobs().stream_prio && ds.uniform_m > 0 &&
+        !is_sharded(h) && !h->phase_timing && knobs().pull_block_mb <= 0) {
+        int64_t cap = (int64_t)(frac * (double)ds.n_rows * 1.25) + 65536;
+        if (cap > ds.n_rows) cap = ds.n_rows;
+        if (cap < 2147483647LL && bucket_geometry(h->m, bits_for(h->m.n_slots), cap, cap * ds.uniform_m, &h->ahead_geom)) {
+            h->ahead_cap = (int32_t)cap;
+            plan_ahead = true;
+        }
+    }
     if (sampled) {
         for (int i = 0; i < 2; ++i) RC(ensure(h, h->b_ids2[i], sizeof(int32_t) * (size_t)ds.n_rows));
         RC(ensure(h, h->b_samp_tmp, select_temp_bytes(ds.n_rows)));
+        if (plan_ahead)
+            for (int i = 0; i < 2; ++i) {
+                RC(ensure(h, h->b_bkt_work2[i], bucket_work_bytes(h->m, h->ahead_geom, h->sm_count)));
+                RC(ensure(h, h->b_bkt_tables2[i], bucket_tables_bytes(h->ahead_geom)));
+            }
         CU(cudaEventRecord(h->ev_used[0], h->stream));
         CU(cudaEventRecord(h->ev_used[1], h->stream));
-        if (n_iters > 0) RC(ahead ? transpose_prefetch(h, first_iter, 0) : sample_prefetch(h, first_iter, 0));
+        if (n_iters > 0) RC(ahead ? transpose_prefetch(h, first_iter, 0) : sample_prefetch(h, first_iter, 0, plan_ahead));
     }
     double* hist = nullptr;
     if (n_iters > 0) CU(cudaMallocHost(&hist, sizeof(double) * SC_N * (size_t)n_iters));
@@ -1995,10 +2041,11 @@ int32_t sfm_train(sfm_handle* h, int64_t first_iter, int64_t n_iters, double* lo
             }
             n = h->h_count2[slot];
             ids_dev = (const int32_t*)h->b_ids2[slot].p;
-            if (cudaStreamWaitEvent(h->stream, h->ev_samp[slot], 0) != cudaSuccess)
+            if (cudaStreamWaitEvent(h->stream, h->ev_samp[slot], 0) != cudaSuccess ||
+                (plan_ahead && cudaStreamWaitEvent(h->stream, h->ev_plan[slot], 0) != cudaSuccess))
                 rc = set_err(h, SFM_ERR_CUDA, "cudaStreamWaitEvent failed");
-            // next iteration's batch is drawn while this one computes
-            if (rc == SFM_OK && t + 1 < n_iters) rc = sample_prefetch(h, first_iter + t + 1, slot ^ 1);
+            // next iteration's batch is drawn (and planned) while this one computes
+            if (rc == SFM_OK && t + 1 < n_iters) rc = sample_prefetch(h, first_iter + t + 1, slot ^ 1, plan_ahead);
         } else if (!parts) {
             rc = sample_device(h, first_iter + t, &ids_dev, &n);
         }
@@ -2010,7 +2057,14 @@ int32_t sfm_train(sfm_handle* h, int64_t first_iter, int64_t n_iters, double* lo
             if (rc == SFM_OK) rc = resident_batch(h, ids_dev, n, &b);
             if (rc == SFM_OK && b.nnz >= 2147483647LL) rc = set_err(h, SFM_ERR_ARG, "batch nnz must be < 2^31-1");
         }
-        if (rc == SFM_OK) rc = train_step_run(h, b, first_iter + t, pc);
+        AheadPlan apv;
+        if (plan_ahead) {
+            apv.geom = h->ahead_geom;
+            apv.cap_rows = h->ahead_cap;
+            apv.work = h->b_bkt_work2[slot].p;
+            apv.tables = h->b_bkt_tables2[slot].p;
+        }
+        if (rc == SFM_OK) rc = train_step_run(h, b, first_iter + t, pc, plan_ahead ? &apv : nullptr);
         if (rc == SFM_OK && sampled && cudaEventRecord(h->ev_used[slot], h->stream) != cudaSuccess)
             rc = set_err(h, SFM_ERR_CUDA, "cudaEventRecord failed");
         if (rc == SFM_OK &&

@@ -197,6 +197,40 @@ bkt_count_kernel(const uint32_t* __restrict__ keys, int n_rows, int m,
     for (int d = threadIdx.x; d < NB; d += 512) counts[(size_t)c * NB + d] = bk_hist[d];
 }
 
+// The same histogram taken ONE STEP AHEAD, straight from the resident data set (all-ones rows of m
+// entries, sampled row numbers in row_ids): the feature ids of a batch do not depend on the model,
+// so the counts and the plan of batch t + 1 are built on the low-priority copy stream while step t
+// computes.  The batch size is only known on the device at launch time.  One warp
+// per row (two rows in flight), same row ranges as bkt_scatter_kernel.
+__global__ void __launch_bounds__(512)
+bkt_count_rows_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ row_ids,
+                      const int32_t* __restrict__ n_rows_dev, int n_rows_cap, int m, int LB,
+                      int NB, uint32_t* __restrict__ counts) {
+    extern __shared__ uint32_t bk_hist[];
+    for (int d = threadIdx.x; d < NB; d += 512) bk_hist[d] = 0;
+    __syncthreads();
+    // a draw larger than the plan's buffers were carved for counts nothing (the plan then holds
+    // one empty item per bucket, inside its tables); the host sees the same and plans in the step
+    const int n_dev = __ldg(n_rows_dev);
+    const int n_rows = n_dev <= n_rows_cap ? n_dev : 0;
+    const int c = blockIdx.x, G = gridDim.x;
+    const int64_t r0 = (int64_t)c * n_rows / G, r1 = (int64_t)(c + 1) * n_rows / G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t r = r0 + warp; r < r1; r += 32) {
+        const int64_t rb = r + 16;
+        const int32_t* pa = idx + (int64_t)__ldg(row_ids + r) * m;
+        const int32_t* pb = rb < r1 ? idx + (int64_t)__ldg(row_ids + rb) * m : nullptr;
+        for (int j = lane; j < m; j += 32) {
+            const uint32_t ka = (uint32_t)__ldg(pa + j);
+            const uint32_t kb = pb ? (uint32_t)__ldg(pb + j) : 0u;
+            atomicAdd(&bk_hist[ka >> LB], 1u);
+            if (pb) atomicAdd(&bk_hist[kb >> LB], 1u);
+        }
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < NB; d += 512) counts[(size_t)c * NB + d] = bk_hist[d];
+}
+
 // counts[c][d] <- sum over ranges c' < c; totals[d] = sum over all ranges.  Grid: NB/32 (>= 1)
 // CTAs of 1024 threads = 32 bucket lanes x 32 blocks of ranges.  The CTA that finishes last
 // (integer ticket, reset for the next launch) then builds the plan: bucket_off[b] (exclusive scan
@@ -1142,23 +1176,59 @@ static size_t scatter_smem(int hb, bool has_val) {
            nb * 4 + nb * 2 + (SC_RANK == 0 ? (size_t)SC_WARPS * nb : 0) + 64;
 }
 
+// counts + plan of a batch of resident all-ones rows, from the row numbers (any stream; the batch
+// size is read on the device)
+cudaError_t bucket_count_plan_rows(const ModelView& m, const BucketGeom& g, const int32_t* idx,
+                                   const int32_t* row_ids, const int32_t* n_rows_dev, int n_rows_cap,
+                                   int uniform_m, void* work, void* tables, unsigned int* ticket, int sm_count,
+                                   cudaStream_t st, int64_t* launches) {
+    if (!idx || !row_ids || !n_rows_dev || uniform_m < 1) return cudaErrorInvalidValue;
+    const WorkPtrs w = carve_work(m, g, sm_count, work);
+    const TablePtrs tp = carve_tables(g, tables);
+    const int G = 2 * sm_count;
+    bkt_count_rows_kernel<<<G, 512, sizeof(uint32_t) * g.NB, st>>>(idx, row_ids, n_rows_dev, n_rows_cap,
+                                                                    uniform_m, g.LB, g.NB, w.counts);
+    bkt_offsets_plan_kernel<<<(g.NB + 31) / 32, 1024, 0, st>>>(w.counts, G, g.NB, w.totals, ticket,
+                                                               tp.bucket_off, tp.item_start, tp.item_bucket,
+                                                               tp.item_order, w.work);
+    *launches += 2;
+    return cudaGetLastError();
+}
+
 cudaError_t bucket_transpose(const ModelView& m, const BatchView& b, const BucketGeom& g,
                              const uint32_t* keys, const uint2* pay, int implicit_div, void* work,
                              void* tables, uint32_t* packed, uint32_t* vals, unsigned int* ticket,
                              int sm_count, cudaStream_t st, int64_t* launches) {
     const WorkPtrs w = carve_work(m, g, sm_count, work);
     const TablePtrs tp = carve_tables(g, tables);
-    uint32_t* bucket_off = tp.bucket_off;
     const int G = 2 * sm_count;
-    const bool has_val = b.val != nullptr;
     const int mm = b.uniform_m >= 0 ? b.uniform_m : 0;
     const int64_t* optr = b.uniform_m >= 0 && !b.out_ptr ? nullptr : b.out_ptr;
     if (!optr && b.uniform_m < 0) return cudaErrorInvalidValue;
     bkt_count_kernel<<<G, 512, sizeof(uint32_t) * g.NB, st>>>(keys, (int)b.n_rows, mm, optr,
                                                                b.out_base, g.LB, g.NB, w.counts);
     bkt_offsets_plan_kernel<<<(g.NB + 31) / 32, 1024, 0, st>>>(w.counts, G, g.NB, w.totals, ticket,
-                                                               bucket_off, tp.item_start, tp.item_bucket,
+                                                               tp.bucket_off, tp.item_start, tp.item_bucket,
                                                                tp.item_order, w.work);
+    *launches += 2;
+    return bucket_scatter(m, b, g, keys, pay, implicit_div, work, tables, packed, vals, sm_count, st,
+                          launches);
+}
+
+// the stable partition alone: counts / plan already sit in `work` / `tables` (built inline by
+// bucket_transpose or one step ahead by bucket_count_plan_rows)
+cudaError_t bucket_scatter(const ModelView& m, const BatchView& b, const BucketGeom& g,
+                           const uint32_t* keys, const uint2* pay, int implicit_div, void* work,
+                           const void* tables, uint32_t* packed, uint32_t* vals, int sm_count,
+                           cudaStream_t st, int64_t* launches) {
+    const WorkPtrs w = carve_work(m, g, sm_count, work);
+    const TablePtrs tp = carve_tables(g, tables);
+    const uint32_t* bucket_off = tp.bucket_off;
+    const int G = 2 * sm_count;
+    const bool has_val = b.val != nullptr;
+    const int mm = b.uniform_m >= 0 ? b.uniform_m : 0;
+    const int64_t* optr = b.uniform_m >= 0 && !b.out_ptr ? nullptr : b.out_ptr;
+    if (!optr && b.uniform_m < 0) return cudaErrorInvalidValue;
     const size_t smem = scatter_smem(g.HB, has_val);
     const unsigned long long magic =
         implicit_div ? ((1ULL << 40) + (unsigned long long)implicit_div - 1) / (unsigned long long)implicit_div : 0ULL;
@@ -1188,7 +1258,7 @@ cudaError_t bucket_transpose(const ModelView& m, const BatchView& b, const Bucke
         SC_LAUNCH(1);
     }
 #undef SC_LAUNCH
-    *launches += 3;
+    *launches += 1;
     return cudaGetLastError();
 }
 

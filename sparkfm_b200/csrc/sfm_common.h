@@ -67,6 +67,15 @@ struct BucketGeom {
     int64_t max_items = 0;
 };
 
+// counts + plan of a batch built one step ahead (bucket_count_plan_rows): geometry they were
+// carved with, and the per-slot work / table buffers
+struct AheadPlan {
+    BucketGeom geom;
+    int64_t cap_rows = 0;   // the count kernel ignores a larger draw: so must the step
+    void* work = nullptr;
+    void* tables = nullptr;
+};
+
 struct PartCache {
     bool built = false;
     int64_t n_rows = 0, nnz = 0;
@@ -160,6 +169,12 @@ struct sfm_handle {
     int32_t* d_count2 = nullptr;   // [2] device
     int32_t* h_count2 = nullptr;   // [2] pinned
     cudaEvent_t ev_samp[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
+    // plan-ahead (sfm_train, Bernoulli sampler, all-ones uniform rows, bucket form): the bucket
+    // counts + work-item plan of the NEXT batch are built on copy_stream right behind its sampler
+    sfm::Buf b_bkt_work2[2], b_bkt_tables2[2];
+    sfm::BucketGeom ahead_geom;
+    int32_t ahead_cap = 0;         // rows the ahead buffers were carved for
+    cudaEvent_t ev_plan[2] = {nullptr, nullptr};
     cudaEvent_t ev_pool[20] = {nullptr};   // reduce / all-reduce overlap (multi-GPU)
     cudaStream_t comm_stream = nullptr;
     int32_t* d_slice = nullptr;            // [16] device
@@ -196,7 +211,8 @@ struct Knobs {
     int ar_slices = 1;         // SFM_AR_SLICES
     int sort_ahead = 0;        // SFM_SORT_AHEAD
     bool bucket_cache = false; // SFM_BUCKET_CACHE=1: PARTITION caches keep the bucket form
-    bool stream_prio = false;  // SFM_STREAM_PRIO=1: compute stream greatest, copy stream least priority
+    bool stream_prio = true;   // SFM_STREAM_PRIO=0: both streams at the default priority (else compute greatest, copy least)
+    bool plan_ahead = true;    // SFM_PLAN_AHEAD=0: bucket counts + plan inside the step instead of one step ahead
     bool p2p_sparse = true;    // SFM_P2P_SPARSE=0: peer-memory exchange moves the dense gradient
     bool step_graph = true;    // SFM_GRAPH=0: plain stream launches instead of the per-step CUDA graph
 };
@@ -310,6 +326,17 @@ cudaError_t bucket_transpose(const ModelView& m, const BatchView& b, const Bucke
                              const uint32_t* keys, const uint2* pay, int implicit_div, void* work,
                              void* tables, uint32_t* packed, uint32_t* vals, unsigned int* ticket,
                              int sm_count, cudaStream_t st, int64_t* launches);
+// the two halves of bucket_transpose: counts + plan of a batch of resident all-ones rows taken from
+// the row numbers (model-independent: runs one step ahead on the copy stream; the batch size is
+// read on the device), and the stable partition alone
+cudaError_t bucket_count_plan_rows(const ModelView& m, const BucketGeom& g, const int32_t* idx,
+                                   const int32_t* row_ids, const int32_t* n_rows_dev, int n_rows_cap,
+                                   int uniform_m, void* work, void* tables, unsigned int* ticket, int sm_count,
+                                   cudaStream_t st, int64_t* launches);
+cudaError_t bucket_scatter(const ModelView& m, const BatchView& b, const BucketGeom& g,
+                           const uint32_t* keys, const uint2* pay, int implicit_div, void* work,
+                           const void* tables, uint32_t* packed, uint32_t* vals, int sm_count,
+                           cudaStream_t st, int64_t* launches);
 // reduce-by-feature over the bucketed entries + SGD update (fused) or dense gradient
 cudaError_t bucket_pull(const ModelView& m, const BucketGeom& g, const uint32_t* packed,
                         const uint32_t* vals, const void* tables, void* work, const float* S,
