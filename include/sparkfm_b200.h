@@ -235,7 +235,9 @@ int32_t sfm_pack_onehot(const int32_t* idx, const float* label, int64_t n_rows, 
  * round trip in between.  loss_history[n_iters] (may be NULL) gets each iteration's mean loss. */
 int32_t sfm_train(sfm_handle* h, int64_t first_iter, int64_t n_iters, double* loss_history);
 /* The built-in sampler, host side: global row ids of
- * [row_lo, row_hi) selected in iteration iter.  out has capacity row_hi - row_lo. */
+ * [row_lo, row_hi) selected in iteration iter -- i.i.d. Bernoulli(floor(fraction * 2^53) / 2^53)
+ * per row, counter-based and bit-sliced over aligned blocks of 64 global rows, bit-identical to
+ * the device sampler.  out has capacity row_hi - row_lo. */
 int32_t sfm_sample_rows(uint64_t seed, int64_t iter, double fraction, int64_t row_lo,
                         int64_t row_hi, int64_t* out, int64_t* n_out);
 /* Host twin of the PARTITION sampler: global row ids of [row_lo, row_hi) that belong to

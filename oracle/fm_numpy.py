@@ -243,16 +243,37 @@ def als_sweep(w0, w, v, row_ptr, idx, val, label, k0=True, k1=True, reg=(0.0, 0.
 
 
 def sample_rows(seed: int, it: int, fraction: float, row_lo: int, row_hi: int) -> np.ndarray:
-    """DESIGN.md section 2.5 (vectorised)."""
+    """DESIGN.md section 2.5 (vectorised over the 64-row blocks): bit-sliced Bernoulli(thr / 2^53)."""
     rows = np.arange(row_lo, row_hi, dtype=np.int64)
     if fraction >= 1.0:
         return rows
-    if not fraction > 0.0:
+    if not fraction > 0.0 or row_hi <= row_lo:
         return rows[:0]
-    thr = np.uint64(math.floor(fraction * 2.0 ** 53))
-    key = np.uint64(mix64((seed + it) & _M64))
-    h = mix64_np(key ^ mix64_np(rows.astype(np.uint64))) >> np.uint64(11)
-    return rows[h < thr]
+    thr = int(math.floor(fraction * 2.0 ** 53))
+    if thr == 0:
+        return rows[:0]
+    key = mix64((seed + it) & _M64)
+    gamma = 0x9E3779B97F4A7C15
+    last = 53 - ((thr & -thr).bit_length() - 1)      # 1-based position of the lowest set digit
+    q = np.arange(row_lo >> 6, ((row_hi - 1) >> 6) + 1, dtype=np.uint64)
+    und = np.full(len(q), _M64, dtype=np.uint64)
+    hit = np.zeros(len(q), dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        ctr = np.uint64(key) + (q << np.uint64(6)) * np.uint64(gamma)
+        for i in range(1, last + 1):
+            if not und.any():
+                break
+            w = mix64_np(ctr)                        # SplitMix64(seed = key), output number 64 q + i - 1
+            ctr = ctr + np.uint64(gamma)
+            if (thr >> (53 - i)) & 1:
+                hit |= und & ~w
+                und &= w
+            else:
+                und &= ~w
+    bits = (hit[:, None] >> np.arange(64, dtype=np.uint64)[None, :]) & np.uint64(1)
+    g = (q.astype(np.int64)[:, None] << 6) + np.arange(64, dtype=np.int64)[None, :]
+    sel = g[bits.astype(bool)]
+    return sel[(sel >= row_lo) & (sel < row_hi)]
 
 
 # ----------------------------------------------------------------------------- LibFM text

@@ -501,6 +501,23 @@ double fmo_fast32_train_step(fmo_fast32* f, const int64_t* row_ptr, const int32_
     return loss_sum;
 }
 
+/* Hits of global block q (rows 64q .. 64q+63) as a bit mask: DESIGN.md section 2.5. */
+static uint64_t fmo_bernoulli_block(uint64_t key, uint64_t thr, int last, uint64_t q) {
+    const uint64_t gamma = 0x9E3779B97F4A7C15ULL;
+    uint64_t und = ~0ULL, hit = 0ULL, ctr = key + (q << 6) * gamma;
+    for (int i = 1; i <= last && und; ++i) {
+        const uint64_t w = fmo_mix64(ctr); /* SplitMix64(seed = key), output number 64q + i - 1 */
+        ctr += gamma;
+        if ((thr >> (53 - i)) & 1ULL) { /* digit i of p is 1: rows whose digit is 0 are below p */
+            hit |= und & ~w;
+            und &= w;
+        } else { /* digit i of p is 0: rows whose digit is 1 are above p */
+            und &= ~w;
+        }
+    }
+    return hit;
+}
+
 int64_t fmo_sample_rows(uint64_t seed, int64_t iter, double fraction, int64_t row_lo,
                         int64_t row_hi, int64_t* out) {
     int64_t n = 0;
@@ -508,11 +525,22 @@ int64_t fmo_sample_rows(uint64_t seed, int64_t iter, double fraction, int64_t ro
         for (int64_t r = row_lo; r < row_hi; ++r) out[n++] = r;
         return n;
     }
-    if (!(fraction > 0.0)) return 0;
+    if (!(fraction > 0.0) || row_hi <= row_lo) return 0;
     const uint64_t thr = (uint64_t)floor(fraction * 9007199254740992.0); /* 2^53 */
+    if (thr == 0) return 0;
     const uint64_t key = fmo_mix64(seed + (uint64_t)iter);
-    for (int64_t r = row_lo; r < row_hi; ++r)
-        if ((fmo_mix64(key ^ fmo_mix64((uint64_t)r)) >> 11) < thr) out[n++] = r;
+    int tz = 0;
+    while (!((thr >> tz) & 1ULL)) ++tz;
+    const int last = 53 - tz; /* no row can be selected after the lowest set digit of p */
+    for (int64_t q = row_lo >> 6; q <= (row_hi - 1) >> 6; ++q) {
+        uint64_t hit = fmo_bernoulli_block(key, thr, last, (uint64_t)q);
+        while (hit) {
+            const int j = __builtin_ctzll(hit);
+            hit &= hit - 1ULL;
+            const int64_t r = (q << 6) + j;
+            if (r >= row_lo && r < row_hi) out[n++] = r;
+        }
+    }
     return n;
 }
 

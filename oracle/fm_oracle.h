@@ -117,10 +117,13 @@ double fmo_fast32_train_step(fmo_fast32* f, const int64_t* row_ptr, const int32_
                              const float* val, const float* label, const int64_t* row_ids,
                              int64_t n_ids, int64_t iter, double step_size, int64_t batch_count);
 
-/* Mini-batch sampler: row r of the GLOBAL dataset is in iteration
- * iter's batch iff (mix64(mix64(seed + iter) ^ mix64(r)) >> 11) < floor(fraction * 2^53);
- * fraction >= 1 selects every row.  Writes the selected global row ids of [row_lo, row_hi)
- * in ascending order to out (capacity row_hi-row_lo) and returns how many. */
+/* Mini-batch sampler: i.i.d. Bernoulli(p) per row of the GLOBAL data set,
+ * p = floor(fraction * 2^53) / 2^53, decided 64 rows (one aligned block q = r >> 6) at a time:
+ * word i = mix64(key + (64 q + i - 1) * 0x9E3779B97F4A7C15) with key = mix64(seed + iter), i.e.
+ * output number 64 q + i - 1 of SplitMix64 seeded with key, holds binary digit i of the uniform
+ * variate of each of the 64 rows; a row is selected iff its variate is below p (first differing
+ * digit).  fraction >= 1 selects every row.  Writes the selected global row ids of
+ * [row_lo, row_hi) in ascending order to out (capacity row_hi-row_lo) and returns how many. */
 int64_t fmo_sample_rows(uint64_t seed, int64_t iter, double fraction, int64_t row_lo,
                         int64_t row_hi, int64_t* out);
 

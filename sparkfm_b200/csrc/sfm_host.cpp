@@ -469,11 +469,37 @@ extern "C" int32_t sfm_sample_rows(uint64_t seed, int64_t iter, double fraction,
     int64_t n = 0;
     if (fraction >= 1.0) {
         for (int64_t r = row_lo; r < row_hi; ++r) out[n++] = r;
-    } else if (fraction > 0.0) {
+    } else if (fraction > 0.0 && row_hi > row_lo) {
+        // bit-sliced Bernoulli(thr / 2^53) over aligned blocks of 64 global rows (DESIGN.md 2.5;
+        // device twin: BernoulliBlock in sfm_scan.cu)
         const uint64_t thr = (uint64_t)floor(fraction * 9007199254740992.0);
         const uint64_t key = mix64(seed + (uint64_t)iter);
-        for (int64_t r = row_lo; r < row_hi; ++r)
-            if ((mix64(key ^ mix64((uint64_t)r)) >> 11) < thr) out[n++] = r;
+        const uint64_t gamma = 0x9E3779B97F4A7C15ULL;
+        int last = 0;
+        if (thr) {
+            int tz = 0;
+            while (!((thr >> tz) & 1ULL)) ++tz;
+            last = 53 - tz;
+        }
+        for (int64_t q = row_lo >> 6; thr && q <= ((row_hi - 1) >> 6); ++q) {
+            uint64_t und = ~0ULL, hit = 0ULL, ctr = key + ((uint64_t)q << 6) * gamma;
+            for (int i = 1; i <= last && und; ++i) {
+                const uint64_t w = mix64(ctr);
+                ctr += gamma;
+                if ((thr >> (53 - i)) & 1ULL) {
+                    hit |= und & ~w;
+                    und &= w;
+                } else {
+                    und &= ~w;
+                }
+            }
+            while (hit) {
+                const int j = __builtin_ctzll(hit);
+                hit &= hit - 1ULL;
+                const int64_t r = (q << 6) + j;
+                if (r >= row_lo && r < row_hi) out[n++] = r;
+            }
+        }
     }
     *n_out = n;
     return SFM_OK;

@@ -148,6 +148,50 @@ def test_mt_step_matches_single_thread():
     assert np.allclose(a.v, b.v, rtol=1e-12, atol=1e-14) and np.allclose(a.w, b.w, rtol=1e-12, atol=1e-14)
 
 
+def test_sampler_is_the_digit_comparison_it_is_defined_as():
+    """DESIGN.md 2.5 from first principles, one row at a time and with no early exit: the 53
+    digit words of the row's block give its uniform variate u (bit j of word i = digit i of row
+    64 q + j); the row is selected iff u < thr.  The bit-sliced samplers must select exactly
+    these rows (ragged block edges, thresholds with trailing zero digits, p close to 1)."""
+    gamma, m64 = 0x9E3779B97F4A7C15, (1 << 64) - 1
+
+    def by_definition(seed, it, frac, lo, hi):
+        thr = int(math.floor(frac * 2.0 ** 53))
+        key = fn.mix64((seed + it) & m64)
+        out = []
+        for r in range(lo, hi):
+            q, j, u = r >> 6, r & 63, 0
+            for i in range(1, 54):
+                u = (u << 1) | ((fn.mix64((key + ((q << 6) + i - 1) * gamma) & m64) >> j) & 1)
+            if u < thr:
+                out.append(r)
+        return np.asarray(out, dtype=np.int64)
+
+    for frac in (0.5, 0.3, float(np.float32(1 / 45)), 0.75, float(np.float32(0.999)), 2.0 ** -20):
+        want = by_definition(42, 3, frac, 100, 1100)
+        assert np.array_equal(capi.sample_rows(42, 3, frac, 100, 1100), want)
+        assert np.array_equal(fn.sample_rows(42, 3, frac, 100, 1100), want)
+
+
+def test_sampler_statistics_are_bernoulli():
+    n, p = 4_000_000, float(np.float32(1 / 45))
+    a = capi.sample_rows(42, 1, p, 0, n)
+    sd = math.sqrt(n * p * (1 - p))
+    assert abs(len(a) - n * p) < 5 * sd                            # count
+    cnt = np.bincount(a & 63, minlength=64)                         # every position of a block alike
+    assert ((cnt - len(a) / 64) ** 2 / (len(a) / 64)).sum() < 130   # chi^2, 63 dof (p ~ 1e-6)
+    gaps = np.diff(a)                                               # geometric gaps
+    assert abs(gaps.mean() - 1 / p) < 0.5 and abs(gaps.std() - math.sqrt(1 - p) / p) < 0.5
+    hit = np.zeros(n, dtype=np.int8)
+    hit[a] = 1
+    pair_sd = math.sqrt(n) * p
+    for lag in (1, 7, 32, 64):                                      # no correlation between rows
+        assert abs(int((hit[lag:] & hit[:-lag]).sum()) - n * p * p) < 6 * pair_sd
+    other = np.zeros(n, dtype=np.int8)
+    other[capi.sample_rows(42, 2, p, 0, n)] = 1                     # nor between iterations
+    assert abs(int((hit & other).sum()) - n * p * p) < 6 * pair_sd
+
+
 def test_sampler_c_vs_numpy_and_shard_union():
     for frac in (0.0, 0.01, 0.3, float(np.float32(0.1)), 1.0, 1.5):
         for it in (1, 2, 50):
