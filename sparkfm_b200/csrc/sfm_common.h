@@ -211,7 +211,7 @@ struct Knobs {
     int ar_slices = 1;         // SFM_AR_SLICES
     int sort_ahead = 0;        // SFM_SORT_AHEAD
     bool bucket_cache = false; // SFM_BUCKET_CACHE=1: PARTITION caches keep the bucket form
-    bool stream_prio = true;   // SFM_STREAM_PRIO=0: both streams at the default priority (else compute greatest, copy least)
+    bool stream_prio = false;  // SFM_STREAM_PRIO=1: compute stream at the greatest, copy stream at the least priority
     bool plan_ahead = false;   // SFM_PLAN_AHEAD=1: bucket counts + plan one step ahead on the copy stream (measured slower)
     bool p2p_sparse = true;    // SFM_P2P_SPARSE=0: peer-memory exchange moves the dense gradient
     bool step_graph = true;    // SFM_GRAPH=0: plain stream launches instead of the per-step CUDA graph

@@ -606,6 +606,72 @@ def test_empty_and_tiny_batches():
     hd.close()
 
 
+@pytest.mark.parametrize("off", [0, 1, 63, 64, 1234, 5_625_000 * 3 + 17])
+def test_sampler_on_a_shard_at_any_global_offset_matches_the_host_twin(off):
+    """The Bernoulli sampler decides aligned blocks of 64 GLOBAL rows; a shard that
+    starts inside a block must clear the rows of its neighbours.  One GPU holds rows
+    [off, off + n) of a larger data set: every iteration's batch size is the host twin's, the mean
+    loss over ~60 rows (one wrong row would move it by ~1e-2) matches the oracle on exactly those
+    rows, and the device loop (sampler prefetched on the copy stream) reproduces the same bits."""
+    rng = np.random.default_rng(7 + off % 1000)
+    n_slots, k, n = 500, 8, 3001
+    row_ptr, idx, val = synth.ragged_rows(n, n_slots, 8, seed=5, values="normal")
+    label = rng.normal(0, 1, n).astype(np.float32)
+    w0, w, v = make_model(rng, n_slots, k)
+    frac = 0.02
+    kw = dict(task=0, reg=(0.0, 1e-3, 1e-3), step_size=0.1, mini_batch_fraction=frac, sampler_seed=11)
+    a, b = Handle(n_slots, k, **kw), Handle(n_slots, k, **kw)
+    for h in (a, b):
+        h.set_model(w0, w, v)
+        h.load_dataset(row_ptr, idx, val, label, global_row_offset=off)
+    orc = OracleFM(n_slots, k, task=0, reg=(0.0, float(np.float32(1e-3)), float(np.float32(1e-3))))
+    orc.set_model(w0, w, v)
+    losses, sizes = [], []
+    for it in range(1, 7):
+        ids = ocapi.sample_rows(11, it, float(np.float32(frac)), off, off + n) - off   # local rows
+        lg, batch = a.train_step(it)
+        assert batch == len(ids), (it, batch, len(ids))
+        if len(ids):
+            lo = orc.train_step(row_ptr, idx, val.astype(np.float64), label, ids, it,
+                                float(np.float32(0.1))) / len(ids)
+            assert abs(lg - lo) <= LOSS_RTOL * max(abs(lo), 1e-6), (it, lg, lo)
+        losses.append(lg)
+        sizes.append(batch)
+    assert 20 < np.mean(sizes) < 120, sizes
+    hist = b.train(1, 6)
+    assert np.array_equal(np.asarray(hist), np.asarray(losses))
+    ma, mb = a.get_model(), b.get_model()
+    assert ma[0] == mb[0] and np.array_equal(ma[1], mb[1]) and np.array_equal(ma[2], mb[2])
+    a.close()
+    b.close()
+
+
+def test_partition_sampler_on_a_shard_at_a_global_offset():
+    """PARTITION sampler on rows [off, off + n) of a larger data set (off inside a 64-row block):
+    batch sizes and losses are those of the host twin's row lists."""
+    rng = np.random.default_rng(17)
+    n_slots, k, n, off, frac = 400, 8, 2000, 1234, 0.26      # P = 4
+    row_ptr, idx, val = synth.ragged_rows(n, n_slots, 8, seed=9, values="normal")
+    label = rng.normal(0, 1, n).astype(np.float32)
+    w0, w, v = make_model(rng, n_slots, k)
+    P = ocapi.n_parts_for(frac)
+    parts = [ocapi.partition_rows(42, P, p, off, off + n) - off for p in range(P)]
+    assert sorted(np.concatenate(parts).tolist()) == list(range(n))
+    hd = Handle(n_slots, k, task=0, reg=(0.0, 1e-3, 1e-3), step_size=0.1, mini_batch_fraction=frac,
+                sampler_seed=42, sampler_mode=1)
+    hd.set_model(w0, w, v)
+    hd.load_dataset(row_ptr, idx, val, label, global_row_offset=off)
+    orc = OracleFM(n_slots, k, task=0, reg=(0.0, float(np.float32(1e-3)), float(np.float32(1e-3))))
+    orc.set_model(w0, w, v)
+    for it in range(1, 7):
+        ids = parts[(it - 1) % P]
+        lg, nb = hd.train_step(it)
+        lo = orc.train_step(row_ptr, idx, val.astype(np.float64), label, ids, it,
+                            float(np.float32(0.1))) / len(ids)
+        assert nb == len(ids) and abs(lg - lo) <= LOSS_RTOL * abs(lo), (it, nb, len(ids), lg, lo)
+    hd.close()
+
+
 def test_long_run_loss_curve_stays_on_the_oracle():
     """60 iterations on Criteo-shaped rows: the fp32 GPU trajectory must track the fp64 oracle well
     inside the 1e-4 tolerance for the whole curve, not just the first steps (150-iteration run at
