@@ -131,6 +131,30 @@ def test_c_abi_sampler_equals_oracle_sampler():
             assert np.array_equal(a, fn.sample_rows(42, it, frac, 100, 9000))
 
 
+def test_sampler_twins_agree_on_random_seeds_fractions_and_shards():
+    """Property test over the three host twins of DESIGN.md 2.5 (C ABI, C oracle, numpy): random
+    seeds, iterations, fp32 fractions from 2^-24 to 1 - 2^-24, shard ranges that start and end
+    anywhere inside a 64-row block, far-away row numbers; and a random 3-way split of the range
+    samples exactly the rows the whole range does."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(seed=st.integers(0, 2 ** 64 - 1), it=st.integers(1, 10 ** 9),
+           frac=st.floats(2.0 ** -24, 1.0 - 2.0 ** -24, width=32),
+           lo=st.integers(0, 2 ** 40), n=st.integers(0, 3000), cuts=st.tuples(st.floats(0, 1), st.floats(0, 1)))
+    def check(seed, it, frac, lo, n, cuts):
+        hi = lo + n
+        a = sample_rows(seed, it, frac, lo, hi)
+        assert np.array_equal(a, ocapi.sample_rows(seed, it, frac, lo, hi))
+        assert np.array_equal(a, fn.sample_rows(seed, it, frac, lo, hi))
+        assert np.all(np.diff(a) > 0) and (len(a) == 0 or (a[0] >= lo and a[-1] < hi))
+        c1, c2 = sorted(lo + int(c * n) for c in cuts)
+        parts = [sample_rows(seed, it, frac, x, y) for x, y in ((lo, c1), (c1, c2), (c2, hi))]
+        assert np.array_equal(np.concatenate(parts), a)
+
+    check()
+
+
 # ------------------------------------------------------------------------------ generators
 def test_ctr_generator_shape_and_determinism():
     card = synth.ctr_field_log2_cards(39)
